@@ -1,0 +1,136 @@
+/*
+ * nsr_b200.h -- C ABI of the B200-native NeRF per-ray renderer (libnsr_b200.so).
+ *
+ * The reference (gyhandy/Neural-Sim-NeRF) is pure Python/PyTorch and has no FFI; these
+ * entry points are what a binding for its render hot path would call.  Each one names
+ * the reference function it replaces:
+ *
+ *   RN = optimization/utils/run_nerf_noscale.py     RH = optimization/utils/run_nerf_helpers.py
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer (CUDA, current device) unless the name ends in _host;
+ *   - tensors are dense row-major fp32 unless stated otherwise;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is
+ *     enqueued on it and nothing synchronises the host;
+ *   - return value: 0 on success, a negative NSR_E_* code otherwise; nsr_last_error() gives the
+ *     message for the calling thread.  Nothing is written to the outputs on a parameter error;
+ *   - the caller owns every buffer (inputs, outputs, packed weights, workspace).
+ */
+#ifndef NSR_B200_H_
+#define NSR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NSR_OK 0
+#define NSR_E_INVALID (-1)     /* bad argument (null pointer, unsupported size ...) */
+#define NSR_E_UNSUPPORTED (-2) /* valid in the reference but not implemented here (e.g. S > 256) */
+#define NSR_E_CUDA (-3)        /* a CUDA runtime call failed; see nsr_last_error() */
+#define NSR_E_DEVICE (-4)      /* not an sm_100 device */
+
+/* render flags (bit mask) */
+#define NSR_FLAG_LINDISP 1u    /* RN:443  sample linearly in inverse depth */
+#define NSR_FLAG_WHITE_BKGD 2u /* RN:384  composite onto white */
+#define NSR_FLAG_PTS_INPUT 4u  /* nsr_mlp_forward: `z_or_pts` holds explicit points [n,S,3] (RN:26 run_network) */
+
+/* network geometry this library is specialised for (RN:261-278, CFG): D=8, W=256, skips=[4],
+ * multires=10 (63 ch), multires_views=4 (27 ch), use_viewdirs=True. */
+#define NSR_NET_NUM_TENSORS 12 /* pts_linears.0-7, views_linears.0, feature_linear, alpha_linear, rgb_linear */
+
+int nsr_version(void);
+const char* nsr_last_error(void);
+
+/* Number of bytes of one packed network (weights re-laid-out as fp16 UMMA operand chunks in the
+ * order the kernel streams them, followed by the fp32 biases and the alpha / rgb heads). */
+size_t nsr_packed_net_bytes(void);
+
+/*
+ * Pack one NeRF MLP (RH:70-97 `class NeRF`, state_dict order below) for the tensor-core kernel.
+ *   weights[i], biases[i]: device fp32, PyTorch nn.Linear layout [out, in] / [out]
+ *     i = 0..7  pts_linears.i   (256x63, 256x256 x4, 256x319, 256x256 x2)
+ *     i = 8     views_linears.0 (128x283)
+ *     i = 9     feature_linear  (256x256)
+ *     i = 10    alpha_linear    (1x256)
+ *     i = 11    rgb_linear      (3x128)
+ *   packed_out: device buffer of nsr_packed_net_bytes() bytes, 128-byte aligned.
+ * Must be called again after the module's parameters change (the Python layer keys its cache on
+ * the tensors' version counters).
+ */
+int nsr_pack_net(const float* const* weights, const float* const* biases, void* packed_out, void* stream);
+
+/*
+ * Positional encoding + MLP for S points on each of n rays -> raw [n,S,4] = (rgb_raw[3], sigma_raw).
+ * Replaces RN:26-40 run_network + RH:18-66 Embedder + RH:99-122 NeRF.forward.
+ *   rays      [n,11]  o(3) d(3) near far viewdir(3)                        (RN:106-112)
+ *   z_or_pts  [n,S]   sample depths, points are o + d*z (RN:463), or, with NSR_FLAG_PTS_INPUT,
+ *             [n,S,3] explicit points (then only rays[:,8:11] is read)
+ */
+int nsr_mlp_forward(const float* rays, const float* z_or_pts, int64_t n_rays, int n_samples, const void* packed_net,
+                    uint32_t flags, float* raw_out, void* stream);
+
+/*
+ * Alpha compositing.  Replaces RN:343-387 raw2outputs (raw_noise_std = 0; pass pre-noised raw otherwise).
+ *   raw [n,S,4], z_vals [n,S], rays_d [n,ld_rays_d] (first 3 columns are the direction; ld = 3 or 11)
+ *   outputs (each may be NULL): rgb_map [n,3], disp_map [n], acc_map [n], weights [n,S], depth_map [n]
+ * disp_map is NaN where acc_map == 0, like the reference (RN:381).
+ */
+int nsr_raw2outputs(const float* raw, const float* z_vals, const float* rays_d, int ld_rays_d, int64_t n_rays,
+                    int n_samples, uint32_t flags, float* rgb_map, float* disp_map, float* acc_map, float* weights,
+                    float* depth_map, void* stream);
+
+/*
+ * Inverse-CDF resampling.  Replaces RH:199-243 sample_pdf.
+ *   bins [n,B], weights [n,B-1]; u = NULL -> deterministic linspace(0,1,N) (det=True, RH:207-209),
+ *   else u [n,N] uniform draws supplied by the caller (det=False, RH:211).  samples_out [n,N].
+ */
+int nsr_sample_pdf(const float* bins, const float* weights, int64_t n_rays, int n_bins, int n_new, const float* u,
+                   float* samples_out, void* stream);
+
+/*
+ * Hierarchical step between the coarse and the fine pass.  Replaces RN:473-477 and RN:495:
+ *   z_mid = .5(z[1:]+z[:-1]); z_samples = sample_pdf(z_mid, weights[:,1:-1], N_importance);
+ *   z_fine = sort(cat[z_coarse, z_samples]); z_std = std(z_samples, unbiased=False)
+ *   z_coarse [n,S], weights [n,S], u = NULL or [n,N_importance]
+ *   outputs: z_fine [n,S+N_importance], z_samples (may be NULL) [n,N_importance], z_std (may be NULL) [n]
+ */
+int nsr_resample_merge(const float* z_coarse, const float* weights, int64_t n_rays, int n_samples, int n_importance,
+                       const float* u, float* z_fine, float* z_samples, float* z_std, void* stream);
+
+/* Bytes of scratch nsr_render_rays_forward needs for n rays. */
+size_t nsr_render_workspace_bytes(int64_t n_rays, int n_samples, int n_importance);
+
+/*
+ * The whole per-ray renderer, forward.  Replaces RN:390-501 render_rays (perturb = 0 unless
+ * t_rand / u are given, raw_noise_std = 0):
+ *   coarse z (RN:439-445) [+ stratified jitter with caller-supplied t_rand [n,S], RN:447-461]
+ *   -> encode + coarse MLP -> raw2outputs -> sample_pdf -> sort/merge -> encode + fine MLP -> raw2outputs.
+ *   packed_fine = NULL uses the coarse network for the fine pass (RN:481).  n_importance = 0 stops
+ *   after the coarse pass (rgb0/disp0/acc0/z_std are then not written).
+ * Outputs (NULL = not wanted): rgb_map [n,3], disp_map [n], acc_map [n], rgb0 [n,3], disp0 [n],
+ *   acc0 [n], z_std [n], raw [n,S+Ni,4] (retraw), z_vals_out [n,S+Ni] (the fine depths; the backward
+ *   pass needs them), weights_out [n,S+Ni].
+ */
+int nsr_render_rays_forward(const float* rays, int64_t n_rays, const void* packed_coarse, const void* packed_fine,
+                            int n_samples, int n_importance, uint32_t flags, const float* t_rand, const float* u,
+                            float* rgb_map, float* disp_map, float* acc_map, float* rgb0, float* disp0, float* acc0,
+                            float* z_std, float* raw, float* z_vals_out, float* weights_out, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
+/*
+ * Ray generation + packing.  Replaces RH:156-165 get_rays and RN:91-112 (use_viewdirs, ndc=False):
+ *   K_host[9], c2w_host[12] are HOST row-major 3x3 / 3x4; rays_out [H*W,11] device.
+ */
+int nsr_make_rays(int H, int W, const float* K_host, const float* c2w_host, float near_, float far_, float* rays_out,
+                  void* stream);
+
+/* Number of kernels this library has launched since load (all threads); used by bench.py's gpu_launches. */
+uint64_t nsr_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NSR_B200_H_ */

@@ -1,0 +1,38 @@
+"""Build libnsr_b200.so in-tree with nvcc for sm_100a (no JIT cache, no torch extension)."""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SOURCES = ['csrc/api.cu', 'csrc/ray_stage.cu', 'csrc/mlp_forward.cu']
+OUT = os.path.join(HERE, 'libnsr_b200.so')
+FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
+         '-shared', '-Xcompiler', '-fPIC']
+
+
+def needs_build():
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    deps = [os.path.join(HERE, 'csrc', f) for f in os.listdir(os.path.join(HERE, 'csrc'))]
+    deps.append(os.path.join(HERE, '..', 'include', 'nsr_b200.h'))
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return OUT
+    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    cmd = [nvcc] + FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', OUT] + SOURCES
+    r = subprocess.run(cmd, cwd=HERE, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError('nvcc failed building libnsr_b200.so')
+    if verbose:
+        print(r.stdout + r.stderr)
+    return OUT
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

@@ -1,0 +1,64 @@
+// Shared declarations of libnsr_b200: packed-network layout, launch helpers, error plumbing.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/nsr_b200.h"
+
+namespace nsr {
+
+// ----------------------------------------------------------------------------- packed network layout
+// One network = NUM_CHUNKS operand chunks (fp16, [128 out-rows x 64 K] each, UMMA K-major
+// "no swizzle" canonical layout: 8x8 core matrices of 128 contiguous bytes, K-adjacent core
+// matrices 128 B apart, 8-row groups 1024 B apart) in the exact order the MMA issuer consumes
+// them, followed by an fp32 tail (biases + the two tiny heads evaluated on CUDA cores).
+//
+// GEMM steps ("layers") per 128-point tile; K-chunk sources: E = xyz encoding (63 ch + pad),
+// A0..A3 = the four 64-wide K slices of the 256 activations, V = view-dir encoding (27 ch + pad).
+//   step 0      pts_linears.0           N=256  K-chunks: E
+//   step 1..4   pts_linears.1-4         N=256  A0 A1 A2 A3
+//   step 5      pts_linears.5 (skip)    N=256  E A0 A1 A2 A3          (RH:105-106: cat[input_pts, h])
+//   step 6..7   pts_linears.6-7         N=256  A0 A1 A2 A3            (+ alpha head in the step-7 epilogue)
+//   step 8      feature_linear          N=256  A0 A1 A2 A3            (no activation, RH:110)
+//   step 9      views_linears.0         N=128  A0 A1 A2 A3 V          (RH:111: cat[feature, input_views]; + rgb head)
+// Chunk order inside a step: for each 128-wide half of N, all its K-chunks.
+constexpr int CHUNK_ROWS = 128;
+constexpr int CHUNK_K = 64;
+constexpr int CHUNK_BYTES = CHUNK_ROWS * CHUNK_K * 2;  // 16384
+constexpr int NUM_STEPS = 10;
+constexpr int NUM_CHUNKS = 2 * 1 + 4 * 8 + 10 + 2 * 8 + 8 + 5;  // 73
+constexpr int WEIGHT_BYTES = NUM_CHUNKS * CHUNK_BYTES;         // 1,196,032
+
+// fp32 tail (offsets in floats)
+constexpr int TAIL_BIAS = 0;            // [10][256]  (step s bias at s*256; step 9 uses 128)
+constexpr int TAIL_WALPHA = 2560;       // [256]
+constexpr int TAIL_WRGB = 2816;         // [128][4]   (w_rgb[0][j], w_rgb[1][j], w_rgb[2][j], 0)
+constexpr int TAIL_MISC = 3328;         // b_alpha, b_rgb[0..2]
+constexpr int TAIL_FLOATS = 3360;
+constexpr int TAIL_BYTES = TAIL_FLOATS * 4;  // 13440
+constexpr int PACKED_BYTES = WEIGHT_BYTES + TAIL_BYTES;
+
+__host__ __device__ constexpr int step_n_halves(int s) { return s == 9 ? 1 : 2; }
+__host__ __device__ constexpr int step_k_chunks(int s) { return s == 0 ? 1 : ((s == 5 || s == 9) ? 5 : 4); }
+
+// ----------------------------------------------------------------------------- host-side plumbing (api.cu)
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+void count_launch();
+
+// ray_stage.cu
+int launch_coarse_z(const float* rays, int64_t n, int S, uint32_t flags, const float* t_rand, float* z, cudaStream_t st);
+int launch_raw2outputs(const float* raw, const float* z, const float* rays_d, int ld, int64_t n, int S, uint32_t flags,
+                       float* rgb, float* disp, float* acc, float* weights, float* depth, cudaStream_t st);
+int launch_sample_pdf(const float* bins, const float* weights, int64_t n, int B, int N, const float* u, float* out,
+                      cudaStream_t st);
+int launch_resample_merge(const float* z, const float* w, int64_t n, int S, int Ni, const float* u, float* z_fine,
+                          float* z_samples, float* z_std, cudaStream_t st);
+int launch_make_rays(int H, int W, const float* K9, const float* c2w12, float near_, float far_, float* rays,
+                     cudaStream_t st);
+// mlp_forward.cu
+int launch_pack_net(const float* const* weights, const float* const* biases, void* packed, cudaStream_t st);
+int launch_mlp_forward(const float* rays, const float* z_or_pts, int64_t n, int S, const void* packed, uint32_t flags,
+                       float* raw, cudaStream_t st);
+
+}  // namespace nsr

@@ -1,0 +1,67 @@
+"""The C-ABI library builds, loads, and exports every entry point include/nsr_b200.h declares
+(no compute calls: this runs without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def built_lib():
+    import neural_sim_nerf_b200.build as b
+    return b.build()
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, 'include', 'nsr_b200.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(nsr_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_header_declares_the_path():
+    syms = declared_symbols()
+    for s in ('nsr_pack_net', 'nsr_mlp_forward', 'nsr_raw2outputs', 'nsr_sample_pdf', 'nsr_resample_merge',
+              'nsr_render_rays_forward', 'nsr_make_rays', 'nsr_last_error'):
+        assert s in syms
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    h = ctypes.CDLL(built_lib)
+    for s in declared_symbols():
+        assert hasattr(h, s), f'{s} declared in include/nsr_b200.h but not exported'
+
+
+def test_python_binding_covers_header(built_lib):
+    import neural_sim_nerf_b200 as nsr
+    assert sorted(nsr.EXPORTED_SYMBOLS) == declared_symbols()
+    L = nsr.lib()
+    assert L.nsr_version() >= 100
+    # 73 operand chunks of 16 KiB + fp32 tail
+    assert L.nsr_packed_net_bytes() == 73 * 16384 + 3360 * 4
+    assert L.nsr_render_workspace_bytes(0, 64, 128) == 0
+    assert L.nsr_render_workspace_bytes(512, 64, 128) >= 512 * (64 * 4 * 2 + 64 * 16 + 192 * 4 + 192 * 16)
+
+
+def test_parameter_errors_do_not_need_a_gpu(built_lib):
+    import neural_sim_nerf_b200 as nsr
+    L = nsr.lib()
+    rc = L.nsr_mlp_forward(None, None, 4, 64, None, 0, None, None)
+    assert rc == -1 and b'null' in L.nsr_last_error()
+    rc = L.nsr_raw2outputs(None, None, None, 3, -1, 64, 0, None, None, None, None, None, None)
+    assert rc == -1
+    assert L.nsr_mlp_forward(None, None, 0, 64, None, 0, None, None) == 0   # empty batch is a no-op
+
+
+def test_sass_is_blackwell_native(built_lib):
+    """tcgen05.mma / tcgen05.ld / bulk-copy must be in the binary (UTCHMMA / LDTM / UBLKCP)."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+    if not os.path.exists(cuobjdump):
+        pytest.skip('cuobjdump not available')
+    sass = subprocess.run([cuobjdump, '-sass', built_lib], capture_output=True, text=True).stdout
+    for mnemonic in ('UTCHMMA', 'LDTM', 'UBLKCP'):
+        assert mnemonic in sass, mnemonic

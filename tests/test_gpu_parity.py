@@ -1,0 +1,266 @@
+"""GPU parity: the CUDA path (through the Python mirror -> ctypes -> C ABI) against the golden vectors
+made by the reference and against the CPU oracle on seeded inputs.  Run on the B200 box: pytest -m gpu.
+
+Tolerances
+  * exact-fp32 stages (depths, compositing, resampling, merge, ray generation): 1e-5 relative to max(1,|ref|)
+    (parallel scans / sums re-associate fp32 adds, nothing more);
+  * MLP raw outputs: operands are fp16 on the tensor cores with fp32 accumulation ->
+    |d raw| <= 2e-2 * max(1, |ref|) per element (measured ~3e-3 typical);
+  * rendered maps (north_star): |d| <= 1e-3 * max(1, |ref|), NaN-equal disparity.
+"""
+import numpy as np
+import pytest
+import torch
+
+import nerf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL_EXACT = 1e-5
+TOL_RAW = 2e-2
+TOL_MAP = 1e-3
+
+
+@pytest.fixture(scope='module')
+def nsr():
+    import neural_sim_nerf_b200 as m
+    assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
+    return m
+
+
+def module_from_sd(nsr, sd):
+    net = nsr.NeRF()
+    net.load_state_dict(sd)
+    return net.cuda()
+
+
+@pytest.fixture(scope='module')
+def nets(nsr, wfit):
+    return module_from_sd(nsr, wfit[0]), module_from_sd(nsr, wfit[1])
+
+
+def C(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def relerr(a, b):
+    a = a.detach().float().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    b = b.detach().float().cpu().numpy() if torch.is_tensor(b) else np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    nan_a, nan_b = np.isnan(a), np.isnan(b)
+    return np.abs(a - b)[~(nan_a | nan_b)] / np.maximum(1.0, np.abs(b[~(nan_a | nan_b)])), (nan_a != nan_b).sum()
+
+
+def assert_close(a, b, tol, what, nan_slack=0):
+    err, nan_mismatch = relerr(a, b)
+    assert nan_mismatch <= nan_slack, f'{what}: {nan_mismatch} NaN mismatches'
+    mx = err.max() if err.size else 0.0
+    assert mx <= tol, f'{what}: max err {mx:.3e} > {tol}'
+    return mx
+
+
+# ----------------------------------------------------------------------------- stage tests on golden vectors
+def test_raw2outputs_matches_reference(nsr, golden):
+    rays = C(golden['rays'])
+    for raw, z, names in ((golden['raw0'], golden['z0'], ('rgb0', 'disp0', 'acc0', 'weights0', 'depth0')),
+                          (golden['raw1'], golden['z1'], ('rgb_map', 'disp_map', 'acc_map', 'weights1', 'depth_map'))):
+        outs = nsr.raw2outputs(C(raw), C(z), rays[:, 3:6].contiguous())
+        for o, nme in zip(outs, names):
+            assert_close(o, golden[nme], TOL_EXACT, nme)
+    wb = nsr.raw2outputs(C(golden['raw1']), C(golden['z1']), rays[:, 3:6].contiguous(), white_bkgd=True)[0]
+    assert_close(wb, golden['wb_rgb_map'], TOL_EXACT, 'white_bkgd')
+
+
+def test_sample_pdf_matches_reference(nsr, golden):
+    z0, w0 = C(golden['z0']), C(golden['weights0'])
+    bins = (.5 * (z0[:, 1:] + z0[:, :-1])).contiguous()
+    zs = nsr.sample_pdf(bins, w0[:, 1:-1].contiguous(), 128, det=True)
+    assert_close(zs, golden['z_samples'], TOL_EXACT, 'z_samples')
+
+
+def test_resample_merge_matches_reference(nsr, golden):
+    import ctypes
+    L = nsr.lib()
+    n = golden['z0'].shape[0]
+    for zk, wk, uk, zsk, z1k in (('z0', 'weights0', None, 'z_samples', 'z1'), ('p_z0', 'p_weights0', 'p_u', 'p_z_samples', 'p_z1')):
+        z0, w0 = C(golden[zk]), C(golden[wk])
+        u = C(golden[uk]) if uk else None
+        z1 = torch.empty(n, 192, device='cuda')
+        zs = torch.empty(n, 128, device='cuda')
+        zstd = torch.empty(n, device='cuda')
+        rc = L.nsr_resample_merge(z0.data_ptr(), w0.data_ptr(), n, 64, 128, u.data_ptr() if u is not None else None,
+                                  z1.data_ptr(), zs.data_ptr(), zstd.data_ptr(), None)
+        assert rc == 0, L.nsr_last_error()
+        torch.cuda.synchronize()
+        assert_close(zs, golden[zsk], TOL_EXACT, zsk)
+        assert_close(z1, golden[z1k], TOL_EXACT, z1k)
+        assert bool((z1[:, 1:] >= z1[:, :-1]).all()), 'merged depths not sorted'
+        if uk is None:
+            assert_close(zstd, golden['z_std'], TOL_EXACT, 'z_std')
+
+
+def test_mlp_matches_reference(nsr, golden, nets):
+    rays = C(golden['rays'])
+    for zkey, net, key in (('z0', nets[0], 'raw0'), ('z1', nets[1], 'raw1')):
+        z = C(golden[zkey])
+        pts = rays[:, None, 0:3] + rays[:, None, 3:6] * z[:, :, None]
+        raw = nsr.run_network(pts, rays[:, 8:11].contiguous(), net)
+        mx = assert_close(raw, golden[key], TOL_RAW, key)
+        print(f'{key}: max err {mx:.3e}')
+
+
+def test_render_rays_matches_reference(nsr, golden, nets):
+    rays = C(golden['rays'])
+    with torch.no_grad():
+        r = nsr.render_rays(rays, nets[0], None, 64, retraw=True, N_importance=128, network_fine=nets[1])
+    torch.cuda.synchronize()
+    for k in ('rgb_map', 'acc_map', 'rgb0', 'acc0', 'z_std'):
+        mx = assert_close(r[k], golden['e2e_' + k], TOL_MAP, k)
+        print(f'{k}: max err {mx:.3e}')
+    # disparity: 1/depth amplifies on near-empty rays; compare where the ray is not almost empty, NaN-equal otherwise
+    for dk, ak in (('disp_map', 'acc_map'), ('disp0', 'acc0')):
+        ref_d, ref_a = golden['e2e_' + dk], golden['e2e_' + ak]
+        got = r[dk].cpu().numpy()
+        solid = ref_a > 1e-2
+        assert_close(got[solid], ref_d[solid], TOL_MAP, dk)
+        empty = ref_a == 0
+        assert np.isnan(got[empty]).all() == np.isnan(ref_d[empty]).all()
+    assert_close(r['raw'], golden['e2e_raw'], TOL_RAW, 'raw (retraw)')
+
+
+def test_make_rays_and_render_c2w(nsr, golden, nets):
+    K, c2w = golden['getrays_K'], golden['getrays_c2w']
+    rays = nsr.make_rays(10, 12, K, torch.from_numpy(c2w), 0.25, 1.75)
+    assert_close(rays[:, 0:3].reshape(10, 12, 3), golden['getrays_o'], 1e-7, 'rays_o')
+    assert_close(rays[:, 3:6].reshape(10, 12, 3), golden['getrays_d'], 1e-6, 'rays_d')
+    d = torch.from_numpy(golden['getrays_d']).reshape(-1, 3)
+    assert_close(rays[:, 8:11], (d / d.norm(dim=-1, keepdim=True)).numpy(), 1e-6, 'viewdirs')
+    # render(c2w=...) == render(rays=...) on the same camera
+    H = W = 24
+    Kc = [[80.0, 0, 11.5], [0, 80.0, 12.5], [0, 0, 1]]
+    pose = O.pose_spherical(90., 22.5 - 180., 1.01)[:3, :4]
+    kw = dict(network_fn=nets[0], network_query_fn=None, N_samples=64, N_importance=128, network_fine=nets[1],
+              use_viewdirs=True, ndc=False, near=O.YCBV_NEAR, far=O.YCBV_FAR)
+    with torch.no_grad():
+        a = nsr.render(H, W, Kc, chunk=512, c2w=pose.cuda(), **kw)
+        ro, rd = nsr.get_rays(H, W, Kc, pose.cuda())
+        b = nsr.render(H, W, Kc, chunk=512, rays=torch.stack([ro.reshape(-1, 3), rd.reshape(-1, 3)], 0), **kw)
+    assert a[0].shape == (H, W, 3) and b[0].shape == (H * W, 3)
+    assert_close(a[0].reshape(-1, 3), b[0], TOL_MAP, 'render c2w vs rays')
+
+
+# ----------------------------------------------------------------------------- seeded inputs vs the CPU oracle
+def camera_rays(n_side, phi, theta=90.):
+    H = W = 400
+    c2w = O.pose_spherical(theta, phi - 180., 1.01)[:3, :4]
+    ro, rd = O.get_rays(H, W, O.YCBV_K_400, c2w)
+    ii = torch.linspace(0, 399, n_side).long()
+    sel = (ii[:, None] * W + ii[None, :]).reshape(-1)
+    return O.pack_rays(ro.reshape(-1, 3)[sel], rd.reshape(-1, 3)[sel], O.YCBV_NEAR, O.YCBV_FAR)
+
+
+@pytest.mark.parametrize('phi,n_side', [(112.5, 23), (292.5, 16)])
+def test_render_rays_vs_oracle_seeded(nsr, wfit, nets, phi, n_side):
+    rays = camera_rays(n_side, phi)
+    with torch.no_grad():
+        ref = O.render_rays(rays, wfit[0], wfit[1], 64, 128)
+        got = nsr.render_rays(rays.cuda(), nets[0], None, 64, N_importance=128, network_fine=nets[1])
+    for k in ('rgb_map', 'acc_map', 'rgb0', 'acc0', 'z_std'):
+        assert_close(got[k], ref[k], TOL_MAP, f'{k} phi={phi}')
+
+
+def test_scaled_random_weights_vs_oracle(nsr):
+    """Default-init weights scaled up: dense fog everywhere (no empty rays), different value ranges."""
+    sdc, sdf = O.random_state_dict(21, scale=3.0), O.random_state_dict(22, scale=3.0)
+    for sd in (sdc, sdf):
+        sd['alpha_linear.bias'] += 2.0
+    rays = camera_rays(12, 22.5)
+    with torch.no_grad():
+        ref = O.render_rays(rays, sdc, sdf, 64, 128)
+        got = nsr.render_rays(rays.cuda(), module_from_sd(nsr, sdc), None, 64, N_importance=128,
+                              network_fine=module_from_sd(nsr, sdf))
+    for k in ('rgb_map', 'acc_map', 'rgb0', 'acc0', 'z_std', 'disp_map', 'disp0'):
+        assert_close(got[k], ref[k], 2 * TOL_MAP if 'disp' in k else TOL_MAP, k)
+
+
+def test_flags_lindisp_white_coarse_only(nsr, wfit, nets):
+    rays = camera_rays(9, 200.0)
+    with torch.no_grad():
+        ref = O.render_rays(rays, wfit[0], wfit[1], 64, 128, lindisp=True, white_bkgd=True)
+        got = nsr.render_rays(rays.cuda(), nets[0], None, 64, N_importance=128, network_fine=nets[1], lindisp=True, white_bkgd=True)
+        ref_c = O.render_rays(rays, wfit[0], None, 48, 0)
+        got_c = nsr.render_rays(rays.cuda(), nets[0], None, 48, N_importance=0)
+    for k in ('rgb_map', 'acc_map', 'rgb0', 'acc0'):
+        assert_close(got[k], ref[k], TOL_MAP, 'lindisp+white ' + k)
+    assert set(got_c) == {'rgb_map', 'disp_map', 'acc_map'}
+    for k in ('rgb_map', 'acc_map'):
+        assert_close(got_c[k], ref_c[k], TOL_MAP, 'coarse-only ' + k)
+
+
+def test_fine_falls_back_to_coarse_network(nsr, wfit, nets):
+    """network_fine=None -> the coarse network evaluates the fine samples too (RN:481)."""
+    rays = camera_rays(8, 60.0)
+    with torch.no_grad():
+        ref = O.render_rays(rays, wfit[0], None, 64, 128)
+        got = nsr.render_rays(rays.cuda(), nets[0], None, 64, N_importance=128, network_fine=None)
+    assert_close(got['rgb_map'], ref['rgb_map'], TOL_MAP, 'rgb_map')
+
+
+# ----------------------------------------------------------------------------- edge cases and size-independent properties
+def test_ragged_and_empty_batches(nsr, nets):
+    for n in (0, 1, 2, 3, 127, 129, 641):
+        rays = camera_rays(26, 22.5)[:n].cuda()
+        with torch.no_grad():
+            r = nsr.render_rays(rays, nets[0], None, 64, N_importance=128, network_fine=nets[1])
+        assert r['rgb_map'].shape == (n, 3) and r['z_std'].shape == (n,)
+        if n:
+            big = nsr.render_rays(camera_rays(26, 22.5).cuda(), nets[0], None, 64, N_importance=128, network_fine=nets[1])
+            assert torch.equal(r['rgb_map'], big['rgb_map'][:n]), f'n={n}: result depends on batch size'
+
+
+def test_weight_update_is_noticed(nsr, wfit):
+    net = module_from_sd(nsr, wfit[0])
+    rays = camera_rays(6, 22.5).cuda()
+    with torch.no_grad():
+        a = nsr.render_rays(rays, net, None, 64)['rgb_map'].clone()
+        net.rgb_linear.bias.add_(0.5)
+        b = nsr.render_rays(rays, net, None, 64)['rgb_map']
+    assert not torch.equal(a, b), 'in-place parameter update did not invalidate the packed-weight cache'
+
+
+def test_full_size_properties(nsr, wfit, nets):
+    """BASELINE config 2 size (400x400, 64+128): chunk invariance, determinism, physical bounds,
+    and a 1024-ray sample against the oracle."""
+    H = W = 400
+    pose = O.pose_spherical(90., 157.5 - 180., 1.01)[:3, :4]
+    kw = dict(network_fn=nets[0], network_query_fn=None, N_samples=64, N_importance=128, network_fine=nets[1],
+              use_viewdirs=True, ndc=False, near=O.YCBV_NEAR, far=O.YCBV_FAR)
+    with torch.no_grad():
+        rgb, disp, acc, ex = nsr.render(H, W, O.YCBV_K_400, chunk=1 << 20, c2w=pose, **kw)
+        rgb2, _, acc2, _ = nsr.render(H, W, O.YCBV_K_400, chunk=1 << 20, c2w=pose, **kw)
+        rays = nsr.make_rays(H, W, O.YCBV_K_400, pose, O.YCBV_NEAR, O.YCBV_FAR)
+        parts = [nsr.render_rays(rays[i:i + 50000], nets[0], None, 64, N_importance=128, network_fine=nets[1])['rgb_map']
+                 for i in range(0, H * W, 50000)]
+    assert rgb.shape == (H, W, 3) and acc.shape == (H, W)
+    assert torch.equal(rgb, rgb2) and torch.equal(acc, acc2), 'render is not deterministic'
+    assert torch.equal(torch.cat(parts, 0).reshape(H, W, 3), rgb), 'result depends on chunking'
+    assert torch.isfinite(rgb).all() and torch.isfinite(acc).all()
+    assert float(acc.min()) >= 0.0 and float(acc.max()) <= 1.0 + 1e-4
+    assert float(rgb.min()) >= 0.0 and float(rgb.max()) <= 1.0 + 1e-4
+    assert bool((torch.isnan(disp) == (acc == 0)).all()), 'NaN disparity must coincide with empty rays'
+    assert 0.02 < float((acc > 0.5).float().mean()) < 0.9
+    sel = torch.randperm(H * W, generator=torch.Generator().manual_seed(3))[:1024]
+    with torch.no_grad():
+        ref = O.render_rays(rays[sel.cuda()].cpu(), wfit[0], wfit[1], 64, 128)
+    assert_close(rgb.reshape(-1, 3)[sel.cuda()], ref['rgb_map'], TOL_MAP, 'full-size sample rgb')
+    assert_close(acc.reshape(-1)[sel.cuda()], ref['acc_map'], TOL_MAP, 'full-size sample acc')
+
+
+def test_no_silent_fallbacks(nsr, nets):
+    with pytest.raises(Exception):
+        nsr.render_rays(camera_rays(4, 0.0), nets[0], None, 64)          # CPU rays: no CPU path
+    with pytest.raises(NotImplementedError):
+        nsr.render_rays(camera_rays(4, 0.0)[:, :8].cuda(), nets[0], None, 64)  # use_viewdirs=False layout
+    small = torch.nn.Module()
+    with pytest.raises(NotImplementedError):
+        nsr.render_rays(camera_rays(4, 0.0).cuda(), small, None, 64)
