@@ -1,0 +1,93 @@
+"""Multi-GPU plumbing for the render path: one process per GPU, rays or whole images
+sharded with NO forward collective; the only exchange is one all-reduce(SUM) per outer step on the
+tiny dL/dpsi (8 floats) -- and dL/dMLP when the NeRF weights train -- plus an optional gather of the
+rendered pixels to the rank that writes the PNGs (RN:245-250).
+
+The reference is single-process (MAIN:1363-1383); the scaling rule it implies is kept: the psi
+gradient is the MEAN over all per-chunk gradients of all images (MAIN:191), so ranks all-reduce
+(sum of chunk gradients, number of chunks) and divide once.
+"""
+import torch
+import torch.distributed as dist
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_bounds(n, rank, world_size):
+    """Contiguous, balanced [lo, hi) of `n` items for `rank`; sizes differ by at most one."""
+    base, rem = divmod(n, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_poses(render_poses, rank=None, world_size=None):
+    """The K poses of one epoch (MAIN:1342) are independent images: rank r renders poses[lo:hi]."""
+    r, w = world()
+    rank = r if rank is None else rank
+    world_size = w if world_size is None else world_size
+    lo, hi = shard_bounds(len(render_poses), rank, world_size)
+    return render_poses[lo:hi], (lo, hi)
+
+
+def render_rays_sharded(rays_flat, render_fn, gather=True):
+    """Render a [N,11] ray batch with every rank taking a contiguous slice.  `render_fn(rays) -> dict`
+    (e.g. functools.partial(render_rays, **render_kwargs)).  With gather=True every rank returns the
+    full-size maps (all_gather of the per-rank slices); otherwise only its own slice."""
+    rank, ws = world()
+    n = rays_flat.shape[0]
+    lo, hi = shard_bounds(n, rank, ws)
+    local = render_fn(rays_flat[lo:hi])
+    if ws == 1 or not gather:
+        return local
+    out = {}
+    sizes = [shard_bounds(n, r, ws) for r in range(ws)]
+    cap = max(b - a for a, b in sizes)
+    for k, v in local.items():
+        # all_gather wants equal shapes: pad every slice to the largest one, trim after
+        padded = torch.zeros((cap,) + tuple(v.shape[1:]), dtype=v.dtype, device=v.device)
+        padded[:v.shape[0]] = v
+        parts = [torch.empty_like(padded) for _ in range(ws)]
+        dist.all_gather(parts, padded)
+        out[k] = torch.cat([p[:b - a] for p, (a, b) in zip(parts, sizes)], 0)
+    return out
+
+
+def reduce_psi_grad(chunk_grads):
+    """chunk_grads: this rank's list of per-chunk dL/dpsi tensors (what render_path_grad returns as
+    `dLdpsis`, RN:190).  Returns the reference's estimator over ALL ranks: mean over every chunk of
+    every image (MAIN:191) -- one all_reduce(SUM) of [sum, count]."""
+    if len(chunk_grads):
+        s = torch.stack([g.reshape(-1).to(torch.float64) for g in chunk_grads], 0).sum(0)
+    else:
+        s = None
+    rank, ws = world()
+    if ws == 1:
+        return (s / max(len(chunk_grads), 1)).to(torch.float32)
+    dev = chunk_grads[0].device if len(chunk_grads) else torch.device('cuda', torch.cuda.current_device()) if dist.get_backend() == 'nccl' else torch.device('cpu')
+    n_psi = torch.tensor([s.numel() if s is not None else 0], device=dev)
+    dist.all_reduce(n_psi, op=dist.ReduceOp.MAX)
+    buf = torch.zeros(int(n_psi.item()) + 1, dtype=torch.float64, device=dev)
+    if s is not None:
+        buf[:-1] = s.to(dev)
+        buf[-1] = len(chunk_grads)
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+    return (buf[:-1] / buf[-1].clamp(min=1)).to(torch.float32)
+
+
+def all_reduce_grads_(tensors):
+    """In-place SUM all-reduce of a list of gradient tensors as one flat bucket (dL/dMLP: 2 x 595 844
+    fp32 = 4.77 MB -- latency-bound on NVLink 5, so one bucket, no compute/communication fusion)."""
+    rank, ws = world()
+    if ws == 1 or not tensors:
+        return tensors
+    flat = torch.cat([t.reshape(-1) for t in tensors])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    off = 0
+    for t in tensors:
+        t.copy_(flat[off:off + t.numel()].view_as(t))
+        off += t.numel()
+    return tensors
