@@ -36,6 +36,9 @@ extern "C" {
 #define NSR_FLAG_LINDISP 1u    /* RN:443  sample linearly in inverse depth */
 #define NSR_FLAG_WHITE_BKGD 2u /* RN:384  composite onto white */
 #define NSR_FLAG_PTS_INPUT 4u  /* nsr_mlp_forward: `z_or_pts` holds explicit points [n,S,3] (RN:26 run_network) */
+#define NSR_FLAG_FAST_FP16 8u  /* MLP products as single fp16 x fp16 MMAs (fp32 accumulate) instead of the default
+                                  error-compensated hi/lo split (3 MMAs): ~3x the MLP throughput, but misses the
+                                  1e-3 parity bar on rays that graze sharp surfaces ("precision") */
 
 /* network geometry this library is specialised for (RN:261-278, CFG): D=8, W=256, skips=[4],
  * multires=10 (63 ch), multires_views=4 (27 ch), use_viewdirs=True. */
@@ -44,7 +47,7 @@ extern "C" {
 int nsr_version(void);
 const char* nsr_last_error(void);
 
-/* Number of bytes of one packed network (weights re-laid-out as fp16 UMMA operand chunks in the
+/* Number of bytes of one packed network (weights re-laid-out as fp16 hi/lo UMMA operand chunks in the
  * order the kernel streams them, followed by the fp32 biases and the alpha / rgb heads). */
 size_t nsr_packed_net_bytes(void);
 

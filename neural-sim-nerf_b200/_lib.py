@@ -42,6 +42,7 @@ EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 FLAG_LINDISP = 1
 FLAG_WHITE_BKGD = 2
 FLAG_PTS_INPUT = 4
+FLAG_FAST_FP16 = 8
 
 
 class NsrError(RuntimeError):

@@ -132,10 +132,11 @@ int nsr_render_rays_forward(const float* rays, int64_t n, const void* packed_coa
   ws += align_up(size_t(n) * T * 4, 256);
   float* raw1 = reinterpret_cast<float*>(ws);
   const uint32_t cflags = flags & NSR_FLAG_WHITE_BKGD;
+  const uint32_t mflags = flags & NSR_FLAG_FAST_FP16;
   int rc;
 
   if ((rc = launch_coarse_z(rays, n, S, flags, t_rand, z0, st))) return rc;                          // RN:439-461
-  if ((rc = launch_mlp_forward(rays, z0, n, S, packed_coarse, 0, raw0, st))) return rc;              // RN:463-466
+  if ((rc = launch_mlp_forward(rays, z0, n, S, packed_coarse, mflags, raw0, st))) return rc;              // RN:463-466
   if (Ni == 0) {
     if ((rc = launch_raw2outputs(raw0, z0, rays + 3, 11, n, S, cflags, rgb_map, disp_map, acc_map, weights_out, nullptr, st))) return rc;
     if (raw) cudaMemcpyAsync(raw, raw0, size_t(n) * S * 16, cudaMemcpyDeviceToDevice, st);
@@ -146,7 +147,7 @@ int nsr_render_rays_forward(const float* rays, int64_t n, const void* packed_coa
   float* zf = z_vals_out ? z_vals_out : z1;
   if ((rc = launch_resample_merge(z0, w0, n, S, Ni, u, zf, nullptr, z_std, st))) return rc;          // RN:473-477, 495
   float* rawf = raw ? raw : raw1;
-  if ((rc = launch_mlp_forward(rays, zf, n, T, packed_fine ? packed_fine : packed_coarse, 0, rawf, st))) return rc;  // RN:478-483
+  if ((rc = launch_mlp_forward(rays, zf, n, T, packed_fine ? packed_fine : packed_coarse, mflags, rawf, st))) return rc;  // RN:478-483
   if ((rc = launch_raw2outputs(rawf, zf, rays + 3, 11, n, T, cflags, rgb_map, disp_map, acc_map, weights_out, nullptr, st))) return rc;  // RN:485
   return NSR_OK;
 }

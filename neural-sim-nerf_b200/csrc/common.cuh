@@ -27,7 +27,8 @@ constexpr int CHUNK_K = 64;
 constexpr int CHUNK_BYTES = CHUNK_ROWS * CHUNK_K * 2;  // 16384
 constexpr int NUM_STEPS = 10;
 constexpr int NUM_CHUNKS = 2 * 1 + 4 * 8 + 10 + 2 * 8 + 8 + 5;  // 73
-constexpr int WEIGHT_BYTES = NUM_CHUNKS * CHUNK_BYTES;         // 1,196,032
+constexpr int CHUNK_PAIR_BYTES = 2 * CHUNK_BYTES;              // [hi chunk | lo chunk], lo = fp16(W - fp16(W))
+constexpr int WEIGHT_BYTES = NUM_CHUNKS * CHUNK_PAIR_BYTES;    // 2,392,064
 
 // fp32 tail (offsets in floats)
 constexpr int TAIL_BIAS = 0;            // [10][256]  (step s bias at s*256; step 9 uses 128)

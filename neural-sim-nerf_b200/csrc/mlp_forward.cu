@@ -1,18 +1,28 @@
 // Positional encoding + 8x256 NeRF MLP (RH:18-66, RH:99-122, RN:26-40) as one tcgen05 kernel.
 //
-// A CTA owns 128 sample points at a time (one UMMA M=128 tile; thread r of the four compute
-// warps == row r == TMEM lane r).  All ten GEMM steps of the network run back to back on that
-// tile without touching HBM:
-//   * the weights arrive as pre-packed 16 KB fp16 operand chunks (common.cuh) streamed by the
-//     TMA engine (cp.async.bulk, mbarrier complete_tx) through a 4-deep shared-memory ring;
-//   * the A operand (encodings / activations, fp16) lives in shared memory in the UMMA K-major
-//     canonical layout and is rewritten in place by the epilogue of the previous step;
-//   * accumulators live in TMEM (128 lanes x 256 fp32 columns); the epilogue reads them with
-//     tcgen05.ld, adds the bias, applies ReLU, rounds to fp16 and writes the next A operand;
-//   * the 1-wide alpha head and 3-wide rgb head are dot products evaluated in fp32 on CUDA
-//     cores inside the step-7 / step-9 epilogues (they would waste a whole MMA N-tile).
-// Warp roles: warps 0-3 compute (encode + epilogue), warp 4 MMA issuer, warp 5 weight producer.
-// Only rays, depths and the packed weights are read from HBM, only raw [P,4] is written.
+// A CTA owns one 128-point tile at a time (UMMA M=128: row r == TMEM lane r == thread r of the
+// epilogue warps) and runs all ten GEMM steps of the network on it without touching HBM.
+//
+//   TMEM (512 columns)   ACC0 [0,128) ACC1 [128,256)  fp32 accumulators of the two 128-wide halves of N
+//                        AHI [256,384) ALO [384,512)  the 256 activations as fp16 hi / lo words (A operand,
+//                                                     tcgen05.mma "TS" form: A from TMEM, B from shared memory)
+//   shared memory        xyz / view-dir encodings of the current and the next tile (A operand, "SS" form),
+//                        a ring of weight chunks streamed by the TMA engine (cp.async.bulk + mbarrier),
+//                        the fp32 tail (biases, alpha / rgb heads)
+//
+// Precision.  fp16 operands with fp32 accumulation are NOT enough for the 1e-3 parity bar on sharp scenes
+// (DESIGN.md "precision"), so by default every product runs as an error-compensated split:
+//     x = x_hi + x_lo,  W = W_hi + W_lo  (fp16 each),   x.W ~= x_hi.W_hi + x_lo.W_hi + x_hi.W_lo
+// (three MMAs per k-step into the same fp32 accumulator; the dropped x_lo.W_lo term is ~2^-22).
+// SPLIT=1 (NSR_FLAG_FAST_FP16) issues only the first term.
+//
+// Pipeline.  For step s the MMA warp issues the N=0..127 half (all K) then the N=128..255 half; the
+// epilogue drains ACC0 while the second half is still being multiplied, keeps the rounded result in
+// registers until every MMA that reads the old activations has retired, then overwrites AHI/ALO[K 0..127];
+// the next step's first K half starts as soon as that store lands, while ACC1 is being drained.
+// Encoder warps prepare tile i+1's encodings during tile i.
+//
+// Warp roles: 0-3 epilogue (TMEM lane quadrant = warp), 4-5 encoders, 6 MMA issuer, 7 weight producer.
 #include <math.h>
 
 #include "common.cuh"
@@ -47,7 +57,8 @@ __global__ void pack_net_kernel(NetPtrs p, uint8_t* __restrict__ out) {
   if (c < NUM_CHUNKS) {
     int step, nh, kc;
     chunk_decode(c, step, nh, kc);
-    __half* dst = reinterpret_cast<__half*>(out + size_t(c) * CHUNK_BYTES);
+    __half* hi = reinterpret_cast<__half*>(out + size_t(c) * CHUNK_PAIR_BYTES);
+    __half* lo = reinterpret_cast<__half*>(out + size_t(c) * CHUNK_PAIR_BYTES + CHUNK_BYTES);
     for (int e = threadIdx.x; e < CHUNK_ROWS * CHUNK_K; e += blockDim.x) {
       const int nl = e / CHUNK_K, kl = e % CHUNK_K;
       const int n = nh * 128 + nl;
@@ -68,7 +79,9 @@ __global__ void pack_net_kernel(NetPtrs p, uint8_t* __restrict__ out) {
         if (kc < 4) v = p.w[8][n * 283 + kc * 64 + kl];
         else if (kl < 27) v = p.w[8][n * 283 + 256 + kl];
       }
-      dst[chunk_off(nl, kl) >> 1] = __float2half_rn(v);
+      const __half h = __float2half_rn(v);
+      hi[chunk_off(nl, kl) >> 1] = h;
+      lo[chunk_off(nl, kl) >> 1] = __float2half_rn(v - __half2float(h));
     }
   } else {  // fp32 tail
     float* t = reinterpret_cast<float*>(out + WEIGHT_BYTES);
@@ -105,17 +118,34 @@ int launch_pack_net(const float* const* weights, const float* const* biases, voi
   return check_launch("pack_net_kernel");
 }
 
-// ----------------------------------------------------------------------------- the MLP kernel
-constexpr int RING = 4;
-constexpr int SM_ACT = 0;                         // [128 x 256] fp16, 8-row groups 4096 B apart
-constexpr int SM_ENC = SM_ACT + 128 * 256 * 2;    // [128 x 64]
-constexpr int SM_DIR = SM_ENC + 128 * 64 * 2;     // [128 x 64]
-constexpr int SM_RING = SM_DIR + 128 * 64 * 2;    // RING x 16 KB
-constexpr int SM_TAIL = SM_RING + RING * CHUNK_BYTES;
-constexpr int SM_BAR = SM_TAIL + TAIL_BYTES;      // mbarriers
-constexpr int SM_TOTAL = SM_BAR + 128;
-constexpr int NUM_COMPUTE = 128;
-constexpr int MLP_THREADS = 192;
+// ----------------------------------------------------------------------------- kernel configuration
+constexpr int MLP_THREADS = 256;
+constexpr int ENC_THREADS = 64;
+constexpr int TM_ACC0 = 0, TM_ACC1 = 128, TM_AHI = 256, TM_ALO = 384;
+
+template <int SPLIT>
+struct Cfg {
+  static constexpr bool kSplit = SPLIT == 3;
+  static constexpr int STAGE_BYTES = kSplit ? CHUNK_PAIR_BYTES : CHUNK_BYTES;
+  static constexpr int ENC_BYTES = 128 * 64 * 2;   // [128 x 64] fp16, 8-row groups 1024 B apart
+  static constexpr int DIR_BYTES = 128 * 32 * 2;   // [128 x 32] fp16, 8-row groups 512 B apart
+  static constexpr int INBUF_BYTES = (ENC_BYTES + DIR_BYTES) * (kSplit ? 2 : 1);
+  static constexpr int OFF_ENC_HI = 0;
+  static constexpr int OFF_DIR_HI = ENC_BYTES;
+  static constexpr int OFF_ENC_LO = ENC_BYTES + DIR_BYTES;
+  static constexpr int OFF_DIR_LO = 2 * ENC_BYTES + DIR_BYTES;
+  // One buffer each: the xyz encoding of tile i is last read by step 5, the view-dir encoding by step 9,
+  // so the encoder warps refill them for tile i+1 during steps 6..9 / 0..8 (enc_free / dir_free barriers).
+  static constexpr int SM_INBUF = 0;
+  static constexpr int SM_RING = INBUF_BYTES;
+  static constexpr int SM_BUDGET = 227 * 1024;
+  static constexpr int STAGES_FIT = (SM_BUDGET - SM_RING - TAIL_BYTES - 256) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 10 ? 10 : STAGES_FIT;
+  static constexpr int SM_TAIL = SM_RING + STAGES * STAGE_BYTES;
+  static constexpr int SM_BAR = SM_TAIL + TAIL_BYTES;
+  static constexpr int SM_TOTAL = SM_BAR + 256;
+  static_assert(STAGES >= 3, "weight ring too shallow");
+};
 
 struct MlpArgs {
   const float* rays;
@@ -126,159 +156,234 @@ struct MlpArgs {
   int S;
   uint32_t flags;
   int num_tiles;
-  int desc_swap;  // debug: swap the LBO / SBO fields of the shared-memory descriptors
 };
 
-__device__ __forceinline__ uint64_t kdesc(uint32_t saddr, uint32_t sbo, int swap) {
-  return swap ? make_sdesc(saddr, sbo, 128, 0) : make_sdesc(saddr, 128, sbo, 0);
-}
+__device__ __forceinline__ uint64_t kdesc(uint32_t saddr, uint32_t sbo) { return make_sdesc(saddr, 128, sbo, 0); }
 
 // 16-byte store of 8 fp16 (4 packed words) into a no-swizzle K-major tile whose 8-row groups are `sbo` bytes apart
 __device__ __forceinline__ void st_a8(uint8_t* tile, int sbo, int row, int kgroup, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
   *reinterpret_cast<uint4*>(tile + (row >> 3) * sbo + kgroup * 128 + (row & 7) * 16) = make_uint4(w0, w1, w2, w3);
 }
 
+// (x0, x1) -> packed fp16 hi word and (SPLIT) the packed fp16 residual word
+template <bool kSplit>
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  hi = pack_f16x2(x0, x1);
+  if (kSplit) {
+    const __half2 h = *reinterpret_cast<const __half2*>(&hi);
+    const float2 f = __half22float2(h);
+    lo = pack_f16x2(x0 - f.x, x1 - f.y);
+  } else {
+    lo = 0u;
+  }
+}
+
+struct Waiter {  // one per (thread, barrier): parity follows the number of completed waits
+  uint32_t n = 0;
+  __device__ __forceinline__ void wait(uint64_t* bar) {
+    mbar_wait(bar, n & 1);
+    ++n;
+  }
+};
+
+// ----------------------------------------------------------------------------- the kernel
+template <int SPLIT>
 __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
+  using C = Cfg<SPLIT>;
+  constexpr bool kSplit = C::kSplit;
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sAct = smem + SM_ACT;
-  uint8_t* sEnc = smem + SM_ENC;
-  uint8_t* sDir = smem + SM_DIR;
-  uint8_t* sRing = smem + SM_RING;
-  const float* sTail = reinterpret_cast<const float*>(smem + SM_TAIL);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM_BAR);  // [RING]
-  uint64_t* empty = full + RING;                                // [RING]
-  uint64_t* act_ready = empty + RING;                           // compute -> MMA (count 128)
-  uint64_t* acc_ready = act_ready + 1;                          // MMA -> compute (count 1)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + 1);
+  uint8_t* sRing = smem + C::SM_RING;
+  const float* sTail = reinterpret_cast<const float*>(smem + C::SM_TAIL);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::SM_BAR);  // [STAGES]   producer -> MMA (tx bytes)
+  uint64_t* empty = full + C::STAGES;                              // [STAGES]   MMA commit -> producer
+  uint64_t* acc_ready = empty + C::STAGES;                         // [2]        MMA commit -> epilogue
+  uint64_t* a_ready = acc_ready + 2;                               // [2]        epilogue (128) -> MMA
+  uint64_t* enc_ready = a_ready + 2;                               // [0] xyz encoding, [1] view-dir encoding: encoders (128) -> MMA
+  uint64_t* enc_free = enc_ready + 2;                              // [0] after step 5, [1] after step 9: MMA commit -> encoders
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(enc_free + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    for (int s = 0; s < RING; ++s) {
+    for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(act_ready, NUM_COMPUTE);
-    mbar_init(acc_ready, 1);
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(&acc_ready[h], 1);
+      mbar_init(&a_ready[h], 128);
+      mbar_init(&enc_ready[h], ENC_THREADS);
+      mbar_init(&enc_free[h], 1);
+    }
     fence_mbar_init();
   }
-  if (warp == 4) tmem_alloc(tmem_slot, 256);
+  if (warp == 6) tmem_alloc(tmem_slot, 512);
   for (int i = tid; i < TAIL_FLOATS; i += MLP_THREADS)
-    reinterpret_cast<float*>(smem + SM_TAIL)[i] = reinterpret_cast<const float*>(a.packed + WEIGHT_BYTES)[i];
+    reinterpret_cast<float*>(smem + C::SM_TAIL)[i] = reinterpret_cast<const float*>(a.packed + WEIGHT_BYTES)[i];
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 5) {
-    // ===================================================================== weight producer
+  if (warp == 7) {
+    // ===================================================================== weight producer (TMA engine)
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
         for (int c = 0; c < NUM_CHUNKS; ++c, ++it) {
-          const int s = it % RING;
-          if (it >= RING) mbar_wait(&empty[s], ((it / RING) - 1) & 1);
-          mbar_arrive_expect_tx(&full[s], CHUNK_BYTES);
-          bulk_g2s(sRing + s * CHUNK_BYTES, a.packed + size_t(c) * CHUNK_BYTES, CHUNK_BYTES, &full[s]);
+          const int s = it % C::STAGES;
+          if (it >= uint32_t(C::STAGES)) mbar_wait(&empty[s], ((it / C::STAGES) - 1) & 1);
+          mbar_arrive_expect_tx(&full[s], C::STAGE_BYTES);
+          bulk_g2s(sRing + s * C::STAGE_BYTES, a.packed + size_t(c) * CHUNK_PAIR_BYTES, C::STAGE_BYTES, &full[s]);
         }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == 6) {
     // ===================================================================== MMA issuer
     if (lane == 0) {
       const uint32_t idesc = make_idesc_f16(128, 128);
-      const uint32_t aAct = smem_u32(sAct), aEnc = smem_u32(sEnc), aDir = smem_u32(sDir), aRing = smem_u32(sRing);
-      uint32_t it = 0, act_phase = 0;
+      const uint32_t aRing = smem_u32(sRing);
+      uint32_t it = 0;
+      Waiter w_a[2], w_enc[2];
+      const uint32_t inbuf = smem_u32(smem + C::SM_INBUF);
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+        w_enc[0].wait(&enc_ready[0]);
         for (int step = 0; step < NUM_STEPS; ++step) {
-          mbar_wait(act_ready, act_phase);
-          act_phase ^= 1;
-          tc_fence_after_sync();
+          if (step == 9) w_enc[1].wait(&enc_ready[1]);
           const int nk = step_k_chunks(step);
-          for (int nh = 0; nh < step_n_halves(step); ++nh) {
+          const int nhs = step_n_halves(step);
+          bool waited1 = false;
+          w_a[0].wait(&a_ready[0]);  // A[K 0..127] of this step written, ACC0 drained
+          if (step == 9) {           // the single 128-wide half of step 9 accumulates in ACC1
+            w_a[1].wait(&a_ready[1]);
+            waited1 = true;
+          }
+          tc_fence_after_sync();
+          for (int nh = 0; nh < nhs; ++nh) {
+            const uint32_t acc = tmem + ((step == 9 || nh == 1) ? TM_ACC1 : TM_ACC0);
             for (int kc = 0; kc < nk; ++kc, ++it) {
-              const int s = it % RING;
-              mbar_wait(&full[s], (it / RING) & 1);
-              // A source of this K-chunk
-              uint32_t abase, asbo;
-              if ((step == 0 || step == 5) && kc == 0) {
-                abase = aEnc;
-                asbo = 1024;
-              } else if (step == 9 && kc == 4) {
-                abase = aDir;
-                asbo = 1024;
-              } else {
-                const int ak = (step == 5) ? kc - 1 : kc;
-                abase = aAct + ak * 1024;
-                asbo = 4096;
+              // ---- A source of this K chunk: 0 = xyz encoding, 1 = TMEM activations, 2 = view-dir encoding
+              int src = 1, ak = kc;
+              if ((step == 0 || step == 5) && kc == 0) src = 0;
+              else if (step == 9 && kc == 4) src = 2;
+              else if (step == 5) ak = kc - 1;
+              if (!waited1 && (nh == 1 || (src == 1 && ak >= 2))) {
+                w_a[1].wait(&a_ready[1]);  // A[K 128..255] written, ACC1 drained
+                tc_fence_after_sync();
+                waited1 = true;
               }
-              const uint32_t bbase = aRing + s * CHUNK_BYTES;
+              const int s = it % C::STAGES;
+              mbar_wait(&full[s], (it / C::STAGES) & 1);
+              const uint32_t w_hi = aRing + s * C::STAGE_BYTES, w_lo = w_hi + CHUNK_BYTES;
+              const int ksteps = (src == 2) ? 2 : 4;
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                umma_ss(tmem + nh * 128, kdesc(abase + j * 256, asbo, a.desc_swap), kdesc(bbase + j * 256, 1024, a.desc_swap), idesc,
-                        (kc | j) != 0);
+              for (int j = 0; j < 4; ++j) {
+                if (j < ksteps) {
+                  const uint32_t first = (kc | j) != 0;
+                  const uint64_t bh = kdesc(w_hi + j * 256, 1024);
+                  const uint64_t bl = kdesc(w_lo + j * 256, 1024);
+                  if (src == 1) {
+                    const uint32_t ah = tmem + TM_AHI + ak * 32 + j * 8, al = tmem + TM_ALO + ak * 32 + j * 8;
+                    umma_ts(acc, ah, bh, idesc, first);
+                    if (kSplit) {
+                      umma_ts(acc, al, bh, idesc, 1);
+                      umma_ts(acc, ah, bl, idesc, 1);
+                    }
+                  } else {
+                    const uint32_t sbo = (src == 0) ? 1024 : 512;
+                    const uint32_t hi = inbuf + (src == 0 ? C::OFF_ENC_HI : C::OFF_DIR_HI) + j * 256;
+                    const uint32_t lo = inbuf + (src == 0 ? C::OFF_ENC_LO : C::OFF_DIR_LO) + j * 256;
+                    umma_ss(acc, kdesc(hi, sbo), bh, idesc, first);
+                    if (kSplit) {
+                      umma_ss(acc, kdesc(lo, sbo), bh, idesc, 1);
+                      umma_ss(acc, kdesc(hi, sbo), bl, idesc, 1);
+                    }
+                  }
+                }
+              }
               umma_commit(&empty[s]);
             }
+            umma_commit(&acc_ready[(step == 9) ? 1 : nh]);
           }
-          umma_commit(acc_ready);
+          if (!waited1) w_a[1].wait(&a_ready[1]);  // keep the parity in step (cannot happen with this network)
+          if (step == 5) umma_commit(&enc_free[0]);  // last reader of the xyz encoding
         }
+        umma_commit(&enc_free[1]);
       }
     }
-  } else {
-    // ===================================================================== compute warps: encode + epilogues
-    const int row = tid;  // == TMEM lane
-    const uint32_t tlane = tmem + (uint32_t(warp * 32) << 16);
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-      const int64_t p = int64_t(tile) * 128 + row;
-      const bool valid = p < a.n_points;
-      // ---- encode (RH:47-48): [x, sin(2^k x), cos(2^k x)]_k
-      {
-        float x[3] = {0.f, 0.f, 0.f}, vd[3] = {0.f, 0.f, 0.f};
-        if (valid) {
+  } else if (warp >= 4) {
+    // ===================================================================== encoders (2 warps, 2 rows per thread):
+    // tile i+1's encodings while tile i is in the tensor pipe
+    uint32_t tl = 0;
+    Waiter w_free[2];
+    uint8_t* inbuf = smem + C::SM_INBUF;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++tl) {
+      float x[2][3], vd[2][3];
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int64_t p = int64_t(tile) * 128 + (tid - 128) + rr * 64;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) x[rr][d] = vd[rr][d] = 0.f;
+        if (p < a.n_points) {
           const int64_t ray = p / a.S;
           const float* rp = a.rays + ray * 11;
           if (a.flags & NSR_FLAG_PTS_INPUT) {
-            x[0] = a.z_or_pts[p * 3 + 0];
-            x[1] = a.z_or_pts[p * 3 + 1];
-            x[2] = a.z_or_pts[p * 3 + 2];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) x[rr][d] = a.z_or_pts[p * 3 + d];
           } else {
             const float z = a.z_or_pts[p];
 #pragma unroll
-            for (int d = 0; d < 3; ++d) x[d] = __fadd_rn(rp[d], __fmul_rn(rp[3 + d], z));  // RN:463
+            for (int d = 0; d < 3; ++d) x[rr][d] = __fadd_rn(rp[d], __fmul_rn(rp[3 + d], z));  // RN:463
           }
 #pragma unroll
-          for (int d = 0; d < 3; ++d) vd[d] = rp[8 + d];
+          for (int d = 0; d < 3; ++d) vd[rr][d] = rp[8 + d];
         }
+      }
+      // ---- gamma(x) (RH:47-48): [x, sin(2^k x), cos(2^k x)]_k, 63 channels + one zero pad
+      if (tl >= 1) w_free[0].wait(&enc_free[0]);  // step 5 of the previous tile has read the old encoding
+#pragma unroll 1
+      for (int rr = 0; rr < 2; ++rr) {
+        const int row = (tid - 128) + rr * 64;
         float e[64];
-        e[0] = x[0];
-        e[1] = x[1];
-        e[2] = x[2];
+        e[0] = x[rr][0];
+        e[1] = x[rr][1];
+        e[2] = x[rr][2];
 #pragma unroll
         for (int k = 0; k < 10; ++k) {
 #pragma unroll
           for (int d = 0; d < 3; ++d) {
             float sn, cs;
-            sincosf(x[d] * float(1 << k), &sn, &cs);
+            sincosf(x[rr][d] * float(1 << k), &sn, &cs);
             e[3 + 6 * k + d] = sn;
             e[3 + 6 * k + 3 + d] = cs;
           }
         }
         e[63] = 0.f;
 #pragma unroll
-        for (int g = 0; g < 8; ++g)
-          st_a8(sEnc, 1024, row, g, pack_f16x2(e[8 * g], e[8 * g + 1]), pack_f16x2(e[8 * g + 2], e[8 * g + 3]),
-                pack_f16x2(e[8 * g + 4], e[8 * g + 5]), pack_f16x2(e[8 * g + 6], e[8 * g + 7]));
+        for (int g = 0; g < 8; ++g) {
+          uint32_t h[4], l[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) split2<kSplit>(e[8 * g + 2 * q], e[8 * g + 2 * q + 1], h[q], l[q]);
+          st_a8(inbuf + C::OFF_ENC_HI, 1024, row, g, h[0], h[1], h[2], h[3]);
+          if (kSplit) st_a8(inbuf + C::OFF_ENC_LO, 1024, row, g, l[0], l[1], l[2], l[3]);
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&enc_ready[0]);
+      if (tl >= 1) w_free[1].wait(&enc_free[1]);  // step 9 of the previous tile has read the old view-dir encoding
+#pragma unroll 1
+      for (int rr = 0; rr < 2; ++rr) {
+        const int row = (tid - 128) + rr * 64;
         float v[32];
-        v[0] = vd[0];
-        v[1] = vd[1];
-        v[2] = vd[2];
+        v[0] = vd[rr][0];
+        v[1] = vd[rr][1];
+        v[2] = vd[rr][2];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
 #pragma unroll
           for (int d = 0; d < 3; ++d) {
             float sn, cs;
-            sincosf(vd[d] * float(1 << k), &sn, &cs);
+            sincosf(vd[rr][d] * float(1 << k), &sn, &cs);
             v[3 + 6 * k + d] = sn;
             v[3 + 6 * k + 3 + d] = cs;
           }
@@ -286,89 +391,149 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
 #pragma unroll
         for (int i = 27; i < 32; ++i) v[i] = 0.f;
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
-          st_a8(sDir, 1024, row, g, pack_f16x2(v[8 * g], v[8 * g + 1]), pack_f16x2(v[8 * g + 2], v[8 * g + 3]),
-                pack_f16x2(v[8 * g + 4], v[8 * g + 5]), pack_f16x2(v[8 * g + 6], v[8 * g + 7]));
+        for (int g = 0; g < 4; ++g) {
+          uint32_t h[4], l[4];
 #pragma unroll
-        for (int g = 4; g < 8; ++g) st_a8(sDir, 1024, row, g, 0u, 0u, 0u, 0u);
+          for (int q = 0; q < 4; ++q) split2<kSplit>(v[8 * g + 2 * q], v[8 * g + 2 * q + 1], h[q], l[q]);
+          st_a8(inbuf + C::OFF_DIR_HI, 512, row, g, h[0], h[1], h[2], h[3]);
+          if (kSplit) st_a8(inbuf + C::OFF_DIR_LO, 512, row, g, l[0], l[1], l[2], l[3]);
+        }
       }
       fence_proxy_async_smem();
-      tc_fence_before_sync();
-      mbar_arrive(act_ready);
-
-      float sigma = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f;
-      for (int step = 0; step < NUM_STEPS; ++step) {
-        mbar_wait(acc_ready, acc_phase);
-        acc_phase ^= 1;
-        tc_fence_after_sync();
+      mbar_arrive(&enc_ready[1]);
+    }
+  } else {
+    // ===================================================================== epilogue warps (row == TMEM lane)
+    const int row = tid;
+    const uint32_t tlane = tmem + (uint32_t(warp * 32) << 16);
+    Waiter w_acc[2];
+    // initial credits: nothing to wait for before the very first step
+    mbar_arrive(&a_ready[0]);
+    mbar_arrive(&a_ready[1]);
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+      const int64_t p = int64_t(tile) * 128 + row;
+      float sigma = 0.f;
+      for (int step = 0; step < 9; ++step) {
         const float* bias = sTail + TAIL_BIAS + step * 256;
-        const int ncols = (step == 9) ? 128 : 256;
-        for (int c0 = 0; c0 < ncols; c0 += 32) {
+        const bool relu = step != 8;  // feature_linear has no activation (RH:110)
+        uint32_t H[64], L[kSplit ? 64 : 1];
+        // ---- first half: drain ACC0 into registers while the second half is still in the tensor pipe
+        w_acc[0].wait(&acc_ready[0]);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int c0 = 0; c0 < 128; c0 += 32) {
           uint32_t u[32];
-          tmem_ld32(tlane + c0, u);
+          tmem_ld32(tlane + TM_ACC0 + c0, u);
           tmem_ld_wait();
-          float f[32];
-          const float4* b4 = reinterpret_cast<const float4*>(bias + c0);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b = b4[j];
-            f[4 * j + 0] = __uint_as_float(u[4 * j + 0]) + b.x;
-            f[4 * j + 1] = __uint_as_float(u[4 * j + 1]) + b.y;
-            f[4 * j + 2] = __uint_as_float(u[4 * j + 2]) + b.z;
-            f[4 * j + 3] = __uint_as_float(u[4 * j + 3]) + b.w;
-          }
-          if (step == 7) {  // alpha head on the fp32 post-ReLU activations (RH:109)
-            const float4* wa = reinterpret_cast<const float4*>(sTail + TAIL_WALPHA + c0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 w = wa[j];
-              sigma = fmaf(fmaxf(f[4 * j + 0], 0.f), w.x, sigma);
-              sigma = fmaf(fmaxf(f[4 * j + 1], 0.f), w.y, sigma);
-              sigma = fmaf(fmaxf(f[4 * j + 2], 0.f), w.z, sigma);
-              sigma = fmaf(fmaxf(f[4 * j + 3], 0.f), w.w, sigma);
+          for (int j = 0; j < 16; ++j) {
+            const float2 bb = *reinterpret_cast<const float2*>(bias + c0 + 2 * j);
+            float x0 = __uint_as_float(u[2 * j]) + bb.x, x1 = __uint_as_float(u[2 * j + 1]) + bb.y;
+            if (relu) {
+              x0 = fmaxf(x0, 0.f);
+              x1 = fmaxf(x1, 0.f);
             }
-          }
-          if (step == 9) {  // rgb head (RH:117)
-            const float4* wr = reinterpret_cast<const float4*>(sTail + TAIL_WRGB) + c0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float h = fmaxf(f[j], 0.f);
-              const float4 w = wr[j];
-              r0 = fmaf(h, w.x, r0);
-              r1 = fmaf(h, w.y, r1);
-              r2 = fmaf(h, w.z, r2);
+            if (step == 7) {  // alpha head on the fp32 post-ReLU activations (RH:109)
+              const float2 wa = *reinterpret_cast<const float2*>(sTail + TAIL_WALPHA + c0 + 2 * j);
+              sigma = fmaf(x0, wa.x, sigma);
+              sigma = fmaf(x1, wa.y, sigma);
             }
-          } else if (step == 8) {  // feature_linear: no activation (RH:110)
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              st_a8(sAct, 4096, row, (c0 >> 3) + g, pack_f16x2(f[8 * g], f[8 * g + 1]), pack_f16x2(f[8 * g + 2], f[8 * g + 3]),
-                    pack_f16x2(f[8 * g + 4], f[8 * g + 5]), pack_f16x2(f[8 * g + 6], f[8 * g + 7]));
-          } else {
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              st_a8(sAct, 4096, row, (c0 >> 3) + g, pack_f16x2_relu(f[8 * g], f[8 * g + 1]), pack_f16x2_relu(f[8 * g + 2], f[8 * g + 3]),
-                    pack_f16x2_relu(f[8 * g + 4], f[8 * g + 5]), pack_f16x2_relu(f[8 * g + 6], f[8 * g + 7]));
+            uint32_t lo;
+            split2<kSplit>(x0, x1, H[c0 / 2 + j], lo);
+            if (kSplit) L[c0 / 2 + j] = lo;
           }
         }
-        if (step < 9) {
-          fence_proxy_async_smem();
-          tc_fence_before_sync();
-          mbar_arrive(act_ready);
+        // ---- every MMA of this step has retired: the old activations may be overwritten
+        w_acc[1].wait(&acc_ready[1]);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          tmem_st16(tlane + TM_AHI + q * 16, *reinterpret_cast<const uint32_t(*)[16]>(&H[q * 16]));
+          if (kSplit) tmem_st16(tlane + TM_ALO + q * 16, *reinterpret_cast<const uint32_t(*)[16]>(&L[q * 16]));
+        }
+        tmem_st_wait();
+        tc_fence_before_sync();
+        mbar_arrive(&a_ready[0]);
+        // ---- second half: drain ACC1 straight into AHI/ALO[K 128..255]
+#pragma unroll
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t u[32], h2[16], l2[16];
+          tmem_ld32(tlane + TM_ACC1 + c0, u);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float2 bb = *reinterpret_cast<const float2*>(bias + 128 + c0 + 2 * j);
+            float x0 = __uint_as_float(u[2 * j]) + bb.x, x1 = __uint_as_float(u[2 * j + 1]) + bb.y;
+            if (relu) {
+              x0 = fmaxf(x0, 0.f);
+              x1 = fmaxf(x1, 0.f);
+            }
+            if (step == 7) {
+              const float2 wa = *reinterpret_cast<const float2*>(sTail + TAIL_WALPHA + 128 + c0 + 2 * j);
+              sigma = fmaf(x0, wa.x, sigma);
+              sigma = fmaf(x1, wa.y, sigma);
+            }
+            split2<kSplit>(x0, x1, h2[j], l2[j]);
+          }
+          tmem_st16(tlane + TM_AHI + 64 + c0 / 2, h2);
+          if (kSplit) tmem_st16(tlane + TM_ALO + 64 + c0 / 2, l2);
+        }
+        tmem_st_wait();
+        tc_fence_before_sync();
+        mbar_arrive(&a_ready[1]);
+      }
+      // ---- step 9: views layer accumulates in ACC1; rgb head on CUDA cores (RH:113-117)
+      w_acc[1].wait(&acc_ready[1]);
+      tc_fence_after_sync();
+      // ACC0 / A[K 0..127] are not touched by this step's epilogue: release them now.  (Not before the wait above:
+      // the MMA warp must have consumed the previous a_ready[0] phase first -- it has once step 9 was issued.)
+      mbar_arrive(&a_ready[0]);
+      float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+      {
+        const float* bias = sTail + TAIL_BIAS + 9 * 256;
+#pragma unroll
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t u[32];
+          tmem_ld32(tlane + TM_ACC1 + c0, u);
+          tmem_ld_wait();
+          const float4* wr = reinterpret_cast<const float4*>(sTail + TAIL_WRGB) + c0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float h = fmaxf(__uint_as_float(u[j]) + bias[c0 + j], 0.f);
+            const float4 w = wr[j];
+            r0 = fmaf(h, w.x, r0);
+            r1 = fmaf(h, w.y, r1);
+            r2 = fmaf(h, w.z, r2);
+          }
         }
       }
-      if (valid) {
+      tc_fence_before_sync();
+      mbar_arrive(&a_ready[1]);
+      if (p < a.n_points) {
         const float* misc = sTail + TAIL_MISC;
         reinterpret_cast<float4*>(a.raw)[p] = make_float4(r0 + misc[1], r1 + misc[2], r2 + misc[3], sigma + misc[0]);  // RH:118
       }
-      tc_fence_before_sync();
     }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, 256);
+  if (warp == 6) tmem_dealloc(tmem, 512);
 }
 
 static int g_num_sms = 0;
+
+template <int SPLIT>
+static int launch_variant(const MlpArgs& a, int grid, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(nerf_mlp_kernel<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<SPLIT>::SM_TOTAL) != cudaSuccess)
+      return check_launch("cudaFuncSetAttribute(nerf_mlp_kernel)");
+    configured = true;
+  }
+  nerf_mlp_kernel<SPLIT><<<grid, MLP_THREADS, Cfg<SPLIT>::SM_TOTAL, st>>>(a);
+  count_launch();
+  return check_launch("nerf_mlp_kernel");
+}
 
 int launch_mlp_forward(const float* rays, const float* z_or_pts, int64_t n, int S, const void* packed, uint32_t flags,
                        float* raw, cudaStream_t st) {
@@ -378,8 +543,7 @@ int launch_mlp_forward(const float* rays, const float* z_or_pts, int64_t n, int 
     set_error("mlp_forward: too many points");
     return NSR_E_UNSUPPORTED;
   }
-  static bool configured = false;
-  if (!configured) {
+  if (g_num_sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceProp prop;
@@ -389,9 +553,6 @@ int launch_mlp_forward(const float* rays, const float* z_or_pts, int64_t n, int 
       return NSR_E_DEVICE;
     }
     g_num_sms = prop.multiProcessorCount;
-    if (cudaFuncSetAttribute(nerf_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL) != cudaSuccess)
-      return check_launch("cudaFuncSetAttribute(nerf_mlp_kernel)");
-    configured = true;
   }
   MlpArgs a;
   a.rays = rays;
@@ -402,12 +563,8 @@ int launch_mlp_forward(const float* rays, const float* z_or_pts, int64_t n, int 
   a.S = S;
   a.flags = flags;
   a.num_tiles = int((n_points + 127) / 128);
-  const char* sw = getenv("NSR_DESC_SWAP");
-  a.desc_swap = (sw && sw[0] == '1') ? 1 : 0;
   const int grid = a.num_tiles < g_num_sms ? a.num_tiles : g_num_sms;
-  nerf_mlp_kernel<<<grid, MLP_THREADS, SM_TOTAL, st>>>(a);
-  count_launch();
-  return check_launch("nerf_mlp_kernel");
+  return (flags & NSR_FLAG_FAST_FP16) ? launch_variant<1>(a, grid, st) : launch_variant<3>(a, grid, st);
 }
 
 }  // namespace nsr

@@ -147,27 +147,18 @@ __device__ void sample_pdf_warp(const float* bins, float* w, float* cdf, int B, 
   }
   s = warp_sum(s);
   __syncwarp();
-  // cdf = [0, cumsum(w / s)]  (RH:202-204): lane-contiguous segments + warp scan
-  const int per = (nw + 31) / 32;
-  const int beg = lane * per;
-  float loc = 0.f;
-  for (int j = 0; j < per; ++j) {
-    const int i = beg + j;
-    if (i < nw) loc += __fdiv_rn(w[i], s);
-  }
-  float incl = loc;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const float v = __shfl_up_sync(FULL, incl, o);
-    if (lane >= o) incl += v;
-  }
-  float run = incl - loc;
-  if (lane == 0) cdf[0] = 0.f;
-  for (int j = 0; j < per; ++j) {
-    const int i = beg + j;
-    if (i < nw) {
-      run += __fdiv_rn(w[i], s);
-      cdf[i + 1] = run;
+  // cdf = [0, cumsum(w / s)]  (RH:202-204).  The `denom < 1e-5` test below (RH:239) sits right on top of the
+  // value empty bins produce (1e-5 / ~1.0006), so the cdf must round the way the reference's does or whole
+  // samples jump by a bin width: ATen's CPU cumsum accumulates fp32 inputs sequentially in fp64 and rounds
+  // each prefix to fp32 -- do exactly that (one lane, <= 255 adds; negligible next to the MLP).
+  for (int i = lane; i < nw; i += 32) w[i] = __fdiv_rn(w[i], s);
+  __syncwarp();
+  if (lane == 0) {
+    double run = 0.0;
+    cdf[0] = 0.f;
+    for (int i = 0; i < nw; ++i) {
+      run += double(w[i]);
+      cdf[i + 1] = float(run);
     }
   }
   __syncwarp();

@@ -22,7 +22,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib
-from ._lib import FLAG_LINDISP, FLAG_PTS_INPUT, FLAG_WHITE_BKGD, check, lib, ptr
+from ._lib import FLAG_FAST_FP16, FLAG_LINDISP, FLAG_PTS_INPUT, FLAG_WHITE_BKGD, check, lib, ptr
 
 device = torch.device('cuda' if torch.cuda.is_available() else 'cpu')
 
@@ -30,6 +30,22 @@ device = torch.device('cuda' if torch.cuda.is_available() else 'cpu')
 # `chunk` only bounds memory ("Does not affect final results", RN:67-68) and 512-ray chunks
 # (CFG:25) would leave most of a B200 idle.
 MIN_RAYS_PER_LAUNCH = int(os.environ.get('NSR_MIN_CHUNK', 1 << 16))
+
+# MLP arithmetic: 'fp16x3' (default) = error-compensated hi/lo split, meets the 1e-3 parity bar;
+# 'fp16' = single fp16 MMA per product (NSR_FLAG_FAST_FP16), ~3x faster MLP, misses the bar on silhouette rays.
+PRECISION = os.environ.get('NSR_PRECISION', 'fp16x3')
+
+
+def set_precision(mode):
+    global PRECISION
+    if mode not in ('fp16x3', 'fp16'):
+        raise ValueError("precision must be 'fp16x3' or 'fp16'")
+    PRECISION = mode
+
+
+def _prec_flag():
+    return FLAG_FAST_FP16 if PRECISION == 'fp16' else 0
+
 
 img2mse = lambda x, y: torch.mean((x - y) ** 2)                                  # RH:12
 mse2psnr = lambda x: -10. * torch.log(x) / torch.log(torch.Tensor([10.]).to(x.device))  # RH:13
@@ -173,7 +189,7 @@ def run_network(inputs, viewdirs, fn, embed_fn=None, embeddirs_fn=None, netchunk
     rays = torch.zeros(n, 11, dtype=torch.float32, device=pts.device)
     rays[:, 8:11] = vd
     raw = torch.empty(n, S, 4, dtype=torch.float32, device=pts.device)
-    check(lib().nsr_mlp_forward(ptr(rays), ptr(pts), n, S, ptr(packed_weights(fn)), FLAG_PTS_INPUT, ptr(raw), _stream()),
+    check(lib().nsr_mlp_forward(ptr(rays), ptr(pts), n, S, ptr(packed_weights(fn)), FLAG_PTS_INPUT | _prec_flag(), ptr(raw), _stream()),
           'nsr_mlp_forward')
     return raw.reshape(list(sh[:-1]) + [4])
 
@@ -237,7 +253,7 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
     S, Ni = int(N_samples), int(N_importance)
     T = S + Ni
     L = lib()
-    flags = (FLAG_LINDISP if lindisp else 0) | (FLAG_WHITE_BKGD if white_bkgd else 0)
+    flags = (FLAG_LINDISP if lindisp else 0) | (FLAG_WHITE_BKGD if white_bkgd else 0) | _prec_flag()
     pc = packed_weights(network_fn)
     pf = packed_weights(network_fine) if (network_fine is not None and Ni > 0) else None
     t_rand = u = None
@@ -294,7 +310,7 @@ def _render_rays_staged(rays, pc, pf, S, Ni, flags, t_rand, u, retraw, raw_noise
     T = S + Ni
     z1, raw1 = new(n, T), new(n, T, 4)
     check(L.nsr_resample_merge(ptr(z0), ptr(w0), n, S, Ni, ptr(u), ptr(z1), None, ptr(ret['z_std']), st), 'nsr_resample_merge')
-    check(L.nsr_mlp_forward(ptr(rays), ptr(z1), n, T, ptr(pf if pf is not None else pc), 0, ptr(raw1), st), 'nsr_mlp_forward')
+    check(L.nsr_mlp_forward(ptr(rays), ptr(z1), n, T, ptr(pf if pf is not None else pc), flags & FLAG_FAST_FP16, ptr(raw1), st), 'nsr_mlp_forward')
     raw1[..., 3] += torch.randn(n, T, device=dev) * raw_noise_std
     check(L.nsr_raw2outputs(ptr(raw1), ptr(z1), ptr(rays[:, 3:6].contiguous()), 3, n, T, cflag, ptr(ret['rgb_map']),
                             ptr(ret['disp_map']), ptr(ret['acc_map']), None, None, st), 'nsr_raw2outputs')

@@ -4,9 +4,12 @@ made by the reference and against the CPU oracle on seeded inputs.  Run on the B
 Tolerances
   * exact-fp32 stages (depths, compositing, resampling, merge, ray generation): 1e-5 relative to max(1,|ref|)
     (parallel scans / sums re-associate fp32 adds, nothing more);
-  * MLP raw outputs: operands are fp16 on the tensor cores with fp32 accumulation ->
-    |d raw| <= 2e-2 * max(1, |ref|) per element (measured ~3e-3 typical);
-  * rendered maps (north_star): |d| <= 1e-3 * max(1, |ref|), NaN-equal disparity.
+  * MLP raw outputs, default precision (fp16 hi/lo split, fp32 accumulate): |d raw| <= 1e-3 * max(1, |ref|);
+  * rendered maps (north_star): |d| <= 1e-3 * max(1, |ref|), NaN-equal disparity;
+  * resampled depths end to end: the reference's `denom < 1e-5` test (RH:239) is discontinuous exactly where
+    empty bins land, so a sample may move inside its (empty, zero-weight) coarse bin when the coarse weights
+    differ in the last bits: at most 0.5 % of the entries may exceed the tolerance, none by more than one bin;
+  * NSR_FLAG_FAST_FP16 (opt-in, single fp16 MMA per product): 99 % of the rays within 1e-3, none beyond 5e-2.
 """
 import numpy as np
 import pytest
@@ -17,7 +20,7 @@ import nerf_oracle as O
 pytestmark = pytest.mark.gpu
 
 TOL_EXACT = 1e-5
-TOL_RAW = 2e-2
+TOL_RAW = 1e-3
 TOL_MAP = 1e-3
 
 
@@ -57,6 +60,15 @@ def assert_close(a, b, tol, what, nan_slack=0):
     mx = err.max() if err.size else 0.0
     assert mx <= tol, f'{what}: max err {mx:.3e} > {tol}'
     return mx
+
+
+def assert_mostly_close(a, b, tol, what, frac=5e-3, cap=0.03):
+    """For quantities behind the reference's discontinuous `denom < 1e-5` branch (RH:239)."""
+    err, nan_mismatch = relerr(a, b)
+    assert nan_mismatch == 0, what
+    bad = (err > tol).mean() if err.size else 0.0
+    assert bad <= frac, f'{what}: {bad:.3%} of entries beyond {tol}'
+    assert err.size == 0 or err.max() <= cap, f'{what}: max err {err.max():.3e} > one coarse bin'
 
 
 # ----------------------------------------------------------------------------- stage tests on golden vectors
@@ -114,9 +126,10 @@ def test_render_rays_matches_reference(nsr, golden, nets):
     with torch.no_grad():
         r = nsr.render_rays(rays, nets[0], None, 64, retraw=True, N_importance=128, network_fine=nets[1])
     torch.cuda.synchronize()
-    for k in ('rgb_map', 'acc_map', 'rgb0', 'acc0', 'z_std'):
+    for k in ('rgb_map', 'acc_map', 'rgb0', 'acc0'):
         mx = assert_close(r[k], golden['e2e_' + k], TOL_MAP, k)
         print(f'{k}: max err {mx:.3e}')
+    assert_mostly_close(r['z_std'], golden['e2e_z_std'], TOL_MAP, 'z_std')
     # disparity: 1/depth amplifies on near-empty rays; compare where the ray is not almost empty, NaN-equal otherwise
     for dk, ak in (('disp_map', 'acc_map'), ('disp0', 'acc0')):
         ref_d, ref_a = golden['e2e_' + dk], golden['e2e_' + ak]
@@ -125,7 +138,8 @@ def test_render_rays_matches_reference(nsr, golden, nets):
         assert_close(got[solid], ref_d[solid], TOL_MAP, dk)
         empty = ref_a == 0
         assert np.isnan(got[empty]).all() == np.isnan(ref_d[empty]).all()
-    assert_close(r['raw'], golden['e2e_raw'], TOL_RAW, 'raw (retraw)')
+    # raw is evaluated at the resampled depths: compare where those agree (see assert_mostly_close)
+    assert_mostly_close(r['raw'], golden['e2e_raw'], TOL_RAW, 'raw (retraw)', frac=5e-3, cap=1e9)
 
 
 def test_make_rays_and_render_c2w(nsr, golden, nets):
@@ -165,8 +179,9 @@ def test_render_rays_vs_oracle_seeded(nsr, wfit, nets, phi, n_side):
     with torch.no_grad():
         ref = O.render_rays(rays, wfit[0], wfit[1], 64, 128)
         got = nsr.render_rays(rays.cuda(), nets[0], None, 64, N_importance=128, network_fine=nets[1])
-    for k in ('rgb_map', 'acc_map', 'rgb0', 'acc0', 'z_std'):
+    for k in ('rgb_map', 'acc_map', 'rgb0', 'acc0'):
         assert_close(got[k], ref[k], TOL_MAP, f'{k} phi={phi}')
+    assert_mostly_close(got['z_std'], ref['z_std'], TOL_MAP, f'z_std phi={phi}')
 
 
 def test_scaled_random_weights_vs_oracle(nsr):
@@ -179,8 +194,9 @@ def test_scaled_random_weights_vs_oracle(nsr):
         ref = O.render_rays(rays, sdc, sdf, 64, 128)
         got = nsr.render_rays(rays.cuda(), module_from_sd(nsr, sdc), None, 64, N_importance=128,
                               network_fine=module_from_sd(nsr, sdf))
-    for k in ('rgb_map', 'acc_map', 'rgb0', 'acc0', 'z_std', 'disp_map', 'disp0'):
-        assert_close(got[k], ref[k], 2 * TOL_MAP if 'disp' in k else TOL_MAP, k)
+    for k in ('rgb_map', 'acc_map', 'rgb0', 'acc0', 'disp_map', 'disp0'):
+        assert_close(got[k], ref[k], TOL_MAP, k)
+    assert_mostly_close(got['z_std'], ref['z_std'], TOL_MAP, 'z_std')
 
 
 def test_flags_lindisp_white_coarse_only(nsr, wfit, nets):
@@ -195,6 +211,26 @@ def test_flags_lindisp_white_coarse_only(nsr, wfit, nets):
     assert set(got_c) == {'rgb_map', 'disp_map', 'acc_map'}
     for k in ('rgb_map', 'acc_map'):
         assert_close(got_c[k], ref_c[k], TOL_MAP, 'coarse-only ' + k)
+
+
+def test_fast_fp16_mode_is_opt_in_and_bounded(nsr, wfit, nets):
+    """NSR_FLAG_FAST_FP16: one fp16 MMA per product.  Not the default (it misses 1e-3 on silhouette rays);
+    its error distribution is pinned here so the trade-off stays documented."""
+    rays = camera_rays(40, 22.5)
+    with torch.no_grad():
+        ref = O.render_rays(rays, wfit[0], wfit[1], 64, 128)
+        exact = nsr.render_rays(rays.cuda(), nets[0], None, 64, N_importance=128, network_fine=nets[1])
+        nsr.set_precision('fp16')
+        try:
+            fast = nsr.render_rays(rays.cuda(), nets[0], None, 64, N_importance=128, network_fine=nets[1])
+        finally:
+            nsr.set_precision('fp16x3')
+    e_fast, _ = relerr(fast['rgb_map'], ref['rgb_map'])
+    e_exact, _ = relerr(exact['rgb_map'], ref['rgb_map'])
+    print(f'rgb_map err: fp16x3 max {e_exact.max():.2e}; fp16 max {e_fast.max():.2e} p99 {np.quantile(e_fast, 0.99):.2e}')
+    assert e_exact.max() <= TOL_MAP
+    assert np.quantile(e_fast, 0.99) <= 1e-3 and e_fast.max() <= 5e-2
+    assert e_fast.max() > e_exact.max()
 
 
 def test_fine_falls_back_to_coarse_network(nsr, wfit, nets):

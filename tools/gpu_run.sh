@@ -1,0 +1,28 @@
+#!/bin/bash
+# usage: tools/gpu_run.sh [tests] [smoke] [bench] [launches] [ncu]
+mkdir -p gpurun_out
+for what in "$@"; do
+case $what in
+tests)
+  timeout 1200 python -m pytest tests -m gpu -q -rA -s > gpurun_out/pytest_gpu.txt 2>&1
+  echo "pytest exit $?" >> gpurun_out/pytest_gpu.txt
+  grep -E "passed|failed|PASSED|FAILED|max err|err:" gpurun_out/pytest_gpu.txt | tail -40 ;;
+smoke)
+  timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.txt 2>&1
+  echo "smoke exit $?" >> gpurun_out/smoke.txt; tail -3 gpurun_out/smoke.txt ;;
+bench)
+  timeout 1200 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.txt 2> gpurun_out/bench.err
+  echo "bench exit $?" >> gpurun_out/bench.err; cat gpurun_out/bench.txt; tail -3 gpurun_out/bench.err ;;
+benchref)
+  timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.txt 2> gpurun_out/bench_ref.err
+  cat gpurun_out/bench_ref.txt ;;
+launches)
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
+      python bench.py --steps 2 --warmup 1 --profile > gpurun_out/launches.log 2>&1
+  echo "launches exit $?" >> gpurun_out/launches.log; tail -2 gpurun_out/launches.log ;;
+ncu)
+  timeout 1500 ncu --set full --clock-control none --import-source on -k regex:nerf_mlp -s 3 -c 1 -f -o gpurun_out/prof \
+      python bench.py --steps 1 --warmup 1 --profile > gpurun_out/ncu.log 2>&1
+  echo "ncu exit $?" >> gpurun_out/ncu.log; tail -3 gpurun_out/ncu.log ;;
+esac
+done
