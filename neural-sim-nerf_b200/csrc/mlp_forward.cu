@@ -242,10 +242,13 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
     // ===================================================================== MMA issuer
     if (lane == 0) {
       const uint32_t idesc = make_idesc_f16(128, 128);
-      const uint32_t aRing = smem_u32(sRing);
+      constexpr uint32_t HI_B = sdesc_hi(1024), HI_DIR = sdesc_hi(512);  // 8-row groups 1024 B apart (512 B for the K=32 tile)
+      const uint32_t ring_lo = sdesc_lo(smem_u32(sRing), 128);
+      const uint32_t inbuf = smem_u32(smem + C::SM_INBUF);
+      const uint32_t enc_hi = sdesc_lo(inbuf + C::OFF_ENC_HI, 128), enc_lo = sdesc_lo(inbuf + C::OFF_ENC_LO, 128);
+      const uint32_t dir_hi = sdesc_lo(inbuf + C::OFF_DIR_HI, 128), dir_lo = sdesc_lo(inbuf + C::OFF_DIR_LO, 128);
       uint32_t it = 0;
       Waiter w_a[2], w_enc[2];
-      const uint32_t inbuf = smem_u32(smem + C::SM_INBUF);
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
         w_enc[0].wait(&enc_ready[0]);
         for (int step = 0; step < NUM_STEPS; ++step) {
@@ -274,30 +277,35 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
               }
               const int s = it % C::STAGES;
               mbar_wait(&full[s], (it / C::STAGES) & 1);
-              const uint32_t w_hi = aRing + s * C::STAGE_BYTES, w_lo = w_hi + CHUNK_BYTES;
-              const int ksteps = (src == 2) ? 2 : 4;
+              // descriptors: only the start-address field moves (16-byte units): +16 per k-step of 16 elements
+              const uint32_t bh = ring_lo + s * (C::STAGE_BYTES >> 4), bl = bh + (CHUNK_BYTES >> 4);
+              const uint32_t acc0 = kc != 0;  // first MMA of a half overwrites the accumulator
+              if (src == 1) {
+                const uint32_t ah = tmem + TM_AHI + ak * 32, al = tmem + TM_ALO + ak * 32;
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                if (j < ksteps) {
-                  const uint32_t first = (kc | j) != 0;
-                  const uint64_t bh = kdesc(w_hi + j * 256, 1024);
-                  const uint64_t bl = kdesc(w_lo + j * 256, 1024);
-                  if (src == 1) {
-                    const uint32_t ah = tmem + TM_AHI + ak * 32 + j * 8, al = tmem + TM_ALO + ak * 32 + j * 8;
-                    umma_ts(acc, ah, bh, idesc, first);
-                    if (kSplit) {
-                      umma_ts(acc, al, bh, idesc, 1);
-                      umma_ts(acc, ah, bl, idesc, 1);
-                    }
-                  } else {
-                    const uint32_t sbo = (src == 0) ? 1024 : 512;
-                    const uint32_t hi = inbuf + (src == 0 ? C::OFF_ENC_HI : C::OFF_DIR_HI) + j * 256;
-                    const uint32_t lo = inbuf + (src == 0 ? C::OFF_ENC_LO : C::OFF_DIR_LO) + j * 256;
-                    umma_ss(acc, kdesc(hi, sbo), bh, idesc, first);
-                    if (kSplit) {
-                      umma_ss(acc, kdesc(lo, sbo), bh, idesc, 1);
-                      umma_ss(acc, kdesc(hi, sbo), bl, idesc, 1);
-                    }
+                for (int j = 0; j < 4; ++j) {
+                  umma_ts2(acc, ah + j * 8, bh + j * 16, HI_B, idesc, j ? 1u : acc0);
+                  if (kSplit) {
+                    umma_ts2(acc, al + j * 8, bh + j * 16, HI_B, idesc, 1u);
+                    umma_ts2(acc, ah + j * 8, bl + j * 16, HI_B, idesc, 1u);
+                  }
+                }
+              } else if (src == 0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  umma_ss2(acc, enc_hi + j * 16, HI_B, bh + j * 16, HI_B, idesc, j ? 1u : acc0);
+                  if (kSplit) {
+                    umma_ss2(acc, enc_lo + j * 16, HI_B, bh + j * 16, HI_B, idesc, 1u);
+                    umma_ss2(acc, enc_hi + j * 16, HI_B, bl + j * 16, HI_B, idesc, 1u);
+                  }
+                }
+              } else {  // view-dir encoding: 27 channels -> two k-steps
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                  umma_ss2(acc, dir_hi + j * 16, HI_DIR, bh + j * 16, HI_B, idesc, 1u);
+                  if (kSplit) {
+                    umma_ss2(acc, dir_lo + j * 16, HI_DIR, bh + j * 16, HI_B, idesc, 1u);
+                    umma_ss2(acc, dir_hi + j * 16, HI_DIR, bl + j * 16, HI_B, idesc, 1u);
                   }
                 }
               }

@@ -135,22 +135,45 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
   }
 }
 
+// torch.sum over the last (contiguous) dimension of a CPU fp32 tensor, bit for bit: ATen's
+// vectorized_inner_sum reduces 8-lane vectors with four interleaved accumulators, then adds the scalar
+// tail and the eight lane partials in order (aten/src/ATen/native/cpu/SumKernel.cpp; no cascade level
+// is reached for n < 512).  x in shared memory; every lane returns the sum.
+__device__ float aten_row_sum(const float* x, int n, int lane) {
+  constexpr int V = 8;
+  const int vs = n / V, size_ilp = vs / 4;
+  float part = 0.f;
+  if (lane < V) {
+    float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+    for (int i = 0; i < size_ilp; ++i) {
+      p0 = __fadd_rn(p0, x[(4 * i + 0) * V + lane]);
+      p1 = __fadd_rn(p1, x[(4 * i + 1) * V + lane]);
+      p2 = __fadd_rn(p2, x[(4 * i + 2) * V + lane]);
+      p3 = __fadd_rn(p3, x[(4 * i + 3) * V + lane]);
+    }
+    for (int i = size_ilp * 4; i < vs; ++i) p0 = __fadd_rn(p0, x[i * V + lane]);
+    part = __fadd_rn(__fadd_rn(__fadd_rn(p0, p1), p2), p3);
+  }
+  float acc = 0.f;
+  for (int k = vs * V; k < n; ++k) acc = __fadd_rn(acc, x[k]);
+#pragma unroll
+  for (int l = 0; l < V; ++l) acc = __fadd_rn(acc, __shfl_sync(FULL, part, l));
+  return acc;
+}
+
 // ----------------------------------------------------------------------------- sample_pdf core, RH:199-243
 // bins[B], w[B-1] in shared memory (w is overwritten with the pdf); cdf[B] scratch in shared memory.
 // Writes N samples to out_s (shared).  u == nullptr -> deterministic linspace.
 __device__ void sample_pdf_warp(const float* bins, float* w, float* cdf, int B, int N, const float* u, float* out_s, int lane) {
   const int nw = B - 1;
-  float s = 0.f;
-  for (int i = lane; i < nw; i += 32) {
-    w[i] = __fadd_rn(w[i], 1e-5f);  // RH:201
-    s += w[i];
-  }
-  s = warp_sum(s);
+  for (int i = lane; i < nw; i += 32) w[i] = __fadd_rn(w[i], 1e-5f);  // RH:201
   __syncwarp();
-  // cdf = [0, cumsum(w / s)]  (RH:202-204).  The `denom < 1e-5` test below (RH:239) sits right on top of the
-  // value empty bins produce (1e-5 / ~1.0006), so the cdf must round the way the reference's does or whole
-  // samples jump by a bin width: ATen's CPU cumsum accumulates fp32 inputs sequentially in fp64 and rounds
-  // each prefix to fp32 -- do exactly that (one lane, <= 255 adds; negligible next to the MLP).
+  // The `denom < 1e-5` test below (RH:239) sits right on top of the value empty bins produce
+  // (1e-5 / ~1.0006), and u = 1.0 sits on top of cdf[-1]; one ulp in the normaliser or in a prefix moves whole
+  // samples by a bin width.  So normaliser and cdf are rounded exactly as ATen's CPU kernels round them:
+  // torch.sum in its vector order (aten_row_sum), cumsum sequentially in fp64 with every prefix rounded to fp32
+  // (one lane, <= 255 adds; negligible next to the MLP).
+  const float s = aten_row_sum(w, nw, lane);
   for (int i = lane; i < nw; i += 32) w[i] = __fdiv_rn(w[i], s);
   __syncwarp();
   if (lane == 0) {
