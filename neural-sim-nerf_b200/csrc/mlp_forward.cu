@@ -24,6 +24,8 @@
 //
 // Warp roles: 0-3 epilogue (TMEM lane quadrant = warp), 4-5 encoders, 6 MMA issuer, 7 weight producer.
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "sm100_prims.cuh"
@@ -156,7 +158,13 @@ struct MlpArgs {
   int S;
   uint32_t flags;
   int num_tiles;
+  unsigned long long* trace;  // debug (NSR_TRACE_FILE): clock64 stamps of CTA 0's first tiles, [tile][step][16]
 };
+
+#define NSR_TR(tl, step, slot)                                                                         \
+  do {                                                                                                 \
+    if (a.trace != nullptr && blockIdx.x == 0 && (tl) < 4) a.trace[((tl) * 10 + (step)) * 16 + (slot)] = clock64(); \
+  } while (0)
 
 __device__ __forceinline__ uint64_t kdesc(uint32_t saddr, uint32_t sbo) { return make_sdesc(saddr, 128, sbo, 0); }
 
@@ -247,16 +255,18 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
       const uint32_t inbuf = smem_u32(smem + C::SM_INBUF);
       const uint32_t enc_hi = sdesc_lo(inbuf + C::OFF_ENC_HI, 128), enc_lo = sdesc_lo(inbuf + C::OFF_ENC_LO, 128);
       const uint32_t dir_hi = sdesc_lo(inbuf + C::OFF_DIR_HI, 128), dir_lo = sdesc_lo(inbuf + C::OFF_DIR_LO, 128);
-      uint32_t it = 0;
+      uint32_t it = 0, tl = 0;
       Waiter w_a[2], w_enc[2];
-      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++tl) {
         w_enc[0].wait(&enc_ready[0]);
         for (int step = 0; step < NUM_STEPS; ++step) {
           if (step == 9) w_enc[1].wait(&enc_ready[1]);
           const int nk = step_k_chunks(step);
           const int nhs = step_n_halves(step);
           bool waited1 = false;
+          NSR_TR(tl, step, 0);
           w_a[0].wait(&a_ready[0]);  // A[K 0..127] of this step written, ACC0 drained
+          NSR_TR(tl, step, 1);
           if (step == 9) {           // the single 128-wide half of step 9 accumulates in ACC1
             w_a[1].wait(&a_ready[1]);
             waited1 = true;
@@ -271,7 +281,9 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
               else if (step == 9 && kc == 4) src = 2;
               else if (step == 5) ak = kc - 1;
               if (!waited1 && (nh == 1 || (src == 1 && ak >= 2))) {
+                NSR_TR(tl, step, 2);
                 w_a[1].wait(&a_ready[1]);  // A[K 128..255] written, ACC1 drained
+                NSR_TR(tl, step, 3);
                 tc_fence_after_sync();
                 waited1 = true;
               }
@@ -314,6 +326,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
             umma_commit(&acc_ready[(step == 9) ? 1 : nh]);
           }
           if (!waited1) w_a[1].wait(&a_ready[1]);  // keep the parity in step (cannot happen with this network)
+          NSR_TR(tl, step, 4);
           if (step == 5) umma_commit(&enc_free[0]);  // last reader of the xyz encoding
         }
         umma_commit(&enc_free[1]);
@@ -418,7 +431,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
     // initial credits: nothing to wait for before the very first step
     mbar_arrive(&a_ready[0]);
     mbar_arrive(&a_ready[1]);
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++tl) {
       const int64_t p = int64_t(tile) * 128 + row;
       float sigma = 0.f;
       for (int step = 0; step < 9; ++step) {
@@ -427,6 +441,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
         uint32_t H[64], L[kSplit ? 64 : 1];
         // ---- first half: drain ACC0 into registers while the second half is still in the tensor pipe
         w_acc[0].wait(&acc_ready[0]);
+        if (tid == 0) NSR_TR(tl, step, 8);
         tc_fence_after_sync();
 #pragma unroll
         for (int c0 = 0; c0 < 128; c0 += 32) {
@@ -452,7 +467,9 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
           }
         }
         // ---- every MMA of this step has retired: the old activations may be overwritten
+        if (tid == 0) NSR_TR(tl, step, 9);
         w_acc[1].wait(&acc_ready[1]);
+        if (tid == 0) NSR_TR(tl, step, 10);
         tc_fence_after_sync();
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -462,6 +479,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
         tmem_st_wait();
         tc_fence_before_sync();
         mbar_arrive(&a_ready[0]);
+        if (tid == 0) NSR_TR(tl, step, 11);
         // ---- second half: drain ACC1 straight into AHI/ALO[K 128..255]
 #pragma unroll
         for (int c0 = 0; c0 < 128; c0 += 32) {
@@ -489,6 +507,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
         tmem_st_wait();
         tc_fence_before_sync();
         mbar_arrive(&a_ready[1]);
+        if (tid == 0) NSR_TR(tl, step, 12);
       }
       // ---- step 9: views layer accumulates in ACC1; rgb head on CUDA cores (RH:113-117)
       w_acc[1].wait(&acc_ready[1]);
@@ -571,7 +590,29 @@ int launch_mlp_forward(const float* rays, const float* z_or_pts, int64_t n, int 
   a.S = S;
   a.flags = flags;
   a.num_tiles = int((n_points + 127) / 128);
+  a.trace = nullptr;
   const int grid = a.num_tiles < g_num_sms ? a.num_tiles : g_num_sms;
+  const char* trace_file = getenv("NSR_TRACE_FILE");  // debug only: synchronous, dumps CTA 0's timeline
+  if (trace_file != nullptr && a.num_tiles >= 4 * grid) {
+    const size_t nb = 4 * 10 * 16 * sizeof(unsigned long long);
+    cudaMalloc(&a.trace, nb);
+    cudaMemset(a.trace, 0, nb);
+    const int rc = (flags & NSR_FLAG_FAST_FP16) ? launch_variant<1>(a, grid, st) : launch_variant<3>(a, grid, st);
+    cudaStreamSynchronize(st);
+    unsigned long long host[4 * 10 * 16];
+    cudaMemcpy(host, a.trace, nb, cudaMemcpyDeviceToHost);
+    cudaFree(a.trace);
+    if (FILE* f = fopen(trace_file, "a")) {
+      fprintf(f, "# launch split=%d tiles=%d\n", (flags & NSR_FLAG_FAST_FP16) ? 1 : 3, a.num_tiles);
+      for (int i = 0; i < 40; ++i) {
+        fprintf(f, "%d %d", i / 10, i % 10);
+        for (int k = 0; k < 16; ++k) fprintf(f, " %llu", host[i * 16 + k]);
+        fprintf(f, "\n");
+      }
+      fclose(f);
+    }
+    return rc;
+  }
   return (flags & NSR_FLAG_FAST_FP16) ? launch_variant<1>(a, grid, st) : launch_variant<3>(a, grid, st);
 }
 
