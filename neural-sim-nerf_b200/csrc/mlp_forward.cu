@@ -121,9 +121,18 @@ int launch_pack_net(const float* const* weights, const float* const* biases, voi
 }
 
 // ----------------------------------------------------------------------------- kernel configuration
-constexpr int MLP_THREADS = 256;
+// Warp roles (384 threads):
+//   0-7   epilogue: warp w drains TMEM lane quadrant (w & 3), columns [64 (w >> 2), +64) of each accumulator half
+//   8-9   encoders (two rows per thread)
+//   10    MMA issuer (all lanes run the control flow, one elected lane issues)
+//   11    weight producer
+constexpr int MLP_THREADS = 384;
+constexpr int EPI_THREADS = 256;
 constexpr int ENC_THREADS = 64;
-constexpr int TM_ACC0 = 0, TM_ACC1 = 128, TM_AHI = 256, TM_ALO = 384;
+constexpr int ENC_WARP0 = 8, MMA_WARP = 10, PROD_WARP = 11;
+// The kernel allocates all 512 TMEM columns of its SM (1 CTA / SM), so the allocation starts at column 0,
+// lane 0; the addresses below are absolute.  (Checked at run time: the kernel traps otherwise.)
+constexpr uint32_t TM_ACC0 = 0, TM_ACC1 = 128, TM_AHI = 256, TM_ALO = 384;
 
 template <int SPLIT>
 struct Cfg {
@@ -137,14 +146,16 @@ struct Cfg {
   static constexpr int OFF_ENC_LO = ENC_BYTES + DIR_BYTES;
   static constexpr int OFF_DIR_LO = 2 * ENC_BYTES + DIR_BYTES;
   // One buffer each: the xyz encoding of tile i is last read by step 5, the view-dir encoding by step 9,
-  // so the encoder warps refill them for tile i+1 during steps 6..9 / 0..8 (enc_free / dir_free barriers).
+  // so the encoder warps refill them for tile i+1 during steps 6..9 / 0..8 (enc_free barriers).
   static constexpr int SM_INBUF = 0;
   static constexpr int SM_RING = INBUF_BYTES;
   static constexpr int SM_BUDGET = 227 * 1024;
-  static constexpr int STAGES_FIT = (SM_BUDGET - SM_RING - TAIL_BYTES - 256) / STAGE_BYTES;
+  static constexpr int SM_XCH_BYTES = 128 * 16;    // per-row partial (r, g, b, sigma) handed between the two column halves
+  static constexpr int STAGES_FIT = (SM_BUDGET - SM_RING - TAIL_BYTES - SM_XCH_BYTES - 256) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 10 ? 10 : STAGES_FIT;
   static constexpr int SM_TAIL = SM_RING + STAGES * STAGE_BYTES;
-  static constexpr int SM_BAR = SM_TAIL + TAIL_BYTES;
+  static constexpr int SM_XCH = SM_TAIL + TAIL_BYTES;
+  static constexpr int SM_BAR = SM_XCH + SM_XCH_BYTES;
   static constexpr int SM_TOTAL = SM_BAR + 256;
   static_assert(STAGES >= 3, "weight ring too shallow");
 };
@@ -165,8 +176,6 @@ struct MlpArgs {
   do {                                                                                                 \
     if (a.trace != nullptr && blockIdx.x == 0 && (tl) < 4) a.trace[((tl) * 10 + (step)) * 16 + (slot)] = clock64(); \
   } while (0)
-
-__device__ __forceinline__ uint64_t kdesc(uint32_t saddr, uint32_t sbo) { return make_sdesc(saddr, 128, sbo, 0); }
 
 // 16-byte store of 8 fp16 (4 packed words) into a no-swizzle K-major tile whose 8-row groups are `sbo` bytes apart
 __device__ __forceinline__ void st_a8(uint8_t* tile, int sbo, int row, int kgroup, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
@@ -194,6 +203,44 @@ struct Waiter {  // one per (thread, barrier): parity follows the number of comp
   }
 };
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\tselp.u32 %0, 1, 0, e;\n\t}" : "=r"(p));
+  return p != 0;
+}
+
+// bias + (ReLU) + fp16 hi/lo split of 32 accumulator columns; optional fp32 dot with the alpha head
+template <bool kSplit>
+__device__ __forceinline__ void epi32(const uint32_t (&u)[32], const float* bias, bool relu, const float* walpha, float& sigma,
+                                      uint32_t* H, uint32_t* L) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 bb = *reinterpret_cast<const float4*>(bias + 4 * j);
+    float x0 = __uint_as_float(u[4 * j]) + bb.x, x1 = __uint_as_float(u[4 * j + 1]) + bb.y;
+    float x2 = __uint_as_float(u[4 * j + 2]) + bb.z, x3 = __uint_as_float(u[4 * j + 3]) + bb.w;
+    if (relu) {
+      x0 = fmaxf(x0, 0.f);
+      x1 = fmaxf(x1, 0.f);
+      x2 = fmaxf(x2, 0.f);
+      x3 = fmaxf(x3, 0.f);
+    }
+    if (walpha != nullptr) {  // alpha head on the fp32 post-ReLU activations (RH:109)
+      const float4 wa = *reinterpret_cast<const float4*>(walpha + 4 * j);
+      sigma = fmaf(x0, wa.x, sigma);
+      sigma = fmaf(x1, wa.y, sigma);
+      sigma = fmaf(x2, wa.z, sigma);
+      sigma = fmaf(x3, wa.w, sigma);
+    }
+    uint32_t l0, l1;
+    split2<kSplit>(x0, x1, H[2 * j], l0);
+    split2<kSplit>(x2, x3, H[2 * j + 1], l1);
+    if (kSplit) {
+      L[2 * j] = l0;
+      L[2 * j + 1] = l1;
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------- the kernel
 template <int SPLIT>
 __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
@@ -202,11 +249,12 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sRing = smem + C::SM_RING;
   const float* sTail = reinterpret_cast<const float*>(smem + C::SM_TAIL);
+  float4* sXch = reinterpret_cast<float4*>(smem + C::SM_XCH);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::SM_BAR);  // [STAGES]   producer -> MMA (tx bytes)
   uint64_t* empty = full + C::STAGES;                              // [STAGES]   MMA commit -> producer
   uint64_t* acc_ready = empty + C::STAGES;                         // [2]        MMA commit -> epilogue
-  uint64_t* a_ready = acc_ready + 2;                               // [2]        epilogue (128) -> MMA
-  uint64_t* enc_ready = a_ready + 2;                               // [0] xyz encoding, [1] view-dir encoding: encoders (128) -> MMA
+  uint64_t* a_ready = acc_ready + 2;                               // [2]        epilogue (256) -> MMA
+  uint64_t* enc_ready = a_ready + 2;                               // [0] xyz encoding, [1] view-dir encoding: encoders -> MMA
   uint64_t* enc_free = enc_ready + 2;                              // [0] after step 5, [1] after step 9: MMA commit -> encoders
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(enc_free + 2);
 
@@ -219,81 +267,95 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
     }
     for (int h = 0; h < 2; ++h) {
       mbar_init(&acc_ready[h], 1);
-      mbar_init(&a_ready[h], 128);
+      mbar_init(&a_ready[h], EPI_THREADS);
       mbar_init(&enc_ready[h], ENC_THREADS);
       mbar_init(&enc_free[h], 1);
     }
     fence_mbar_init();
   }
-  if (warp == 6) tmem_alloc(tmem_slot, 512);
+  if (warp == MMA_WARP) tmem_alloc(tmem_slot, 512);
   for (int i = tid; i < TAIL_FLOATS; i += MLP_THREADS)
     reinterpret_cast<float*>(smem + C::SM_TAIL)[i] = reinterpret_cast<const float*>(a.packed + WEIGHT_BYTES)[i];
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem = *tmem_slot;
+  if (*tmem_slot != 0u) __trap();  // the whole TMEM of the SM is ours: the allocation must start at 0
 
-  if (warp == 7) {
+  if (warp == PROD_WARP) {
     // ===================================================================== weight producer (TMA engine)
     if (lane == 0) {
-      uint32_t it = 0;
+      uint32_t stage = 0, phase = 0;
+      bool first_lap = true;
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-        for (int c = 0; c < NUM_CHUNKS; ++c, ++it) {
-          const int s = it % C::STAGES;
-          if (it >= uint32_t(C::STAGES)) mbar_wait(&empty[s], ((it / C::STAGES) - 1) & 1);
-          mbar_arrive_expect_tx(&full[s], C::STAGE_BYTES);
-          bulk_g2s(sRing + s * C::STAGE_BYTES, a.packed + size_t(c) * CHUNK_PAIR_BYTES, C::STAGE_BYTES, &full[s]);
+        for (int c = 0; c < NUM_CHUNKS; ++c) {
+          if (!first_lap) mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
+          bulk_g2s(sRing + stage * C::STAGE_BYTES, a.packed + size_t(c) * CHUNK_PAIR_BYTES, C::STAGE_BYTES, &full[stage]);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+            first_lap = false;
+          }
         }
       }
     }
-  } else if (warp == 6) {
+  } else if (warp == MMA_WARP) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(128, 128);
-      constexpr uint32_t HI_B = sdesc_hi(1024), HI_DIR = sdesc_hi(512);  // 8-row groups 1024 B apart (512 B for the K=32 tile)
-      const uint32_t ring_lo = sdesc_lo(smem_u32(sRing), 128);
-      const uint32_t inbuf = smem_u32(smem + C::SM_INBUF);
-      const uint32_t enc_hi = sdesc_lo(inbuf + C::OFF_ENC_HI, 128), enc_lo = sdesc_lo(inbuf + C::OFF_ENC_LO, 128);
-      const uint32_t dir_hi = sdesc_lo(inbuf + C::OFF_DIR_HI, 128), dir_lo = sdesc_lo(inbuf + C::OFF_DIR_LO, 128);
-      uint32_t it = 0, tl = 0;
-      Waiter w_a[2], w_enc[2];
-      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++tl) {
-        w_enc[0].wait(&enc_ready[0]);
-        for (int step = 0; step < NUM_STEPS; ++step) {
-          if (step == 9) w_enc[1].wait(&enc_ready[1]);
-          const int nk = step_k_chunks(step);
-          const int nhs = step_n_halves(step);
-          bool waited1 = false;
-          NSR_TR(tl, step, 0);
-          w_a[0].wait(&a_ready[0]);  // A[K 0..127] of this step written, ACC0 drained
-          NSR_TR(tl, step, 1);
-          if (step == 9) {           // the single 128-wide half of step 9 accumulates in ACC1
-            w_a[1].wait(&a_ready[1]);
-            waited1 = true;
-          }
-          tc_fence_after_sync();
-          for (int nh = 0; nh < nhs; ++nh) {
-            const uint32_t acc = tmem + ((step == 9 || nh == 1) ? TM_ACC1 : TM_ACC0);
-            for (int kc = 0; kc < nk; ++kc, ++it) {
-              // ---- A source of this K chunk: 0 = xyz encoding, 1 = TMEM activations, 2 = view-dir encoding
-              int src = 1, ak = kc;
-              if ((step == 0 || step == 5) && kc == 0) src = 0;
-              else if (step == 9 && kc == 4) src = 2;
-              else if (step == 5) ak = kc - 1;
-              if (!waited1 && (nh == 1 || (src == 1 && ak >= 2))) {
-                NSR_TR(tl, step, 2);
-                w_a[1].wait(&a_ready[1]);  // A[K 128..255] written, ACC1 drained
-                NSR_TR(tl, step, 3);
-                tc_fence_after_sync();
-                waited1 = true;
-              }
-              const int s = it % C::STAGES;
-              mbar_wait(&full[s], (it / C::STAGES) & 1);
-              // descriptors: only the start-address field moves (16-byte units): +16 per k-step of 16 elements
-              const uint32_t bh = ring_lo + s * (C::STAGE_BYTES >> 4), bl = bh + (CHUNK_BYTES >> 4);
-              const uint32_t acc0 = kc != 0;  // first MMA of a half overwrites the accumulator
+    // The whole warp runs the (uniform) control flow and waits; one elected lane issues the tcgen05
+    // instructions, so descriptors and addresses live in uniform registers.
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc_f16(128, 128);
+    constexpr uint32_t HI_B = sdesc_hi(1024), HI_DIR = sdesc_hi(512);  // 8-row groups 1024 B apart (512 B for the K=32 tile)
+    const uint32_t ring_lo = sdesc_lo(smem_u32(sRing), 128);
+    const uint32_t inbuf = smem_u32(smem + C::SM_INBUF);
+    const uint32_t enc_hi = sdesc_lo(inbuf + C::OFF_ENC_HI, 128), enc_lo = sdesc_lo(inbuf + C::OFF_ENC_LO, 128);
+    const uint32_t dir_hi = sdesc_lo(inbuf + C::OFF_DIR_HI, 128), dir_lo = sdesc_lo(inbuf + C::OFF_DIR_LO, 128);
+    uint32_t stage = 0, phase = 0, tl = 0;
+    Waiter w_a[2], w_enc[2];
+    bool ready = false;  // result of an early try_wait on full[stage]
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++tl) {
+      w_enc[0].wait(&enc_ready[0]);
+      for (int step = 0; step < NUM_STEPS; ++step) {
+        if (step == 9) w_enc[1].wait(&enc_ready[1]);
+        const int nk = step_k_chunks(step);
+        const int nhs = step_n_halves(step);
+        bool waited1 = false;
+        if (lane == 0) NSR_TR(tl, step, 0);
+        w_a[0].wait(&a_ready[0]);  // A[K 0..127] of this step written, ACC0 drained
+        if (lane == 0) NSR_TR(tl, step, 1);
+        if (step == 9) {           // the single 128-wide half of step 9 accumulates in ACC1
+          w_a[1].wait(&a_ready[1]);
+          waited1 = true;
+        }
+        tc_fence_after_sync();
+        for (int nh = 0; nh < nhs; ++nh) {
+          const uint32_t acc = (step == 9 || nh == 1) ? TM_ACC1 : TM_ACC0;
+          for (int kc = 0; kc < nk; ++kc) {
+            // ---- A source of this K chunk: 0 = xyz encoding, 1 = TMEM activations, 2 = view-dir encoding
+            int src = 1, ak = kc;
+            if ((step == 0 || step == 5) && kc == 0) src = 0;
+            else if (step == 9 && kc == 4) src = 2;
+            else if (step == 5) ak = kc - 1;
+            if (!waited1 && (nh == 1 || (src == 1 && ak >= 2))) {
+              if (lane == 0) NSR_TR(tl, step, 2);
+              w_a[1].wait(&a_ready[1]);  // A[K 128..255] written, ACC1 drained
+              if (lane == 0) NSR_TR(tl, step, 3);
+              tc_fence_after_sync();
+              waited1 = true;
+            }
+            if (!ready) mbar_wait(&full[stage], phase);
+            // descriptors: only the start-address field moves (16-byte units): +16 per k-step of 16 elements
+            const uint32_t bh = ring_lo + stage * (C::STAGE_BYTES >> 4), bl = bh + (CHUNK_BYTES >> 4);
+            const uint32_t acc0 = kc != 0;  // first MMA of a half overwrites the accumulator
+            const uint32_t cur = stage;
+            if (++stage == C::STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+            ready = mbar_try_wait(&full[stage], phase);  // probe the next stage now, look at the answer after issuing
+            if (leader) {
               if (src == 1) {
-                const uint32_t ah = tmem + TM_AHI + ak * 32, al = tmem + TM_ALO + ak * 32;
+                const uint32_t ah = TM_AHI + ak * 32, al = TM_ALO + ak * 32;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   umma_ts2(acc, ah + j * 8, bh + j * 16, HI_B, idesc, j ? 1u : acc0);
@@ -321,20 +383,25 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
                   }
                 }
               }
-              umma_commit(&empty[s]);
+              umma_commit(&empty[cur]);
             }
-            umma_commit(&acc_ready[(step == 9) ? 1 : nh]);
+            __syncwarp();
           }
-          if (!waited1) w_a[1].wait(&a_ready[1]);  // keep the parity in step (cannot happen with this network)
-          NSR_TR(tl, step, 4);
-          if (step == 5) umma_commit(&enc_free[0]);  // last reader of the xyz encoding
+          if (leader) umma_commit(&acc_ready[(step == 9) ? 1 : nh]);
+          __syncwarp();
         }
-        umma_commit(&enc_free[1]);
+        if (!waited1) w_a[1].wait(&a_ready[1]);  // keep the parity in step (cannot happen with this network)
+        if (lane == 0) NSR_TR(tl, step, 4);
+        if (step == 5 && leader) umma_commit(&enc_free[0]);  // last reader of the xyz encoding
+        __syncwarp();
       }
+      if (leader) umma_commit(&enc_free[1]);
+      __syncwarp();
     }
-  } else if (warp >= 4) {
+  } else if (warp >= ENC_WARP0) {
     // ===================================================================== encoders (2 warps, 2 rows per thread):
     // tile i+1's encodings while tile i is in the tensor pipe
+    const int er = tid - ENC_WARP0 * 32;
     uint32_t tl = 0;
     Waiter w_free[2];
     uint8_t* inbuf = smem + C::SM_INBUF;
@@ -342,7 +409,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
       float x[2][3], vd[2][3];
 #pragma unroll
       for (int rr = 0; rr < 2; ++rr) {
-        const int64_t p = int64_t(tile) * 128 + (tid - 128) + rr * 64;
+        const int64_t p = int64_t(tile) * 128 + er + rr * 64;
 #pragma unroll
         for (int d = 0; d < 3; ++d) x[rr][d] = vd[rr][d] = 0.f;
         if (p < a.n_points) {
@@ -364,7 +431,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
       if (tl >= 1) w_free[0].wait(&enc_free[0]);  // step 5 of the previous tile has read the old encoding
 #pragma unroll 1
       for (int rr = 0; rr < 2; ++rr) {
-        const int row = (tid - 128) + rr * 64;
+        const int row = er + rr * 64;
         float e[64];
         e[0] = x[rr][0];
         e[1] = x[rr][1];
@@ -394,7 +461,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
       if (tl >= 1) w_free[1].wait(&enc_free[1]);  // step 9 of the previous tile has read the old view-dir encoding
 #pragma unroll 1
       for (int rr = 0; rr < 2; ++rr) {
-        const int row = (tid - 128) + rr * 64;
+        const int row = er + rr * 64;
         float v[32];
         v[0] = vd[rr][0];
         v[1] = vd[rr][1];
@@ -424,9 +491,12 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
       mbar_arrive(&enc_ready[1]);
     }
   } else {
-    // ===================================================================== epilogue warps (row == TMEM lane)
-    const int row = tid;
-    const uint32_t tlane = tmem + (uint32_t(warp * 32) << 16);
+    // ===================================================================== epilogue warps
+    // thread = (row, column half): row = 32 (warp & 3) + lane == TMEM lane; columns [col0, col0 + 64) of ACC0 / ACC1
+    const int row = (warp & 3) * 32 + lane;
+    const int ch = warp >> 2;
+    const int col0 = ch * 64;
+    const uint32_t tlane = uint32_t((warp & 3) * 32) << 16;
     Waiter w_acc[2];
     // initial credits: nothing to wait for before the very first step
     mbar_arrive(&a_ready[0]);
@@ -436,73 +506,52 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
       const int64_t p = int64_t(tile) * 128 + row;
       float sigma = 0.f;
       for (int step = 0; step < 9; ++step) {
-        const float* bias = sTail + TAIL_BIAS + step * 256;
+        const float* bias = sTail + TAIL_BIAS + step * 256 + col0;
+        const float* walpha = (step == 7) ? sTail + TAIL_WALPHA + col0 : nullptr;
         const bool relu = step != 8;  // feature_linear has no activation (RH:110)
-        uint32_t H[64], L[kSplit ? 64 : 1];
+        uint32_t H[32], L[kSplit ? 32 : 1];
         // ---- first half: drain ACC0 into registers while the second half is still in the tensor pipe
         w_acc[0].wait(&acc_ready[0]);
         if (tid == 0) NSR_TR(tl, step, 8);
         tc_fence_after_sync();
-#pragma unroll
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          uint32_t u[32];
-          tmem_ld32(tlane + TM_ACC0 + c0, u);
+        {
+          uint32_t u0[32], u1[32];
+          tmem_ld32(tlane + TM_ACC0 + col0, u0);
+          tmem_ld32(tlane + TM_ACC0 + col0 + 32, u1);
           tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float2 bb = *reinterpret_cast<const float2*>(bias + c0 + 2 * j);
-            float x0 = __uint_as_float(u[2 * j]) + bb.x, x1 = __uint_as_float(u[2 * j + 1]) + bb.y;
-            if (relu) {
-              x0 = fmaxf(x0, 0.f);
-              x1 = fmaxf(x1, 0.f);
-            }
-            if (step == 7) {  // alpha head on the fp32 post-ReLU activations (RH:109)
-              const float2 wa = *reinterpret_cast<const float2*>(sTail + TAIL_WALPHA + c0 + 2 * j);
-              sigma = fmaf(x0, wa.x, sigma);
-              sigma = fmaf(x1, wa.y, sigma);
-            }
-            uint32_t lo;
-            split2<kSplit>(x0, x1, H[c0 / 2 + j], lo);
-            if (kSplit) L[c0 / 2 + j] = lo;
-          }
+          epi32<kSplit>(u0, bias, relu, walpha, sigma, H, L);
+          epi32<kSplit>(u1, bias + 32, relu, walpha ? walpha + 32 : nullptr, sigma, H + 16, L + (kSplit ? 16 : 0));
         }
         // ---- every MMA of this step has retired: the old activations may be overwritten
         if (tid == 0) NSR_TR(tl, step, 9);
         w_acc[1].wait(&acc_ready[1]);
         if (tid == 0) NSR_TR(tl, step, 10);
         tc_fence_after_sync();
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          tmem_st16(tlane + TM_AHI + q * 16, *reinterpret_cast<const uint32_t(*)[16]>(&H[q * 16]));
-          if (kSplit) tmem_st16(tlane + TM_ALO + q * 16, *reinterpret_cast<const uint32_t(*)[16]>(&L[q * 16]));
+        // accumulator column c is K index c of the next step: fp16 pairs -> packed column c / 2
+        tmem_st16(tlane + TM_AHI + col0 / 2, *reinterpret_cast<const uint32_t(*)[16]>(&H[0]));
+        tmem_st16(tlane + TM_AHI + col0 / 2 + 16, *reinterpret_cast<const uint32_t(*)[16]>(&H[16]));
+        if (kSplit) {
+          tmem_st16(tlane + TM_ALO + col0 / 2, *reinterpret_cast<const uint32_t(*)[16]>(&L[0]));
+          tmem_st16(tlane + TM_ALO + col0 / 2 + 16, *reinterpret_cast<const uint32_t(*)[16]>(&L[kSplit ? 16 : 0]));
         }
         tmem_st_wait();
         tc_fence_before_sync();
         mbar_arrive(&a_ready[0]);
         if (tid == 0) NSR_TR(tl, step, 11);
         // ---- second half: drain ACC1 straight into AHI/ALO[K 128..255]
-#pragma unroll
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          uint32_t u[32], h2[16], l2[16];
-          tmem_ld32(tlane + TM_ACC1 + c0, u);
+        {
+          uint32_t u0[32], u1[32];
+          tmem_ld32(tlane + TM_ACC1 + col0, u0);
+          tmem_ld32(tlane + TM_ACC1 + col0 + 32, u1);
           tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float2 bb = *reinterpret_cast<const float2*>(bias + 128 + c0 + 2 * j);
-            float x0 = __uint_as_float(u[2 * j]) + bb.x, x1 = __uint_as_float(u[2 * j + 1]) + bb.y;
-            if (relu) {
-              x0 = fmaxf(x0, 0.f);
-              x1 = fmaxf(x1, 0.f);
-            }
-            if (step == 7) {
-              const float2 wa = *reinterpret_cast<const float2*>(sTail + TAIL_WALPHA + 128 + c0 + 2 * j);
-              sigma = fmaf(x0, wa.x, sigma);
-              sigma = fmaf(x1, wa.y, sigma);
-            }
-            split2<kSplit>(x0, x1, h2[j], l2[j]);
-          }
-          tmem_st16(tlane + TM_AHI + 64 + c0 / 2, h2);
-          if (kSplit) tmem_st16(tlane + TM_ALO + 64 + c0 / 2, l2);
+          epi32<kSplit>(u0, bias + 128, relu, walpha ? walpha + 128 : nullptr, sigma, H, L);
+          epi32<kSplit>(u1, bias + 160, relu, walpha ? walpha + 160 : nullptr, sigma, H + 16, L + (kSplit ? 16 : 0));
+        }
+        tmem_st16(tlane + TM_AHI + 64 + col0 / 2, *reinterpret_cast<const uint32_t(*)[16]>(&H[0]));
+        tmem_st16(tlane + TM_AHI + 64 + col0 / 2 + 16, *reinterpret_cast<const uint32_t(*)[16]>(&H[16]));
+        if (kSplit) {
+          tmem_st16(tlane + TM_ALO + 64 + col0 / 2, *reinterpret_cast<const uint32_t(*)[16]>(&L[0]));
+          tmem_st16(tlane + TM_ALO + 64 + col0 / 2 + 16, *reinterpret_cast<const uint32_t(*)[16]>(&L[kSplit ? 16 : 0]));
         }
         tmem_st_wait();
         tc_fence_before_sync();
@@ -517,34 +566,41 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
       mbar_arrive(&a_ready[0]);
       float r0 = 0.f, r1 = 0.f, r2 = 0.f;
       {
-        const float* bias = sTail + TAIL_BIAS + 9 * 256;
+        const float* bias = sTail + TAIL_BIAS + 9 * 256 + col0;
+        const float4* wr = reinterpret_cast<const float4*>(sTail + TAIL_WRGB) + col0;
+        uint32_t u0[32], u1[32];
+        tmem_ld32(tlane + TM_ACC1 + col0, u0);
+        tmem_ld32(tlane + TM_ACC1 + col0 + 32, u1);
+        tmem_ld_wait();
 #pragma unroll
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          uint32_t u[32];
-          tmem_ld32(tlane + TM_ACC1 + c0, u);
-          tmem_ld_wait();
-          const float4* wr = reinterpret_cast<const float4*>(sTail + TAIL_WRGB) + c0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float h = fmaxf(__uint_as_float(u[j]) + bias[c0 + j], 0.f);
-            const float4 w = wr[j];
-            r0 = fmaf(h, w.x, r0);
-            r1 = fmaf(h, w.y, r1);
-            r2 = fmaf(h, w.z, r2);
-          }
+        for (int j = 0; j < 32; ++j) {
+          const float h0 = fmaxf(__uint_as_float(u0[j]) + bias[j], 0.f);
+          const float h1 = fmaxf(__uint_as_float(u1[j]) + bias[32 + j], 0.f);
+          const float4 w0 = wr[j], w1 = wr[32 + j];
+          r0 = fmaf(h0, w0.x, r0);
+          r1 = fmaf(h0, w0.y, r1);
+          r2 = fmaf(h0, w0.z, r2);
+          r0 = fmaf(h1, w1.x, r0);
+          r1 = fmaf(h1, w1.y, r1);
+          r2 = fmaf(h1, w1.z, r2);
         }
       }
       tc_fence_before_sync();
       mbar_arrive(&a_ready[1]);
-      if (p < a.n_points) {
+      // ---- the two column halves of a row meet in shared memory; the ch == 0 thread writes raw[p]
+      if (ch == 1) sXch[row] = make_float4(r0, r1, r2, sigma);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (ch == 0 && p < a.n_points) {
+        const float4 o = sXch[row];
         const float* misc = sTail + TAIL_MISC;
-        reinterpret_cast<float4*>(a.raw)[p] = make_float4(r0 + misc[1], r1 + misc[2], r2 + misc[3], sigma + misc[0]);  // RH:118
+        reinterpret_cast<float4*>(a.raw)[p] =
+            make_float4((r0 + o.x) + misc[1], (r1 + o.y) + misc[2], (r2 + o.z) + misc[3], (sigma + o.w) + misc[0]);  // RH:118
       }
     }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 6) tmem_dealloc(tmem, 512);
+  if (warp == MMA_WARP) tmem_dealloc(0u, 512);
 }
 
 static int g_num_sms = 0;
