@@ -347,12 +347,6 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
             // descriptors: only the start-address field moves (16-byte units): +16 per k-step of 16 elements
             const uint32_t bh = ring_lo + stage * (C::STAGE_BYTES >> 4), bl = bh + (CHUNK_BYTES >> 4);
             const uint32_t acc0 = kc != 0;  // first MMA of a half overwrites the accumulator
-            const uint32_t cur = stage;
-            if (++stage == C::STAGES) {
-              stage = 0;
-              phase ^= 1;
-            }
-            ready = mbar_try_wait(&full[stage], phase);  // probe the next stage now, look at the answer after issuing
             if (leader) {
               if (src == 1) {
                 const uint32_t ah = TM_AHI + ak * 32, al = TM_ALO + ak * 32;
@@ -383,20 +377,22 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
                   }
                 }
               }
-              umma_commit(&empty[cur]);
+              umma_commit(&empty[stage]);
             }
-            __syncwarp();
+            if (++stage == C::STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+            // probe the next stage AFTER queueing this chunk's MMAs: the probe's latency then overlaps their execution
+            ready = mbar_try_wait(&full[stage], phase);
           }
           if (leader) umma_commit(&acc_ready[(step == 9) ? 1 : nh]);
-          __syncwarp();
         }
         if (!waited1) w_a[1].wait(&a_ready[1]);  // keep the parity in step (cannot happen with this network)
         if (lane == 0) NSR_TR(tl, step, 4);
         if (step == 5 && leader) umma_commit(&enc_free[0]);  // last reader of the xyz encoding
-        __syncwarp();
       }
       if (leader) umma_commit(&enc_free[1]);
-      __syncwarp();
     }
   } else if (warp >= ENC_WARP0) {
     // ===================================================================== encoders (2 warps, 2 rows per thread):
