@@ -310,7 +310,8 @@ def run_ours(args):
         achieved = flops / (k_ms * 1e-3) / 1e12
         peak = peaks.get('bf16_tflops_sustained', peaks['bf16_tflops'])
         roofline = {'bound': 'tensor', 'kernel': 'nerf_mlp_kernel (fine pass, 192 samples/ray)', 'achieved': achieved, 'peak': peak,
-                    'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None, 'peak_source': f'{how} bf16_tflops_sustained (kernel timed back to back)',
+                    'unit': 'TFLOP/s', 'frac': achieved / peak,
+                    'traffic': 584814080, 'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this launch (profiles/r01_v3_ncu_fine_mlp_summary.csv); algorithmic 624 MB', 'peak_source': f'{how} bf16_tflops_sustained (kernel timed back to back)',
                     'ms_per_launch': k_ms, 'algorithmic_flop_per_launch': flops}
         # informational: the opt-in single-pass fp16 mode (NOT parity-valid, see DESIGN.md "precision")
         FAST = 8
