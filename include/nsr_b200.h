@@ -123,6 +123,23 @@ int nsr_render_rays_forward(const float* rays, int64_t n_rays, const void* packe
                             float* z_std, float* raw, float* z_vals_out, float* weights_out, void* workspace,
                             size_t workspace_bytes, void* stream);
 
+/* Bytes of scratch nsr_render_rays_backward needs for n rays of T = n_samples + n_importance depths. */
+size_t nsr_render_backward_workspace_bytes(int64_t n_rays, int n_total_samples);
+
+/*
+ * Backward of render_rays for the pose path.  Replaces the autograd tape behind
+ *   dLdray = torch.autograd.grad(rgb_p, batch_rays, grad_outputs=patch_grad_E)            (RN:177-178)
+ * at the render_rays boundary: given dL/drgb_map [n,3] it returns dL/d(ray_batch) [n,11] (columns 0:3 origin,
+ * 3:6 direction, 8:11 unit view direction; 6:8 near/far are constants of the graph and get 0).  Only the last
+ * network pass carries gradient (z_samples is detached, RN:475): `packed_net` is the network that produced
+ * `raw` (the fine one, or the coarse one when N_importance == 0 / network_fine is None), `z_vals` [n,T] and
+ * `raw` [n,T,4] are the z_vals_out / raw outputs of nsr_render_rays_forward.  Activations are recomputed, not
+ * stored.  Flags: NSR_FLAG_WHITE_BKGD as in the forward call.
+ */
+int nsr_render_rays_backward(const float* rays, const float* z_vals, const float* raw, int64_t n_rays, int n_total_samples,
+                             const void* packed_net, uint32_t flags, const float* d_rgb_map, float* d_rays, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
 /*
  * Ray generation + packing.  Replaces RH:156-165 get_rays and RN:91-112 (use_viewdirs, ndc=False):
  *   K_host[9], c2w_host[12] are HOST row-major 3x3 / 3x4; rays_out [H*W,11] device.

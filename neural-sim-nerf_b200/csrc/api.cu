@@ -152,6 +152,34 @@ int nsr_render_rays_forward(const float* rays, int64_t n, const void* packed_coa
   return NSR_OK;
 }
 
+// workspace layout: d_raw [n,T,4] | d_pts [n,T,8] | d_dnorm [n]
+size_t nsr_render_backward_workspace_bytes(int64_t n, int T) {
+  return align_up(size_t(n) * T * 16, 256) + align_up(size_t(n) * T * 32, 256) + align_up(size_t(n) * 4, 256);
+}
+
+int nsr_render_rays_backward(const float* rays, const float* z_vals, const float* raw, int64_t n, int T, const void* packed_net,
+                             uint32_t flags, const float* d_rgb_map, float* d_rays, void* workspace, size_t workspace_bytes,
+                             void* stream) {
+  NSR_REQUIRE(n >= 0 && T > 0, "nsr_render_rays_backward: bad sizes");
+  if (n == 0) return NSR_OK;
+  NSR_REQUIRE(rays && z_vals && raw && packed_net && d_rgb_map && d_rays, "nsr_render_rays_backward: null argument");
+  NSR_REQUIRE(workspace && workspace_bytes >= nsr_render_backward_workspace_bytes(n, T), "nsr_render_rays_backward: workspace too small");
+  NSR_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0 && (reinterpret_cast<uintptr_t>(raw) & 15) == 0,
+              "nsr_render_rays_backward: workspace must be 256-byte and raw 16-byte aligned");
+  NSR_REQUIRE(!(flags & NSR_FLAG_FAST_FP16), "nsr_render_rays_backward: only the default (fp16 hi/lo split) precision is built");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  float* d_raw = reinterpret_cast<float*>(ws);
+  ws += align_up(size_t(n) * T * 16, 256);
+  float* d_pts = reinterpret_cast<float*>(ws);
+  ws += align_up(size_t(n) * T * 32, 256);
+  float* d_dnorm = reinterpret_cast<float*>(ws);
+  int rc;
+  if ((rc = launch_raw2outputs_backward(raw, z_vals, rays, n, T, flags & NSR_FLAG_WHITE_BKGD, d_rgb_map, d_raw, d_dnorm, st))) return rc;
+  if ((rc = launch_mlp_backward(rays, z_vals, n, T, packed_net, d_raw, d_pts, st))) return rc;
+  return launch_ray_grad_reduce(rays, z_vals, d_pts, d_dnorm, n, T, d_rays, st);
+}
+
 int nsr_make_rays(int H, int W, const float* K_host, const float* c2w_host, float near_, float far_, float* rays_out, void* stream) {
   NSR_REQUIRE(H > 0 && W > 0 && K_host && c2w_host && rays_out, "nsr_make_rays: bad argument");
   return launch_make_rays(H, W, K_host, c2w_host, near_, far_, rays_out, static_cast<cudaStream_t>(stream));

@@ -28,7 +28,20 @@ constexpr int CHUNK_BYTES = CHUNK_ROWS * CHUNK_K * 2;  // 16384
 constexpr int NUM_STEPS = 10;
 constexpr int NUM_CHUNKS = 2 * 1 + 4 * 8 + 10 + 2 * 8 + 8 + 5;  // 73
 constexpr int CHUNK_PAIR_BYTES = 2 * CHUNK_BYTES;              // [hi chunk | lo chunk], lo = fp16(W - fp16(W))
-constexpr int WEIGHT_BYTES = NUM_CHUNKS * CHUNK_PAIR_BYTES;    // 2,392,064
+// Backward (data-gradient) chunks follow the forward ones: same [128 x 64] operand tiles of the TRANSPOSED
+// weights (row = forward input feature, K = forward output feature), in the order the backward steps use them:
+//   bstep 0  views_linears^T, view-dir rows   side N=32   K=128 (2 chunks)      -> dL/d(view-dir encoding)
+//   bstep 1  views_linears^T, feature rows    N=256       K=128 (2 per half)    -> dL/dfeature
+//   bstep 2  feature_linear^T                 N=256       K=256                 -> dL/dh7 (+ alpha head)
+//   bstep 3,4  pts_linears.7^T, .6^T          N=256       K=256
+//   bstep 5  pts_linears.5^T, xyz rows        side N=64   K=256 (4 chunks)      -> dL/d(xyz encoding), skip branch
+//   bstep 6  pts_linears.5^T, h rows          N=256       K=256
+//   bstep 7..10  pts_linears.4^T .. .1^T      N=256       K=256
+//   bstep 11 pts_linears.0^T                  side N=64   K=256 (4 chunks)      -> dL/d(xyz encoding)
+constexpr int NUM_BSTEPS = 12;
+constexpr int NUM_BWD_CHUNKS = 2 + 4 + 3 * 8 + 4 + 5 * 8 + 4;  // 78
+constexpr int BWD_CHUNK0 = NUM_CHUNKS;                         // index of the first backward chunk pair
+constexpr int WEIGHT_BYTES = (NUM_CHUNKS + NUM_BWD_CHUNKS) * CHUNK_PAIR_BYTES;  // 4,947,968
 
 // fp32 tail (offsets in floats)
 constexpr int TAIL_BIAS = 0;            // [10][256]  (step s bias at s*256; step 9 uses 128)
@@ -41,6 +54,10 @@ constexpr int PACKED_BYTES = WEIGHT_BYTES + TAIL_BYTES;
 
 __host__ __device__ constexpr int step_n_halves(int s) { return s == 9 ? 1 : 2; }
 __host__ __device__ constexpr int step_k_chunks(int s) { return s == 0 ? 1 : ((s == 5 || s == 9) ? 5 : 4); }
+__host__ __device__ constexpr bool bstep_is_side(int b) { return b == 0 || b == 5 || b == 11; }
+__host__ __device__ constexpr int bstep_n_halves(int b) { return bstep_is_side(b) ? 1 : 2; }
+__host__ __device__ constexpr int bstep_k_chunks(int b) { return b <= 1 ? 2 : 4; }
+__host__ __device__ constexpr int bstep_side_n(int b) { return b == 0 ? 32 : 64; }
 
 // ----------------------------------------------------------------------------- host-side plumbing (api.cu)
 void set_error(const char* fmt, ...);
@@ -61,5 +78,13 @@ int launch_make_rays(int H, int W, const float* K9, const float* c2w12, float ne
 int launch_pack_net(const float* const* weights, const float* const* biases, void* packed, cudaStream_t st);
 int launch_mlp_forward(const float* rays, const float* z_or_pts, int64_t n, int S, const void* packed, uint32_t flags,
                        float* raw, cudaStream_t st);
+// mlp_backward.cu: d_raw [n,S,4] -> d_pts [n,S,8] = (dL/dpoint[3], 0, dL/dviewdir[3], 0) per sample
+int launch_mlp_backward(const float* rays, const float* z, int64_t n, int S, const void* packed, const float* d_raw,
+                        float* d_pts, cudaStream_t st);
+// ray_stage.cu
+int launch_raw2outputs_backward(const float* raw, const float* z, const float* rays, int64_t n, int S, uint32_t flags,
+                                const float* d_rgb, float* d_raw, float* d_dnorm, cudaStream_t st);
+int launch_ray_grad_reduce(const float* rays, const float* z, const float* d_pts, const float* d_dnorm, int64_t n, int S,
+                           float* d_rays, cudaStream_t st);
 
 }  // namespace nsr

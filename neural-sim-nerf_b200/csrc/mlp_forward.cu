@@ -27,8 +27,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
-#include "common.cuh"
-#include "sm100_prims.cuh"
+#include "mlp_common.cuh"
 
 namespace nsr {
 
@@ -54,9 +53,50 @@ __device__ __forceinline__ void chunk_decode(int c, int& step, int& nh, int& kc)
   kc = c % step_k_chunks(s);
 }
 
+// backward chunk index (0-based within the backward list) -> (bstep, n_half, k_chunk)
+__device__ __forceinline__ void bwd_chunk_decode(int c, int& bstep, int& nh, int& kc) {
+  int b = 0;
+  for (; b < NUM_BSTEPS; ++b) {
+    const int cnt = bstep_n_halves(b) * bstep_k_chunks(b);
+    if (c < cnt) break;
+    c -= cnt;
+  }
+  bstep = b;
+  nh = c / bstep_k_chunks(b);
+  kc = c % bstep_k_chunks(b);
+}
+
 __global__ void pack_net_kernel(NetPtrs p, uint8_t* __restrict__ out) {
   const int c = blockIdx.x;
-  if (c < NUM_CHUNKS) {
+  if (c >= NUM_CHUNKS && c < NUM_CHUNKS + NUM_BWD_CHUNKS) {
+    // transposed weights for the data-gradient pass: element (row n, k) = W_forward[k][n]
+    int bstep, nh, kc;
+    bwd_chunk_decode(c - NUM_CHUNKS, bstep, nh, kc);
+    __half* hi = reinterpret_cast<__half*>(out + size_t(c) * CHUNK_PAIR_BYTES);
+    __half* lo = reinterpret_cast<__half*>(out + size_t(c) * CHUNK_PAIR_BYTES + CHUNK_BYTES);
+    for (int e = threadIdx.x; e < CHUNK_ROWS * CHUNK_K; e += blockDim.x) {
+      const int nl = e / CHUNK_K, kl = e % CHUNK_K;
+      const int n = nh * 128 + nl, k = kc * 64 + kl;
+      float v = 0.f;
+      switch (bstep) {
+        case 0: if (nl < 27) v = p.w[8][k * 283 + 256 + nl]; break;   // views_linears [128 x 283], dirs columns
+        case 1: v = p.w[8][k * 283 + n]; break;                        // views_linears, feature columns
+        case 2: v = p.w[9][k * 256 + n]; break;                        // feature_linear
+        case 3: v = p.w[7][k * 256 + n]; break;
+        case 4: v = p.w[6][k * 256 + n]; break;
+        case 5: if (nl < 63) v = p.w[5][k * 319 + nl]; break;          // pts_linears.5 [256 x 319], xyz columns
+        case 6: v = p.w[5][k * 319 + 63 + n]; break;
+        case 7: v = p.w[4][k * 256 + n]; break;
+        case 8: v = p.w[3][k * 256 + n]; break;
+        case 9: v = p.w[2][k * 256 + n]; break;
+        case 10: v = p.w[1][k * 256 + n]; break;
+        default: if (nl < 63) v = p.w[0][k * 63 + nl]; break;          // pts_linears.0 [256 x 63]
+      }
+      const __half h = __float2half_rn(v);
+      hi[chunk_off(nl, kl) >> 1] = h;
+      lo[chunk_off(nl, kl) >> 1] = __float2half_rn(v - __half2float(h));
+    }
+  } else if (c < NUM_CHUNKS) {
     int step, nh, kc;
     chunk_decode(c, step, nh, kc);
     __half* hi = reinterpret_cast<__half*>(out + size_t(c) * CHUNK_PAIR_BYTES);
@@ -115,24 +155,10 @@ int launch_pack_net(const float* const* weights, const float* const* biases, voi
     p.w[i] = weights[i];
     p.b[i] = biases[i];
   }
-  pack_net_kernel<<<NUM_CHUNKS + 1, 256, 0, st>>>(p, static_cast<uint8_t*>(packed));
+  pack_net_kernel<<<NUM_CHUNKS + NUM_BWD_CHUNKS + 1, 256, 0, st>>>(p, static_cast<uint8_t*>(packed));
   count_launch();
   return check_launch("pack_net_kernel");
 }
-
-// ----------------------------------------------------------------------------- kernel configuration
-// Warp roles (384 threads):
-//   0-7   epilogue: warp w drains TMEM lane quadrant (w & 3), columns [64 (w >> 2), +64) of each accumulator half
-//   8-9   encoders (two rows per thread)
-//   10    MMA issuer (all lanes run the control flow, one elected lane issues)
-//   11    weight producer
-constexpr int MLP_THREADS = 384;
-constexpr int EPI_THREADS = 256;
-constexpr int ENC_THREADS = 64;
-constexpr int ENC_WARP0 = 8, MMA_WARP = 10, PROD_WARP = 11;
-// The kernel allocates all 512 TMEM columns of its SM (1 CTA / SM), so the allocation starts at column 0,
-// lane 0; the addresses below are absolute.  (Checked at run time: the kernel traps otherwise.)
-constexpr uint32_t TM_ACC0 = 0, TM_ACC1 = 128, TM_AHI = 256, TM_ALO = 384;
 
 template <int SPLIT>
 struct Cfg {
@@ -176,70 +202,6 @@ struct MlpArgs {
   do {                                                                                                 \
     if (a.trace != nullptr && blockIdx.x == 0 && (tl) < 4) a.trace[((tl) * 10 + (step)) * 16 + (slot)] = clock64(); \
   } while (0)
-
-// 16-byte store of 8 fp16 (4 packed words) into a no-swizzle K-major tile whose 8-row groups are `sbo` bytes apart
-__device__ __forceinline__ void st_a8(uint8_t* tile, int sbo, int row, int kgroup, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
-  *reinterpret_cast<uint4*>(tile + (row >> 3) * sbo + kgroup * 128 + (row & 7) * 16) = make_uint4(w0, w1, w2, w3);
-}
-
-// (x0, x1) -> packed fp16 hi word and (SPLIT) the packed fp16 residual word
-template <bool kSplit>
-__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-  hi = pack_f16x2(x0, x1);
-  if (kSplit) {
-    const __half2 h = *reinterpret_cast<const __half2*>(&hi);
-    const float2 f = __half22float2(h);
-    lo = pack_f16x2(x0 - f.x, x1 - f.y);
-  } else {
-    lo = 0u;
-  }
-}
-
-struct Waiter {  // one per (thread, barrier): parity follows the number of completed waits
-  uint32_t n = 0;
-  __device__ __forceinline__ void wait(uint64_t* bar) {
-    mbar_wait(bar, n & 1);
-    ++n;
-  }
-};
-
-__device__ __forceinline__ bool elect_one() {
-  uint32_t p;
-  asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\tselp.u32 %0, 1, 0, e;\n\t}" : "=r"(p));
-  return p != 0;
-}
-
-// bias + (ReLU) + fp16 hi/lo split of 32 accumulator columns; optional fp32 dot with the alpha head
-template <bool kSplit>
-__device__ __forceinline__ void epi32(const uint32_t (&u)[32], const float* bias, bool relu, const float* walpha, float& sigma,
-                                      uint32_t* H, uint32_t* L) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float4 bb = *reinterpret_cast<const float4*>(bias + 4 * j);
-    float x0 = __uint_as_float(u[4 * j]) + bb.x, x1 = __uint_as_float(u[4 * j + 1]) + bb.y;
-    float x2 = __uint_as_float(u[4 * j + 2]) + bb.z, x3 = __uint_as_float(u[4 * j + 3]) + bb.w;
-    if (relu) {
-      x0 = fmaxf(x0, 0.f);
-      x1 = fmaxf(x1, 0.f);
-      x2 = fmaxf(x2, 0.f);
-      x3 = fmaxf(x3, 0.f);
-    }
-    if (walpha != nullptr) {  // alpha head on the fp32 post-ReLU activations (RH:109)
-      const float4 wa = *reinterpret_cast<const float4*>(walpha + 4 * j);
-      sigma = fmaf(x0, wa.x, sigma);
-      sigma = fmaf(x1, wa.y, sigma);
-      sigma = fmaf(x2, wa.z, sigma);
-      sigma = fmaf(x3, wa.w, sigma);
-    }
-    uint32_t l0, l1;
-    split2<kSplit>(x0, x1, H[2 * j], l0);
-    split2<kSplit>(x2, x3, H[2 * j + 1], l1);
-    if (kSplit) {
-      L[2 * j] = l0;
-      L[2 * j + 1] = l1;
-    }
-  }
-}
 
 // ----------------------------------------------------------------------------- the kernel
 template <int SPLIT>

@@ -135,6 +135,125 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
   }
 }
 
+// ----------------------------------------------------------------------------- raw2outputs backward (for RN:177-178)
+// Given g = dL/drgb_map: dL/draw [n,S,4] and dL/d||rays_d|| [n] (through dists = dz * ||d||, RN:361).
+//   w_i = a_i T_i,  T_i = prod_{j<i} (1 - a_j + 1e-10),  a_i = 1 - exp(-relu(s_i) dist_i),  c_i = sigmoid(raw_rgb_i)
+//   dL/dw_i = g . c_i (- sum(g) with white_bkgd);   dL/da_i = T_i dL/dw_i - (sum_{k>i} dL/dw_k w_k) / (1 - a_i + 1e-10)
+//   dL/ds_i = dL/da_i dist_i (1 - a_i) [s_i > 0];   dL/ddist_i = dL/da_i relu(s_i) (1 - a_i);   dL/draw_rgb_i = w_i g c_i (1 - c_i)
+template <int C>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+    raw2outputs_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays, int64_t n, int S,
+                           uint32_t flags, const float* __restrict__ d_rgb, float4* __restrict__ d_raw, float* __restrict__ d_dnorm) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = blockIdx.x * int64_t(WARPS_PER_BLOCK) + (threadIdx.x >> 5);
+  if (ray >= n) return;
+  const float* zr = z + ray * S;
+  const float4* rr = raw + ray * S;
+  const float dx = rays[ray * 11 + 3], dy = rays[ray * 11 + 4], dz = rays[ray * 11 + 5];
+  const float dnorm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+  const float g0 = d_rgb[ray * 3], g1 = d_rgb[ray * 3 + 1], g2 = d_rgb[ray * 3 + 2];
+  const float gw_bias = (flags & NSR_FLAG_WHITE_BKGD) ? -(g0 + g1 + g2) : 0.f;  // rgb += 1 - acc  (RN:385)
+
+  float alpha[C], sig[C], dzs[C], cr[C], cg[C], cb[C];
+  float lane_prod = 1.f;
+#pragma unroll
+  for (int j = 0; j < C; ++j) {
+    const int i = lane * C + j;
+    alpha[j] = sig[j] = dzs[j] = cr[j] = cg[j] = cb[j] = 0.f;
+    if (i < S) {
+      const float zi = zr[i];
+      dzs[j] = (i == S - 1) ? 1e10f : __fsub_rn(zr[i + 1], zi);
+      const float4 q = rr[i];
+      sig[j] = q.w;
+      alpha[j] = __fsub_rn(1.f, expf(-__fmul_rn(fmaxf(q.w, 0.f), __fmul_rn(dzs[j], dnorm))));
+      cr[j] = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-q.x)));
+      cg[j] = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-q.y)));
+      cb[j] = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-q.z)));
+      lane_prod *= __fadd_rn(__fsub_rn(1.f, alpha[j]), 1e-10f);
+    }
+  }
+  float incl = lane_prod;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float v = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl *= v;
+  }
+  float T = __shfl_up_sync(FULL, incl, 1);
+  if (lane == 0) T = 1.f;
+  // forward sweep inside the lane: T_i, w_i, dL/dw_i; lane total of dL/dw_k w_k
+  float Ti[C], wi[C], dw[C];
+  float lane_sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < C; ++j) {
+    Ti[j] = T;
+    wi[j] = alpha[j] * T;
+    dw[j] = g0 * cr[j] + g1 * cg[j] + g2 * cb[j] + gw_bias;
+    lane_sum += dw[j] * wi[j];
+    if (lane * C + j < S) T *= __fadd_rn(__fsub_rn(1.f, alpha[j]), 1e-10f);
+  }
+  // exclusive SUFFIX sum over lanes
+  float suf = lane_sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float v = __shfl_down_sync(FULL, suf, o);
+    if (lane + o < 32) suf += v;
+  }
+  float after = __shfl_down_sync(FULL, suf, 1);  // sum over lanes > this one
+  if (lane == 31) after = 0.f;
+  float dn = 0.f;
+#pragma unroll
+  for (int j = C - 1; j >= 0; --j) {
+    const int i = lane * C + j;
+    if (i < S) {
+      const float one_m = __fadd_rn(__fsub_rn(1.f, alpha[j]), 1e-10f);
+      const float dalpha = Ti[j] * dw[j] - after / one_m;
+      const float e = 1.f - alpha[j];                       // exp(-relu(s) dist)
+      const float dist = dzs[j] * dnorm;
+      const float dsig = (sig[j] > 0.f) ? dalpha * dist * e : 0.f;
+      const float ddist = dalpha * fmaxf(sig[j], 0.f) * e;
+      dn += ddist * dzs[j];
+      const float w = wi[j];
+      d_raw[ray * S + i] = make_float4(w * g0 * cr[j] * (1.f - cr[j]), w * g1 * cg[j] * (1.f - cg[j]), w * g2 * cb[j] * (1.f - cb[j]), dsig);
+      after += dw[j] * w;
+    }
+  }
+  dn = warp_sum(dn);
+  if (lane == 0) d_dnorm[ray] = dn;
+}
+
+// dL/d(ray_batch [n,11]) from the per-sample gradients: pts = o + d z (RN:463), dists = dz ||d|| (RN:361), viewdirs
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+    ray_grad_reduce_kernel(const float* __restrict__ rays, const float* __restrict__ z, const float4* __restrict__ d_pts,
+                           const float* __restrict__ d_dnorm, int64_t n, int S, float* __restrict__ d_rays) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = blockIdx.x * int64_t(WARPS_PER_BLOCK) + (threadIdx.x >> 5);
+  if (ray >= n) return;
+  float so[3] = {0.f, 0.f, 0.f}, sd[3] = {0.f, 0.f, 0.f}, sv[3] = {0.f, 0.f, 0.f};
+  for (int i = lane; i < S; i += 32) {
+    const float4 p = d_pts[(ray * S + i) * 2], v = d_pts[(ray * S + i) * 2 + 1];
+    const float zi = z[ray * S + i];
+    so[0] += p.x; so[1] += p.y; so[2] += p.z;
+    sd[0] += zi * p.x; sd[1] += zi * p.y; sd[2] += zi * p.z;
+    sv[0] += v.x; sv[1] += v.y; sv[2] += v.z;
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    so[d] = warp_sum(so[d]);
+    sd[d] = warp_sum(sd[d]);
+    sv[d] = warp_sum(sv[d]);
+  }
+  if (lane == 0) {
+    const float dx = rays[ray * 11 + 3], dy = rays[ray * 11 + 4], dz = rays[ray * 11 + 5];
+    const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
+    const float k = d_dnorm[ray] / nrm;
+    float* o = d_rays + ray * 11;
+    o[0] = so[0]; o[1] = so[1]; o[2] = so[2];
+    o[3] = sd[0] + k * dx; o[4] = sd[1] + k * dy; o[5] = sd[2] + k * dz;
+    o[6] = 0.f; o[7] = 0.f;   // near / far: the sampled depths are constants of the graph (python floats at RN:109)
+    o[8] = sv[0]; o[9] = sv[1]; o[10] = sv[2];
+  }
+}
+
 // torch.sum over the last (contiguous) dimension of a CPU fp32 tensor, bit for bit: ATen's
 // vectorized_inner_sum reduces 8-lane vectors with four interleaved accumulators, then adds the scalar
 // tail and the eight lane partials in order (aten/src/ATen/native/cpu/SumKernel.cpp; no cascade level
@@ -349,6 +468,38 @@ int launch_resample_merge(const float* z, const float* w, int64_t n, int S, int 
   resample_merge_kernel<<<grid, WARPS_PER_BLOCK * 32, smem, st>>>(z, w, n, S, Ni, u, z_fine, z_samples, z_std);
   count_launch();
   return check_launch("resample_merge_kernel");
+}
+
+int launch_raw2outputs_backward(const float* raw, const float* z, const float* rays, int64_t n, int S, uint32_t flags,
+                                const float* d_rgb, float* d_raw, float* d_dnorm, cudaStream_t st) {
+  if (n == 0) return NSR_OK;
+  const int C = (S + 31) / 32;
+  if (C > 8) {
+    set_error("raw2outputs backward: n_samples=%d > 256 not supported", S);
+    return NSR_E_UNSUPPORTED;
+  }
+  const unsigned grid = unsigned((n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+  const float4* r4 = reinterpret_cast<const float4*>(raw);
+  float4* d4 = reinterpret_cast<float4*>(d_raw);
+#define NSR_R2OB(CC)                                                                                              \
+  case CC:                                                                                                        \
+    raw2outputs_bwd_kernel<CC><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(r4, z, rays, n, S, flags, d_rgb, d4, d_dnorm); \
+    break;
+  switch (C) {
+    NSR_R2OB(1) NSR_R2OB(2) NSR_R2OB(3) NSR_R2OB(4) NSR_R2OB(5) NSR_R2OB(6) NSR_R2OB(7) NSR_R2OB(8)
+  }
+#undef NSR_R2OB
+  count_launch();
+  return check_launch("raw2outputs_bwd_kernel");
+}
+
+int launch_ray_grad_reduce(const float* rays, const float* z, const float* d_pts, const float* d_dnorm, int64_t n, int S,
+                           float* d_rays, cudaStream_t st) {
+  if (n == 0) return NSR_OK;
+  const unsigned grid = unsigned((n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+  ray_grad_reduce_kernel<<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(rays, z, reinterpret_cast<const float4*>(d_pts), d_dnorm, n, S, d_rays);
+  count_launch();
+  return check_launch("ray_grad_reduce_kernel");
 }
 
 int launch_make_rays(int H, int W, const float* K9, const float* c2w12, float near_, float far_, float* rays, cudaStream_t st) {

@@ -161,8 +161,8 @@ def _f32c(t, name):
 
 def _no_grad_inputs(*ts):
     if torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad for t in ts):
-        raise NotImplementedError('backward through the sm_100a renderer (SURVEY.md §8 a-11) is not built yet; '
-                                  'call under torch.no_grad() or detach the rays')
+        raise NotImplementedError('only render()/render_rays() carry a backward (dL/d rays, SURVEY.md a-11); '
+                                  'call this stage under torch.no_grad() or detach its inputs')
 
 
 # ----------------------------------------------------------------------------- RN:14-40
@@ -246,13 +246,11 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
     (RN:281-284) are the fixed multires=10 / 4 ones compiled into the kernel."""
     if ray_batch.shape[-1] <= 8:
         raise NotImplementedError('use_viewdirs=False ray batches are not built (CFG:8 sets use_viewdirs=True)')
-    _no_grad_inputs(ray_batch)
+    needs_grad = torch.is_grad_enabled() and torch.is_tensor(ray_batch) and ray_batch.requires_grad
     rays = _f32c(ray_batch, 'ray_batch')
     n = rays.shape[0]
     dev = rays.device
     S, Ni = int(N_samples), int(N_importance)
-    T = S + Ni
-    L = lib()
     flags = (FLAG_LINDISP if lindisp else 0) | (FLAG_WHITE_BKGD if white_bkgd else 0) | _prec_flag()
     pc = packed_weights(network_fn)
     pf = packed_weights(network_fine) if (network_fine is not None and Ni > 0) else None
@@ -266,24 +264,80 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
         else:
             t_rand = torch.rand(n, S, device=dev)
             u = torch.rand(n, Ni, device=dev) if Ni > 0 else None
-
-    new = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
-    ret = {'rgb_map': new(n, 3), 'disp_map': new(n), 'acc_map': new(n)}
-    if Ni > 0:
-        ret.update({'rgb0': new(n, 3), 'disp0': new(n), 'acc0': new(n), 'z_std': new(n)})
-    raw = new(n, T, 4) if (retraw or raw_noise_std > 0.) else None
     if raw_noise_std > 0.:
+        if needs_grad:
+            raise NotImplementedError('backward with raw_noise_std > 0 is not built')
+        new = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        ret = {'rgb_map': new(n, 3), 'disp_map': new(n), 'acc_map': new(n)}
+        if Ni > 0:
+            ret.update({'rgb0': new(n, 3), 'disp0': new(n), 'acc0': new(n), 'z_std': new(n)})
         # noise is injected between the MLP and the compositor (RN:365-374): run the stages one by one
         return _render_rays_staged(rays, pc, pf, S, Ni, flags, t_rand, u, retraw, raw_noise_std, white_bkgd, ret)
+    cfg = dict(pc=pc, pf=pf, S=S, Ni=Ni, flags=flags, t_rand=t_rand, u=u, retraw=retraw)
+    if needs_grad:
+        if flags & FLAG_FAST_FP16:
+            raise NotImplementedError("backward is built for the default precision only (NSR_PRECISION='fp16x3')")
+        outs = _RenderRaysFn.apply(ray_batch, cfg)
+    else:
+        outs = _forward_impl(rays, cfg, keep_for_backward=False)[0]
+    keys = ['rgb_map', 'disp_map', 'acc_map'] + (['rgb0', 'disp0', 'acc0', 'z_std'] if Ni > 0 else []) + (['raw'] if retraw else [])
+    return dict(zip(keys, outs))
+
+
+def _forward_impl(rays, cfg, keep_for_backward):
+    """One call of nsr_render_rays_forward.  Returns (outputs tuple, z_vals [n,T] or None, raw [n,T,4] or None)."""
+    L = lib()
+    n, dev = rays.shape[0], rays.device
+    S, Ni = cfg['S'], cfg['Ni']
+    T = S + Ni
+    new = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+    rgb, disp, acc = new(n, 3), new(n), new(n)
+    rgb0 = disp0 = acc0 = zstd = None
+    if Ni > 0:
+        rgb0, disp0, acc0, zstd = new(n, 3), new(n), new(n), new(n)
+    raw = new(n, T, 4) if (cfg['retraw'] or keep_for_backward) else None
+    zv = new(n, T) if keep_for_backward else None
     ws_bytes = L.nsr_render_workspace_bytes(n, S, Ni)
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
-    check(L.nsr_render_rays_forward(ptr(rays), n, ptr(pc), ptr(pf), S, Ni, flags, ptr(t_rand), ptr(u),
-                                    ptr(ret['rgb_map']), ptr(ret['disp_map']), ptr(ret['acc_map']),
-                                    ptr(ret.get('rgb0')), ptr(ret.get('disp0')), ptr(ret.get('acc0')), ptr(ret.get('z_std')),
-                                    ptr(raw), None, None, ptr(ws), ws_bytes, _stream()), 'nsr_render_rays_forward')
-    if retraw:
-        ret['raw'] = raw
-    return ret
+    check(L.nsr_render_rays_forward(ptr(rays), n, ptr(cfg['pc']), ptr(cfg['pf']), S, Ni, cfg['flags'], ptr(cfg['t_rand']), ptr(cfg['u']),
+                                    ptr(rgb), ptr(disp), ptr(acc), ptr(rgb0), ptr(disp0), ptr(acc0), ptr(zstd),
+                                    ptr(raw), ptr(zv), None, ptr(ws), ws_bytes, _stream()), 'nsr_render_rays_forward')
+    outs = [rgb, disp, acc] + ([rgb0, disp0, acc0, zstd] if Ni > 0 else []) + ([raw] if cfg['retraw'] else [])
+    return tuple(outs), zv, raw
+
+
+class _RenderRaysFn(torch.autograd.Function):
+    """render_rays with the gradient the pose path needs (RN:177-178): dL/d(ray_batch) from dL/d(rgb_map).
+    Everything else the reference's tape could deliver (gradients of disp / acc / rgb0 / raw, gradients to the MLP
+    parameters -- SURVEY.md a-12) is not built: those outputs are marked non-differentiable so asking fails loudly."""
+
+    @staticmethod
+    def forward(ctx, ray_batch, cfg):
+        rays = ray_batch.detach().to(torch.float32).contiguous()
+        outs, zv, raw = _forward_impl(rays, cfg, keep_for_backward=True)
+        ctx.save_for_backward(rays, zv, raw)
+        ctx.cfg = cfg
+        ctx.in_dtype = ray_batch.dtype
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(*outs[1:])
+        return outs
+
+    @staticmethod
+    def backward(ctx, d_rgb, *unused):
+        if d_rgb is None:
+            return None, None
+        rays, zv, raw = ctx.saved_tensors
+        cfg = ctx.cfg
+        L = lib()
+        n, T = zv.shape
+        g = d_rgb.detach().to(torch.float32).contiguous()
+        d_rays = torch.empty(n, 11, dtype=torch.float32, device=rays.device)
+        ws_bytes = L.nsr_render_backward_workspace_bytes(n, T)
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=rays.device)
+        net = cfg['pf'] if (cfg['Ni'] > 0 and cfg['pf'] is not None) else cfg['pc']   # the pass that produced rgb_map (RN:481)
+        check(L.nsr_render_rays_backward(ptr(rays), ptr(zv), ptr(raw), n, T, ptr(net), cfg['flags'] & FLAG_WHITE_BKGD, ptr(g),
+                                         ptr(d_rays), ptr(ws), ws_bytes, _stream()), 'nsr_render_rays_backward')
+        return d_rays.to(ctx.in_dtype), None
 
 
 def _render_rays_staged(rays, pc, pf, S, Ni, flags, t_rand, u, retraw, raw_noise_std, white_bkgd, ret):

@@ -1,0 +1,104 @@
+"""GPU parity of the backward pass: dL/d(rays) from dL/d(rgb_map), against PyTorch autograd
+through the CPU oracle (the reference's own tape, RN:168-181, is autograd over the same ops).
+
+Tolerance: |d| <= 2e-3 * max|grad| per tensor (gradients of a sharp scene span many decades; the bound is relative
+to the largest component of the same gradient tensor) and a cosine similarity > 0.99999.
+"""
+import numpy as np
+import pytest
+import torch
+
+import nerf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def nsr():
+    import neural_sim_nerf_b200 as m
+    assert torch.cuda.is_available()
+    return m
+
+
+@pytest.fixture(scope='module')
+def nets(nsr, wfit):
+    out = []
+    for sd in wfit:
+        m = nsr.NeRF()
+        m.load_state_dict(sd)
+        out.append(m.cuda())
+    return out
+
+
+def camera_rays(n_side, phi):
+    H = W = 400
+    c2w = O.pose_spherical(90., phi - 180., 1.01)[:3, :4]
+    ro, rd = O.get_rays(H, W, O.YCBV_K_400, c2w)
+    ii = torch.linspace(0, 399, n_side).long()
+    sel = (ii[:, None] * W + ii[None, :]).reshape(-1)
+    return O.pack_rays(ro.reshape(-1, 3)[sel], rd.reshape(-1, 3)[sel], O.YCBV_NEAR, O.YCBV_FAR)
+
+
+def check_grad(got, ref, what, tol=2e-3):
+    got, ref = got.detach().cpu().double(), ref.detach().cpu().double()
+    scale = ref.abs().max().item()
+    err = (got - ref).abs().max().item()
+    cos = torch.nn.functional.cosine_similarity(got.reshape(1, -1), ref.reshape(1, -1)).item()
+    print(f'{what}: max|ref| {scale:.3e}  max err {err:.3e} ({err / max(scale, 1e-30):.2e} rel)  cos {cos:.8f}')
+    assert err <= tol * scale, f'{what}: {err:.3e} > {tol} * {scale:.3e}'
+    assert cos > 0.99999, f'{what}: cosine {cos}'
+
+
+@pytest.mark.parametrize('phi,n_side,white', [(22.5, 14, False), (200.0, 10, True)])
+def test_render_rays_backward_matches_autograd(nsr, wfit, nets, phi, n_side, white):
+    rays = camera_rays(n_side, phi)
+    n = rays.shape[0]
+    g = torch.randn(n, 3, generator=torch.Generator().manual_seed(1))
+    # reference: autograd through the oracle (fine pass only carries gradient: z_samples is detached, RN:475)
+    r_cpu = rays.clone().requires_grad_(True)
+    ref = O.render_rays(r_cpu, wfit[0], wfit[1], 64, 128, white_bkgd=white)
+    (ref_grad,) = torch.autograd.grad(ref['rgb_map'], r_cpu, grad_outputs=g)
+    r_gpu = rays.cuda().requires_grad_(True)
+    out = nsr.render_rays(r_gpu, nets[0], None, 64, N_importance=128, network_fine=nets[1], white_bkgd=white, retraw=True)
+    (got_grad,) = torch.autograd.grad(out['rgb_map'], r_gpu, grad_outputs=g.cuda())
+    assert got_grad.shape == (n, 11)
+    check_grad(got_grad[:, 0:3], ref_grad[:, 0:3], 'dL/d rays_o')
+    check_grad(got_grad[:, 3:6], ref_grad[:, 3:6], 'dL/d rays_d')
+    check_grad(got_grad[:, 8:11], ref_grad[:, 8:11], 'dL/d viewdirs')
+    assert float(got_grad[:, 6:8].abs().max()) == 0.0
+
+
+def test_render_backward_through_get_rays_to_c2w(nsr, wfit, nets):
+    """The reference's use (RN:148-181): rays come from get_rays(c2w(psi)); chain dL/drays on to the pose."""
+    H = W = 20
+    K = [[66.0, 0, 9.5], [0, 66.0, 10.5], [0, 0, 1]]
+    pose = O.pose_spherical(90., 157.5 - 180., 1.01)[:3, :4]
+    g = torch.randn(H * W, 3, generator=torch.Generator().manual_seed(2))
+    kw = dict(N_samples=64, N_importance=128)
+
+    c_cpu = pose.clone().requires_grad_(True)
+    ro, rd = O.get_rays(H, W, K, c_cpu)
+    ref = O.render(H, W, K, wfit[0], wfit[1], chunk=512, rays=(ro.reshape(-1, 3), rd.reshape(-1, 3)), near=O.YCBV_NEAR, far=O.YCBV_FAR, **kw)
+    (ref_grad,) = torch.autograd.grad(ref[0], c_cpu, grad_outputs=g)
+
+    c_gpu = pose.cuda().requires_grad_(True)
+    ro, rd = nsr.get_rays(H, W, K, c_gpu)
+    batch_rays = torch.stack([ro.reshape(-1, 3), rd.reshape(-1, 3)], 0)                      # RN:163
+    rgb, _, _, _ = nsr.render(H, W, K, chunk=512, rays=batch_rays, retraw=True, network_fn=nets[0], network_query_fn=None,
+                              network_fine=nets[1], use_viewdirs=True, ndc=False, near=O.YCBV_NEAR, far=O.YCBV_FAR, **kw)
+    dLdray = torch.autograd.grad(rgb, batch_rays, grad_outputs=g.cuda(), retain_graph=True)  # RN:177-178
+    (got_grad,) = torch.autograd.grad(batch_rays, c_gpu, grad_outputs=dLdray)                 # RN:179-181
+    check_grad(got_grad, ref_grad, 'dL/d c2w')
+
+
+def test_coarse_only_backward_and_unsupported_grads(nsr, wfit, nets):
+    rays = camera_rays(8, 60.0)
+    g = torch.randn(rays.shape[0], 3, generator=torch.Generator().manual_seed(3))
+    r_cpu = rays.clone().requires_grad_(True)
+    ref = O.render_rays(r_cpu, wfit[0], None, 64, 0)
+    (ref_grad,) = torch.autograd.grad(ref['rgb_map'], r_cpu, grad_outputs=g)
+    r_gpu = rays.cuda().requires_grad_(True)
+    out = nsr.render_rays(r_gpu, nets[0], None, 64, N_importance=0)
+    (got_grad,) = torch.autograd.grad(out['rgb_map'], r_gpu, grad_outputs=g.cuda())
+    check_grad(got_grad[:, 0:6], ref_grad[:, 0:6], 'coarse-only dL/d(o,d)')
+    assert not out['acc_map'].requires_grad and not out['disp_map'].requires_grad   # not built -> not differentiable, loudly
