@@ -285,7 +285,7 @@ def run_ours(args):
     e2e_value = world * n * args.steps / (ms_e2e * 1e-3)
 
     # ------------------------------------------------------------- roofline of the dominant kernel (fine-pass MLP)
-    roofline = cpu_base = fast = None
+    roofline = cpu_base = fast = fwd_bwd = None
     if rank == 0:
         zf = new(n, T)
         rawf = new(n, T, 4)
@@ -336,6 +336,35 @@ def run_ours(args):
                 'rays_per_s_device_resident': n / (fast_ms * 1e-3), 'ms_per_step': fast_ms,
                 'fine_mlp_ms_per_launch': fk_ms, 'fine_mlp_tflops': flops / (fk_ms * 1e-3) / 1e12,
                 'fine_mlp_frac_of_peak': flops / (fk_ms * 1e-3) / 1e12 / peak}
+        # secondary (BASELINE config 3): forward + backward dL/d(rays) for the pose path, same 160 000 rays
+        bws_bytes = L.nsr_render_backward_workspace_bytes(n, T)
+        bws = torch.empty(bws_bytes, dtype=torch.uint8, device=dev)
+        g_rgb = torch.randn(n, 3, device=dev)
+        d_rays = new(n, 11)
+        zsave, rawsave = new(n, T), new(n, T, 4)
+
+        def step_fwd_bwd(s):
+            r = rays_dev[s % len(rays_dev)]
+            rc = L.nsr_render_rays_forward(P(r), n, P(pc), P(pf), N_SAMPLES, N_IMPORTANCE, 0, None, None, P(outs['rgb']), P(outs['disp']),
+                                           P(outs['acc']), P(outs['rgb0']), P(outs['disp0']), P(outs['acc0']), P(outs['zstd']), P(rawsave),
+                                           P(zsave), None, P(ws), ws_bytes, stream)
+            rc = rc or L.nsr_render_rays_backward(P(r), P(zsave), P(rawsave), n, T, P(pf), 0, P(g_rgb), P(d_rays), P(bws), bws_bytes, stream)
+            if rc != 0:
+                raise RuntimeError(L.nsr_last_error().decode())
+
+        for s in range(2):
+            step_fwd_bwd(s)
+        torch.cuda.synchronize()
+        e0.record()
+        for s in range(args.steps):
+            step_fwd_bwd(s)
+        e1.record()
+        torch.cuda.synchronize()
+        fb_ms = e0.elapsed_time(e1) / args.steps
+        fwd_bwd = {'workload': 'BASELINE config 3: forward + backward dL/d(rays) from dL/d(rgb_map), 160000 rays, 64+128 samples (fine pass recomputed in the backward kernel)',
+                   'rays_per_s': n / (fb_ms * 1e-3), 'ms_per_step': fb_ms, 'algorithmic_flop_per_ray': (64 + 192 + 192) * FLOP_PER_POINT,
+                   'algorithmic_tflops': n * (64 + 192 + 192) * FLOP_PER_POINT / (fb_ms * 1e-3) / 1e12}
+        del bws, zsave, rawsave
         # CPU baseline: the oracle port on this box's host cores, bounded sample
         rate, cores, times = cpu_render_rate(4096, 2)
         cpu_base = {'value': rate, 'unit': 'rays/s', 'cores': cores, 'kind': 'port',
@@ -358,7 +387,7 @@ def run_ours(args):
                     'api': 'render(H, W, K, chunk, rays=<pinned host [2,N,3] -> cuda>, **render_kwargs_test) + D2H of rgb/disp/acc'},
             'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_base,
             'flop_per_ray': FLOP_PER_RAY, 'tflops_device_resident': value * FLOP_PER_RAY / 1e12,
-            'tensor_flop_issued_per_algorithmic_flop': 3, 'fast_fp16_mode': fast,
+            'tensor_flop_issued_per_algorithmic_flop': 3, 'fast_fp16_mode': fast, 'fwd_bwd': fwd_bwd,
         }))
 
 
