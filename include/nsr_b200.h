@@ -103,7 +103,9 @@ int nsr_sample_pdf(const float* bins, const float* weights, int64_t n_rays, int 
 int nsr_resample_merge(const float* z_coarse, const float* weights, int64_t n_rays, int n_samples, int n_importance,
                        const float* u, float* z_fine, float* z_samples, float* z_std, void* stream);
 
-/* Bytes of scratch nsr_render_rays_forward needs for n rays. */
+/* Bytes of scratch nsr_render_rays_forward needs for n rays.  Layout (each block padded to 256 bytes), left valid
+ * after the call: z0 [n,S] | weights0 [n,S] | raw0 [n,S,4] | z_fine [n,S+Ni] | raw_fine [n,S+Ni,4] -- the coarse pass's
+ * depths and raw outputs are what a backward through rgb0 needs. */
 size_t nsr_render_workspace_bytes(int64_t n_rays, int n_samples, int n_importance);
 
 /*
@@ -135,10 +137,19 @@ size_t nsr_render_backward_workspace_bytes(int64_t n_rays, int n_total_samples);
  * `raw` (the fine one, or the coarse one when N_importance == 0 / network_fine is None), `z_vals` [n,T] and
  * `raw` [n,T,4] are the z_vals_out / raw outputs of nsr_render_rays_forward.  Activations are recomputed, not
  * stored.  Flags: NSR_FLAG_WHITE_BKGD as in the forward call.
+ *
+ * `dump` (optional, NULL = off) receives what the weight gradients of that pass need (the
+ * loss.backward() of RN:691-707): every layer's input activations and pre-activation gradients as row-major fp16,
+ * P = 128 * ceil(n_rays * n_total_samples / 128) rows (rows beyond the real points carry zero gradients), in this order:
+ *   EX [P,64] xyz encoding | EV [P,32] view-dir encoding | H0..H7 [P,256] | F [P,256] feature | HV [P,128] |
+ *   GV [P,128] dL/d(views pre-activation) | GF [P,256] dL/dfeature | G0..G7 [P,256] dL/d(pts_linears.l pre-activation) |
+ *   SCALE [P] fp32: the gradient rows are stored divided by a per-row power of two (fp16 range), multiply back
+ * so that dW_l = (SCALE . G_l)^T H_{l-1}, db_l = column sums of SCALE . G_l (dL/draw itself is workspace[0 : n*T*16]).
  */
+size_t nsr_mlp_dump_bytes(int64_t n_rays, int n_total_samples);
 int nsr_render_rays_backward(const float* rays, const float* z_vals, const float* raw, int64_t n_rays, int n_total_samples,
-                             const void* packed_net, uint32_t flags, const float* d_rgb_map, float* d_rays, void* workspace,
-                             size_t workspace_bytes, void* stream);
+                             const void* packed_net, uint32_t flags, const float* d_rgb_map, float* d_rays, void* dump,
+                             void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Ray generation + packing.  Replaces RH:156-165 get_rays and RN:91-112 (use_viewdirs, ndc=False):

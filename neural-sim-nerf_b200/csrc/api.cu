@@ -157,9 +157,11 @@ size_t nsr_render_backward_workspace_bytes(int64_t n, int T) {
   return align_up(size_t(n) * T * 16, 256) + align_up(size_t(n) * T * 32, 256) + align_up(size_t(n) * 4, 256);
 }
 
+size_t nsr_mlp_dump_bytes(int64_t n_rays, int n_total_samples) { return mlp_dump_bytes(n_rays * n_total_samples); }
+
 int nsr_render_rays_backward(const float* rays, const float* z_vals, const float* raw, int64_t n, int T, const void* packed_net,
-                             uint32_t flags, const float* d_rgb_map, float* d_rays, void* workspace, size_t workspace_bytes,
-                             void* stream) {
+                             uint32_t flags, const float* d_rgb_map, float* d_rays, void* dump, void* workspace,
+                             size_t workspace_bytes, void* stream) {
   NSR_REQUIRE(n >= 0 && T > 0, "nsr_render_rays_backward: bad sizes");
   if (n == 0) return NSR_OK;
   NSR_REQUIRE(rays && z_vals && raw && packed_net && d_rgb_map && d_rays, "nsr_render_rays_backward: null argument");
@@ -176,7 +178,7 @@ int nsr_render_rays_backward(const float* rays, const float* z_vals, const float
   float* d_dnorm = reinterpret_cast<float*>(ws);
   int rc;
   if ((rc = launch_raw2outputs_backward(raw, z_vals, rays, n, T, flags & NSR_FLAG_WHITE_BKGD, d_rgb_map, d_raw, d_dnorm, st))) return rc;
-  if ((rc = launch_mlp_backward(rays, z_vals, n, T, packed_net, d_raw, d_pts, st))) return rc;
+  if ((rc = launch_mlp_backward(rays, z_vals, n, T, packed_net, d_raw, d_pts, dump, st))) return rc;
   return launch_ray_grad_reduce(rays, z_vals, d_pts, d_dnorm, n, T, d_rays, st);
 }
 

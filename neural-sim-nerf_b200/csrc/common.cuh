@@ -80,7 +80,8 @@ int launch_mlp_forward(const float* rays, const float* z_or_pts, int64_t n, int 
                        float* raw, cudaStream_t st);
 // mlp_backward.cu: d_raw [n,S,4] -> d_pts [n,S,8] = (dL/dpoint[3], 0, dL/dviewdir[3], 0) per sample
 int launch_mlp_backward(const float* rays, const float* z, int64_t n, int S, const void* packed, const float* d_raw,
-                        float* d_pts, cudaStream_t st);
+                        float* d_pts, void* dump, cudaStream_t st);
+size_t mlp_dump_bytes(int64_t n_points);
 // ray_stage.cu
 int launch_raw2outputs_backward(const float* raw, const float* z, const float* rays, int64_t n, int S, uint32_t flags,
                                 const float* d_rgb, float* d_raw, float* d_dnorm, cudaStream_t st);

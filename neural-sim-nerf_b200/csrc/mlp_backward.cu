@@ -37,7 +37,29 @@ struct BwdArgs {
   int64_t n_points;
   int S;
   int num_tiles;
+  uint8_t* dump;  // optional: fp16 activations / pre-activation gradients of every layer, for the weight gradients
 };
+
+// Dump layout (row-major fp16, P = num_tiles * 128 rows): the operands of dW_l = G_l^T H_{l-1} (RN:691-707's backward)
+//   EX [P,64] xyz encoding | EV [P,32] view-dir encoding | H0..H7 [P,256] post-ReLU | F [P,256] feature |
+//   HV [P,128] views hidden | GV [P,128] dL/d(views pre-act) | GF [P,256] dL/dfeature | G0..G7 [P,256] dL/d(pre-act) |
+//   SCALE [P] fp32 -- the gradient rows (GV, GF, G*) are stored divided by their row's power-of-two scale
+__host__ __device__ inline size_t dump_off_ex(size_t) { return 0; }
+__host__ __device__ inline size_t dump_off_ev(size_t P) { return P * 128; }
+__host__ __device__ inline size_t dump_off_h(size_t P, int l) { return P * 192 + size_t(l) * P * 512; }   // l = 8 -> F
+__host__ __device__ inline size_t dump_off_hv(size_t P) { return dump_off_h(P, 9); }
+__host__ __device__ inline size_t dump_off_gv(size_t P) { return dump_off_hv(P) + P * 256; }
+__host__ __device__ inline size_t dump_off_gf(size_t P) { return dump_off_gv(P) + P * 256; }
+__host__ __device__ inline size_t dump_off_g(size_t P, int l) { return dump_off_gf(P) + P * 512 + size_t(l) * P * 512; }
+__host__ __device__ inline size_t dump_off_scale(size_t P) { return dump_off_g(P, 8); }               // [P] fp32: G rows are stored divided by this
+__host__ __device__ inline size_t dump_total(size_t P) { return dump_off_scale(P) + P * 4; }
+
+// 64 consecutive fp16 (32 packed words) of row p at column `col` of a [P, ld] fp16 array
+__device__ __forceinline__ void dump64(uint8_t* base, int64_t p, int ld, int col, const uint32_t* H) {
+  uint4* dst = reinterpret_cast<uint4*>(base + (p * ld + col) * 2);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) dst[q] = make_uint4(H[4 * q], H[4 * q + 1], H[4 * q + 2], H[4 * q + 3]);
+}
 
 __device__ __forceinline__ bool gstep_is_side(int g) { return g == 9 || (g >= 10 && bstep_is_side(g - 10)); }
 __device__ __forceinline__ int gstep_k_chunks(int g) { return g < 10 ? step_k_chunks(g) : bstep_k_chunks(g - 10); }
@@ -124,6 +146,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(enc_free + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const size_t P = size_t(a.num_tiles) * 128;  // rows of the optional dump
 
   if (tid == 0) {
     for (int s = 0; s < BWD_STAGES; ++s) {
@@ -293,6 +316,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
           for (int q = 0; q < 4; ++q) split2<true>(e[8 * gq + 2 * q], e[8 * gq + 2 * q + 1], h[q], l[q]);
           st_a8(inbuf + B_OFF_ENC_HI, 1024, row, gq, h[0], h[1], h[2], h[3]);
           st_a8(inbuf + B_OFF_ENC_LO, 1024, row, gq, l[0], l[1], l[2], l[3]);
+          if (a.dump != nullptr)
+            *reinterpret_cast<uint4*>(a.dump + dump_off_ex(P) + (int64_t(tile) * 128 + row) * 128 + gq * 16) = make_uint4(h[0], h[1], h[2], h[3]);
         }
       }
       fence_proxy_async_smem();
@@ -324,6 +349,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
           for (int q = 0; q < 4; ++q) split2<true>(v[8 * gq + 2 * q], v[8 * gq + 2 * q + 1], h[q], l[q]);
           st_a8(inbuf + B_OFF_DIR_HI, 512, row, gq, h[0], h[1], h[2], h[3]);
           st_a8(inbuf + B_OFF_DIR_LO, 512, row, gq, l[0], l[1], l[2], l[3]);
+          if (a.dump != nullptr)
+            *reinterpret_cast<uint4*>(a.dump + dump_off_ev(P) + (int64_t(tile) * 128 + row) * 64 + gq * 16) = make_uint4(h[0], h[1], h[2], h[3]);
         }
       }
       fence_proxy_async_smem();
@@ -342,6 +369,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
     uint32_t* my_mask = sMask + (ch * 2) * 128 + row;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
       const int64_t p = int64_t(tile) * 128 + row;
+      const int64_t p_row = p;  // row in the dump arrays (padded to whole tiles)
       float x[3] = {0.f, 0.f, 0.f}, vd[3] = {0.f, 0.f, 0.f};
       float4 gr = make_float4(0.f, 0.f, 0.f, 0.f);
       if (p < a.n_points) {
@@ -396,6 +424,10 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
               bwd32(u1, m1, mlayer >= 0, extra ? extra + 32 : nullptr, gr.w, H + 16, L + 16);
             }
           }
+          // forward step g writes H_g (g = 8: F); backward steps write GF (g = 11) or G_l of the layer whose ReLU gated them
+          uint8_t* dump_arr = a.dump == nullptr ? nullptr
+                              : a.dump + (fwd ? dump_off_h(P, g) : (g == 11 ? dump_off_gf(P) : dump_off_g(P, mlayer)));
+          if (dump_arr != nullptr) dump64(dump_arr, p_row, 256, col0, H);
           w_acc[1].wait(&acc_ready[1]);
           tc_fence_after_sync();
           tmem_st16(tlane + TM_AHI + col0 / 2, *reinterpret_cast<const uint32_t(*)[16]>(&H[0]));
@@ -424,6 +456,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
               bwd32(u1, m1, mlayer >= 0, extra ? extra + 160 : nullptr, gr.w, H + 16, L + 16);
             }
           }
+          if (dump_arr != nullptr) dump64(dump_arr, p_row, 256, 128 + col0, H);
           tmem_st16(tlane + TM_AHI + 64 + col0 / 2, *reinterpret_cast<const uint32_t(*)[16]>(&H[0]));
           tmem_st16(tlane + TM_AHI + 64 + col0 / 2 + 16, *reinterpret_cast<const uint32_t(*)[16]>(&H[16]));
           tmem_st16(tlane + TM_ALO + 64 + col0 / 2, *reinterpret_cast<const uint32_t(*)[16]>(&L[0]));
@@ -437,7 +470,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
           tc_fence_after_sync();
           const float* bias = sTail + TAIL_BIAS + 9 * 256 + col0;
           const float4* wr = reinterpret_cast<const float4*>(sTail + TAIL_WRGB) + col0;
-          uint32_t H[32], L[32];
+          uint32_t H[32], L[32], HV[32];
           {
             uint32_t u0[32], u1[32];
             tmem_ld32(tlane + TM_ACC1 + col0, u0);
@@ -445,17 +478,24 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              float gg[4];
+              float gg[4], hh[4];
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 const int c = (q < 2) ? 2 * j + q : 32 + 2 * j + (q - 2);
                 const float hv = __uint_as_float((q < 2) ? u0[2 * j + q] : u1[2 * j + (q - 2)]) + bias[c];
                 const float4 w = wr[c];
+                hh[q] = fmaxf(hv, 0.f);
                 gg[q] = (hv > 0.f) ? (gr.x * w.x + gr.y * w.y + gr.z * w.z) : 0.f;   // RH:117 backwards, gated by RH:115
               }
               split2<true>(gg[0], gg[1], H[j], L[j]);
               split2<true>(gg[2], gg[3], H[16 + j], L[16 + j]);
+              HV[j] = pack_f16x2(hh[0], hh[1]);
+              HV[16 + j] = pack_f16x2(hh[2], hh[3]);
             }
+          }
+          if (a.dump != nullptr) {
+            dump64(a.dump + dump_off_hv(P), p_row, 128, col0, HV);
+            dump64(a.dump + dump_off_gv(P), p_row, 128, col0, H);
           }
           tmem_st16(tlane + TM_AHI + col0 / 2, *reinterpret_cast<const uint32_t(*)[16]>(&H[0]));
           tmem_st16(tlane + TM_AHI + col0 / 2 + 16, *reinterpret_cast<const uint32_t(*)[16]>(&H[16]));
@@ -493,6 +533,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
         sXch[2 * row + 1] = make_float4(dv[0], dv[1], dv[2], 0.f);
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (ch == 0 && a.dump != nullptr) reinterpret_cast<float*>(a.dump + dump_off_scale(P))[p_row] = scale;
       if (ch == 0 && p < a.n_points) {
         const float4 o0 = sXch[2 * row], o1 = sXch[2 * row + 1];
         float4* out = reinterpret_cast<float4*>(a.d_pts) + 2 * p;
@@ -506,8 +547,10 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
   if (warp == MMA_WARP) tmem_dealloc(0u, 512);
 }
 
+size_t mlp_dump_bytes(int64_t n_points) { return dump_total(size_t((n_points + 127) / 128) * 128); }
+
 int launch_mlp_backward(const float* rays, const float* z, int64_t n, int S, const void* packed, const float* d_raw, float* d_pts,
-                        cudaStream_t st) {
+                        void* dump, cudaStream_t st) {
   const int64_t n_points = n * S;
   if (n_points == 0) return NSR_OK;
   static int num_sms = 0;
@@ -533,6 +576,7 @@ int launch_mlp_backward(const float* rays, const float* z, int64_t n, int S, con
   a.n_points = n_points;
   a.S = S;
   a.num_tiles = int((n_points + 127) / 128);
+  a.dump = static_cast<uint8_t*>(dump);
   const int grid = a.num_tiles < num_sms ? a.num_tiles : num_sms;
   nerf_mlp_bwd_kernel<<<grid, MLP_THREADS, B_SM_TOTAL, st>>>(a);
   count_launch();

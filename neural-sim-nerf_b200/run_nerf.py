@@ -246,7 +246,8 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
     (RN:281-284) are the fixed multires=10 / 4 ones compiled into the kernel."""
     if ray_batch.shape[-1] <= 8:
         raise NotImplementedError('use_viewdirs=False ray batches are not built (CFG:8 sets use_viewdirs=True)')
-    needs_grad = torch.is_grad_enabled() and torch.is_tensor(ray_batch) and ray_batch.requires_grad
+    params = _params_of(network_fn) + (_params_of(network_fine) if (network_fine is not None and int(N_importance) > 0) else [])
+    needs_grad = torch.is_grad_enabled() and (ray_batch.requires_grad or any(p.requires_grad for p in params))
     rays = _f32c(ray_batch, 'ray_batch')
     n = rays.shape[0]
     dev = rays.device
@@ -277,7 +278,7 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
     if needs_grad:
         if flags & FLAG_FAST_FP16:
             raise NotImplementedError("backward is built for the default precision only (NSR_PRECISION='fp16x3')")
-        outs = _RenderRaysFn.apply(ray_batch, cfg)
+        outs = _RenderRaysFn.apply(ray_batch, cfg, *params)
     else:
         outs = _forward_impl(rays, cfg, keep_for_backward=False)[0]
     keys = ['rgb_map', 'disp_map', 'acc_map'] + (['rgb0', 'disp0', 'acc0', 'z_std'] if Ni > 0 else []) + (['raw'] if retraw else [])
@@ -285,7 +286,8 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
 
 
 def _forward_impl(rays, cfg, keep_for_backward):
-    """One call of nsr_render_rays_forward.  Returns (outputs tuple, z_vals [n,T] or None, raw [n,T,4] or None)."""
+    """One call of nsr_render_rays_forward.  Returns (outputs tuple, saved) with saved = (z_vals [n,T], raw [n,T,4],
+    z0 [n,S], raw0 [n,S,4]) of the last and (when N_importance > 0) the coarse pass, or Nones."""
     L = lib()
     n, dev = rays.shape[0], rays.device
     S, Ni = cfg['S'], cfg['Ni']
@@ -302,42 +304,129 @@ def _forward_impl(rays, cfg, keep_for_backward):
     check(L.nsr_render_rays_forward(ptr(rays), n, ptr(cfg['pc']), ptr(cfg['pf']), S, Ni, cfg['flags'], ptr(cfg['t_rand']), ptr(cfg['u']),
                                     ptr(rgb), ptr(disp), ptr(acc), ptr(rgb0), ptr(disp0), ptr(acc0), ptr(zstd),
                                     ptr(raw), ptr(zv), None, ptr(ws), ws_bytes, _stream()), 'nsr_render_rays_forward')
+    z0 = raw0 = None
+    if keep_for_backward and Ni > 0:
+        # the coarse pass's depths and raw outputs sit at the head of the workspace (include/nsr_b200.h layout: z0 | w0 | raw0 | ...)
+        a256 = lambda x: (x + 255) // 256 * 256
+        o_z0, o_raw0 = 0, 2 * a256(n * S * 4)
+        z0 = ws[o_z0:o_z0 + n * S * 4].view(torch.float32).view(n, S).clone()
+        raw0 = ws[o_raw0:o_raw0 + n * S * 16].view(torch.float32).view(n, S, 4).clone()
     outs = [rgb, disp, acc] + ([rgb0, disp0, acc0, zstd] if Ni > 0 else []) + ([raw] if cfg['retraw'] else [])
-    return tuple(outs), zv, raw
+    return tuple(outs), (zv, raw, z0, raw0)
+
+
+def _params_of(net):
+    layers = _net_tensors(net)
+    return [l.weight for l in layers] + [l.bias for l in layers]
+
+
+def _weight_grads(dump, d_raw, n_points):
+    """dL/d(parameters) of one network pass from the backward kernel's dump (include/nsr_b200.h): dW_l = (SCALE.G_l)^T H_{l-1},
+    db_l = column sums.  These are plain [out x points] x [points x in] reductions over HBM-resident operands, done with
+    torch.matmul in fp32 (a library GEMM; the fused tcgen05 kernels produce the operands).  Returns the 24 tensors in
+    _params_of() order."""
+    P = (n_points + 127) // 128 * 128
+    off = [0]
+
+    def take(cols, dtype=torch.float16):
+        nbytes = P * cols * (2 if dtype == torch.float16 else 4)
+        t = dump[off[0]:off[0] + nbytes].view(dtype).view(P, cols) if cols > 1 else dump[off[0]:off[0] + nbytes].view(dtype)
+        off[0] += nbytes
+        return t
+    EX, EV = take(64), take(32)
+    H = [take(256) for _ in range(8)]
+    F_, HV, GV, GF = take(256), take(128), take(128), take(256)
+    G = [take(256) for _ in range(8)]
+    scale = dump[off[0]:off[0] + P * 4].view(torch.float32)
+    f = lambda t: t.float()
+    gs = lambda t: t.float() * scale[:, None]
+    ex, ev = f(EX)[:, :63], f(EV)[:, :27]
+    dW, dB = [None] * 12, [None] * 12
+    g0 = gs(G[0])
+    dW[0], dB[0] = g0.t() @ ex, g0.sum(0)
+    for l in range(1, 8):
+        gl = gs(G[l])
+        hin = f(H[l - 1])
+        dW[l] = torch.cat([gl.t() @ ex, gl.t() @ hin], 1) if l == 5 else gl.t() @ hin   # RH:106: cat[input_pts, h]
+        dB[l] = gl.sum(0)
+    gv, gf, h7 = gs(GV), gs(GF), f(H[7])
+    dW[8], dB[8] = gv.t() @ torch.cat([f(F_), ev], 1), gv.sum(0)                          # views_linears.0 on cat[feature, dirs]
+    dW[9], dB[9] = gf.t() @ h7, gf.sum(0)                                                 # feature_linear
+    g_raw = d_raw.reshape(-1, 4)[:n_points]
+    dW[10], dB[10] = g_raw[:, 3:4].t() @ h7[:n_points], g_raw[:, 3].sum().reshape(1)      # alpha_linear
+    dW[11], dB[11] = g_raw[:, :3].t() @ f(HV)[:n_points], g_raw[:, :3].sum(0)             # rgb_linear
+    return dW + dB
 
 
 class _RenderRaysFn(torch.autograd.Function):
-    """render_rays with the gradient the pose path needs (RN:177-178): dL/d(ray_batch) from dL/d(rgb_map).
-    Everything else the reference's tape could deliver (gradients of disp / acc / rgb0 / raw, gradients to the MLP
-    parameters -- SURVEY.md a-12) is not built: those outputs are marked non-differentiable so asking fails loudly."""
+    """render_rays as an autograd node.  Differentiable outputs: rgb_map and rgb0; differentiable inputs: ray_batch
+    (the pose path, RN:177-178) and the parameters of both networks (the training step, RN:691-707).  disp / acc /
+    z_std / raw are marked non-differentiable, so asking for their gradients fails loudly instead of returning zeros."""
 
     @staticmethod
-    def forward(ctx, ray_batch, cfg):
+    def forward(ctx, ray_batch, cfg, *params):
         rays = ray_batch.detach().to(torch.float32).contiguous()
-        outs, zv, raw = _forward_impl(rays, cfg, keep_for_backward=True)
-        ctx.save_for_backward(rays, zv, raw)
+        outs, saved = _forward_impl(rays, cfg, keep_for_backward=True)
+        ctx.save_for_backward(rays, *[t for t in saved if t is not None])
+        ctx.have_coarse = saved[2] is not None
         ctx.cfg = cfg
         ctx.in_dtype = ray_batch.dtype
         ctx.set_materialize_grads(False)
-        ctx.mark_non_differentiable(*outs[1:])
+        nondiff = [o for i, o in enumerate(outs) if not (i == 0 or (cfg['Ni'] > 0 and i == 3))]
+        ctx.mark_non_differentiable(*nondiff)
         return outs
 
     @staticmethod
-    def backward(ctx, d_rgb, *unused):
-        if d_rgb is None:
-            return None, None
-        rays, zv, raw = ctx.saved_tensors
-        cfg = ctx.cfg
+    def _one_pass(rays, zv, raw, net_blob, flags, g, want_dump):
         L = lib()
         n, T = zv.shape
-        g = d_rgb.detach().to(torch.float32).contiguous()
         d_rays = torch.empty(n, 11, dtype=torch.float32, device=rays.device)
         ws_bytes = L.nsr_render_backward_workspace_bytes(n, T)
         ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=rays.device)
-        net = cfg['pf'] if (cfg['Ni'] > 0 and cfg['pf'] is not None) else cfg['pc']   # the pass that produced rgb_map (RN:481)
-        check(L.nsr_render_rays_backward(ptr(rays), ptr(zv), ptr(raw), n, T, ptr(net), cfg['flags'] & FLAG_WHITE_BKGD, ptr(g),
-                                         ptr(d_rays), ptr(ws), ws_bytes, _stream()), 'nsr_render_rays_backward')
-        return d_rays.to(ctx.in_dtype), None
+        dump = torch.empty(L.nsr_mlp_dump_bytes(n, T), dtype=torch.uint8, device=rays.device) if want_dump else None
+        check(L.nsr_render_rays_backward(ptr(rays), ptr(zv), ptr(raw), n, T, ptr(net_blob), flags, ptr(g), ptr(d_rays), ptr(dump),
+                                         ptr(ws), ws_bytes, _stream()), 'nsr_render_rays_backward')
+        grads = None
+        if want_dump:
+            d_raw = ws[:n * T * 16].view(torch.float32)
+            grads = _weight_grads(dump, d_raw, n * T)
+        return d_rays, grads
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        cfg = ctx.cfg
+        saved = list(ctx.saved_tensors)
+        rays, zv, raw = saved[0], saved[1], saved[2]
+        z0, raw0 = (saved[3], saved[4]) if ctx.have_coarse else (None, None)
+        d_rgb = gouts[0]
+        d_rgb0 = gouts[3] if cfg['Ni'] > 0 else None
+        n_par = 24
+        need_rays = ctx.needs_input_grad[0]
+        need_c = any(ctx.needs_input_grad[2:2 + n_par])
+        need_f = any(ctx.needs_input_grad[2 + n_par:2 + 2 * n_par])
+        fine_is_coarse = cfg['pf'] is None           # RN:481: no fine network -> the coarse one evaluates the last pass too
+        wflag = cfg['flags'] & FLAG_WHITE_BKGD
+        d_rays = None
+        g_c = g_f = None
+        if d_rgb is not None:
+            blob = cfg['pc'] if fine_is_coarse else cfg['pf']
+            want = need_c if fine_is_coarse else need_f
+            dr, gr = _RenderRaysFn._one_pass(rays, zv, raw, blob, wflag, d_rgb.detach().float().contiguous(), want)
+            d_rays = dr
+            if fine_is_coarse:
+                g_c = gr
+            else:
+                g_f = gr
+        if d_rgb0 is not None and (need_rays or need_c):
+            dr, gr = _RenderRaysFn._one_pass(rays, z0, raw0, cfg['pc'], wflag, d_rgb0.detach().float().contiguous(), need_c)
+            d_rays = dr if d_rays is None else d_rays + dr
+            if gr is not None:
+                g_c = gr if g_c is None else [a + b for a, b in zip(g_c, gr)]
+        out = [d_rays.to(ctx.in_dtype) if (d_rays is not None and need_rays) else None, None]
+        out += g_c if g_c is not None else [None] * n_par
+        if len(ctx.needs_input_grad) > 2 + n_par:
+            out += g_f if g_f is not None else [None] * n_par
+        return tuple(out)
 
 
 def _render_rays_staged(rays, pc, pf, S, Ni, flags, t_rand, u, retraw, raw_noise_std, white_bkgd, ret):

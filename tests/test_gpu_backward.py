@@ -102,3 +102,30 @@ def test_coarse_only_backward_and_unsupported_grads(nsr, wfit, nets):
     (got_grad,) = torch.autograd.grad(out['rgb_map'], r_gpu, grad_outputs=g.cuda())
     check_grad(got_grad[:, 0:6], ref_grad[:, 0:6], 'coarse-only dL/d(o,d)')
     assert not out['acc_map'].requires_grad and not out['disp_map'].requires_grad   # not built -> not differentiable, loudly
+
+
+def test_parameter_gradients_match_autograd(nsr, wfit):
+    """loss = mse(rgb, target) + mse(rgb0, target) (RN:691-696), loss.backward() -> dL/dMLP for BOTH networks."""
+    rays = camera_rays(12, 22.5)
+    n = rays.shape[0]
+    target = torch.rand(n, 3, generator=torch.Generator().manual_seed(5))
+    # reference: autograd through the oracle with the state-dict tensors as leaves
+    sdc = {k: v.clone().requires_grad_(True) for k, v in wfit[0].items()}
+    sdf = {k: v.clone().requires_grad_(True) for k, v in wfit[1].items()}
+    ref = O.render_rays(rays, sdc, sdf, 64, 128)
+    loss_ref = ((ref['rgb_map'] - target) ** 2).mean() + ((ref['rgb0'] - target) ** 2).mean()
+    loss_ref.backward()
+    # ours
+    nets = []
+    for sd in wfit:
+        m = nsr.NeRF()
+        m.load_state_dict(sd)
+        nets.append(m.cuda())
+    out = nsr.render_rays(rays.cuda(), nets[0], None, 64, N_importance=128, network_fine=nets[1])
+    loss = ((out['rgb_map'] - target.cuda()) ** 2).mean() + ((out['rgb0'] - target.cuda()) ** 2).mean()
+    loss.backward()
+    assert abs(loss.item() - loss_ref.item()) <= 1e-4 * max(1.0, abs(loss_ref.item()))
+    for net, sd, tag in ((nets[0], sdc, 'coarse'), (nets[1], sdf, 'fine')):
+        for name, prm in net.named_parameters():
+            assert prm.grad is not None, f'{tag}.{name} got no gradient'
+            check_grad(prm.grad, sd[name].grad, f'{tag}.{name}', tol=3e-3)
