@@ -138,10 +138,12 @@ def sample_pdf(bins, weights, n_samples, det=True, u=None):
 # --------------------------------------------------------------------------
 def render_rays(ray_batch, sd_coarse, sd_fine, N_samples=64, N_importance=128,
                 retraw=False, lindisp=False, perturb=0., white_bkgd=False,
-                netchunk=1024 * 64, t_rand=None, u=None, return_internals=False):
+                netchunk=1024 * 64, t_rand=None, u=None, return_internals=False, z_fine=None):
     """ray_batch [n,11] = o(3) d(3) near far viewdir(3)  (RN:433-437).
     perturb>0 needs t_rand [n,N_samples] and u [n,N_importance] given explicitly
-    (the reference draws torch.rand there, RN:453 / RH:211)."""
+    (the reference draws torch.rand there, RN:453 / RH:211).  `z_fine` [n, N_samples+N_importance] replaces the merged
+    depths of RN:477 (tests use it to compare gradients on identical sample positions: sample_pdf's `denom < 1e-5`
+    branch, RH:239, is discontinuous in the last bits of the coarse weights)."""
     n = ray_batch.shape[0]
     rays_o, rays_d = ray_batch[:, 0:3], ray_batch[:, 3:6]
     viewdirs = ray_batch[:, -3:]
@@ -168,6 +170,8 @@ def render_rays(ray_batch, sd_coarse, sd_fine, N_samples=64, N_importance=128,
         z_samples = sample_pdf(z_mid, weights[..., 1:-1], N_importance,
                                det=(perturb == 0.), u=u).detach()             # RN:474-475
         z_vals, _ = torch.sort(torch.cat([z_vals, z_samples], -1), -1)        # RN:477
+        if z_fine is not None:
+            z_vals = z_fine
         pts = rays_o[..., None, :] + rays_d[..., None, :] * z_vals[..., :, None]
         raw = run_network(pts, viewdirs, sd_fine if sd_fine is not None else sd_coarse, netchunk)
         rgb_map, disp_map, acc_map, weights, depth_map = raw2outputs(raw, z_vals, rays_d, None, white_bkgd)

@@ -110,22 +110,65 @@ def test_parameter_gradients_match_autograd(nsr, wfit):
     n = rays.shape[0]
     target = torch.rand(n, 3, generator=torch.Generator().manual_seed(5))
     # reference: autograd through the oracle with the state-dict tensors as leaves
-    sdc = {k: v.clone().requires_grad_(True) for k, v in wfit[0].items()}
-    sdf = {k: v.clone().requires_grad_(True) for k, v in wfit[1].items()}
-    ref = O.render_rays(rays, sdc, sdf, 64, 128)
-    loss_ref = ((ref['rgb_map'] - target) ** 2).mean() + ((ref['rgb0'] - target) ** 2).mean()
-    loss_ref.backward()
-    # ours
     nets = []
     for sd in wfit:
         m = nsr.NeRF()
         m.load_state_dict(sd)
         nets.append(m.cuda())
+    # The fine depths come out of sample_pdf, whose `denom < 1e-5` branch (RH:239) flips on last-bit differences of
+    # the coarse weights; gradients are compared on identical sample positions, so take ours (C ABI, z_vals_out).
+    import ctypes
+    L = nsr.lib()
+    rg = rays.cuda()
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    new = lambda *s: torch.empty(*s, device='cuda')
+    zf = new(n, 192)
+    o = [new(n, 3), new(n), new(n), new(n, 3), new(n), new(n), new(n)]
+    wsb = L.nsr_render_workspace_bytes(n, 64, 128)
+    ws = torch.empty(wsb, dtype=torch.uint8, device='cuda')
+    rc = L.nsr_render_rays_forward(P(rg), n, P(nsr.packed_weights(nets[0])), P(nsr.packed_weights(nets[1])), 64, 128, 0, None, None,
+                                   *[P(t) for t in o], None, P(zf), None, P(ws), wsb, None)
+    assert rc == 0, L.nsr_last_error()
+    torch.cuda.synchronize()
+    # reference: autograd through the oracle with the state-dict tensors as leaves
+    sdc = {k: v.clone().requires_grad_(True) for k, v in wfit[0].items()}
+    sdf = {k: v.clone().requires_grad_(True) for k, v in wfit[1].items()}
+    ref = O.render_rays(rays, sdc, sdf, 64, 128, z_fine=zf.cpu())
+    loss_ref = ((ref['rgb_map'] - target) ** 2).mean() + ((ref['rgb0'] - target) ** 2).mean()
+    loss_ref.backward()
+    # ours, through the public render_rays + loss.backward()
     out = nsr.render_rays(rays.cuda(), nets[0], None, 64, N_importance=128, network_fine=nets[1])
     loss = ((out['rgb_map'] - target.cuda()) ** 2).mean() + ((out['rgb0'] - target.cuda()) ** 2).mean()
     loss.backward()
     assert abs(loss.item() - loss_ref.item()) <= 1e-4 * max(1.0, abs(loss_ref.item()))
+    failures = []
     for net, sd, tag in ((nets[0], sdc, 'coarse'), (nets[1], sdf, 'fine')):
         for name, prm in net.named_parameters():
             assert prm.grad is not None, f'{tag}.{name} got no gradient'
-            check_grad(prm.grad, sd[name].grad, f'{tag}.{name}', tol=3e-3)
+            try:
+                check_grad(prm.grad, sd[name].grad, f'{tag}.{name}', tol=3e-3)
+            except AssertionError as e:
+                failures.append(str(e))
+    assert not failures, failures
+
+
+def test_parameter_gradients_many_samples_no_resampling(nsr, wfit):
+    """Same check with 192 coarse samples and no hierarchical step: isolates operand precision from RH:239 flips."""
+    rays = camera_rays(10, 22.5)
+    n = rays.shape[0]
+    target = torch.rand(n, 3, generator=torch.Generator().manual_seed(6))
+    sdf = {k: v.clone().requires_grad_(True) for k, v in wfit[1].items()}
+    ref = O.render_rays(rays, sdf, None, 192, 0)
+    ((ref['rgb_map'] - target) ** 2).mean().backward()
+    m = nsr.NeRF()
+    m.load_state_dict(wfit[1])
+    m = m.cuda()
+    out = nsr.render_rays(rays.cuda(), m, None, 192, N_importance=0)
+    ((out['rgb_map'] - target.cuda()) ** 2).mean().backward()
+    failures = []
+    for name, prm in m.named_parameters():
+        try:
+            check_grad(prm.grad, sdf[name].grad, f'S192.{name}', tol=3e-3)
+        except AssertionError as e:
+            failures.append(str(e))
+    assert not failures, failures
