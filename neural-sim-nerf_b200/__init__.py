@@ -6,8 +6,9 @@ The directory is named `neural-sim-nerf_b200`; import it as `neural_sim_nerf_b20
 """
 from ._lib import EXPORTED_SYMBOLS, LIB_PATH, NsrError, lib  # noqa: F401
 from .run_nerf import (NeRF, Embedder, batchify, batchify_rays, get_embedder, get_rays, img2mse, install,  # noqa: F401
-                       make_rays, mse2psnr, ndc_rays, packed_weights, raw2outputs, render, render_rays,
+                       make_rays, mse2psnr, ndc_rays, packed_weights, raw2outputs, render, render_path, render_path_grad, render_rays,
                        run_network, sample_pdf, set_precision, to8b)
 
 __all__ = ['NeRF', 'Embedder', 'batchify', 'batchify_rays', 'get_embedder', 'get_rays', 'install', 'make_rays',
-           'ndc_rays', 'packed_weights', 'raw2outputs', 'render', 'render_rays', 'run_network', 'sample_pdf']
+           'ndc_rays', 'packed_weights', 'raw2outputs', 'render', 'render_path', 'render_path_grad', 'render_rays', 'run_network',
+           'sample_pdf', 'set_precision']

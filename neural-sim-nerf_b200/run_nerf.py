@@ -544,9 +544,75 @@ def render(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far
     return [all_ret[k] for k in k_extract] + [{k: all_ret[k] for k in all_ret if k not in k_extract}]
 
 
-def install(reference_module):
+# ----------------------------------------------------------------------------- RN:126-255 (callers of render)
+def _imwrite(filename, rgb8):
+    """PNG writer: imageio when present (RN:206/250), else Pillow."""
+    try:
+        import imageio
+        imageio.imwrite(filename, rgb8)
+    except ImportError:
+        from PIL import Image
+        Image.fromarray(rgb8).save(filename)
+
+
+def render_path(categorical_prob, render_poses, hwf, K, chunk, render_kwargs, gt_imgs=None, savedir=None, object_id=2,
+                render_factor=0):
+    """RN:213-255: render every pose under no_grad, optionally write <savedir>/<object_id>/NNN.png.  One kernel
+    sequence per image (rays are generated on the device from c2w, RH:156-165 fused with RN:91-112)."""
+    H, W, focal = hwf
+    if render_factor != 0:                                         # RN:217-221
+        H, W, focal = H // render_factor, W // render_factor, focal / render_factor
+    rgbs, disps = [], []
+    if savedir is not None:
+        os.makedirs(os.path.join(savedir, str(object_id)), exist_ok=True)
+    with torch.no_grad():
+        for i, c2w in enumerate(render_poses):
+            rgb, disp, acc, _ = render(H, W, K, chunk=chunk, c2w=c2w[:3, :4], **render_kwargs)    # RN:233
+            rgbs.append(rgb.cpu().numpy())
+            disps.append(disp.cpu().numpy())
+            if savedir is not None:
+                _imwrite(os.path.join(savedir, str(object_id), '{:03d}.png'.format(i)), to8b(rgbs[-1]))   # RN:245-250
+    return np.stack(rgbs, 0), np.stack(disps, 0)
+
+
+def render_path_grad(categorical_prob, render_poses, hwf, K, chunk, grad_E, render_kwargs, gt_imgs=None, savedir=None,
+                     object_id=2, render_factor=0):
+    """RN:126-210 with the image rendered and back-propagated in ONE pass instead of ceil(H*W/chunk) passes.
+
+    The reference returns one dL/dpsi per `chunk` rays and its caller averages them all (MAIN:191), i.e. the estimator is
+    sum_over_chunks(g_chunk) / (n_images * n_chunks).  Gradients add over rays, so the whole image's gradient equals
+    sum_over_chunks(g_chunk); one entry per image, divided by n_chunks = ceil(H*W/chunk), leaves that mean unchanged."""
+    H, W, focal = hwf
+    if render_factor != 0:
+        H, W, focal = H // render_factor, W // render_factor, focal / render_factor
+    rgbs, dLdpsis = [], []
+    n_chunks = max(1, math.ceil(H * W / chunk))
+    for i_pose, c2w in enumerate(render_poses):
+        if i_pose >= len(grad_E):
+            break                                                                               # RN:142
+        pose = c2w[:3, :4]
+        rays_o, rays_d = get_rays(H, W, K, pose)                                                # RN:148 (graph-attached to psi)
+        g = grad_E[i_pose]['grad_E'][0]
+        g = (g if torch.is_tensor(g) else torch.as_tensor(g)).to(rays_d.device).permute(1, 2, 0).reshape(-1, 3).float()   # RN:154-155
+        batch_rays = torch.stack([rays_o.reshape(-1, 3), rays_d.reshape(-1, 3)], 0)             # RN:163, all rays at once
+        rgb_p, _, _, _ = render(H, W, K, chunk=max(chunk, H * W), rays=batch_rays, retraw=True, **render_kwargs)   # RN:168-170
+        dLdray = torch.autograd.grad(rgb_p, batch_rays, grad_outputs=g, retain_graph=True)      # RN:177-178
+        dLdpsi = torch.autograd.grad(batch_rays, categorical_prob, grad_outputs=dLdray, retain_graph=True)       # RN:179-181
+        dLdpsis.append((dLdpsi[0] / n_chunks).cpu().detach())
+        rgbs.append(rgb_p.detach().reshape(H, W, 3).cpu().numpy())
+        if savedir is not None:
+            os.makedirs(os.path.join(savedir, str(object_id), 'withgrad'), exist_ok=True)
+            _imwrite(os.path.join(savedir, str(object_id), 'withgrad', '{:03d}.png'.format(i_pose)), to8b(rgbs[-1]))   # RN:200-206
+    return np.stack(rgbs, 0), dLdpsis
+
+
+def install(reference_module, loops=False):
     """Monkey-patch a loaded reference `utils.run_nerf_noscale` module so its callers
-    (render_path RN:233, render_path_grad RN:168, MAIN:128/184) run on this renderer."""
-    for name in ('render', 'batchify_rays', 'render_rays', 'run_network', 'raw2outputs', 'sample_pdf', 'get_rays'):
+    (render_path RN:233, render_path_grad RN:168, MAIN:128/184) run on this renderer.  With loops=True the two image
+    loops themselves are replaced too (one launch sequence per image; same return values / same mean gradient)."""
+    names = ['render', 'batchify_rays', 'render_rays', 'run_network', 'raw2outputs', 'sample_pdf', 'get_rays']
+    if loops:
+        names += ['render_path', 'render_path_grad']
+    for name in names:
         setattr(reference_module, name, globals()[name])
     return reference_module

@@ -1,0 +1,161 @@
+"""GPU tests of the flag combinations INTEGRATION.md lists as supported and of the two image loops
+(render_path RN:213-255, render_path_grad RN:126-210) that call the renderer."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import nerf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def nsr():
+    import neural_sim_nerf_b200 as m
+    assert torch.cuda.is_available()
+    return m
+
+
+@pytest.fixture(scope='module')
+def nets(nsr, wfit):
+    out = []
+    for sd in wfit:
+        m = nsr.NeRF()
+        m.load_state_dict(sd)
+        out.append(m.cuda())
+    return out
+
+
+def kwargs(nets, **over):
+    kw = dict(network_fn=nets[0], network_query_fn=None, N_samples=64, N_importance=128, network_fine=nets[1],
+              use_viewdirs=True, ndc=False, near=O.YCBV_NEAR, far=O.YCBV_FAR, white_bkgd=False, raw_noise_std=0., perturb=False)
+    kw.update(over)
+    return kw
+
+
+def rel(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    m = ~(torch.isnan(a) | torch.isnan(b))
+    return ((a - b).abs()[m] / b.abs()[m].clamp(min=1.0)).max().item()
+
+
+K24 = [[80.0, 0, 11.5], [0, 80.0, 12.5], [0, 0, 1]]
+
+
+def test_perturb_with_pytest_seed_matches_oracle(nsr, wfit, nets):
+    """perturb=1 with the reference's pytest hooks (RN:455-459, RH:213-222): numpy seed 0 draws for t_rand and u."""
+    H = W = 24
+    pose = O.pose_spherical(90., 22.5 - 180., 1.01)[:3, :4]
+    ro, rd = O.get_rays(H, W, K24, pose)
+    rays = O.pack_rays(ro.reshape(-1, 3), rd.reshape(-1, 3), O.YCBV_NEAR, O.YCBV_FAR)
+    n = rays.shape[0]
+    np.random.seed(0)
+    t_rand = torch.Tensor(np.random.rand(n, 64))
+    np.random.seed(0)
+    u = torch.Tensor(np.random.rand(n, 128))
+    with torch.no_grad():
+        ref = O.render_rays(rays, wfit[0], wfit[1], 64, 128, perturb=1., t_rand=t_rand, u=u)
+        got = nsr.render_rays(rays.cuda(), nets[0], None, 64, N_importance=128, network_fine=nets[1], perturb=1., pytest=True)
+    for k in ('rgb_map', 'acc_map', 'rgb0', 'acc0'):
+        assert rel(got[k], ref[k]) <= 1e-3, k
+
+
+def test_ndc_and_staticcam_paths_are_consistent(nsr, nets):
+    """ndc=True (RN:101-103, RH:178-195) and c2w_staticcam (RN:94-96) only reshape the ray batch: render() must equal
+    render_rays() on rays prepared with the same formulas."""
+    H = W = 16
+    Kc = [[60.0, 0, 7.5], [0, 60.0, 8.5], [0, 0, 1]]
+    pose = O.pose_spherical(60., 30., 1.3)[:3, :4].cuda()
+    other = O.pose_spherical(75., 40., 1.2)[:3, :4].cuda()
+    with torch.no_grad():
+        # ndc
+        a = nsr.render(H, W, Kc, chunk=512, c2w=pose, **kwargs(nets, ndc=True, near=0., far=1.))
+        ro, rd = nsr.get_rays(H, W, Kc, pose)
+        vd = (rd / rd.norm(dim=-1, keepdim=True)).reshape(-1, 3)
+        no, nd = nsr.ndc_rays(H, W, Kc[0][0], 1., ro, rd)
+        packed = torch.cat([no.reshape(-1, 3), nd.reshape(-1, 3), torch.zeros(H * W, 1, device='cuda'), torch.ones(H * W, 1, device='cuda'), vd], -1)
+        b = nsr.render_rays(packed, nets[0], None, 64, N_importance=128, network_fine=nets[1])
+        assert torch.equal(a[0].reshape(-1, 3), b['rgb_map'])
+        # static camera: rays from `other`, view directions from `pose`
+        c = nsr.render(H, W, Kc, chunk=512, c2w=pose, c2w_staticcam=other, **kwargs(nets))
+        so, sd = nsr.get_rays(H, W, Kc, other)
+        packed = torch.cat([so.reshape(-1, 3), sd.reshape(-1, 3), torch.full((H * W, 1), O.YCBV_NEAR, device='cuda'),
+                            torch.full((H * W, 1), O.YCBV_FAR, device='cuda'), vd], -1)
+        d = nsr.render_rays(packed, nets[0], None, 64, N_importance=128, network_fine=nets[1])
+        assert torch.equal(c[0].reshape(-1, 3), d['rgb_map'])
+    assert torch.isfinite(a[0]).all() and torch.isfinite(c[0]).all()
+
+
+def test_raw_noise_perturbs_density_only_where_it_matters(nsr, nets):
+    H = W = 16
+    pose = O.pose_spherical(90., 22.5 - 180., 1.01)[:3, :4].cuda()
+    with torch.no_grad():
+        clean = nsr.render(H, W, K24, chunk=512, c2w=pose, **kwargs(nets))
+        torch.manual_seed(0)
+        noisy = nsr.render(H, W, K24, chunk=512, c2w=pose, **kwargs(nets, raw_noise_std=1.0))
+    assert noisy[0].shape == clean[0].shape and torch.isfinite(noisy[0]).all()
+    d = (noisy[0] - clean[0]).abs()
+    assert 0 < float(d.max()) < 0.5          # sigma noise of 1.0 moves colours a little, never wildly
+    assert set(noisy[3]) == set(clean[3])
+
+
+def diff_pose(phi_deg, radius=1.01):
+    """pose_spherical(theta=90, phi, r) with torch ops so that d(pose)/d(phi) exists (LL:25-71 in spirit)."""
+    ph = phi_deg / 180. * math.pi
+    c, s = torch.cos(ph), torch.sin(ph)
+    one, zero = torch.ones_like(c), torch.zeros_like(c)
+    rot_phi = torch.stack([torch.stack([one, zero, zero, zero]), torch.stack([zero, c, -s, zero]),
+                           torch.stack([zero, s, c, zero]), torch.stack([zero, zero, zero, one])])
+    trans = torch.eye(4, device=ph.device)
+    trans[2, 3] = radius
+    th = torch.tensor(math.pi / 2, device=ph.device)
+    rot_th = torch.tensor([[math.cos(th), 0, -math.sin(th), 0], [0, 1, 0, 0], [math.sin(th), 0, math.cos(th), 0], [0, 0, 0, 1]],
+                          device=ph.device)
+    flip = torch.tensor([[-1., 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], device=ph.device)
+    return flip @ rot_th @ rot_phi @ trans
+
+
+def test_render_path_and_render_path_grad(nsr, nets, tmp_path):
+    """render_path writes the PNGs render_images expects; render_path_grad's single-pass gradient has the same MEAN
+    (MAIN:191) as the reference's loop over `chunk`-ray patches (emulated here with this renderer, chunk = 100)."""
+    H = W = 20
+    Kc = [[66.0, 0, 9.5], [0, 66.0, 10.5], [0, 0, 1]]
+    hwf = [H, W, 66.0]
+    degrees = torch.tensor([0, 45, 90, 135, 180, 225, 270, 315], dtype=torch.float32, device='cuda') + 22.5
+    prob = torch.tensor([0.05, 0.05, 0.05, 0.05, 0.6, 0.1, 0.05, 0.05], device='cuda', requires_grad=True)
+    offsets = [0.0, 7.0]
+    poses = [diff_pose((prob * degrees).sum() + o - 180.0) for o in offsets]
+    g = torch.Generator().manual_seed(4)
+    grad_E = [{'image_index': i, 'grad_E': torch.randn(1, 3, H, W, generator=g) * 1e-3} for i in range(2)]
+    kw = kwargs(nets)
+    chunk = 100
+    # --- reference loop (RN:141-194), patch by patch
+    ref_list = []
+    for i_pose, c2w in enumerate(poses):
+        ro, rd = nsr.get_rays(H, W, Kc, c2w[:3, :4])
+        gi = grad_E[i_pose]['grad_E'][0].permute(1, 2, 0).reshape(-1, 3).cuda()
+        ro, rd = ro.reshape(-1, 3), rd.reshape(-1, 3)
+        for i in range(0, H * W, chunk):
+            batch_rays = torch.stack([ro[i:i + chunk], rd[i:i + chunk]], 0)
+            rgb_p, _, _, _ = nsr.render(H, W, Kc, chunk=chunk, rays=batch_rays, retraw=True, **kw)
+            dLdray = torch.autograd.grad(rgb_p, batch_rays, grad_outputs=gi[i:i + chunk])
+            dLdpsi = torch.autograd.grad(batch_rays, prob, grad_outputs=dLdray, retain_graph=True)
+            ref_list.append(dLdpsi[0].cpu())
+    ref_mean = torch.mean(torch.stack(ref_list), 0)
+    # --- one pass per image
+    rgbs, dLdpsis = nsr.render_path_grad(prob, poses, hwf, Kc, chunk, grad_E, kw, savedir=str(tmp_path), object_id=2)
+    got_mean = torch.mean(torch.stack(dLdpsis), 0)
+    assert rgbs.shape == (2, H, W, 3) and len(dLdpsis) == 2
+    scale = ref_mean.abs().max().item()
+    assert (got_mean - ref_mean).abs().max().item() <= 2e-3 * scale, (got_mean, ref_mean)
+    assert os.path.exists(tmp_path / '2' / 'withgrad' / '001.png')
+    # --- render_path
+    imgs, disps = nsr.render_path(prob, [p.detach() for p in poses], hwf, Kc, chunk, kw, savedir=str(tmp_path), object_id=2)
+    assert imgs.shape == (2, H, W, 3) and disps.shape == (2, H, W)
+    assert np.allclose(imgs, rgbs, atol=1e-5)
+    from PIL import Image
+    png = np.asarray(Image.open(tmp_path / '2' / '000.png'))
+    assert png.shape == (H, W, 3) and np.array_equal(png, nsr.to8b(imgs[0]))
