@@ -368,15 +368,42 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
   }
   v = warp_sum(v);
   if (lane == 0 && z_std) z_std[ray] = sqrtf(v / float(Ni));
-  // sort(cat[z, z_samples])  RN:477 -- rank sort (ties broken by position, so it is a permutation)
-  for (int i = lane; i < T; i += 32) {
-    const float e = all[i];
-    int rank = 0;
-    for (int j = 0; j < T; ++j) {
-      const float o = all[j];
-      rank += (o < e) || (o == e && j < i);
+  // sort(cat[z, z_samples])  RN:477.  Both lists are normally already sorted (the coarse depths always; the new
+  // samples whenever u is ascending, i.e. det=True): merge by binary search -- rank = own index + number of elements of
+  // the other list in front (ties: coarse first, so the ranks form a permutation).  Otherwise fall back to a rank sort.
+  const float* zs = all + S;
+  bool sorted = true;
+  for (int i = lane; i < S - 1; i += 32) sorted = sorted && (all[i] <= all[i + 1]);
+  for (int i = lane; i < Ni - 1; i += 32) sorted = sorted && (zs[i] <= zs[i + 1]);
+  if (__all_sync(FULL, sorted)) {
+    for (int i = lane; i < S; i += 32) {      // coarse element: samples strictly smaller go first
+      const float e = all[i];
+      int lo = 0, hi = Ni;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (zs[mid] < e) lo = mid + 1; else hi = mid;
+      }
+      z_fine[ray * T + i + lo] = e;
     }
-    z_fine[ray * T + rank] = e;
+    for (int i = lane; i < Ni; i += 32) {     // new sample: coarse elements smaller or equal go first
+      const float e = zs[i];
+      int lo = 0, hi = S;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (all[mid] <= e) lo = mid + 1; else hi = mid;
+      }
+      z_fine[ray * T + i + lo] = e;
+    }
+  } else {
+    for (int i = lane; i < T; i += 32) {
+      const float e = all[i];
+      int rank = 0;
+      for (int j = 0; j < T; ++j) {
+        const float o = all[j];
+        rank += (o < e) || (o == e && j < i);
+      }
+      z_fine[ray * T + rank] = e;
+    }
   }
 }
 

@@ -23,11 +23,16 @@ using namespace nsr;
     }                                                                                 \
   } while (0)
 
-enum { V_SS_NOSW = 0, V_SS_NOSW_SWAPPED = 1, V_SS_SW128 = 2, V_TS_NOSW = 3, V_TS_NOSW_SWAPPED = 4, V_TS_SW128 = 5 };
+enum { V_SS_NOSW = 0, V_SS_NOSW_SWAPPED = 1, V_SS_SW128 = 2, V_TS_NOSW = 3, V_TS_NOSW_SWAPPED = 4, V_TS_SW128 = 5, V_SS_MN_NOSW = 6, V_SS_MN_NOSW_SWAPPED = 7 };
 
 // byte offset of element (row r, k) in a K-major operand tile with `K` columns
 __device__ __forceinline__ uint32_t off_nosw(int r, int k, int K) {
   return (r >> 3) * (K / 8) * 128 + (k >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2;
+}
+// MN-major, no swizzle: 8x8 core matrices stored [k][mn] (mn contiguous, 16 B per k); mn-blocks 128 B apart,
+// k-blocks (rows/8)*128 B apart
+__device__ __forceinline__ uint32_t off_mn_nosw(int r, int k, int rows) {
+  return (k >> 3) * (rows / 8) * 128 + (r >> 3) * 128 + (k & 7) * 16 + (r & 7) * 2;
 }
 __device__ __forceinline__ uint32_t off_sw128(int r, int k) {  // K == 64 slab
   int chunk = (k >> 3) ^ (r & 7);
@@ -44,7 +49,8 @@ __global__ void __launch_bounds__(128) probe_kernel(const __half* A, const __hal
   const int tid = threadIdx.x, warp = tid >> 5;
   const bool sw128 = (variant == V_SS_SW128 || variant == V_TS_SW128);
   const bool swapped = (variant == V_SS_NOSW_SWAPPED || variant == V_TS_NOSW_SWAPPED);
-  const bool ts = variant >= V_TS_NOSW;
+  const bool ts = variant >= V_TS_NOSW && variant <= V_TS_SW128;
+  const bool mn = variant >= V_SS_MN_NOSW;
 
   if (warp == 0) tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
@@ -53,12 +59,12 @@ __global__ void __launch_bounds__(128) probe_kernel(const __half* A, const __hal
   }
   for (int i = tid; i < 128 * K; i += 128) {
     int r = i / K, k = i % K;
-    uint32_t o = sw128 ? off_sw128(r, k) : off_nosw(r, k, K);
+    uint32_t o = mn ? off_mn_nosw(r, k, 128) : (sw128 ? off_sw128(r, k) : off_nosw(r, k, K));
     *reinterpret_cast<__half*>(sA + o) = A[i];
   }
   for (int i = tid; i < N * K; i += 128) {
     int r = i / K, k = i % K;
-    uint32_t o = sw128 ? off_sw128(r, k) : off_nosw(r, k, K);
+    uint32_t o = mn ? off_mn_nosw(r, k, N) : (sw128 ? off_sw128(r, k) : off_nosw(r, k, K));
     *reinterpret_cast<__half*>(sB + o) = B[i];
   }
   fence_proxy_async_smem();
@@ -85,11 +91,16 @@ __global__ void __launch_bounds__(128) probe_kernel(const __half* A, const __hal
   }
 
   if (tid == 0) {
-    const uint32_t idesc = make_idesc_f16(128, N);
+    const uint32_t idesc = make_idesc_f16(128, N) | (mn ? ((1u << 15) | (1u << 16)) : 0u);
     const uint32_t s_k = 128, s_mn = (K / 8) * 128;
     for (int k = 0; k < K / 16; ++k) {
       uint64_t bdesc, adesc;
-      if (sw128) {
+      if (mn) {  // k-block stride: (rows/8)*128, mn-block stride: 128; a K=16 step spans two k-blocks
+        const uint32_t ka = (128 / 8) * 128, kb = (N / 8) * 128;
+        const bool sw = (variant == V_SS_MN_NOSW_SWAPPED);
+        adesc = make_sdesc(smem_u32(sA) + k * 2 * ka, sw ? 128 : ka, sw ? ka : 128, 0);
+        bdesc = make_sdesc(smem_u32(sB) + k * 2 * kb, sw ? 128 : kb, sw ? kb : 128, 0);
+      } else if (sw128) {
         adesc = make_sdesc(smem_u32(sA) + k * 32, 16, 1024, 2);
         bdesc = make_sdesc(smem_u32(sB) + k * 32, 16, 1024, 2);
       } else {
@@ -252,8 +263,9 @@ static void correctness() {
       for (int k = 0; k < K; ++k) acc += fA[m * K + k] * fB[n * K + k];
       ref[m * N + n] = acc;
     }
-  const char* names[] = {"SS nosw (LBO=K-stride,SBO=MN-stride)", "SS nosw swapped", "SS sw128", "TS nosw", "TS nosw swapped", "TS sw128"};
-  for (int v = 0; v < 6; ++v) {
+  const char* names[] = {"SS nosw (LBO=K-stride,SBO=MN-stride)", "SS nosw swapped", "SS sw128", "TS nosw", "TS nosw swapped", "TS sw128",
+                         "SS MN-major nosw (LBO=K-block stride,SBO=MN-block stride)", "SS MN-major nosw swapped"};
+  for (int v = 0; v < 8; ++v) {
     double e = run_variant<N, K>(v, hA, hB, ref);
     printf("PROBE N=%d variant %d [%s]: max_abs_err=%g %s\n", N, v, names[v], e, e == 0.0 ? "PASS" : "FAIL");
   }
@@ -315,6 +327,7 @@ int main() {
   printf("device %s sm_%d%d SMs=%d clock=%d kHz\n", p.name, p.major, p.minor, p.multiProcessorCount, p.clockRate);
   correctness<128>();
   correctness<256>();
+  if (getenv("PROBE_QUICK")) return 0;
   for (int grid : {1, 148}) {
     tput<256, false, false>(grid);
     tput<256, false, true>(grid);
