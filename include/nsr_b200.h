@@ -138,18 +138,15 @@ size_t nsr_render_backward_workspace_bytes(int64_t n_rays, int n_total_samples);
  * `raw` [n,T,4] are the z_vals_out / raw outputs of nsr_render_rays_forward.  Activations are recomputed, not
  * stored.  Flags: NSR_FLAG_WHITE_BKGD as in the forward call.
  *
- * `dump` (optional, NULL = off) receives what the weight gradients of that pass need (the
- * loss.backward() of RN:691-707): every layer's input activations and pre-activation gradients as row-major fp16,
- * P = 128 * ceil(n_rays * n_total_samples / 128) rows (rows beyond the real points carry zero gradients), in this order:
- *   EX [P,64] xyz encoding | EV [P,32] view-dir encoding | H0..H7 [P,256] | F [P,256] feature | HV [P,128] |
- *   GV [P,128] dL/d(views pre-activation) | GF [P,256] dL/dfeature | G0..G7 [P,256] dL/d(pts_linears.l pre-activation) |
- *   SCALE [P] fp32: the gradient rows are stored divided by a per-row power of two (fp16 range), multiply back
- * so that dW_l = (SCALE . G_l)^T H_{l-1}, db_l = column sums of SCALE . G_l (dL/draw itself is workspace[0 : n*T*16]).
+ * Parameter gradients (the loss.backward() of RN:691-707): pass dW[12] / dB[12] (device fp32 tensors in
+ * the nsr_pack_net order and shapes, e.g. dW[5] is [256,319]) and a `dump` scratch buffer of nsr_mlp_dump_bytes() bytes;
+ * dL/dW and dL/db of THIS pass are ADDED to them (zero them first; call once per pass that carries gradient -- the fine
+ * pass through rgb_map, the coarse pass through rgb0).  dW = dB = dump = NULL skips all of that.
  */
 size_t nsr_mlp_dump_bytes(int64_t n_rays, int n_total_samples);
 int nsr_render_rays_backward(const float* rays, const float* z_vals, const float* raw, int64_t n_rays, int n_total_samples,
                              const void* packed_net, uint32_t flags, const float* d_rgb_map, float* d_rays, void* dump,
-                             void* workspace, size_t workspace_bytes, void* stream);
+                             float* const* dW, float* const* dB, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Ray generation + packing.  Replaces RH:156-165 get_rays and RN:91-112 (use_viewdirs, ndc=False):

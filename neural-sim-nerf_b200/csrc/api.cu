@@ -152,16 +152,16 @@ int nsr_render_rays_forward(const float* rays, int64_t n, const void* packed_coa
   return NSR_OK;
 }
 
-// workspace layout: d_raw [n,T,4] | d_pts [n,T,8] | d_dnorm [n]
+// workspace layout: d_raw [n,T,4] | d_pts [n,T,8] | d_dnorm [n] | gmax (1 float)
 size_t nsr_render_backward_workspace_bytes(int64_t n, int T) {
-  return align_up(size_t(n) * T * 16, 256) + align_up(size_t(n) * T * 32, 256) + align_up(size_t(n) * 4, 256);
+  return align_up(size_t(n) * T * 16, 256) + align_up(size_t(n) * T * 32, 256) + align_up(size_t(n) * 4, 256) + 256;
 }
 
 size_t nsr_mlp_dump_bytes(int64_t n_rays, int n_total_samples) { return mlp_dump_bytes(n_rays * n_total_samples); }
 
 int nsr_render_rays_backward(const float* rays, const float* z_vals, const float* raw, int64_t n, int T, const void* packed_net,
-                             uint32_t flags, const float* d_rgb_map, float* d_rays, void* dump, void* workspace,
-                             size_t workspace_bytes, void* stream) {
+                             uint32_t flags, const float* d_rgb_map, float* d_rays, void* dump, float* const* dW,
+                             float* const* dB, void* workspace, size_t workspace_bytes, void* stream) {
   NSR_REQUIRE(n >= 0 && T > 0, "nsr_render_rays_backward: bad sizes");
   if (n == 0) return NSR_OK;
   NSR_REQUIRE(rays && z_vals && raw && packed_net && d_rgb_map && d_rays, "nsr_render_rays_backward: null argument");
@@ -169,6 +169,11 @@ int nsr_render_rays_backward(const float* rays, const float* z_vals, const float
   NSR_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0 && (reinterpret_cast<uintptr_t>(raw) & 15) == 0,
               "nsr_render_rays_backward: workspace must be 256-byte and raw 16-byte aligned");
   NSR_REQUIRE(!(flags & NSR_FLAG_FAST_FP16), "nsr_render_rays_backward: only the default (fp16 hi/lo split) precision is built");
+  NSR_REQUIRE((dW == nullptr) == (dB == nullptr), "nsr_render_rays_backward: dW and dB go together");
+  NSR_REQUIRE(dW == nullptr || dump != nullptr, "nsr_render_rays_backward: parameter gradients need the dump scratch buffer");
+  if (dW)
+    for (int i = 0; i < NSR_NET_NUM_TENSORS; ++i) NSR_REQUIRE(dW[i] && dB[i], "nsr_render_rays_backward: gradient tensor %d is null", i);
+  NSR_REQUIRE(dump == nullptr || (reinterpret_cast<uintptr_t>(dump) & 127) == 0, "nsr_render_rays_backward: dump must be 128-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   float* d_raw = reinterpret_cast<float*>(ws);
@@ -176,10 +181,16 @@ int nsr_render_rays_backward(const float* rays, const float* z_vals, const float
   float* d_pts = reinterpret_cast<float*>(ws);
   ws += align_up(size_t(n) * T * 32, 256);
   float* d_dnorm = reinterpret_cast<float*>(ws);
+  ws += align_up(size_t(n) * 4, 256);
+  float* gmax = reinterpret_cast<float*>(ws);
   int rc;
-  if ((rc = launch_raw2outputs_backward(raw, z_vals, rays, n, T, flags & NSR_FLAG_WHITE_BKGD, d_rgb_map, d_raw, d_dnorm, st))) return rc;
-  if ((rc = launch_mlp_backward(rays, z_vals, n, T, packed_net, d_raw, d_pts, dump, st))) return rc;
-  return launch_ray_grad_reduce(rays, z_vals, d_pts, d_dnorm, n, T, d_rays, st);
+  if (dW) cudaMemsetAsync(gmax, 0, 4, st);
+  if ((rc = launch_raw2outputs_backward(raw, z_vals, rays, n, T, flags & NSR_FLAG_WHITE_BKGD, d_rgb_map, d_raw, d_dnorm,
+                                        dW ? gmax : nullptr, st))) return rc;
+  if ((rc = launch_mlp_backward(rays, z_vals, n, T, packed_net, d_raw, d_pts, dW ? dump : nullptr, gmax, st))) return rc;
+  if ((rc = launch_ray_grad_reduce(rays, z_vals, d_pts, d_dnorm, n, T, d_rays, st))) return rc;
+  if (dW) return launch_weight_grads(dump, d_raw, n * int64_t(T), gmax, dW, dB, st);
+  return NSR_OK;
 }
 
 int nsr_make_rays(int H, int W, const float* K_host, const float* c2w_host, float near_, float far_, float* rays_out, void* stream) {

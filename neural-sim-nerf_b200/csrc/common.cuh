@@ -59,6 +59,28 @@ __host__ __device__ constexpr int bstep_n_halves(int b) { return bstep_is_side(b
 __host__ __device__ constexpr int bstep_k_chunks(int b) { return b <= 1 ? 2 : 4; }
 __host__ __device__ constexpr int bstep_side_n(int b) { return b == 0 ? 32 : 64; }
 
+// ----------------------------------------------------------------------------- backward "dump" (operands of dL/dMLP, RN:691-707)
+// With dump != NULL the backward kernel writes, for P = 128 * tiles points, every weight layer's input activations
+// and pre-activation gradients as fp16, one array after the other:
+//   EX [P,64] xyz encoding | EV [P,32] view-dir encoding | H0..H7 [P,256] post-ReLU | F [P,256] feature |
+//   HV [P,128] views hidden | GV [P,128] dL/d(views pre-act) | GF [P,256] dL/dfeature | G0..G7 [P,256] dL/d(pts_linears.l pre-act)
+// (gradients divided by one power-of-two `gscale`).  Each array is stored tile by tile (128 points) in the UMMA
+// MN-major no-swizzle canonical layout, i.e. 8x8 blocks [8 points][8 features] of 128 contiguous bytes, feature blocks
+// adjacent, point blocks (W/8)*128 bytes apart, so the weight-gradient kernel can feed slices of it to tcgen05.mma
+// as BOTH operands of dW = G^T H with the points as the K dimension -- no transposition anywhere.
+__host__ __device__ inline size_t dump_off_ex(size_t) { return 0; }
+__host__ __device__ inline size_t dump_off_ev(size_t P) { return P * 128; }
+__host__ __device__ inline size_t dump_off_h(size_t P, int l) { return P * 192 + size_t(l) * P * 512; }   // l = 8 -> F
+__host__ __device__ inline size_t dump_off_hv(size_t P) { return dump_off_h(P, 9); }
+__host__ __device__ inline size_t dump_off_gv(size_t P) { return dump_off_hv(P) + P * 256; }
+__host__ __device__ inline size_t dump_off_gf(size_t P) { return dump_off_gv(P) + P * 256; }
+__host__ __device__ inline size_t dump_off_g(size_t P, int l) { return dump_off_gf(P) + P * 512 + size_t(l) * P * 512; }
+__host__ __device__ inline size_t dump_total(size_t P) { return dump_off_g(P, 8); }
+// byte offset inside a [P, W] array of the 16-byte group (tile, row, feature group fg = feature / 8)
+__host__ __device__ inline size_t dump_blocked_off(int tile, int row, int W, int fg) {
+  return size_t(tile) * (size_t(128) * W * 2) + size_t(row >> 3) * (W / 8) * 128 + size_t(fg) * 128 + size_t(row & 7) * 16;
+}
+
 // ----------------------------------------------------------------------------- host-side plumbing (api.cu)
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
@@ -80,11 +102,14 @@ int launch_mlp_forward(const float* rays, const float* z_or_pts, int64_t n, int 
                        float* raw, cudaStream_t st);
 // mlp_backward.cu: d_raw [n,S,4] -> d_pts [n,S,8] = (dL/dpoint[3], 0, dL/dviewdir[3], 0) per sample
 int launch_mlp_backward(const float* rays, const float* z, int64_t n, int S, const void* packed, const float* d_raw,
-                        float* d_pts, void* dump, cudaStream_t st);
+                        float* d_pts, void* dump, const float* gscale, cudaStream_t st);
+// wgrad.cu: dL/dW, dL/db of one network pass from the dump; accumulates (atomicAdd) into dW[12], dB[12] (fp32, reference shapes)
+int launch_weight_grads(const void* dump, const float* d_raw, int64_t n_points, const float* gscale, float* const* dW,
+                        float* const* dB, cudaStream_t st);
 size_t mlp_dump_bytes(int64_t n_points);
 // ray_stage.cu
 int launch_raw2outputs_backward(const float* raw, const float* z, const float* rays, int64_t n, int S, uint32_t flags,
-                                const float* d_rgb, float* d_raw, float* d_dnorm, cudaStream_t st);
+                                const float* d_rgb, float* d_raw, float* d_dnorm, float* gmax, cudaStream_t st);
 int launch_ray_grad_reduce(const float* rays, const float* z, const float* d_pts, const float* d_dnorm, int64_t n, int S,
                            float* d_rays, cudaStream_t st);
 

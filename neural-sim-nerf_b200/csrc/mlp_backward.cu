@@ -37,28 +37,15 @@ struct BwdArgs {
   int64_t n_points;
   int S;
   int num_tiles;
-  uint8_t* dump;  // optional: fp16 activations / pre-activation gradients of every layer, for the weight gradients
+  uint8_t* dump;        // optional: fp16 activations / pre-activation gradients of every layer (common.cuh), for dL/dMLP
+  const float* gscale;  // with dump: one power-of-two scale for ALL rows (max |dL/draw| of the batch), device scalar
 };
 
-// Dump layout (row-major fp16, P = num_tiles * 128 rows): the operands of dW_l = G_l^T H_{l-1} (RN:691-707's backward)
-//   EX [P,64] xyz encoding | EV [P,32] view-dir encoding | H0..H7 [P,256] post-ReLU | F [P,256] feature |
-//   HV [P,128] views hidden | GV [P,128] dL/d(views pre-act) | GF [P,256] dL/dfeature | G0..G7 [P,256] dL/d(pre-act) |
-//   SCALE [P] fp32 -- the gradient rows (GV, GF, G*) are stored divided by their row's power-of-two scale
-__host__ __device__ inline size_t dump_off_ex(size_t) { return 0; }
-__host__ __device__ inline size_t dump_off_ev(size_t P) { return P * 128; }
-__host__ __device__ inline size_t dump_off_h(size_t P, int l) { return P * 192 + size_t(l) * P * 512; }   // l = 8 -> F
-__host__ __device__ inline size_t dump_off_hv(size_t P) { return dump_off_h(P, 9); }
-__host__ __device__ inline size_t dump_off_gv(size_t P) { return dump_off_hv(P) + P * 256; }
-__host__ __device__ inline size_t dump_off_gf(size_t P) { return dump_off_gv(P) + P * 256; }
-__host__ __device__ inline size_t dump_off_g(size_t P, int l) { return dump_off_gf(P) + P * 512 + size_t(l) * P * 512; }
-__host__ __device__ inline size_t dump_off_scale(size_t P) { return dump_off_g(P, 8); }               // [P] fp32: G rows are stored divided by this
-__host__ __device__ inline size_t dump_total(size_t P) { return dump_off_scale(P) + P * 4; }
-
-// 64 consecutive fp16 (32 packed words) of row p at column `col` of a [P, ld] fp16 array
-__device__ __forceinline__ void dump64(uint8_t* base, int64_t p, int ld, int col, const uint32_t* H) {
-  uint4* dst = reinterpret_cast<uint4*>(base + (p * ld + col) * 2);
+// 64 consecutive features (32 packed fp16 words) of tile-row `row` at feature `col` of a blocked [P, W] dump array
+__device__ __forceinline__ void dump64(uint8_t* arr, int tile, int row, int W, int col, const uint32_t* H) {
+  uint8_t* dst = arr + dump_blocked_off(tile, row, W, col >> 3);
 #pragma unroll
-  for (int q = 0; q < 8; ++q) dst[q] = make_uint4(H[4 * q], H[4 * q + 1], H[4 * q + 2], H[4 * q + 3]);
+  for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(dst + q * 128) = make_uint4(H[4 * q], H[4 * q + 1], H[4 * q + 2], H[4 * q + 3]);
 }
 
 __device__ __forceinline__ bool gstep_is_side(int g) { return g == 9 || (g >= 10 && bstep_is_side(g - 10)); }
@@ -317,7 +304,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
           st_a8(inbuf + B_OFF_ENC_HI, 1024, row, gq, h[0], h[1], h[2], h[3]);
           st_a8(inbuf + B_OFF_ENC_LO, 1024, row, gq, l[0], l[1], l[2], l[3]);
           if (a.dump != nullptr)
-            *reinterpret_cast<uint4*>(a.dump + dump_off_ex(P) + (int64_t(tile) * 128 + row) * 128 + gq * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(a.dump + dump_off_ex(P) + dump_blocked_off(tile, row, 64, gq)) = make_uint4(h[0], h[1], h[2], h[3]);
         }
       }
       fence_proxy_async_smem();
@@ -350,7 +337,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
           st_a8(inbuf + B_OFF_DIR_HI, 512, row, gq, h[0], h[1], h[2], h[3]);
           st_a8(inbuf + B_OFF_DIR_LO, 512, row, gq, l[0], l[1], l[2], l[3]);
           if (a.dump != nullptr)
-            *reinterpret_cast<uint4*>(a.dump + dump_off_ev(P) + (int64_t(tile) * 128 + row) * 64 + gq * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(a.dump + dump_off_ev(P) + dump_blocked_off(tile, row, 32, gq)) = make_uint4(h[0], h[1], h[2], h[3]);
         }
       }
       fence_proxy_async_smem();
@@ -369,7 +356,6 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
     uint32_t* my_mask = sMask + (ch * 2) * 128 + row;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
       const int64_t p = int64_t(tile) * 128 + row;
-      const int64_t p_row = p;  // row in the dump arrays (padded to whole tiles)
       float x[3] = {0.f, 0.f, 0.f}, vd[3] = {0.f, 0.f, 0.f};
       float4 gr = make_float4(0.f, 0.f, 0.f, 0.f);
       if (p < a.n_points) {
@@ -384,7 +370,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
       }
       // power-of-two row scale: largest |dL/draw| component -> [1, 2)
       const float gmax = fmaxf(fmaxf(fabsf(gr.x), fabsf(gr.y)), fmaxf(fabsf(gr.z), fabsf(gr.w)));
-      float scale = __uint_as_float(__float_as_uint(gmax) & 0x7f800000u);
+      // (in dump mode one scale serves the whole batch, so that dW = scale * G'^T H needs no per-row factor)
+      float scale = __uint_as_float(__float_as_uint(a.gscale != nullptr ? *a.gscale : gmax) & 0x7f800000u);
       if (!(scale > 0.f) || !(scale < 3.0e38f)) scale = 1.f;
       const float inv = 1.f / scale;
       gr.x *= inv;
@@ -427,7 +414,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
           // forward step g writes H_g (g = 8: F); backward steps write GF (g = 11) or G_l of the layer whose ReLU gated them
           uint8_t* dump_arr = a.dump == nullptr ? nullptr
                               : a.dump + (fwd ? dump_off_h(P, g) : (g == 11 ? dump_off_gf(P) : dump_off_g(P, mlayer)));
-          if (dump_arr != nullptr) dump64(dump_arr, p_row, 256, col0, H);
+          if (dump_arr != nullptr) dump64(dump_arr, tile, row, 256, col0, H);
           w_acc[1].wait(&acc_ready[1]);
           tc_fence_after_sync();
           tmem_st16(tlane + TM_AHI + col0 / 2, *reinterpret_cast<const uint32_t(*)[16]>(&H[0]));
@@ -456,7 +443,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
               bwd32(u1, m1, mlayer >= 0, extra ? extra + 160 : nullptr, gr.w, H + 16, L + 16);
             }
           }
-          if (dump_arr != nullptr) dump64(dump_arr, p_row, 256, 128 + col0, H);
+          if (dump_arr != nullptr) dump64(dump_arr, tile, row, 256, 128 + col0, H);
           tmem_st16(tlane + TM_AHI + 64 + col0 / 2, *reinterpret_cast<const uint32_t(*)[16]>(&H[0]));
           tmem_st16(tlane + TM_AHI + 64 + col0 / 2 + 16, *reinterpret_cast<const uint32_t(*)[16]>(&H[16]));
           tmem_st16(tlane + TM_ALO + 64 + col0 / 2, *reinterpret_cast<const uint32_t(*)[16]>(&L[0]));
@@ -494,8 +481,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
             }
           }
           if (a.dump != nullptr) {
-            dump64(a.dump + dump_off_hv(P), p_row, 128, col0, HV);
-            dump64(a.dump + dump_off_gv(P), p_row, 128, col0, H);
+            dump64(a.dump + dump_off_hv(P), tile, row, 128, col0, HV);
+            dump64(a.dump + dump_off_gv(P), tile, row, 128, col0, H);
           }
           tmem_st16(tlane + TM_AHI + col0 / 2, *reinterpret_cast<const uint32_t(*)[16]>(&H[0]));
           tmem_st16(tlane + TM_AHI + col0 / 2 + 16, *reinterpret_cast<const uint32_t(*)[16]>(&H[16]));
@@ -533,7 +520,6 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
         sXch[2 * row + 1] = make_float4(dv[0], dv[1], dv[2], 0.f);
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (ch == 0 && a.dump != nullptr) reinterpret_cast<float*>(a.dump + dump_off_scale(P))[p_row] = scale;
       if (ch == 0 && p < a.n_points) {
         const float4 o0 = sXch[2 * row], o1 = sXch[2 * row + 1];
         float4* out = reinterpret_cast<float4*>(a.d_pts) + 2 * p;
@@ -550,7 +536,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
 size_t mlp_dump_bytes(int64_t n_points) { return dump_total(size_t((n_points + 127) / 128) * 128); }
 
 int launch_mlp_backward(const float* rays, const float* z, int64_t n, int S, const void* packed, const float* d_raw, float* d_pts,
-                        void* dump, cudaStream_t st) {
+                        void* dump, const float* gscale, cudaStream_t st) {
   const int64_t n_points = n * S;
   if (n_points == 0) return NSR_OK;
   static int num_sms = 0;
@@ -577,6 +563,7 @@ int launch_mlp_backward(const float* rays, const float* z, int64_t n, int S, con
   a.S = S;
   a.num_tiles = int((n_points + 127) / 128);
   a.dump = static_cast<uint8_t*>(dump);
+  a.gscale = dump != nullptr ? gscale : nullptr;
   const int grid = a.num_tiles < num_sms ? a.num_tiles : num_sms;
   nerf_mlp_bwd_kernel<<<grid, MLP_THREADS, B_SM_TOTAL, st>>>(a);
   count_launch();

@@ -143,7 +143,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 template <int C>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
     raw2outputs_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays, int64_t n, int S,
-                           uint32_t flags, const float* __restrict__ d_rgb, float4* __restrict__ d_raw, float* __restrict__ d_dnorm) {
+                           uint32_t flags, const float* __restrict__ d_rgb, float4* __restrict__ d_raw, float* __restrict__ d_dnorm,
+                           float* __restrict__ gmax) {
   const int lane = threadIdx.x & 31;
   const int64_t ray = blockIdx.x * int64_t(WARPS_PER_BLOCK) + (threadIdx.x >> 5);
   if (ray >= n) return;
@@ -200,7 +201,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
   }
   float after = __shfl_down_sync(FULL, suf, 1);  // sum over lanes > this one
   if (lane == 31) after = 0.f;
-  float dn = 0.f;
+  float dn = 0.f, amax = 0.f;
 #pragma unroll
   for (int j = C - 1; j >= 0; --j) {
     const int i = lane * C + j;
@@ -213,12 +214,19 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
       const float ddist = dalpha * fmaxf(sig[j], 0.f) * e;
       dn += ddist * dzs[j];
       const float w = wi[j];
-      d_raw[ray * S + i] = make_float4(w * g0 * cr[j] * (1.f - cr[j]), w * g1 * cg[j] * (1.f - cg[j]), w * g2 * cb[j] * (1.f - cb[j]), dsig);
+      const float4 o = make_float4(w * g0 * cr[j] * (1.f - cr[j]), w * g1 * cg[j] * (1.f - cg[j]), w * g2 * cb[j] * (1.f - cb[j]), dsig);
+      d_raw[ray * S + i] = o;
+      amax = fmaxf(fmaxf(amax, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
       after += dw[j] * w;
     }
   }
   dn = warp_sum(dn);
   if (lane == 0) d_dnorm[ray] = dn;
+  if (gmax != nullptr) {  // batch-wide max |dL/draw| (non-negative floats order like unsigned integers)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(FULL, amax, o));
+    if (lane == 0 && amax < 3.0e38f) atomicMax(reinterpret_cast<unsigned int*>(gmax), __float_as_uint(amax));
+  }
 }
 
 // dL/d(ray_batch [n,11]) from the per-sample gradients: pts = o + d z (RN:463), dists = dz ||d|| (RN:361), viewdirs
@@ -498,7 +506,7 @@ int launch_resample_merge(const float* z, const float* w, int64_t n, int S, int 
 }
 
 int launch_raw2outputs_backward(const float* raw, const float* z, const float* rays, int64_t n, int S, uint32_t flags,
-                                const float* d_rgb, float* d_raw, float* d_dnorm, cudaStream_t st) {
+                                const float* d_rgb, float* d_raw, float* d_dnorm, float* gmax, cudaStream_t st) {
   if (n == 0) return NSR_OK;
   const int C = (S + 31) / 32;
   if (C > 8) {
@@ -510,7 +518,7 @@ int launch_raw2outputs_backward(const float* raw, const float* z, const float* r
   float4* d4 = reinterpret_cast<float4*>(d_raw);
 #define NSR_R2OB(CC)                                                                                              \
   case CC:                                                                                                        \
-    raw2outputs_bwd_kernel<CC><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(r4, z, rays, n, S, flags, d_rgb, d4, d_dnorm); \
+    raw2outputs_bwd_kernel<CC><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(r4, z, rays, n, S, flags, d_rgb, d4, d_dnorm, gmax); \
     break;
   switch (C) {
     NSR_R2OB(1) NSR_R2OB(2) NSR_R2OB(3) NSR_R2OB(4) NSR_R2OB(5) NSR_R2OB(6) NSR_R2OB(7) NSR_R2OB(8)

@@ -1,0 +1,207 @@
+// Weight gradients of one network pass (the loss.backward() of RN:691-707 as far as the MLP parameters go):
+//   dW_l = G_l^T H_{l-1}   ([out x points] . [points x in]),   db_l = column sums of G_l,
+// from the fp16 operands the backward kernel dumped (common.cuh "dump").  The dump is already in the UMMA MN-major
+// canonical layout, so 32-point slices of it go by cp.async.bulk straight into shared memory and serve as BOTH
+// operands of tcgen05.mma with the POINT index as K: D[out feature (lane), in feature (column)] accumulates in
+// TMEM over all the tiles a CTA owns (split-K over CTAs), and is added to the fp32 gradient with atomics at the end.
+// The 1-row alpha head, the 3-row rgb head and the biases are skinny reductions done on CUDA cores.
+#include "common.cuh"
+#include "sm100_prims.cuh"
+
+namespace nsr {
+
+constexpr int WG_STAGES = 5;
+constexpr int WG_STAGE_BYTES = 32 * 1024;   // [G slice: 32 points x <=256 features][H slice: 32 points x <=256 features]
+constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 256;
+constexpr int WG_NUM_JOBS = 12;
+
+struct WJob {
+  unsigned long long g_off, h_off;  // byte offsets of the two dump arrays
+  int g_w, h_w;                     // their widths (features): g_w in {128, 256}, h_w in {32, 64, 256}
+  float* out;                       // dW [g_w, ld] fp32
+  int ld, col_off, n_valid;         // output columns [col_off, col_off + n_valid)
+};
+struct WJobs {
+  WJob j[WG_NUM_JOBS];
+};
+
+__global__ void __launch_bounds__(128, 1) wgrad_gemm_kernel(const uint8_t* __restrict__ dump, WJobs jobs, int n_tiles, const float* gscale) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
+  uint64_t* empty = full + WG_STAGES;
+  uint64_t* done = empty + WG_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  const WJob job = jobs.j[blockIdx.y];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int my_tiles = (n_tiles > int(blockIdx.x)) ? (n_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x) : 0;
+  if (my_tiles == 0) return;
+  if (tid == 0) {
+    for (int s = 0; s < WG_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const int m_halves = job.g_w / 128;
+
+  if (tid == 0) {
+    const uint32_t g_bytes = 32u * job.g_w * 2u, h_bytes = 32u * job.h_w * 2u;
+    const uint32_t lbo_g = (job.g_w / 8) * 128, lbo_h = (job.h_w / 8) * 128;       // next 8 points
+    const uint32_t idesc = make_idesc_f16(128, job.h_w) | (1u << 15) | (1u << 16);  // A and B MN-major
+    const int n_slices = my_tiles * 4;
+    const uint8_t* gbase = dump + job.g_off;
+    const uint8_t* hbase = dump + job.h_off;
+    for (int it = 0; it < n_slices + WG_STAGES - 1; ++it) {
+      if (it < n_slices) {  // producer side: slice `it` -> stage it % STAGES
+        const int s = it % WG_STAGES;
+        if (it >= WG_STAGES) mbar_wait(&empty[s], ((it / WG_STAGES) - 1) & 1);
+        const int tile = int(blockIdx.x) + (it >> 2) * int(gridDim.x), sl = it & 3;
+        uint8_t* dst = smem + s * WG_STAGE_BYTES;
+        mbar_arrive_expect_tx(&full[s], g_bytes + h_bytes);
+        bulk_g2s(dst, gbase + size_t(tile) * 128 * job.g_w * 2 + size_t(sl) * g_bytes, g_bytes, &full[s]);
+        bulk_g2s(dst + 16384, hbase + size_t(tile) * 128 * job.h_w * 2 + size_t(sl) * h_bytes, h_bytes, &full[s]);
+      }
+      const int jt = it - (WG_STAGES - 1);
+      if (jt >= 0) {        // consumer side: slice `jt`
+        const int s = jt % WG_STAGES;
+        mbar_wait(&full[s], (jt / WG_STAGES) & 1);
+        const uint32_t sg = smem_u32(smem + s * WG_STAGE_BYTES), sh = sg + 16384;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {   // 16 points per MMA
+          for (int mh = 0; mh < m_halves; ++mh) {
+            const uint64_t ad = make_sdesc(sg + mh * 16 * 128 + ks * 2 * lbo_g, lbo_g, 128, 0);
+            const uint64_t bd = make_sdesc(sh + ks * 2 * lbo_h, lbo_h, 128, 0);
+            umma_ss(tmem + mh * job.h_w, ad, bd, idesc, (jt | ks) != 0);
+          }
+        }
+        umma_commit(&empty[s]);
+      }
+    }
+    umma_commit(done);
+  }
+  mbar_wait(done, 0);
+  tc_fence_after_sync();
+  float scale = __uint_as_float(__float_as_uint(*gscale) & 0x7f800000u);
+  if (!(scale > 0.f) || !(scale < 3.0e38f)) scale = 1.f;
+  const uint32_t tlane = tmem + (uint32_t(warp * 32) << 16);
+  for (int mh = 0; mh < m_halves; ++mh) {
+    float* orow = job.out + size_t(mh * 128 + tid) * job.ld + job.col_off;
+    for (int c0 = 0; c0 < job.h_w; c0 += 16) {
+      uint32_t u[16];
+      tmem_ld16(tlane + mh * job.h_w + c0, u);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (c0 + j < job.n_valid) atomicAdd(orow + c0 + j, __uint_as_float(u[j]) * scale);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ----------------------------------------------------------------------------- skinny reductions
+// out[j][c] += sum_p coef[p][j] * X[p][c]  (coef = dL/draw columns, or 1 for the bias sums), X a blocked dump array
+struct SJob {
+  unsigned long long x_off;
+  int w;              // width of X
+  int coef_col;       // first column of d_raw used as coefficient, -1: coefficient 1 (scaled by gscale)
+  int n_out;          // rows of out (1..3)
+  float* out;         // [n_out][ld]
+  int ld;
+  float* out_coef;    // optional [n_out]: plain sums of the coefficients (bias of the head), written by thread 0
+};
+constexpr int SK_NUM_JOBS = 12;
+struct SJobs {
+  SJob j[SK_NUM_JOBS];
+};
+
+__global__ void __launch_bounds__(256) wgrad_skinny_kernel(const uint8_t* __restrict__ dump, const float* __restrict__ d_raw,
+                                                           long long n_points, SJobs jobs, int n_tiles, const float* gscale) {
+  const SJob job = jobs.j[blockIdx.y];
+  const int c = threadIdx.x;
+  float acc[3] = {0.f, 0.f, 0.f}, csum[3] = {0.f, 0.f, 0.f};
+  float scale = __uint_as_float(__float_as_uint(*gscale) & 0x7f800000u);
+  if (!(scale > 0.f) || !(scale < 3.0e38f)) scale = 1.f;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int r = 0; r < 128; ++r) {
+      const long long p = (long long)tile * 128 + r;
+      float co[3] = {1.f, 0.f, 0.f};
+      if (job.coef_col >= 0) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) co[j] = (j < job.n_out && p < n_points) ? d_raw[p * 4 + job.coef_col + j] : 0.f;
+      }
+      if (c < job.w) {
+        const __half x = *reinterpret_cast<const __half*>(dump + job.x_off + dump_blocked_off(tile, r, job.w, c >> 3) + (c & 7) * 2);
+        const float xf = __half2float(x);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc[j] = fmaf(co[j], xf, acc[j]);
+      }
+      if (c == 0 && job.out_coef != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) csum[j] += co[j];
+      }
+    }
+  }
+  const float mul = (job.coef_col >= 0) ? 1.f : scale;
+  if (c < job.w)
+    for (int j = 0; j < job.n_out; ++j) atomicAdd(job.out + size_t(j) * job.ld + c, acc[j] * mul);
+  if (c == 0 && job.out_coef != nullptr)
+    for (int j = 0; j < job.n_out; ++j) atomicAdd(job.out_coef + j, csum[j]);
+}
+
+int launch_weight_grads(const void* dump_v, const float* d_raw, int64_t n_points, const float* gscale, float* const* dW,
+                        float* const* dB, cudaStream_t st) {
+  if (n_points == 0) return NSR_OK;
+  const uint8_t* dump = static_cast<const uint8_t*>(dump_v);
+  const int n_tiles = int((n_points + 127) / 128);
+  const size_t P = size_t(n_tiles) * 128;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM) != cudaSuccess)
+      return check_launch("cudaFuncSetAttribute(wgrad_gemm_kernel)");
+    configured = true;
+  }
+  // parameter order (include/nsr_b200.h): 0..7 pts_linears, 8 views_linears.0, 9 feature_linear, 10 alpha_linear, 11 rgb_linear
+  WJobs g;
+  int k = 0;
+  auto add = [&](size_t g_off, int g_w, size_t h_off, int h_w, float* out, int ld, int col_off, int n_valid) {
+    g.j[k++] = WJob{(unsigned long long)g_off, (unsigned long long)h_off, g_w, h_w, out, ld, col_off, n_valid};
+  };
+  add(dump_off_g(P, 0), 256, dump_off_ex(P), 64, dW[0], 63, 0, 63);                                   // pts_linears.0 [256,63]
+  for (int l = 1; l <= 7; ++l) {
+    if (l == 5) {                                                                                      // [256,319] = cat[xyz(63), h(256)]
+      add(dump_off_g(P, 5), 256, dump_off_ex(P), 64, dW[5], 319, 0, 63);
+      add(dump_off_g(P, 5), 256, dump_off_h(P, 4), 256, dW[5], 319, 63, 256);
+    } else {
+      add(dump_off_g(P, l), 256, dump_off_h(P, l - 1), 256, dW[l], 256, 0, 256);
+    }
+  }
+  add(dump_off_gv(P), 128, dump_off_h(P, 8), 256, dW[8], 283, 0, 256);                                 // views_linears.0 [128,283] = cat[feature, dirs]
+  add(dump_off_gv(P), 128, dump_off_ev(P), 32, dW[8], 283, 256, 27);
+  add(dump_off_gf(P), 256, dump_off_h(P, 7), 256, dW[9], 256, 0, 256);                                 // feature_linear
+  const int splits = 12;
+  wgrad_gemm_kernel<<<dim3(splits, WG_NUM_JOBS), 128, WG_SMEM, st>>>(dump, g, n_tiles, gscale);
+  count_launch();
+  int rc = check_launch("wgrad_gemm_kernel");
+  if (rc) return rc;
+
+  SJobs s;
+  k = 0;
+  for (int l = 0; l <= 7; ++l) s.j[k++] = SJob{(unsigned long long)dump_off_g(P, l), 256, -1, 1, dB[l], 256, nullptr};   // db_l
+  s.j[k++] = SJob{(unsigned long long)dump_off_gv(P), 128, -1, 1, dB[8], 128, nullptr};
+  s.j[k++] = SJob{(unsigned long long)dump_off_gf(P), 256, -1, 1, dB[9], 256, nullptr};
+  s.j[k++] = SJob{(unsigned long long)dump_off_h(P, 7), 256, 3, 1, dW[10], 256, dB[10]};                                   // alpha_linear: sigma column
+  s.j[k++] = SJob{(unsigned long long)dump_off_hv(P), 128, 0, 3, dW[11], 128, dB[11]};                                     // rgb_linear: rgb columns
+  wgrad_skinny_kernel<<<dim3(24, SK_NUM_JOBS), 256, 0, st>>>(dump, d_raw, (long long)n_points, s, n_tiles, gscale);
+  count_launch();
+  return check_launch("wgrad_skinny_kernel");
+}
+
+}  // namespace nsr

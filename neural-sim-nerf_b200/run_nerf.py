@@ -320,44 +320,6 @@ def _params_of(net):
     return [l.weight for l in layers] + [l.bias for l in layers]
 
 
-def _weight_grads(dump, d_raw, n_points):
-    """dL/d(parameters) of one network pass from the backward kernel's dump (include/nsr_b200.h): dW_l = (SCALE.G_l)^T H_{l-1},
-    db_l = column sums.  These are plain [out x points] x [points x in] reductions over HBM-resident operands, done with
-    torch.matmul in fp32 (a library GEMM; the fused tcgen05 kernels produce the operands).  Returns the 24 tensors in
-    _params_of() order."""
-    P = (n_points + 127) // 128 * 128
-    off = [0]
-
-    def take(cols, dtype=torch.float16):
-        nbytes = P * cols * (2 if dtype == torch.float16 else 4)
-        t = dump[off[0]:off[0] + nbytes].view(dtype).view(P, cols) if cols > 1 else dump[off[0]:off[0] + nbytes].view(dtype)
-        off[0] += nbytes
-        return t
-    EX, EV = take(64), take(32)
-    H = [take(256) for _ in range(8)]
-    F_, HV, GV, GF = take(256), take(128), take(128), take(256)
-    G = [take(256) for _ in range(8)]
-    scale = dump[off[0]:off[0] + P * 4].view(torch.float32)
-    f = lambda t: t.float()
-    gs = lambda t: t.float() * scale[:, None]
-    ex, ev = f(EX)[:, :63], f(EV)[:, :27]
-    dW, dB = [None] * 12, [None] * 12
-    g0 = gs(G[0])
-    dW[0], dB[0] = g0.t() @ ex, g0.sum(0)
-    for l in range(1, 8):
-        gl = gs(G[l])
-        hin = f(H[l - 1])
-        dW[l] = torch.cat([gl.t() @ ex, gl.t() @ hin], 1) if l == 5 else gl.t() @ hin   # RH:106: cat[input_pts, h]
-        dB[l] = gl.sum(0)
-    gv, gf, h7 = gs(GV), gs(GF), f(H[7])
-    dW[8], dB[8] = gv.t() @ torch.cat([f(F_), ev], 1), gv.sum(0)                          # views_linears.0 on cat[feature, dirs]
-    dW[9], dB[9] = gf.t() @ h7, gf.sum(0)                                                 # feature_linear
-    g_raw = d_raw.reshape(-1, 4)[:n_points]
-    dW[10], dB[10] = g_raw[:, 3:4].t() @ h7[:n_points], g_raw[:, 3].sum().reshape(1)      # alpha_linear
-    dW[11], dB[11] = g_raw[:, :3].t() @ f(HV)[:n_points], g_raw[:, :3].sum(0)             # rgb_linear
-    return dW + dB
-
-
 class _RenderRaysFn(torch.autograd.Function):
     """render_rays as an autograd node.  Differentiable outputs: rgb_map and rgb0; differentiable inputs: ray_batch
     (the pose path, RN:177-178) and the parameters of both networks (the training step, RN:691-707).  disp / acc /
@@ -383,13 +345,16 @@ class _RenderRaysFn(torch.autograd.Function):
         d_rays = torch.empty(n, 11, dtype=torch.float32, device=rays.device)
         ws_bytes = L.nsr_render_backward_workspace_bytes(n, T)
         ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=rays.device)
-        dump = torch.empty(L.nsr_mlp_dump_bytes(n, T), dtype=torch.uint8, device=rays.device) if want_dump else None
+        dump = grads = dWp = dBp = None
+        if want_dump:   # parameter gradients: the kernels ADD this pass's dL/dW, dL/db into zero-initialised fp32 tensors
+            dump = torch.empty(L.nsr_mlp_dump_bytes(n, T), dtype=torch.uint8, device=rays.device)
+            shapes = _EXPECTED_SHAPES
+            grads = [torch.zeros(s, dtype=torch.float32, device=rays.device) for s in shapes] + \
+                    [torch.zeros(s[0], dtype=torch.float32, device=rays.device) for s in shapes]
+            dWp = (ctypes.c_void_p * 12)(*[t.data_ptr() for t in grads[:12]])
+            dBp = (ctypes.c_void_p * 12)(*[t.data_ptr() for t in grads[12:]])
         check(L.nsr_render_rays_backward(ptr(rays), ptr(zv), ptr(raw), n, T, ptr(net_blob), flags, ptr(g), ptr(d_rays), ptr(dump),
-                                         ptr(ws), ws_bytes, _stream()), 'nsr_render_rays_backward')
-        grads = None
-        if want_dump:
-            d_raw = ws[:n * T * 16].view(torch.float32)
-            grads = _weight_grads(dump, d_raw, n * T)
+                                         dWp, dBp, ptr(ws), ws_bytes, _stream()), 'nsr_render_rays_backward')
         return d_rays, grads
 
     @staticmethod
