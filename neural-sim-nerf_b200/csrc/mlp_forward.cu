@@ -530,21 +530,27 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
         tmem_ld32(tlane + TM_ACC1 + col0, u0);
         tmem_ld32(tlane + TM_ACC1 + col0 + 32, u1);
         tmem_ld_wait();
+        // ACC1 now lives in registers: hand it back before the head arithmetic, so the next tile's step 0 is not held up
+        tc_fence_before_sync();
+        mbar_arrive(&a_ready[1]);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float h0 = fmaxf(__uint_as_float(u0[j]) + bias[j], 0.f);
-          const float h1 = fmaxf(__uint_as_float(u1[j]) + bias[32 + j], 0.f);
-          const float4 w0 = wr[j], w1 = wr[32 + j];
-          r0 = fmaf(h0, w0.x, r0);
-          r1 = fmaf(h0, w0.y, r1);
-          r2 = fmaf(h0, w0.z, r2);
-          r0 = fmaf(h1, w1.x, r0);
-          r1 = fmaf(h1, w1.y, r1);
-          r2 = fmaf(h1, w1.z, r2);
+        for (int j = 0; j < 8; ++j) {
+          const float4 b0 = *reinterpret_cast<const float4*>(bias + 4 * j), b1 = *reinterpret_cast<const float4*>(bias + 32 + 4 * j);
+          const float bb0[4] = {b0.x, b0.y, b0.z, b0.w}, bb1[4] = {b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float h0 = fmaxf(__uint_as_float(u0[4 * j + q]) + bb0[q], 0.f);
+            const float h1 = fmaxf(__uint_as_float(u1[4 * j + q]) + bb1[q], 0.f);
+            const float4 w0 = wr[4 * j + q], w1 = wr[32 + 4 * j + q];
+            r0 = fmaf(h0, w0.x, r0);
+            r1 = fmaf(h0, w0.y, r1);
+            r2 = fmaf(h0, w0.z, r2);
+            r0 = fmaf(h1, w1.x, r0);
+            r1 = fmaf(h1, w1.y, r1);
+            r2 = fmaf(h1, w1.z, r2);
+          }
         }
       }
-      tc_fence_before_sync();
-      mbar_arrive(&a_ready[1]);
       // ---- the two column halves of a row meet in shared memory; the ch == 0 thread writes raw[p]
       if (ch == 1) sXch[row] = make_float4(r0, r1, r2, sigma);
       asm volatile("bar.sync 1, 256;" ::: "memory");
