@@ -348,7 +348,8 @@ def run_ours(args):
             rc = L.nsr_render_rays_forward(P(r), n, P(pc), P(pf), N_SAMPLES, N_IMPORTANCE, 0, None, None, P(outs['rgb']), P(outs['disp']),
                                            P(outs['acc']), P(outs['rgb0']), P(outs['disp0']), P(outs['acc0']), P(outs['zstd']), P(rawsave),
                                            P(zsave), None, P(ws), ws_bytes, stream)
-            rc = rc or L.nsr_render_rays_backward(P(r), P(zsave), P(rawsave), n, T, P(pf), 0, P(g_rgb), P(d_rays), P(bws), bws_bytes, stream)
+            rc = rc or L.nsr_render_rays_backward(P(r), P(zsave), P(rawsave), n, T, P(pf), 0, P(g_rgb), P(d_rays), None, None, None,
+                                                  P(bws), bws_bytes, stream)
             if rc != 0:
                 raise RuntimeError(L.nsr_last_error().decode())
 
