@@ -109,3 +109,35 @@ def test_oracle_vs_live_reference(wfit):
             close(y.numpy(), x.numpy(), 1e-6, nme)
         for k in ref[3]:
             close(mine[3][k].numpy(), ref[3][k].numpy(), 1e-6, k)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason='reference tree only exists in the build container')
+def test_oracle_autograd_vs_live_reference_tape(wfit):
+    """The backward tests compare against autograd through the oracle; pin that tape to the reference's own
+    (RN:168-181: autograd.grad(rgb_p, batch_rays, grad_outputs=patch_grad_E)) and to loss.backward() (RN:691-707)."""
+    RN, RH = ref_import.load()
+    torch.autograd.set_detect_anomaly(False)
+    sdc, sdf = wfit
+    H = W = 400
+    c2w = O.pose_spherical(90., 22.5 - 180., 1.01)[:3, :4]
+    ro, rd = O.get_rays(H, W, O.YCBV_K_400, c2w)
+    sel = torch.arange(80000 - 600, 80000 + 600, 37)
+    g = torch.randn(len(sel), 3, generator=torch.Generator().manual_seed(0))
+    # reference tape
+    coarse, fine, query = ref_import.build_models(sdc, sdf)
+    kw = ref_import.render_kwargs(sdc, sdf, O.YCBV_NEAR, O.YCBV_FAR)
+    kw.update(network_fn=coarse, network_fine=fine, network_query_fn=query)
+    br = torch.stack([ro.reshape(-1, 3)[sel], rd.reshape(-1, 3)[sel]], 0).clone().requires_grad_(True)
+    rgb_ref = RN.render(H, W, torch.tensor(O.YCBV_K_400), chunk=512, rays=br, retraw=True, **kw)[0]
+    (g_ref,) = torch.autograd.grad(rgb_ref, br, grad_outputs=g, retain_graph=True)
+    loss = ((rgb_ref - 0.5) ** 2).mean()
+    loss.backward()
+    # oracle tape
+    sf = {k: v.clone().requires_grad_(True) for k, v in sdf.items()}
+    bo = br.detach().clone().requires_grad_(True)
+    rgb = O.render(H, W, O.YCBV_K_400, sdc, sf, chunk=512, rays=bo, near=O.YCBV_NEAR, far=O.YCBV_FAR)[0]
+    (g_or,) = torch.autograd.grad(rgb, bo, grad_outputs=g, retain_graph=True)
+    ((rgb - 0.5) ** 2).mean().backward()
+    assert (g_or - g_ref).abs().max() <= 1e-5 * g_ref.abs().max()
+    for name, p in fine.named_parameters():
+        assert (sf[name].grad - p.grad).abs().max() <= 1e-5 * max(1e-12, p.grad.abs().max()), name
