@@ -28,6 +28,41 @@ int check_launch(const char* what) {
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+// SM count of the CURRENT device (must be sm_100), cached per device ordinal
+int current_device_sms(int* sms) {
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return check_launch("cudaGetDevice");
+  if (dev >= 0 && dev < 64 && cache[dev] > 0) {
+    *sms = cache[dev];
+    return NSR_OK;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return check_launch("cudaGetDeviceProperties");
+  if (prop.major != 10) {
+    set_error("libnsr_b200 needs an sm_100 device, found sm_%d%d", prop.major, prop.minor);
+    return NSR_E_DEVICE;
+  }
+  if (dev >= 0 && dev < 64) cache[dev] = prop.multiProcessorCount;
+  *sms = prop.multiProcessorCount;
+  return NSR_OK;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device setting: apply it once per (kernel, device)
+int ensure_dynamic_smem(const void* func, int bytes) {
+  struct Entry { const void* f; int dev; };
+  static Entry done[256];
+  static int n_done = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  for (int i = 0; i < n_done; ++i)
+    if (done[i].f == func && done[i].dev == dev) return NSR_OK;
+  if (cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess)
+    return check_launch("cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+  if (n_done < 256) done[n_done++] = Entry{func, dev};
+  return NSR_OK;
+}
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace nsr

@@ -85,6 +85,8 @@ __host__ __device__ inline size_t dump_blocked_off(int tile, int row, int W, int
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 void count_launch();
+int current_device_sms(int* sms);
+int ensure_dynamic_smem(const void* func, int bytes);
 
 // ray_stage.cu
 int launch_coarse_z(const float* rays, int64_t n, int S, uint32_t flags, const float* t_rand, float* z, cudaStream_t st);

@@ -539,20 +539,9 @@ int launch_mlp_backward(const float* rays, const float* z, int64_t n, int S, con
                         void* dump, const float* gscale, cudaStream_t st) {
   const int64_t n_points = n * S;
   if (n_points == 0) return NSR_OK;
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return check_launch("cudaGetDeviceProperties");
-    if (prop.major != 10) {
-      set_error("libnsr_b200 needs an sm_100 device, found sm_%d%d", prop.major, prop.minor);
-      return NSR_E_DEVICE;
-    }
-    if (cudaFuncSetAttribute(nerf_mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SM_TOTAL) != cudaSuccess)
-      return check_launch("cudaFuncSetAttribute(nerf_mlp_bwd_kernel)");
-    num_sms = prop.multiProcessorCount;
-  }
+  int num_sms = 0;
+  if (int rc = current_device_sms(&num_sms)) return rc;
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(&nerf_mlp_bwd_kernel), B_SM_TOTAL)) return rc;
   BwdArgs a;
   a.rays = rays;
   a.z = z;

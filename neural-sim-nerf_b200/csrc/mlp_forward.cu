@@ -567,16 +567,9 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
   if (warp == MMA_WARP) tmem_dealloc(0u, 512);
 }
 
-static int g_num_sms = 0;
-
 template <int SPLIT>
 static int launch_variant(const MlpArgs& a, int grid, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(nerf_mlp_kernel<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<SPLIT>::SM_TOTAL) != cudaSuccess)
-      return check_launch("cudaFuncSetAttribute(nerf_mlp_kernel)");
-    configured = true;
-  }
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(&nerf_mlp_kernel<SPLIT>), Cfg<SPLIT>::SM_TOTAL)) return rc;
   nerf_mlp_kernel<SPLIT><<<grid, MLP_THREADS, Cfg<SPLIT>::SM_TOTAL, st>>>(a);
   count_launch();
   return check_launch("nerf_mlp_kernel");
@@ -590,17 +583,8 @@ int launch_mlp_forward(const float* rays, const float* z_or_pts, int64_t n, int 
     set_error("mlp_forward: too many points");
     return NSR_E_UNSUPPORTED;
   }
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return check_launch("cudaGetDeviceProperties");
-    if (prop.major != 10) {
-      set_error("libnsr_b200 needs an sm_100 device, found sm_%d%d", prop.major, prop.minor);
-      return NSR_E_DEVICE;
-    }
-    g_num_sms = prop.multiProcessorCount;
-  }
+  int num_sms = 0;
+  if (int rc = current_device_sms(&num_sms)) return rc;
   MlpArgs a;
   a.rays = rays;
   a.z_or_pts = z_or_pts;
@@ -611,7 +595,7 @@ int launch_mlp_forward(const float* rays, const float* z_or_pts, int64_t n, int 
   a.flags = flags;
   a.num_tiles = int((n_points + 127) / 128);
   a.trace = nullptr;
-  const int grid = a.num_tiles < g_num_sms ? a.num_tiles : g_num_sms;
+  const int grid = a.num_tiles < num_sms ? a.num_tiles : num_sms;
   const char* trace_file = getenv("NSR_TRACE_FILE");  // debug only: synchronous, dumps CTA 0's timeline
   if (trace_file != nullptr && a.num_tiles >= 4 * grid) {
     const size_t nb = 4 * 10 * 16 * sizeof(unsigned long long);

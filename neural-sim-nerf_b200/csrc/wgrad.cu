@@ -162,12 +162,9 @@ int launch_weight_grads(const void* dump_v, const float* d_raw, int64_t n_points
   const uint8_t* dump = static_cast<const uint8_t*>(dump_v);
   const int n_tiles = int((n_points + 127) / 128);
   const size_t P = size_t(n_tiles) * 128;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM) != cudaSuccess)
-      return check_launch("cudaFuncSetAttribute(wgrad_gemm_kernel)");
-    configured = true;
-  }
+  int num_sms = 0;
+  if (int rc = current_device_sms(&num_sms)) return rc;
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(&wgrad_gemm_kernel), WG_SMEM)) return rc;
   // parameter order (include/nsr_b200.h): 0..7 pts_linears, 8 views_linears.0, 9 feature_linear, 10 alpha_linear, 11 rgb_linear
   WJobs g;
   int k = 0;
