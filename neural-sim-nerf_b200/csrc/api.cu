@@ -108,6 +108,9 @@ int nsr_raw2outputs(const float* raw, const float* z_vals, const float* rays_d, 
                     int n_samples, uint32_t flags, float* rgb_map, float* disp_map, float* acc_map, float* weights,
                     float* depth_map, void* stream) {
   NSR_REQUIRE(n_rays >= 0 && n_samples > 0 && ld_rays_d >= 3, "nsr_raw2outputs: bad sizes");
+  // with one sample the reference's dists tensor is EMPTY (RN:358-359 expands to dists[..., :1].shape == [n, 0]) and every
+  // output collapses to a sum over nothing; that degenerate case is not reproduced
+  NSR_REQUIRE(n_samples >= 2, "nsr_raw2outputs: needs at least 2 samples per ray");
   if (n_rays == 0) return NSR_OK;
   NSR_REQUIRE(raw && z_vals && rays_d, "nsr_raw2outputs: null input");
   NSR_REQUIRE((reinterpret_cast<uintptr_t>(raw) & 15) == 0, "nsr_raw2outputs: raw must be 16-byte aligned");
@@ -148,7 +151,7 @@ int nsr_render_rays_forward(const float* rays, int64_t n, const void* packed_coa
                             int Ni, uint32_t flags, const float* t_rand, const float* u, float* rgb_map, float* disp_map,
                             float* acc_map, float* rgb0, float* disp0, float* acc0, float* z_std, float* raw,
                             float* z_vals_out, float* weights_out, void* workspace, size_t workspace_bytes, void* stream) {
-  NSR_REQUIRE(n >= 0 && S > 0 && Ni >= 0, "nsr_render_rays_forward: bad sizes");
+  NSR_REQUIRE(n >= 0 && S >= 2 && Ni >= 0, "nsr_render_rays_forward: bad sizes (needs at least 2 samples per ray)");
   if (n == 0) return NSR_OK;
   NSR_REQUIRE(rays && packed_coarse, "nsr_render_rays_forward: null rays / weights");
   NSR_REQUIRE(workspace && workspace_bytes >= nsr_render_workspace_bytes(n, S, Ni), "nsr_render_rays_forward: workspace too small");

@@ -35,7 +35,7 @@ def rel(a, b):
     return ((a - b).abs()[m] / b.abs()[m].clamp(min=1.0)).max().item() if m.any() else 0.0
 
 
-@pytest.mark.parametrize('S', [1, 3, 31, 32, 33, 64, 100, 192, 256])
+@pytest.mark.parametrize('S', [2, 3, 31, 32, 33, 64, 100, 192, 256])
 def test_raw2outputs_shapes_and_extremes(nsr, S):
     g = torch.Generator().manual_seed(S)
     n = 257
@@ -102,6 +102,8 @@ def test_unsupported_sizes_are_errors_not_garbage(nsr, nets):
         nsr.render_rays(rays, nets[0], None, 300, N_importance=0)        # > 256 samples per ray: not built
     with pytest.raises(nsr.NsrError):
         nsr.render_rays(rays, nets[0], None, 200, N_importance=100, network_fine=nets[1])
+    with pytest.raises(nsr.NsrError):   # one sample: the reference's dists tensor is empty (RN:358-359), not reproduced
+        nsr.raw2outputs(torch.zeros(4, 1, 4, device='cuda'), torch.ones(4, 1, device='cuda'), rays[:, 3:6].contiguous())
 
 
 @pytest.mark.parametrize('S', [5, 64, 192])
