@@ -132,8 +132,9 @@ def test_raw2outputs_backward_kernel_vs_autograd(nsr, S):
     ws = torch.empty(wsb, dtype=torch.uint8, device='cuda')
     d_rays = torch.empty(n, 11, device='cuda')
     P = lambda t: ctypes.c_void_p(t.data_ptr())
-    rc = L.nsr_render_rays_backward(P(rays.cuda()), P(z.cuda()), P(raw.detach().cuda().contiguous()), n, T, P(m.packed_weights(net)), 0,
-                                    P(gout.cuda()), P(d_rays), None, None, None, P(ws), wsb, None)
+    keep = [rays.cuda(), z.cuda(), raw.detach().cuda().contiguous(), gout.cuda(), m.packed_weights(net)]   # keep the device buffers alive
+    rc = L.nsr_render_rays_backward(P(keep[0]), P(keep[1]), P(keep[2]), n, T, P(keep[4]), 0,
+                                    P(keep[3]), P(d_rays), None, None, None, P(ws), wsb, None)
     assert rc == 0, L.nsr_last_error()
     torch.cuda.synchronize()
     got_raw = ws[:n * T * 16].view(torch.float32).view(n, T, 4).cpu()
