@@ -10,6 +10,8 @@
 // Gradients are linear in dL/draw, so every row is scaled by a power of two to put its largest input at
 // [1,2) before entering fp16 hi/lo operands and scaled back at the end.
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "mlp_common.cuh"
 
@@ -39,6 +41,7 @@ struct BwdArgs {
   int num_tiles;
   uint8_t* dump;        // optional: fp16 activations / pre-activation gradients of every layer (common.cuh), for dL/dMLP
   const float* gscale;  // with dump: one power-of-two scale for ALL rows (max |dL/draw| of the batch), device scalar
+  unsigned long long* trace;  // debug (NSR_TRACE_FILE_BWD): clock64 stamps of CTA 0's first tiles, [tile][gstep][16]
 };
 
 // 64 consecutive features (32 packed fp16 words) of tile-row `row` at feature `col` of a blocked [P, W] dump array
@@ -47,6 +50,11 @@ __device__ __forceinline__ void dump64(uint8_t* arr, int tile, int row, int W, i
 #pragma unroll
   for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(dst + q * 128) = make_uint4(H[4 * q], H[4 * q + 1], H[4 * q + 2], H[4 * q + 3]);
 }
+
+#define NSR_TRB(tl, g, slot)                                                                              \
+  do {                                                                                                  \
+    if (a.trace != nullptr && blockIdx.x == 0 && (tl) < 3) a.trace[((tl) * 22 + (g)) * 16 + (slot)] = clock64(); \
+  } while (0)
 
 __device__ __forceinline__ bool gstep_is_side(int g) { return g == 9 || (g >= 10 && bstep_is_side(g - 10)); }
 __device__ __forceinline__ int gstep_k_chunks(int g) { return g < 10 ? step_k_chunks(g) : bstep_k_chunks(g - 10); }
@@ -182,10 +190,10 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
     const uint32_t inbuf = smem_u32(smem + B_SM_INBUF);
     const uint32_t enc_hi = sdesc_lo(inbuf + B_OFF_ENC_HI, 128), enc_lo = sdesc_lo(inbuf + B_OFF_ENC_LO, 128);
     const uint32_t dir_hi = sdesc_lo(inbuf + B_OFF_DIR_HI, 128), dir_lo = sdesc_lo(inbuf + B_OFF_DIR_LO, 128);
-    uint32_t stage = 0, phase = 0;
+    uint32_t stage = 0, phase = 0, tl = 0;
     Waiter w_a[2], w_enc[2];
     bool ready = false;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++tl) {
       w_enc[0].wait(&enc_ready[0]);
       for (int g = 0; g < NUM_GSTEPS; ++g) {
         if (g == 9) w_enc[1].wait(&enc_ready[1]);
@@ -194,7 +202,9 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
         const int nhs = side ? 1 : 2;
         const uint32_t idesc = side ? make_idesc_f16(128, gstep_side_n(g)) : make_idesc_f16(128, 128);
         bool waited1 = false;
+        if (lane == 0) NSR_TRB(tl, g, 0);
         w_a[0].wait(&a_ready[0]);
+        if (lane == 0) NSR_TRB(tl, g, 1);
         if (side) {  // a side step accumulates in ACC1
           w_a[1].wait(&a_ready[1]);
           waited1 = true;
@@ -208,11 +218,17 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
             else if (g == 9 && kc == 4) src = 2;
             else if (g == 5) ak = kc - 1;
             if (!waited1 && (nh == 1 || (src == 1 && ak >= 2))) {
+              if (lane == 0) NSR_TRB(tl, g, 2);
               w_a[1].wait(&a_ready[1]);
+              if (lane == 0) NSR_TRB(tl, g, 3);
               tc_fence_after_sync();
               waited1 = true;
             }
-            if (!ready) mbar_wait(&full[stage], phase);
+            if (!ready) {
+              if (lane == 0) NSR_TRB(tl, g, 5);   // weight ring not ready: last stamp = a stall on the TMA stream
+              mbar_wait(&full[stage], phase);
+              if (lane == 0) NSR_TRB(tl, g, 6);
+            }
             const uint32_t bh = ring_lo + stage * (CHUNK_PAIR_BYTES >> 4), bl = bh + (CHUNK_BYTES >> 4);
             const uint32_t acc0 = kc != 0;
             if (leader) {
@@ -250,6 +266,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
           if (leader) umma_commit(&acc_ready[side ? 1 : nh]);
         }
         if (!waited1) w_a[1].wait(&a_ready[1]);
+        if (lane == 0) NSR_TRB(tl, g, 4);
         if (g == 5 && leader) umma_commit(&enc_free[0]);
         if (g == 9 && leader) umma_commit(&enc_free[1]);
       }
@@ -354,7 +371,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
     mbar_arrive(&a_ready[1]);
     // sign-bit words of this thread: layer l, accumulator half h, 32-column group q  ->  sMask[(l*8 + h*4 + ch*2 + q)*128 + row]
     uint32_t* my_mask = sMask + (ch * 2) * 128 + row;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++tl) {
       const int64_t p = int64_t(tile) * 128 + row;
       float x[3] = {0.f, 0.f, 0.f}, vd[3] = {0.f, 0.f, 0.f};
       float4 gr = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -391,6 +409,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
           const float* extra = (g == 12) ? sTail + TAIL_WALPHA + col0 : nullptr;      // alpha head: dL/dh7 += w_alpha * dL/dsigma
           uint32_t H[32], L[32];
           w_acc[0].wait(&acc_ready[0]);
+          if (tid == 0) NSR_TRB(tl, g, 8);
           tc_fence_after_sync();
           {
             uint32_t u0[32], u1[32];
@@ -415,7 +434,9 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
           uint8_t* dump_arr = a.dump == nullptr ? nullptr
                               : a.dump + (fwd ? dump_off_h(P, g) : (g == 11 ? dump_off_gf(P) : dump_off_g(P, mlayer)));
           if (dump_arr != nullptr) dump64(dump_arr, tile, row, 256, col0, H);
+          if (tid == 0) NSR_TRB(tl, g, 9);
           w_acc[1].wait(&acc_ready[1]);
+          if (tid == 0) NSR_TRB(tl, g, 10);
           tc_fence_after_sync();
           tmem_st16(tlane + TM_AHI + col0 / 2, *reinterpret_cast<const uint32_t(*)[16]>(&H[0]));
           tmem_st16(tlane + TM_AHI + col0 / 2 + 16, *reinterpret_cast<const uint32_t(*)[16]>(&H[16]));
@@ -424,6 +445,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
           tmem_st_wait();
           tc_fence_before_sync();
           mbar_arrive(&a_ready[0]);
+          if (tid == 0) NSR_TRB(tl, g, 11);
           {
             uint32_t u0[32], u1[32];
             tmem_ld32(tlane + TM_ACC1 + col0, u0);
@@ -451,6 +473,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
           tmem_st_wait();
           tc_fence_before_sync();
           mbar_arrive(&a_ready[1]);
+          if (tid == 0) NSR_TRB(tl, g, 12);
         } else if (g == 9) {
           // ------------------------------------------------ forward views layer (ACC1, 128 wide) -> dL/dh_views into A[K 0..127]
           w_acc[1].wait(&acc_ready[1]);
@@ -553,6 +576,29 @@ int launch_mlp_backward(const float* rays, const float* z, int64_t n, int S, con
   a.num_tiles = int((n_points + 127) / 128);
   a.dump = static_cast<uint8_t*>(dump);
   a.gscale = dump != nullptr ? gscale : nullptr;
+  a.trace = nullptr;
+  const char* trace_file = getenv("NSR_TRACE_FILE_BWD");  // debug only: synchronous, dumps CTA 0's timeline
+  if (trace_file != nullptr && a.num_tiles >= 3 * num_sms) {
+    const size_t nb = 3 * 22 * 16 * sizeof(unsigned long long);
+    cudaMalloc(&a.trace, nb);
+    cudaMemset(a.trace, 0, nb);
+    nerf_mlp_bwd_kernel<<<num_sms, MLP_THREADS, B_SM_TOTAL, st>>>(a);
+    cudaStreamSynchronize(st);
+    unsigned long long host[3 * 22 * 16];
+    cudaMemcpy(host, a.trace, nb, cudaMemcpyDeviceToHost);
+    cudaFree(a.trace);
+    if (FILE* f = fopen(trace_file, "a")) {
+      fprintf(f, "# bwd launch tiles=%d\n", a.num_tiles);
+      for (int i = 0; i < 66; ++i) {
+        fprintf(f, "%d %d", i / 22, i % 22);
+        for (int k = 0; k < 16; ++k) fprintf(f, " %llu", host[i * 16 + k]);
+        fprintf(f, "\n");
+      }
+      fclose(f);
+    }
+    count_launch();
+    return check_launch("nerf_mlp_bwd_kernel");
+  }
   const int grid = a.num_tiles < num_sms ? a.num_tiles : num_sms;
   nerf_mlp_bwd_kernel<<<grid, MLP_THREADS, B_SM_TOTAL, st>>>(a);
   count_launch();

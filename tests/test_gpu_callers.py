@@ -159,3 +159,43 @@ def test_render_path_and_render_path_grad(nsr, nets, tmp_path):
     from PIL import Image
     png = np.asarray(Image.open(tmp_path / '2' / '000.png'))
     assert png.shape == (H, W, 3) and np.array_equal(png, nsr.to8b(imgs[0]))
+
+
+def test_forward_is_cuda_graph_capturable(nsr, nets):
+    """Nothing in nsr_render_rays_forward synchronises the host or allocates: the whole 6-kernel sequence can be captured
+    once and replayed (how a serving loop removes launch overhead for small ray chunks)."""
+    import ctypes
+    L = nsr.lib()
+    H = W = 400
+    pose = O.pose_spherical(90., 22.5 - 180., 1.01)[:3, :4]
+    n = 4096
+    rays_all = nsr.make_rays(H, W, O.YCBV_K_400, pose, O.YCBV_NEAR, O.YCBV_FAR)
+    rays = rays_all[60000:60000 + n].clone()
+    pc, pf = nsr.packed_weights(nets[0]), nsr.packed_weights(nets[1])
+    new = lambda *s: torch.empty(*s, device='cuda')
+    outs = [new(n, 3), new(n), new(n), new(n, 3), new(n), new(n), new(n)]
+    wsb = L.nsr_render_workspace_bytes(n, 64, 128)
+    ws = torch.empty(wsb, dtype=torch.uint8, device='cuda')
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+
+    def launch(stream):
+        rc = L.nsr_render_rays_forward(P(rays), n, P(pc), P(pf), 64, 128, 0, None, None, *[P(t) for t in outs], None, None, None,
+                                       P(ws), wsb, ctypes.c_void_p(stream.cuda_stream))
+        assert rc == 0, L.nsr_last_error()
+
+    launch(torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    eager = outs[0].clone()
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            launch(side)
+    rays.copy_(rays_all[90000:90000 + n])          # new input, same buffers
+    graph.replay()
+    torch.cuda.synchronize()
+    replayed = outs[0].clone()
+    launch(torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    assert torch.equal(replayed, outs[0]) and not torch.equal(replayed, eager)
