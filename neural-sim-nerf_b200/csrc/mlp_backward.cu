@@ -163,6 +163,10 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
   __syncthreads();
   tc_fence_after_sync();
   if (*tmem_slot != 0u) __trap();
+  // register budget: the two epilogue warpgroups carry 64 + 64 live accumulator words plus the hi/lo results; the third
+  // warpgroup (encoders, MMA issuer, producer) gives its share up (8 x 32 x 200 + 4 x 32 x 104 = 64512 <= 65536)
+  if (warp >= ENC_WARP0) asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
+  else asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
 
   if (warp == PROD_WARP) {
     // ===================================================================== weight producer: forward chunks then backward chunks
@@ -489,10 +493,12 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               float gg[4], hh[4];
+              const float2 bA = *reinterpret_cast<const float2*>(bias + 2 * j), bB = *reinterpret_cast<const float2*>(bias + 32 + 2 * j);
+              const float bq[4] = {bA.x, bA.y, bB.x, bB.y};
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 const int c = (q < 2) ? 2 * j + q : 32 + 2 * j + (q - 2);
-                const float hv = __uint_as_float((q < 2) ? u0[2 * j + q] : u1[2 * j + (q - 2)]) + bias[c];
+                const float hv = __uint_as_float((q < 2) ? u0[2 * j + q] : u1[2 * j + (q - 2)]) + bq[q];
                 const float4 w = wr[c];
                 hh[q] = fmaxf(hv, 0.f);
                 gg[q] = (hv > 0.f) ? (gr.x * w.x + gr.y * w.y + gr.z * w.z) : 0.f;   // RH:117 backwards, gated by RH:115
@@ -520,21 +526,20 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
           w_acc[1].wait(&acc_ready[1]);
           tc_fence_after_sync();
           mbar_arrive(&a_ready[0]);  // A is only read by this step
-          if (g == 10) {             // dL/d(view-dir encoding), 27 channels: the ch == 0 threads take all 32 columns
-            if (ch == 0) {
-              uint32_t u[32];
-              tmem_ld32(tlane + TM_ACC1, u);
-              tmem_ld_wait();
-              enc_backward32(u, 0, 27, vd, dv);
-            }
-          } else {                   // dL/d(xyz encoding), 63 channels: 32 per column half
-            uint32_t u[32];
-            tmem_ld32(tlane + TM_ACC1 + ch * 32, u);
+          // ACC1 is copied to registers and handed back at once: the sin/cos Jacobian below takes thousands of cycles and
+          // must not hold up the next step's second half
+          uint32_t u[32];
+          const bool mine = (g != 10) || (ch == 0);   // dL/d(view-dir encoding), 27 channels: the ch == 0 threads take all 32 columns
+          if (mine) {
+            tmem_ld32(tlane + TM_ACC1 + (g == 10 ? 0 : ch * 32), u);
             tmem_ld_wait();
-            enc_backward32(u, ch * 32, 63, x, dx);
           }
           tc_fence_before_sync();
           mbar_arrive(&a_ready[1]);
+          if (mine) {
+            if (g == 10) enc_backward32(u, 0, 27, vd, dv);
+            else enc_backward32(u, ch * 32, 63, x, dx);   // dL/d(xyz encoding), 63 channels: 32 per column half
+          }
         }
       }
       // ---- the two column halves of a row meet in shared memory; the ch == 0 thread writes d_pts[p]
