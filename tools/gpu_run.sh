@@ -24,5 +24,9 @@ ncu)
   timeout 1500 ncu --set full --clock-control none --import-source on -k regex:nerf_mlp -s 3 -c 1 -f -o gpurun_out/prof \
       python bench.py --steps 1 --warmup 1 --profile > gpurun_out/ncu.log 2>&1
   echo "ncu exit $?" >> gpurun_out/ncu.log; tail -3 gpurun_out/ncu.log ;;
+ncubwd)
+  timeout 1500 ncu --set full --clock-control none --import-source on -k regex:nerf_mlp_bwd -s 1 -c 1 -f -o gpurun_out/prof_bwd \
+      python tools/trace_bwd_plain.py > gpurun_out/ncu_bwd.log 2>&1
+  echo "ncubwd exit $?" >> gpurun_out/ncu_bwd.log; tail -3 gpurun_out/ncu_bwd.log ;;
 esac
 done
