@@ -450,16 +450,16 @@ def get_rays(H, W, K, c2w):
 
 
 def ndc_rays(H, W, focal, near, rays_o, rays_d):
-    """RH:178-195."""
-    t = -(near + rays_o[..., 2]) / rays_d[..., 2]
-    rays_o = rays_o + t[..., None] * rays_d
-    o0 = -1. / (W / (2. * focal)) * rays_o[..., 0] / rays_o[..., 2]
-    o1 = -1. / (H / (2. * focal)) * rays_o[..., 1] / rays_o[..., 2]
-    o2 = 1. + 2. * near / rays_o[..., 2]
-    d0 = -1. / (W / (2. * focal)) * (rays_d[..., 0] / rays_d[..., 2] - rays_o[..., 0] / rays_o[..., 2])
-    d1 = -1. / (H / (2. * focal)) * (rays_d[..., 1] / rays_d[..., 2] - rays_o[..., 1] / rays_o[..., 2])
-    d2 = -2. * near / rays_o[..., 2]
-    return torch.stack([o0, o1, o2], -1), torch.stack([d0, d1, d2], -1)
+    """RH:178-195: move the origins onto the near plane, then map origins / directions to normalised device
+    coordinates (forward-facing scenes).  Same operation order as the reference, so the floats agree."""
+    shift = -(near + rays_o[..., 2]) / rays_d[..., 2]
+    org = rays_o + shift[..., None] * rays_d
+    ox, oy, oz = org[..., 0], org[..., 1], org[..., 2]
+    dx, dy, dz = rays_d[..., 0], rays_d[..., 1], rays_d[..., 2]
+    sx, sy = -1. / (W / (2. * focal)), -1. / (H / (2. * focal))
+    o_ndc = torch.stack([sx * ox / oz, sy * oy / oz, 1. + 2. * near / oz], -1)
+    d_ndc = torch.stack([sx * (dx / dz - ox / oz), sy * (dy / dz - oy / oz), -2. * near / oz], -1)
+    return o_ndc, d_ndc
 
 
 def make_rays(H, W, K, c2w, near, far):

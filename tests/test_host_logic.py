@@ -68,3 +68,13 @@ def test_signatures_match_the_reference():
             if name == 'run_network' and p in ('embed_fn', 'embeddirs_fn'):
                 continue                     # optional here: the encoders are compiled into the kernel
             assert rd == md or (rd is inspect._empty and md is inspect._empty), (name, p)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason='reference tree only exists in the build container')
+def test_ndc_rays_matches_the_reference_bit_for_bit():
+    RN, RH = ref_import.load()
+    g = torch.Generator().manual_seed(0)
+    ro, rd = torch.randn(64, 3, generator=g), torch.randn(64, 3, generator=g)
+    a = nsr.ndc_rays(400, 300, 555.0, 1.0, ro, rd)
+    b = RH.ndc_rays(400, 300, 555.0, 1.0, ro, rd)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
