@@ -8,7 +8,8 @@ from ._lib import EXPORTED_SYMBOLS, LIB_PATH, NsrError, lib  # noqa: F401
 from .run_nerf import (NeRF, Embedder, batchify, batchify_rays, get_embedder, get_rays, img2mse, install,  # noqa: F401
                        make_rays, mse2psnr, ndc_rays, packed_weights, raw2outputs, render, render_path, render_path_grad, render_rays,
                        run_network, sample_pdf, set_precision, to8b)
+from .pose_sampler import pose_spherical, sample_pose, sample_pose_nograd  # noqa: F401
 
 __all__ = ['NeRF', 'Embedder', 'batchify', 'batchify_rays', 'get_embedder', 'get_rays', 'install', 'make_rays',
-           'ndc_rays', 'packed_weights', 'raw2outputs', 'render', 'render_path', 'render_path_grad', 'render_rays', 'run_network',
+           'ndc_rays', 'packed_weights', 'pose_spherical', 'sample_pose', 'sample_pose_nograd', 'raw2outputs', 'render', 'render_path', 'render_path_grad', 'render_rays', 'run_network',
            'sample_pdf', 'set_precision']

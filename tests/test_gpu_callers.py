@@ -199,3 +199,37 @@ def test_forward_is_cuda_graph_capturable(nsr, nets):
     launch(torch.cuda.current_stream())
     torch.cuda.synchronize()
     assert torch.equal(replayed, outs[0]) and not torch.equal(replayed, eager)
+
+
+def test_bilevel_psi_gradient_end_to_end(nsr, wfit, nets):
+    """MAIN:134-191 on the device: psi -> softmax -> sample_pose (all K poses in one op) -> render_path_grad -> mean
+    dL/dpsi, against the same chain evaluated on the CPU with the oracle renderer and autograd."""
+    H = W = 20
+    Kc = [[66.0, 0, 9.5], [0, 66.0, 10.5], [0, 0, 1]]
+    hwf = [H, W, 66.0]
+    n_k = 3
+    psi = torch.tensor([0.1, -0.2, 0.3, 0.0, 0.5, -0.1, 0.2, -0.3])
+    _, log = nsr.sample_pose_nograd(torch.softmax(psi / 0.25, 0), n_k, 0.5, seed=11)
+    gen = torch.Generator().manual_seed(6)
+    grad_E = [{'image_index': i, 'grad_E': torch.randn(1, 3, H, W, generator=gen) * 1e-3} for i in range(n_k)]
+    # --- oracle chain on the CPU
+    prob_c = torch.softmax(psi / 0.25, 0).requires_grad_()
+    poses_c = nsr.sample_pose(prob_c, n_k, 0.5, log)
+    ref = []
+    for i in range(n_k):
+        ro, rd = O.get_rays(H, W, Kc, poses_c[i, :3, :4])
+        out = O.render(H, W, Kc, wfit[0], wfit[1], chunk=512, rays=(ro.reshape(-1, 3), rd.reshape(-1, 3)),
+                       near=O.YCBV_NEAR, far=O.YCBV_FAR, N_samples=64, N_importance=128)
+        gi = grad_E[i]['grad_E'][0].permute(1, 2, 0).reshape(-1, 3)
+        ref.append(torch.autograd.grad(out[0], prob_c, grad_outputs=gi, retain_graph=True)[0])
+    ref_mean = torch.stack(ref).mean(0)
+    # --- device chain
+    prob_g = torch.softmax(psi.cuda() / 0.25, 0).requires_grad_()
+    poses_g = nsr.sample_pose(prob_g, n_k, 0.5, log)
+    assert poses_g.is_cuda and poses_g.shape == (n_k, 4, 4)
+    assert (poses_g.detach().cpu() - poses_c.detach()).abs().max().item() < 1e-5
+    _, dLdpsis = nsr.render_path_grad(prob_g, poses_g, hwf, Kc, H * W, grad_E, kwargs(nets))
+    got_mean = torch.stack(dLdpsis).mean(0)
+    scale = ref_mean.abs().max().item()
+    assert scale > 0
+    assert (got_mean - ref_mean).abs().max().item() <= 2e-3 * scale, (got_mean, ref_mean)
