@@ -141,6 +141,31 @@ __device__ __forceinline__ void umma_ts2(uint32_t d_tmem, uint32_t a_tmem, uint3
       "r"(a_tmem), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::f8f6f4 forms (8-bit operands, K = 32 per instruction).  The instruction descriptor has the same fields; formats
+// [7,10) / [10,13): 0 = e4m3, 1 = e5m2.  K-major no-swizzle core matrices are still 8 rows x 16 BYTES (16 elements of K).
+// TS form: A in TMEM packs four K-consecutive bytes per 32-bit column (8 columns per instruction).
+__host__ __device__ constexpr uint32_t make_idesc_f8(int M, int N, bool a_e5m2 = false, bool b_e5m2 = false) {
+  return (1u << 4) | ((a_e5m2 ? 1u : 0u) << 7) | ((b_e5m2 ? 1u : 0u) << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_ss2_f8(uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+      "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ts2_f8(uint32_t d_tmem, uint32_t a_tmem, uint32_t blo, uint32_t bhi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], db, %4, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // All previously issued MMAs of this thread arrive on `bar` when complete (implies fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -201,6 +226,17 @@ __device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
 __device__ __forceinline__ uint32_t pack_f16x2_relu(float a, float b) {
   uint32_t r;
   asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+// four fp32 -> packed e4m3 bytes (byte i = value i), round-to-nearest, saturating to +-448
+__device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float d) {
+  uint32_t r;
+  asm("{\n\t.reg .b16 lo, hi;\n\t"
+      "cvt.rn.satfinite.e4m3x2.f32 lo, %2, %1;\n\t"
+      "cvt.rn.satfinite.e4m3x2.f32 hi, %4, %3;\n\t"
+      "mov.b32 %0, {lo, hi};\n\t}"
+      : "=r"(r)
+      : "f"(a), "f"(b), "f"(c), "f"(d));
   return r;
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
