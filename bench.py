@@ -285,7 +285,7 @@ def run_ours(args):
     e2e_value = world * n * args.steps / (ms_e2e * 1e-3)
 
     # ------------------------------------------------------------- roofline of the dominant kernel (fine-pass MLP)
-    roofline = cpu_base = fast = fwd_bwd = None
+    roofline = cpu_base = fast = mixed = fwd_bwd = None
     if rank == 0:
         zf = new(n, T)
         rawf = new(n, T, 4)
@@ -336,6 +336,19 @@ def run_ours(args):
                 'rays_per_s_device_resident': n / (fast_ms * 1e-3), 'ms_per_step': fast_ms,
                 'fine_mlp_ms_per_launch': fk_ms, 'fine_mlp_tflops': flops / (fk_ms * 1e-3) / 1e12,
                 'fine_mlp_frac_of_peak': flops / (fk_ms * 1e-3) / 1e12 / peak}
+        # informational: the opt-in mixed mode (fp16 + e4m3 residual products; holds 1e-3 on the fitted scene, not on every network)
+        MIXED = 16
+        for _ in range(2):
+            step_device(0, MIXED)
+        torch.cuda.synchronize()
+        e0.record()
+        for s in range(args.steps):
+            step_device(s, MIXED)
+        e1.record()
+        torch.cuda.synchronize()
+        mixed_ms = e0.elapsed_time(e1) / args.steps
+        mixed = {'note': 'NSR_FLAG_MIXED_F8: 2.25 tensor passes per product (fp16 main term + two e4m3 residual products in layers 3-9); opt-in, informational only',
+                 'rays_per_s_device_resident': n / (mixed_ms * 1e-3), 'ms_per_step': mixed_ms}
         # secondary (BASELINE config 3): forward + backward dL/d(rays) for the pose path, same 160 000 rays
         bws_bytes = L.nsr_render_backward_workspace_bytes(n, T)
         bws = torch.empty(bws_bytes, dtype=torch.uint8, device=dev)
@@ -388,7 +401,7 @@ def run_ours(args):
                     'api': 'render(H, W, K, chunk, rays=<pinned host [2,N,3] -> cuda>, **render_kwargs_test) + D2H of rgb/disp/acc'},
             'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_base,
             'flop_per_ray': FLOP_PER_RAY, 'tflops_device_resident': value * FLOP_PER_RAY / 1e12,
-            'tensor_flop_issued_per_algorithmic_flop': 3, 'fast_fp16_mode': fast, 'fwd_bwd': fwd_bwd,
+            'tensor_flop_issued_per_algorithmic_flop': 3, 'fast_fp16_mode': fast, 'mixed_f8_mode': mixed, 'fwd_bwd': fwd_bwd,
         }))
 
 

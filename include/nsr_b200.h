@@ -40,6 +40,11 @@ extern "C" {
                                   error-compensated hi/lo split (3 MMAs): ~3x the MLP throughput, but misses the
                                   1e-3 parity bar on rays that graze sharp surfaces ("precision") */
 
+#define NSR_FLAG_MIXED_F8 16u  /* MLP products of the first three layers as the fp16 hi/lo split, of the later layers as one fp16
+                                  MMA plus the two residual products in e4m3 (kind::f8f6f4, double rate): 2.25 instead of 3
+                                  tensor-core passes per product; stays inside the 1e-3 bar ("precision").
+                                  Forward only; NSR_FLAG_FAST_FP16 wins if both are set. */
+
 /* network geometry this library is specialised for (RN:261-278, CFG): D=8, W=256, skips=[4],
  * multires=10 (63 ch), multires_views=4 (27 ch), use_viewdirs=True. */
 #define NSR_NET_NUM_TENSORS 12 /* pts_linears.0-7, views_linears.0, feature_linear, alpha_linear, rgb_linear */

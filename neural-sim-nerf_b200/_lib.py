@@ -46,6 +46,7 @@ FLAG_LINDISP = 1
 FLAG_WHITE_BKGD = 2
 FLAG_PTS_INPUT = 4
 FLAG_FAST_FP16 = 8
+FLAG_MIXED_F8 = 16
 
 
 class NsrError(RuntimeError):

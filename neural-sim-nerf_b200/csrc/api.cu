@@ -170,7 +170,7 @@ int nsr_render_rays_forward(const float* rays, int64_t n, const void* packed_coa
   ws += align_up(size_t(n) * T * 4, 256);
   float* raw1 = reinterpret_cast<float*>(ws);
   const uint32_t cflags = flags & NSR_FLAG_WHITE_BKGD;
-  const uint32_t mflags = flags & NSR_FLAG_FAST_FP16;
+  const uint32_t mflags = flags & (NSR_FLAG_FAST_FP16 | NSR_FLAG_MIXED_F8);
   int rc;
 
   if ((rc = launch_coarse_z(rays, n, S, flags, t_rand, z0, st))) return rc;                          // RN:439-461

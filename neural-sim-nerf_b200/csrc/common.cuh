@@ -41,19 +41,34 @@ constexpr int CHUNK_PAIR_BYTES = 2 * CHUNK_BYTES;              // [hi chunk | lo
 constexpr int NUM_BSTEPS = 12;
 constexpr int NUM_BWD_CHUNKS = 2 + 4 + 3 * 8 + 4 + 5 * 8 + 4;  // 78
 constexpr int BWD_CHUNK0 = NUM_CHUNKS;                         // index of the first backward chunk pair
-constexpr int WEIGHT_BYTES = (NUM_CHUNKS + NUM_BWD_CHUNKS) * CHUNK_PAIR_BYTES;  // 4,947,968
+// Mixed-precision forward chunks (NSR_FLAG_MIXED_F8) follow the backward ones: the 73 forward chunks again, every layer
+// scaled by its own power of two 2^b (max|W| 2^b in [2^14, 2^15); the epilogue multiplies the accumulator by 2^-b).
+//   steps < MIX_X3_STEPS and the chunks whose A operand is an encoding (step 5 kc 0, step 9 kc 4):
+//       [fp16(W 2^b) | fp16 residual]                           -- the error-compensated split, as above
+//   all other chunks:
+//       [fp16(W 2^b) = Wh, 16 KB | e4m3(Wh 2^-11), 8 KB | e4m3(W 2^b - Wh), 8 KB]
+//   the two 8-bit tiles are [128 x 64] K-major no-swizzle (core matrix = 8 rows x 16 bytes, 8-row groups 512 B apart): the
+//   B operands of the kind::f8f6f4 correction products  e4m3(x_lo 2^11) . e4m3(Wh 2^-11)  +  e4m3(x_hi) . e4m3(W_lo).
+constexpr int MIX_CHUNK0 = NUM_CHUNKS + NUM_BWD_CHUNKS;
+constexpr int MIX_X3_STEPS = 3;
+constexpr int MIX_XLO_SHIFT = 11;
+constexpr int F8_TILE_BYTES = CHUNK_ROWS * CHUNK_K;            // 8192
+constexpr int WEIGHT_BYTES = (2 * NUM_CHUNKS + NUM_BWD_CHUNKS) * CHUNK_PAIR_BYTES;  // 7,340,032
 
 // fp32 tail (offsets in floats)
 constexpr int TAIL_BIAS = 0;            // [10][256]  (step s bias at s*256; step 9 uses 128)
 constexpr int TAIL_WALPHA = 2560;       // [256]
 constexpr int TAIL_WRGB = 2816;         // [128][4]   (w_rgb[0][j], w_rgb[1][j], w_rgb[2][j], 0)
 constexpr int TAIL_MISC = 3328;         // b_alpha, b_rgb[0..2]
+constexpr int TAIL_MIXSCALE = 3336;     // [10] 2^-b of each step's mixed-precision chunks
 constexpr int TAIL_FLOATS = 3360;
 constexpr int TAIL_BYTES = TAIL_FLOATS * 4;  // 13440
 constexpr int PACKED_BYTES = WEIGHT_BYTES + TAIL_BYTES;
 
 __host__ __device__ constexpr int step_n_halves(int s) { return s == 9 ? 1 : 2; }
 __host__ __device__ constexpr int step_k_chunks(int s) { return s == 0 ? 1 : ((s == 5 || s == 9) ? 5 : 4); }
+// mixed mode: does chunk (step, kc) carry fp8 correction tiles (else the fp16 hi/lo split)?
+__host__ __device__ constexpr bool mix_chunk_is_f8(int s, int kc) { return s >= MIX_X3_STEPS && !(s == 5 && kc == 0) && !(s == 9 && kc == 4); }
 __host__ __device__ constexpr bool bstep_is_side(int b) { return b == 0 || b == 5 || b == 11; }
 __host__ __device__ constexpr int bstep_n_halves(int b) { return bstep_is_side(b) ? 1 : 2; }
 __host__ __device__ constexpr int bstep_k_chunks(int b) { return b <= 1 ? 2 : 4; }

@@ -19,6 +19,9 @@ constexpr int ENC_WARP0 = 8, MMA_WARP = 10, PROD_WARP = 11;
 // The kernel allocates all 512 TMEM columns of its SM (1 CTA / SM), so the allocation starts at column 0,
 // lane 0; the addresses below are absolute.  (Checked at run time: the kernel traps otherwise.)
 constexpr uint32_t TM_ACC0 = 0, TM_ACC1 = 128, TM_AHI = 256, TM_ALO = 384;
+// mixed precision: the ALO columns hold two 8-bit copies of the 256 activations instead (four K-consecutive bytes per column)
+constexpr uint32_t TM_A8L = 384;  // e4m3((x - fp16(x)) 2^11)
+constexpr uint32_t TM_A8H = 448;  // e4m3(x)
 
 // 16-byte store of 8 fp16 (4 packed words) into a no-swizzle K-major tile whose 8-row groups are `sbo` bytes apart
 __device__ __forceinline__ void st_a8(uint8_t* tile, int sbo, int row, int kgroup, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
@@ -84,5 +87,44 @@ __device__ __forceinline__ void epi32(const uint32_t (&u)[32], const float* bias
   }
 }
 
+// Mixed-precision variant: x = acc * scale + bias.  F8NEXT = false: fp16 hi words H[16] + fp16 residual words L[16]
+// (the next step runs the fp16 hi/lo split); true: H[16] + e4m3 residuals L8[8] + e4m3 copies H8[8] (four K-consecutive
+// values per word) for the next step's kind::f8f6f4 residual products.
+template <bool F8NEXT>
+__device__ __forceinline__ void epi32_mix(const uint32_t (&u)[32], const float* bias, float scale, bool relu, const float* walpha,
+                                          float& sigma, uint32_t* H, uint32_t* L, uint32_t* L8, uint32_t* H8) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 bb = *reinterpret_cast<const float4*>(bias + 4 * j);
+    float x0 = fmaf(__uint_as_float(u[4 * j]), scale, bb.x), x1 = fmaf(__uint_as_float(u[4 * j + 1]), scale, bb.y);
+    float x2 = fmaf(__uint_as_float(u[4 * j + 2]), scale, bb.z), x3 = fmaf(__uint_as_float(u[4 * j + 3]), scale, bb.w);
+    if (relu) {
+      x0 = fmaxf(x0, 0.f);
+      x1 = fmaxf(x1, 0.f);
+      x2 = fmaxf(x2, 0.f);
+      x3 = fmaxf(x3, 0.f);
+    }
+    if (walpha != nullptr) {  // alpha head on the fp32 post-ReLU activations (RH:109)
+      const float4 wa = *reinterpret_cast<const float4*>(walpha + 4 * j);
+      sigma = fmaf(x0, wa.x, sigma);
+      sigma = fmaf(x1, wa.y, sigma);
+      sigma = fmaf(x2, wa.z, sigma);
+      sigma = fmaf(x3, wa.w, sigma);
+    }
+    const uint32_t h01 = pack_f16x2(x0, x1), h23 = pack_f16x2(x2, x3);
+    H[2 * j] = h01;
+    H[2 * j + 1] = h23;
+    const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&h01));
+    const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&h23));
+    if (F8NEXT) {
+      constexpr float kS = float(1 << MIX_XLO_SHIFT);
+      L8[j] = pack_e4m3x4((x0 - f01.x) * kS, (x1 - f01.y) * kS, (x2 - f23.x) * kS, (x3 - f23.y) * kS);
+      H8[j] = pack_e4m3x4(x0, x1, x2, x3);
+    } else {
+      L[2 * j] = pack_f16x2(x0 - f01.x, x1 - f01.y);
+      L[2 * j + 1] = pack_f16x2(x2 - f23.x, x3 - f23.y);
+    }
+  }
+}
 
 }  // namespace nsr

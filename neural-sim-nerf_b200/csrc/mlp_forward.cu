@@ -27,6 +27,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <cuda_fp8.h>
+
 #include "mlp_common.cuh"
 
 namespace nsr {
@@ -66,6 +68,45 @@ __device__ __forceinline__ void bwd_chunk_decode(int c, int& bstep, int& nh, int
   kc = c % bstep_k_chunks(b);
 }
 
+// forward weight of GEMM step `step` (common.cuh): output row n, K chunk kc, column kl of the chunk (0 where padded)
+__device__ __forceinline__ float fwd_weight(const NetPtrs& p, int step, int n, int kc, int kl) {
+  if (step == 0) return kl < 63 ? p.w[0][n * 63 + kl] : 0.f;
+  if (step == 5) {  // cat[input_pts(63), h(256)]  RH:106
+    if (kc == 0) return kl < 63 ? p.w[5][n * 319 + kl] : 0.f;
+    return p.w[5][n * 319 + 63 + (kc - 1) * 64 + kl];
+  }
+  if (step <= 7) return p.w[step][n * 256 + kc * 64 + kl];
+  if (step == 8) return p.w[9][n * 256 + kc * 64 + kl];  // feature_linear
+  // views_linears.0 on cat[feature(256), dirs(27)]  RH:111
+  if (kc < 4) return p.w[8][n * 283 + kc * 64 + kl];
+  return kl < 27 ? p.w[8][n * 283 + 256 + kl] : 0.f;
+}
+
+// canonical no-swizzle K-major offset (bytes) of element (row, k) inside a [128 x 64] 8-bit tile
+__host__ __device__ __forceinline__ int f8_off(int row, int k) { return (row >> 3) * 512 + (k >> 4) * 128 + (row & 7) * 16 + (k & 15); }
+
+// Power-of-two exponent b of a step's weight matrix for the mixed-precision chunks: max|W| 2^b in [2^14, 2^15).
+// Every thread of the block returns the same value.  `red` = 8 floats of shared memory.
+__device__ int layer_shift(const NetPtrs& p, int step, float* red) {
+  const int tensor = step <= 7 ? step : (step == 8 ? 9 : 8);
+  const int count = step == 0 ? 256 * 63 : (step == 5 ? 256 * 319 : (step == 9 ? 128 * 283 : 65536));
+  const float* w = p.w[tensor];
+  float m = 0.f;
+  for (int i = threadIdx.x; i < count; i += blockDim.x) m = fmaxf(m, fabsf(w[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = 0.f;
+  for (int i = 0; i < int(blockDim.x >> 5); ++i) m = fmaxf(m, red[i]);
+  if (!(m > 0.f) || !isfinite(m)) return 0;
+  int e;
+  frexpf(m, &e);  // m = f 2^e, f in [0.5, 1)
+  const int b = 15 - e;
+  return b < -60 ? -60 : (b > 60 ? 60 : b);
+}
+
 __global__ void pack_net_kernel(NetPtrs p, uint8_t* __restrict__ out) {
   const int c = blockIdx.x;
   if (c >= NUM_CHUNKS && c < NUM_CHUNKS + NUM_BWD_CHUNKS) {
@@ -103,27 +144,34 @@ __global__ void pack_net_kernel(NetPtrs p, uint8_t* __restrict__ out) {
     __half* lo = reinterpret_cast<__half*>(out + size_t(c) * CHUNK_PAIR_BYTES + CHUNK_BYTES);
     for (int e = threadIdx.x; e < CHUNK_ROWS * CHUNK_K; e += blockDim.x) {
       const int nl = e / CHUNK_K, kl = e % CHUNK_K;
-      const int n = nh * 128 + nl;
-      float v = 0.f;
-      if (step == 0) {
-        if (kl < 63) v = p.w[0][n * 63 + kl];
-      } else if (step == 5) {  // cat[input_pts(63), h(256)]  RH:106
-        if (kc == 0) {
-          if (kl < 63) v = p.w[5][n * 319 + kl];
-        } else {
-          v = p.w[5][n * 319 + 63 + (kc - 1) * 64 + kl];
-        }
-      } else if (step <= 7) {
-        v = p.w[step][n * 256 + kc * 64 + kl];
-      } else if (step == 8) {  // feature_linear
-        v = p.w[9][n * 256 + kc * 64 + kl];
-      } else {  // views_linears.0 on cat[feature(256), dirs(27)]  RH:111
-        if (kc < 4) v = p.w[8][n * 283 + kc * 64 + kl];
-        else if (kl < 27) v = p.w[8][n * 283 + 256 + kl];
-      }
+      const float v = fwd_weight(p, step, nh * 128 + nl, kc, kl);
       const __half h = __float2half_rn(v);
       hi[chunk_off(nl, kl) >> 1] = h;
       lo[chunk_off(nl, kl) >> 1] = __float2half_rn(v - __half2float(h));
+    }
+  } else if (c >= MIX_CHUNK0 && c < MIX_CHUNK0 + NUM_CHUNKS) {
+    // mixed-precision forward chunks: layer scaled by 2^b, fp8 correction tiles for the late layers (common.cuh)
+    int step, nh, kc;
+    chunk_decode(c - MIX_CHUNK0, step, nh, kc);
+    __shared__ float s_red[8];
+    const float scale = exp2f(float(layer_shift(p, step, s_red)));
+    uint8_t* base = out + size_t(c) * CHUNK_PAIR_BYTES;
+    __half* hi = reinterpret_cast<__half*>(base);
+    __half* lo = reinterpret_cast<__half*>(base + CHUNK_BYTES);
+    uint8_t* h8 = base + CHUNK_BYTES;
+    uint8_t* l8 = base + CHUNK_BYTES + F8_TILE_BYTES;
+    const bool f8 = mix_chunk_is_f8(step, kc);
+    for (int e = threadIdx.x; e < CHUNK_ROWS * CHUNK_K; e += blockDim.x) {
+      const int nl = e / CHUNK_K, kl = e % CHUNK_K;
+      const float v = fwd_weight(p, step, nh * 128 + nl, kc, kl) * scale;
+      const __half h = __float2half_rn(v);
+      hi[chunk_off(nl, kl) >> 1] = h;
+      if (f8) {
+        h8[f8_off(nl, kl)] = __nv_cvt_float_to_fp8(__half2float(h) * (1.f / float(1 << MIX_XLO_SHIFT)), __NV_SATFINITE, __NV_E4M3);
+        l8[f8_off(nl, kl)] = __nv_cvt_float_to_fp8(v - __half2float(h), __NV_SATFINITE, __NV_E4M3);
+      } else {
+        lo[chunk_off(nl, kl) >> 1] = __float2half_rn(v - __half2float(h));
+      }
     }
   } else {  // fp32 tail
     float* t = reinterpret_cast<float*>(out + WEIGHT_BYTES);
@@ -146,6 +194,11 @@ __global__ void pack_net_kernel(NetPtrs p, uint8_t* __restrict__ out) {
       }
       t[i] = v;
     }
+    __shared__ float s_red[8];
+    for (int step = 0; step < NUM_STEPS; ++step) {
+      const int b = layer_shift(p, step, s_red);
+      if (threadIdx.x == 0) t[TAIL_MIXSCALE + step] = exp2f(float(-b));
+    }
   }
 }
 
@@ -155,14 +208,15 @@ int launch_pack_net(const float* const* weights, const float* const* biases, voi
     p.w[i] = weights[i];
     p.b[i] = biases[i];
   }
-  pack_net_kernel<<<NUM_CHUNKS + NUM_BWD_CHUNKS + 1, 256, 0, st>>>(p, static_cast<uint8_t*>(packed));
+  pack_net_kernel<<<2 * NUM_CHUNKS + NUM_BWD_CHUNKS + 1, 256, 0, st>>>(p, static_cast<uint8_t*>(packed));
   count_launch();
   return check_launch("pack_net_kernel");
 }
 
 template <int SPLIT>
 struct Cfg {
-  static constexpr bool kSplit = SPLIT == 3;
+  static constexpr bool kSplit = SPLIT >= 2;   // operands carried as fp16 hi + a residual (3: fp16 everywhere, 2: mixed)
+  static constexpr bool kMixed = SPLIT == 2;   // residual products of the late layers in e4m3 (common.cuh, MIX_*)
   static constexpr int STAGE_BYTES = kSplit ? CHUNK_PAIR_BYTES : CHUNK_BYTES;
   static constexpr int ENC_BYTES = 128 * 64 * 2;   // [128 x 64] fp16, 8-row groups 1024 B apart
   static constexpr int DIR_BYTES = 128 * 32 * 2;   // [128 x 32] fp16, 8-row groups 512 B apart
@@ -208,6 +262,7 @@ template <int SPLIT>
 __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
   using C = Cfg<SPLIT>;
   constexpr bool kSplit = C::kSplit;
+  constexpr bool kMixed = C::kMixed;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sRing = smem + C::SM_RING;
   const float* sTail = reinterpret_cast<const float*>(smem + C::SM_TAIL);
@@ -252,7 +307,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
         for (int c = 0; c < NUM_CHUNKS; ++c) {
           if (!first_lap) mbar_wait(&empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
-          bulk_g2s(sRing + stage * C::STAGE_BYTES, a.packed + size_t(c) * CHUNK_PAIR_BYTES, C::STAGE_BYTES, &full[stage]);
+          bulk_g2s(sRing + stage * C::STAGE_BYTES, a.packed + size_t(c + (kMixed ? MIX_CHUNK0 : 0)) * CHUNK_PAIR_BYTES, C::STAGE_BYTES,
+                   &full[stage]);
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -266,8 +322,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
     // The whole warp runs the (uniform) control flow and waits; one elected lane issues the tcgen05
     // instructions, so descriptors and addresses live in uniform registers.
     const bool leader = elect_one();
-    const uint32_t idesc = make_idesc_f16(128, 128);
-    constexpr uint32_t HI_B = sdesc_hi(1024), HI_DIR = sdesc_hi(512);  // 8-row groups 1024 B apart (512 B for the K=32 tile)
+    const uint32_t idesc = make_idesc_f16(128, 128), idesc8 = make_idesc_f8(128, 128);
+    constexpr uint32_t HI_B = sdesc_hi(1024), HI_DIR = sdesc_hi(512), HI_8 = sdesc_hi(512);  // 8-row groups 1024 B apart (512 B for the K=32 tile)
     const uint32_t ring_lo = sdesc_lo(smem_u32(sRing), 128);
     const uint32_t inbuf = smem_u32(smem + C::SM_INBUF);
     const uint32_t enc_hi = sdesc_lo(inbuf + C::OFF_ENC_HI, 128), enc_lo = sdesc_lo(inbuf + C::OFF_ENC_LO, 128);
@@ -282,7 +338,13 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
         const int nk = step_k_chunks(step);
         const int nhs = step_n_halves(step);
         bool waited1 = false;
+        long long w_cycles = 0, w_count = 0;
         if (lane == 0) NSR_TR(tl, step, 0);
+        if (lane == 0 && a.trace != nullptr && blockIdx.x == 0 && tl < 4) {
+          unsigned long long gt;
+          asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+          a.trace[(tl * 10 + step) * 16 + 7] = gt;
+        }
         w_a[0].wait(&a_ready[0]);  // A[K 0..127] of this step written, ACC0 drained
         if (lane == 0) NSR_TR(tl, step, 1);
         if (step == 9) {           // the single 128-wide half of step 9 accumulates in ACC1
@@ -305,12 +367,32 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
               tc_fence_after_sync();
               waited1 = true;
             }
-            if (!ready) mbar_wait(&full[stage], phase);
+            if (!ready) {
+              if (a.trace != nullptr) {  // debug: cycles this step spent waiting for weights
+                const long long t0 = clock64();
+                mbar_wait(&full[stage], phase);
+                w_cycles += clock64() - t0;
+                ++w_count;
+              } else {
+                mbar_wait(&full[stage], phase);
+              }
+            }
             // descriptors: only the start-address field moves (16-byte units): +16 per k-step of 16 elements
             const uint32_t bh = ring_lo + stage * (C::STAGE_BYTES >> 4), bl = bh + (CHUNK_BYTES >> 4);
             const uint32_t acc0 = kc != 0;  // first MMA of a half overwrites the accumulator
             if (leader) {
-              if (src == 1) {
+              if (kMixed && src == 1 && step >= MIX_X3_STEPS) {
+                // fp16 main term + the two residual products as e4m3 MMAs (K = 32 each) into the same accumulator
+                const uint32_t ah = TM_AHI + ak * 32, a8l = TM_A8L + ak * 16, a8h = TM_A8H + ak * 16;
+                const uint32_t b8h = bl, b8l = bl + (F8_TILE_BYTES >> 4);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) umma_ts2(acc, ah + j * 8, bh + j * 16, HI_B, idesc, j ? 1u : acc0);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                  umma_ts2_f8(acc, a8l + j * 8, b8h + j * 16, HI_8, idesc8, 1u);
+                  umma_ts2_f8(acc, a8h + j * 8, b8l + j * 16, HI_8, idesc8, 1u);
+                }
+              } else if (src == 1) {
                 const uint32_t ah = TM_AHI + ak * 32, al = TM_ALO + ak * 32;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -352,6 +434,10 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
         }
         if (!waited1) w_a[1].wait(&a_ready[1]);  // keep the parity in step (cannot happen with this network)
         if (lane == 0) NSR_TR(tl, step, 4);
+        if (lane == 0 && a.trace != nullptr && blockIdx.x == 0 && tl < 4) {
+          a.trace[(tl * 10 + step) * 16 + 5] = w_cycles;
+          a.trace[(tl * 10 + step) * 16 + 6] = w_count;
+        }
         if (step == 5 && leader) umma_commit(&enc_free[0]);  // last reader of the xyz encoding
       }
       if (leader) umma_commit(&enc_free[1]);
@@ -467,7 +553,41 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
         const float* bias = sTail + TAIL_BIAS + step * 256 + col0;
         const float* walpha = (step == 7) ? sTail + TAIL_WALPHA + col0 : nullptr;
         const bool relu = step != 8;  // feature_linear has no activation (RH:110)
+        const float sc = kMixed ? sTail[TAIL_MIXSCALE + step] : 1.f;
+        const bool f8next = kMixed && step + 1 >= MIX_X3_STEPS;  // operand format the NEXT step consumes
+        // H: fp16 hi words.  L: fp16 residual words, or (f8next) [16 words e4m3 residuals | 16 words e4m3 copies]
         uint32_t H[32], L[kSplit ? 32 : 1];
+        // bias (+ReLU, + alpha head) and operand split of this thread's 64 columns of accumulator half `half`
+        auto convert = [&](const uint32_t(&u0)[32], const uint32_t(&u1)[32], int half) {
+          const float* bh = bias + 128 * half;
+          const float* wa = walpha ? walpha + 128 * half : nullptr;
+          if constexpr (kMixed) {
+            if (f8next) {
+              epi32_mix<true>(u0, bh, sc, relu, wa, sigma, H, nullptr, L, L + 16);
+              epi32_mix<true>(u1, bh + 32, sc, relu, wa ? wa + 32 : nullptr, sigma, H + 16, nullptr, L + 8, L + 24);
+            } else {
+              epi32_mix<false>(u0, bh, sc, relu, wa, sigma, H, L, nullptr, nullptr);
+              epi32_mix<false>(u1, bh + 32, sc, relu, wa ? wa + 32 : nullptr, sigma, H + 16, L + 16, nullptr, nullptr);
+            }
+          } else {
+            epi32<kSplit>(u0, bh, relu, wa, sigma, H, L);
+            epi32<kSplit>(u1, bh + 32, relu, wa ? wa + 32 : nullptr, sigma, H + 16, L + (kSplit ? 16 : 0));
+          }
+        };
+        // accumulator column c is K index c of the next step: fp16 pairs -> packed column c / 2, e4m3 quads -> c / 4
+        auto store = [&](int half) {
+          tmem_st16(tlane + TM_AHI + 64 * half + col0 / 2, *reinterpret_cast<const uint32_t(*)[16]>(&H[0]));
+          tmem_st16(tlane + TM_AHI + 64 * half + col0 / 2 + 16, *reinterpret_cast<const uint32_t(*)[16]>(&H[16]));
+          if (kMixed && f8next) {
+            tmem_st16(tlane + TM_A8L + 32 * half + col0 / 4, *reinterpret_cast<const uint32_t(*)[16]>(&L[0]));
+            tmem_st16(tlane + TM_A8H + 32 * half + col0 / 4, *reinterpret_cast<const uint32_t(*)[16]>(&L[kSplit ? 16 : 0]));
+          } else if (kSplit) {
+            tmem_st16(tlane + TM_ALO + 64 * half + col0 / 2, *reinterpret_cast<const uint32_t(*)[16]>(&L[0]));
+            tmem_st16(tlane + TM_ALO + 64 * half + col0 / 2 + 16, *reinterpret_cast<const uint32_t(*)[16]>(&L[kSplit ? 16 : 0]));
+          }
+          tmem_st_wait();
+          tc_fence_before_sync();
+        };
         // ---- first half: drain ACC0 into registers while the second half is still in the tensor pipe
         w_acc[0].wait(&acc_ready[0]);
         if (tid == 0) NSR_TR(tl, step, 8);
@@ -477,42 +597,25 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
           tmem_ld32(tlane + TM_ACC0 + col0, u0);
           tmem_ld32(tlane + TM_ACC0 + col0 + 32, u1);
           tmem_ld_wait();
-          epi32<kSplit>(u0, bias, relu, walpha, sigma, H, L);
-          epi32<kSplit>(u1, bias + 32, relu, walpha ? walpha + 32 : nullptr, sigma, H + 16, L + (kSplit ? 16 : 0));
+          convert(u0, u1, 0);
         }
         // ---- every MMA of this step has retired: the old activations may be overwritten
         if (tid == 0) NSR_TR(tl, step, 9);
         w_acc[1].wait(&acc_ready[1]);
         if (tid == 0) NSR_TR(tl, step, 10);
         tc_fence_after_sync();
-        // accumulator column c is K index c of the next step: fp16 pairs -> packed column c / 2
-        tmem_st16(tlane + TM_AHI + col0 / 2, *reinterpret_cast<const uint32_t(*)[16]>(&H[0]));
-        tmem_st16(tlane + TM_AHI + col0 / 2 + 16, *reinterpret_cast<const uint32_t(*)[16]>(&H[16]));
-        if (kSplit) {
-          tmem_st16(tlane + TM_ALO + col0 / 2, *reinterpret_cast<const uint32_t(*)[16]>(&L[0]));
-          tmem_st16(tlane + TM_ALO + col0 / 2 + 16, *reinterpret_cast<const uint32_t(*)[16]>(&L[kSplit ? 16 : 0]));
-        }
-        tmem_st_wait();
-        tc_fence_before_sync();
+        store(0);
         mbar_arrive(&a_ready[0]);
         if (tid == 0) NSR_TR(tl, step, 11);
-        // ---- second half: drain ACC1 straight into AHI/ALO[K 128..255]
+        // ---- second half: drain ACC1 straight into the operands for K 128..255
         {
           uint32_t u0[32], u1[32];
           tmem_ld32(tlane + TM_ACC1 + col0, u0);
           tmem_ld32(tlane + TM_ACC1 + col0 + 32, u1);
           tmem_ld_wait();
-          epi32<kSplit>(u0, bias + 128, relu, walpha ? walpha + 128 : nullptr, sigma, H, L);
-          epi32<kSplit>(u1, bias + 160, relu, walpha ? walpha + 160 : nullptr, sigma, H + 16, L + (kSplit ? 16 : 0));
+          convert(u0, u1, 1);
         }
-        tmem_st16(tlane + TM_AHI + 64 + col0 / 2, *reinterpret_cast<const uint32_t(*)[16]>(&H[0]));
-        tmem_st16(tlane + TM_AHI + 64 + col0 / 2 + 16, *reinterpret_cast<const uint32_t(*)[16]>(&H[16]));
-        if (kSplit) {
-          tmem_st16(tlane + TM_ALO + 64 + col0 / 2, *reinterpret_cast<const uint32_t(*)[16]>(&L[0]));
-          tmem_st16(tlane + TM_ALO + 64 + col0 / 2 + 16, *reinterpret_cast<const uint32_t(*)[16]>(&L[kSplit ? 16 : 0]));
-        }
-        tmem_st_wait();
-        tc_fence_before_sync();
+        store(1);
         mbar_arrive(&a_ready[1]);
         if (tid == 0) NSR_TR(tl, step, 12);
       }
@@ -526,6 +629,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
       {
         const float* bias = sTail + TAIL_BIAS + 9 * 256 + col0;
         const float4* wr = reinterpret_cast<const float4*>(sTail + TAIL_WRGB) + col0;
+        const float sc9 = kMixed ? sTail[TAIL_MIXSCALE + 9] : 1.f;
         uint32_t u0[32], u1[32];
         tmem_ld32(tlane + TM_ACC1 + col0, u0);
         tmem_ld32(tlane + TM_ACC1 + col0 + 32, u1);
@@ -539,8 +643,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
           const float bb0[4] = {b0.x, b0.y, b0.z, b0.w}, bb1[4] = {b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float h0 = fmaxf(__uint_as_float(u0[4 * j + q]) + bb0[q], 0.f);
-            const float h1 = fmaxf(__uint_as_float(u1[4 * j + q]) + bb1[q], 0.f);
+            const float h0 = fmaxf(kMixed ? fmaf(__uint_as_float(u0[4 * j + q]), sc9, bb0[q]) : __uint_as_float(u0[4 * j + q]) + bb0[q], 0.f);
+            const float h1 = fmaxf(kMixed ? fmaf(__uint_as_float(u1[4 * j + q]), sc9, bb1[q]) : __uint_as_float(u1[4 * j + q]) + bb1[q], 0.f);
             const float4 w0 = wr[4 * j + q], w1 = wr[32 + 4 * j + q];
             r0 = fmaf(h0, w0.x, r0);
             r1 = fmaf(h0, w0.y, r1);
@@ -575,6 +679,12 @@ static int launch_variant(const MlpArgs& a, int grid, cudaStream_t st) {
   return check_launch("nerf_mlp_kernel");
 }
 
+static int launch_by_flags(const MlpArgs& a, int grid, uint32_t flags, cudaStream_t st) {
+  if (flags & NSR_FLAG_FAST_FP16) return launch_variant<1>(a, grid, st);
+  if (flags & NSR_FLAG_MIXED_F8) return launch_variant<2>(a, grid, st);
+  return launch_variant<3>(a, grid, st);
+}
+
 int launch_mlp_forward(const float* rays, const float* z_or_pts, int64_t n, int S, const void* packed, uint32_t flags,
                        float* raw, cudaStream_t st) {
   const int64_t n_points = n * S;
@@ -601,13 +711,13 @@ int launch_mlp_forward(const float* rays, const float* z_or_pts, int64_t n, int 
     const size_t nb = 4 * 10 * 16 * sizeof(unsigned long long);
     cudaMalloc(&a.trace, nb);
     cudaMemset(a.trace, 0, nb);
-    const int rc = (flags & NSR_FLAG_FAST_FP16) ? launch_variant<1>(a, grid, st) : launch_variant<3>(a, grid, st);
+    const int rc = launch_by_flags(a, grid, flags, st);
     cudaStreamSynchronize(st);
     unsigned long long host[4 * 10 * 16];
     cudaMemcpy(host, a.trace, nb, cudaMemcpyDeviceToHost);
     cudaFree(a.trace);
     if (FILE* f = fopen(trace_file, "a")) {
-      fprintf(f, "# launch split=%d tiles=%d\n", (flags & NSR_FLAG_FAST_FP16) ? 1 : 3, a.num_tiles);
+      fprintf(f, "# launch split=%d tiles=%d\n", (flags & NSR_FLAG_FAST_FP16) ? 1 : ((flags & NSR_FLAG_MIXED_F8) ? 2 : 3), a.num_tiles);
       for (int i = 0; i < 40; ++i) {
         fprintf(f, "%d %d", i / 10, i % 10);
         for (int k = 0; k < 16; ++k) fprintf(f, " %llu", host[i * 16 + k]);
@@ -617,7 +727,7 @@ int launch_mlp_forward(const float* rays, const float* z_or_pts, int64_t n, int 
     }
     return rc;
   }
-  return (flags & NSR_FLAG_FAST_FP16) ? launch_variant<1>(a, grid, st) : launch_variant<3>(a, grid, st);
+  return launch_by_flags(a, grid, flags, st);
 }
 
 }  // namespace nsr

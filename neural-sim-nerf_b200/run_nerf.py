@@ -22,7 +22,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib
-from ._lib import FLAG_FAST_FP16, FLAG_LINDISP, FLAG_PTS_INPUT, FLAG_WHITE_BKGD, check, lib, ptr
+from ._lib import FLAG_FAST_FP16, FLAG_LINDISP, FLAG_MIXED_F8, FLAG_PTS_INPUT, FLAG_WHITE_BKGD, check, lib, ptr
 
 device = torch.device('cuda' if torch.cuda.is_available() else 'cpu')
 
@@ -31,20 +31,27 @@ device = torch.device('cuda' if torch.cuda.is_available() else 'cpu')
 # (CFG:25) would leave most of a B200 idle.
 MIN_RAYS_PER_LAUNCH = int(os.environ.get('NSR_MIN_CHUNK', 1 << 16))
 
-# MLP arithmetic: 'fp16x3' (default) = error-compensated hi/lo split, meets the 1e-3 parity bar;
-# 'fp16' = single fp16 MMA per product (NSR_FLAG_FAST_FP16), ~3x faster MLP, misses the bar on silhouette rays.
+# MLP arithmetic of the forward pass (DESIGN.md "precision"):
+#   'fp16x3'  error-compensated fp16 hi/lo split everywhere (3 MMAs per product): ~1e-5 from the fp32 reference;
+#   'mixed'   the split for the first three layers, fp16 + e4m3 residual products (NSR_FLAG_MIXED_F8) for the rest:
+#             2.25 tensor passes per product, ~2e-4 from the reference -- inside the 1e-3 bar;
+#   'fp16'    single fp16 MMA per product (NSR_FLAG_FAST_FP16): misses the bar on silhouette rays, opt-in only.
+# Passes that carry gradient always run 'fp16x3' (the backward kernel recomputes activations in that arithmetic).
 PRECISION = os.environ.get('NSR_PRECISION', 'fp16x3')
+_PREC_FLAGS = {'fp16x3': 0, 'mixed': FLAG_MIXED_F8, 'fp16': FLAG_FAST_FP16}
 
 
 def set_precision(mode):
     global PRECISION
-    if mode not in ('fp16x3', 'fp16'):
-        raise ValueError("precision must be 'fp16x3' or 'fp16'")
+    if mode not in _PREC_FLAGS:
+        raise ValueError(f"precision must be one of {sorted(_PREC_FLAGS)}")
     PRECISION = mode
 
 
 def _prec_flag():
-    return FLAG_FAST_FP16 if PRECISION == 'fp16' else 0
+    if PRECISION not in _PREC_FLAGS:
+        raise ValueError(f"NSR_PRECISION={PRECISION!r}: must be one of {sorted(_PREC_FLAGS)}")
+    return _PREC_FLAGS[PRECISION]
 
 
 img2mse = lambda x, y: torch.mean((x - y) ** 2)                                  # RH:12
@@ -277,7 +284,8 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
     cfg = dict(pc=pc, pf=pf, S=S, Ni=Ni, flags=flags, t_rand=t_rand, u=u, retraw=retraw)
     if needs_grad:
         if flags & FLAG_FAST_FP16:
-            raise NotImplementedError("backward is built for the default precision only (NSR_PRECISION='fp16x3')")
+            raise NotImplementedError("backward is not built for NSR_PRECISION='fp16'")
+        cfg['flags'] = flags & ~FLAG_MIXED_F8      # gradient-carrying passes: same arithmetic as the backward kernel's recompute
         outs = _RenderRaysFn.apply(ray_batch, cfg, *params)
     else:
         outs = _forward_impl(rays, cfg, keep_for_backward=False)[0]
@@ -418,7 +426,7 @@ def _render_rays_staged(rays, pc, pf, S, Ni, flags, t_rand, u, retraw, raw_noise
     T = S + Ni
     z1, raw1 = new(n, T), new(n, T, 4)
     check(L.nsr_resample_merge(ptr(z0), ptr(w0), n, S, Ni, ptr(u), ptr(z1), None, ptr(ret['z_std']), st), 'nsr_resample_merge')
-    check(L.nsr_mlp_forward(ptr(rays), ptr(z1), n, T, ptr(pf if pf is not None else pc), flags & FLAG_FAST_FP16, ptr(raw1), st), 'nsr_mlp_forward')
+    check(L.nsr_mlp_forward(ptr(rays), ptr(z1), n, T, ptr(pf if pf is not None else pc), flags & (FLAG_FAST_FP16 | FLAG_MIXED_F8), ptr(raw1), st), 'nsr_mlp_forward')
     raw1[..., 3] += torch.randn(n, T, device=dev) * raw_noise_std
     check(L.nsr_raw2outputs(ptr(raw1), ptr(z1), ptr(rays[:, 3:6].contiguous()), 3, n, T, cflag, ptr(ret['rgb_map']),
                             ptr(ret['disp_map']), ptr(ret['acc_map']), None, None, st), 'nsr_raw2outputs')

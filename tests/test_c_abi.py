@@ -39,8 +39,8 @@ def test_python_binding_covers_header(built_lib):
     assert sorted(nsr.EXPORTED_SYMBOLS) == declared_symbols()
     L = nsr.lib()
     assert L.nsr_version() >= 100
-    # 73 forward + 78 backward (transposed) operand chunk pairs (fp16 hi + lo, 16 KiB each) + fp32 tail
-    assert L.nsr_packed_net_bytes() == (73 + 78) * 32768 + 3360 * 4
+    # 73 forward + 78 backward (transposed) + 73 mixed-precision forward operand chunk pairs (32 KiB each) + fp32 tail
+    assert L.nsr_packed_net_bytes() == (73 + 78 + 73) * 32768 + 3360 * 4
     assert L.nsr_render_backward_workspace_bytes(512, 192) >= 512 * 192 * (16 + 32)
     assert L.nsr_render_workspace_bytes(0, 64, 128) == 0
     assert L.nsr_render_workspace_bytes(512, 64, 128) >= 512 * (64 * 4 * 2 + 64 * 16 + 192 * 4 + 192 * 16)
@@ -64,5 +64,5 @@ def test_sass_is_blackwell_native(built_lib):
     if not os.path.exists(cuobjdump):
         pytest.skip('cuobjdump not available')
     sass = subprocess.run([cuobjdump, '-sass', built_lib], capture_output=True, text=True).stdout
-    for mnemonic in ('UTCHMMA', 'LDTM', 'UBLKCP'):
+    for mnemonic in ('UTCHMMA', 'UTCQMMA', 'LDTM', 'UBLKCP'):
         assert mnemonic in sass, mnemonic
