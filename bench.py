@@ -285,7 +285,7 @@ def run_ours(args):
     e2e_value = world * n * args.steps / (ms_e2e * 1e-3)
 
     # ------------------------------------------------------------- roofline of the dominant kernel (fine-pass MLP)
-    roofline = cpu_base = fast = mixed = fwd_bwd = None
+    roofline = cpu_base = fast = mixed = fwd_bwd = stages = train = None
     if rank == 0:
         zf = new(n, T)
         rawf = new(n, T, 4)
@@ -313,76 +313,151 @@ def run_ours(args):
                     'unit': 'TFLOP/s', 'frac': achieved / peak,
                     'traffic': 584814080, 'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this launch (profiles/r01_v3_ncu_fine_mlp_summary.csv); algorithmic 624 MB', 'peak_source': f'{how} bf16_tflops_sustained (kernel timed back to back)',
                     'ms_per_launch': k_ms, 'algorithmic_flop_per_launch': flops}
-        # informational: the opt-in single-pass fp16 mode (NOT parity-valid, see DESIGN.md "precision")
-        FAST = 8
-        for _ in range(2):
-            step_device(0, FAST)
-        torch.cuda.synchronize()
-        e0.record()
-        for s in range(args.steps):
-            step_device(s, FAST)
-        e1.record()
-        torch.cuda.synchronize()
-        fast_ms = e0.elapsed_time(e1) / args.steps
-        L.nsr_mlp_forward(P(rays_dev[0]), P(zf), n, T, P(pf), FAST, P(rawf), stream)
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(reps):
+        if world == 1:          # side legs only at N=1 (the scaling runs stay short; cpu_baseline is an N=1 figure)
+            # informational: the opt-in single-pass fp16 mode (NOT parity-valid, see DESIGN.md "precision")
+            FAST = 8
+            for _ in range(2):
+                step_device(0, FAST)
+            torch.cuda.synchronize()
+            e0.record()
+            for s in range(args.steps):
+                step_device(s, FAST)
+            e1.record()
+            torch.cuda.synchronize()
+            fast_ms = e0.elapsed_time(e1) / args.steps
             L.nsr_mlp_forward(P(rays_dev[0]), P(zf), n, T, P(pf), FAST, P(rawf), stream)
-        e1.record()
-        torch.cuda.synchronize()
-        fk_ms = e0.elapsed_time(e1) / reps
-        fast = {'note': 'NSR_FLAG_FAST_FP16: one fp16 MMA per product; misses the 1e-3 parity bar on silhouette rays -- informational only',
-                'rays_per_s_device_resident': n / (fast_ms * 1e-3), 'ms_per_step': fast_ms,
-                'fine_mlp_ms_per_launch': fk_ms, 'fine_mlp_tflops': flops / (fk_ms * 1e-3) / 1e12,
-                'fine_mlp_frac_of_peak': flops / (fk_ms * 1e-3) / 1e12 / peak}
-        # informational: the opt-in mixed mode (fp16 + e4m3 residual products; holds 1e-3 on the fitted scene, not on every network)
-        MIXED = 16
-        for _ in range(2):
-            step_device(0, MIXED)
-        torch.cuda.synchronize()
-        e0.record()
-        for s in range(args.steps):
-            step_device(s, MIXED)
-        e1.record()
-        torch.cuda.synchronize()
-        mixed_ms = e0.elapsed_time(e1) / args.steps
-        mixed = {'note': 'NSR_FLAG_MIXED_F8: 2.25 tensor passes per product (fp16 main term + two e4m3 residual products in layers 3-9); opt-in, informational only',
-                 'rays_per_s_device_resident': n / (mixed_ms * 1e-3), 'ms_per_step': mixed_ms}
-        # secondary (BASELINE config 3): forward + backward dL/d(rays) for the pose path, same 160 000 rays
-        bws_bytes = L.nsr_render_backward_workspace_bytes(n, T)
-        bws = torch.empty(bws_bytes, dtype=torch.uint8, device=dev)
-        g_rgb = torch.randn(n, 3, device=dev)
-        d_rays = new(n, 11)
-        zsave, rawsave = new(n, T), new(n, T, 4)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                L.nsr_mlp_forward(P(rays_dev[0]), P(zf), n, T, P(pf), FAST, P(rawf), stream)
+            e1.record()
+            torch.cuda.synchronize()
+            fk_ms = e0.elapsed_time(e1) / reps
+            fast = {'note': 'NSR_FLAG_FAST_FP16: one fp16 MMA per product; misses the 1e-3 parity bar on silhouette rays -- informational only',
+                    'rays_per_s_device_resident': n / (fast_ms * 1e-3), 'ms_per_step': fast_ms,
+                    'fine_mlp_ms_per_launch': fk_ms, 'fine_mlp_tflops': flops / (fk_ms * 1e-3) / 1e12,
+                    'fine_mlp_frac_of_peak': flops / (fk_ms * 1e-3) / 1e12 / peak}
+            # informational: the opt-in mixed mode (fp16 + e4m3 residual products; holds 1e-3 on the fitted scene, not on every network)
+            MIXED = 16
+            for _ in range(2):
+                step_device(0, MIXED)
+            torch.cuda.synchronize()
+            e0.record()
+            for s in range(args.steps):
+                step_device(s, MIXED)
+            e1.record()
+            torch.cuda.synchronize()
+            mixed_ms = e0.elapsed_time(e1) / args.steps
+            mixed = {'note': 'NSR_FLAG_MIXED_F8: 2.25 tensor passes per product (fp16 main term + two e4m3 residual products in layers 3-9); opt-in, informational only',
+                     'rays_per_s_device_resident': n / (mixed_ms * 1e-3), 'ms_per_step': mixed_ms}
+            # secondary (BASELINE config 3): forward + backward dL/d(rays) for the pose path, same 160 000 rays
+            bws_bytes = L.nsr_render_backward_workspace_bytes(n, T)
+            bws = torch.empty(bws_bytes, dtype=torch.uint8, device=dev)
+            g_rgb = torch.randn(n, 3, device=dev)
+            d_rays = new(n, 11)
+            zsave, rawsave = new(n, T), new(n, T, 4)
 
-        def step_fwd_bwd(s):
-            r = rays_dev[s % len(rays_dev)]
-            rc = L.nsr_render_rays_forward(P(r), n, P(pc), P(pf), N_SAMPLES, N_IMPORTANCE, 0, None, None, P(outs['rgb']), P(outs['disp']),
-                                           P(outs['acc']), P(outs['rgb0']), P(outs['disp0']), P(outs['acc0']), P(outs['zstd']), P(rawsave),
-                                           P(zsave), None, P(ws), ws_bytes, stream)
-            rc = rc or L.nsr_render_rays_backward(P(r), P(zsave), P(rawsave), n, T, P(pf), 0, P(g_rgb), P(d_rays), None, None, None,
-                                                  P(bws), bws_bytes, stream)
-            if rc != 0:
-                raise RuntimeError(L.nsr_last_error().decode())
+            def step_fwd_bwd(s):
+                r = rays_dev[s % len(rays_dev)]
+                rc = L.nsr_render_rays_forward(P(r), n, P(pc), P(pf), N_SAMPLES, N_IMPORTANCE, 0, None, None, P(outs['rgb']), P(outs['disp']),
+                                               P(outs['acc']), P(outs['rgb0']), P(outs['disp0']), P(outs['acc0']), P(outs['zstd']), P(rawsave),
+                                               P(zsave), None, P(ws), ws_bytes, stream)
+                rc = rc or L.nsr_render_rays_backward(P(r), P(zsave), P(rawsave), n, T, P(pf), 0, P(g_rgb), P(d_rays), None, None, None,
+                                                      P(bws), bws_bytes, stream)
+                if rc != 0:
+                    raise RuntimeError(L.nsr_last_error().decode())
 
-        for s in range(2):
-            step_fwd_bwd(s)
-        torch.cuda.synchronize()
-        e0.record()
-        for s in range(args.steps):
-            step_fwd_bwd(s)
-        e1.record()
-        torch.cuda.synchronize()
-        fb_ms = e0.elapsed_time(e1) / args.steps
-        fwd_bwd = {'workload': 'BASELINE config 3: forward + backward dL/d(rays) from dL/d(rgb_map), 160000 rays, 64+128 samples (fine pass recomputed in the backward kernel)',
-                   'rays_per_s': n / (fb_ms * 1e-3), 'ms_per_step': fb_ms, 'algorithmic_flop_per_ray': (64 + 192 + 192) * FLOP_PER_POINT,
-                   'algorithmic_tflops': n * (64 + 192 + 192) * FLOP_PER_POINT / (fb_ms * 1e-3) / 1e12}
-        del bws, zsave, rawsave
-        # CPU baseline: the oracle port on this box's host cores, bounded sample
-        rate, cores, times = cpu_render_rate(4096, 2)
-        cpu_base = {'value': rate, 'unit': 'rays/s', 'cores': cores, 'kind': 'port',
-                    'sample': f'2 passes over 4096 rays of the same image (chunk=512, netchunk=65536, fp32 torch CPU, {cores} of {os.cpu_count()} threads = fastest tried, {sum(times):.1f} s)'}
+            for s in range(2):
+                step_fwd_bwd(s)
+            torch.cuda.synchronize()
+            e0.record()
+            for s in range(args.steps):
+                step_fwd_bwd(s)
+            e1.record()
+            torch.cuda.synchronize()
+            fb_ms = e0.elapsed_time(e1) / args.steps
+            fwd_bwd = {'workload': 'BASELINE config 3: forward + backward dL/d(rays) from dL/d(rgb_map), 160000 rays, 64+128 samples (fine pass recomputed in the backward kernel)',
+                       'rays_per_s': n / (fb_ms * 1e-3), 'ms_per_step': fb_ms, 'algorithmic_flop_per_ray': (64 + 192 + 192) * FLOP_PER_POINT,
+                       'algorithmic_tflops': n * (64 + 192 + 192) * FLOP_PER_POINT / (fb_ms * 1e-3) / 1e12}
+            del bws, zsave, rawsave
+            # secondary (SURVEY a-12 / RN:643-716): one optimisation step of both networks on N_rand = 1024 random rays through the
+            # public API: render(rays=...) -> img2mse(rgb) + img2mse(rgb0) -> backward (dL/dMLP of both nets) -> Adam -> re-pack
+            import copy
+            tnets = [copy.deepcopy(m) for m in nets]
+            opt = torch.optim.Adam([p_ for m in tnets for p_ in m.parameters()], lr=5e-4, betas=(0.9, 0.999))
+            tkw = dict(kw, network_fn=tnets[0], network_fine=tnets[1], perturb=1.0)      # stratified sampling as in training (RN:447-461)
+            n_rand = 1024
+            gen = torch.Generator(device=dev).manual_seed(0)
+            target = torch.rand(n_rand, 3, device=dev, generator=gen)
+
+            def train_step(s):
+                sel = torch.randint(0, n, (n_rand,), device=dev, generator=gen)
+                r = rays_dev[s % len(rays_dev)][sel]
+                batch = torch.stack([r[:, 0:3], r[:, 3:6]], 0)
+                rgb, _, _, extras = nsr.render(H, W, O.YCBV_K_400, chunk=1 << 15, rays=batch, retraw=True, **tkw)
+                opt.zero_grad()
+                loss = nsr.img2mse(rgb, target) + nsr.img2mse(extras['rgb0'], target)
+                loss.backward()
+                opt.step()
+
+            launches_t0 = L.nsr_launch_count()
+            for s in range(3):
+                train_step(s)
+            torch.cuda.synchronize()
+            t_steps = max(10, args.steps)
+            e0.record()
+            for s in range(t_steps):
+                train_step(s)
+            e1.record()
+            torch.cuda.synchronize()
+            tr_ms = e0.elapsed_time(e1) / t_steps
+            train = {'workload': 'one Adam step of both networks on N_rand=1024 rays, 64+128 samples, loss = mse(rgb) + mse(rgb0) (RN:643-716) through render() + autograd + torch.optim.Adam',
+                     'ms_per_step': tr_ms, 'rays_per_s': n_rand / (tr_ms * 1e-3), 'steps_per_s': 1e3 / tr_ms,
+                     'kernels_per_step': (L.nsr_launch_count() - launches_t0) / (t_steps + 3)}
+            del tnets, opt
+            # per-stage table: the HBM-bound ray-stage kernels, each timed alone (CUDA events, 20 launches back to back)
+            hbm = peaks.get('hbm_gbs', 6650.0)
+
+            def time_stage(fn, reps=20):
+                fn()
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(reps):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                return e0.elapsed_time(e1) / reps
+
+            S_, T_ = N_SAMPLES, T
+            raw0 = new(n, S_, 4).normal_()
+            wts = new(n, T_)
+            rgb8 = torch.empty(n * 3, dtype=torch.uint8, device=dev)
+            d3 = rays_dev[0][:, 3:6].contiguous()
+            Kh = (ctypes.c_float * 9)(*[float(v) for row in O.YCBV_K_400 for v in row])
+            c2wh = (ctypes.c_float * 12)(*[float(v) for v in pose_for(0, 0).reshape(-1).tolist()])
+            rays_tmp = new(n, 11)
+            stage_defs = [
+                ('make_rays_kernel (RH:156-165 + RN:91-112)', n * 44,
+                 lambda: L.nsr_make_rays(H, W, Kh, c2wh, float(O.YCBV_NEAR), float(O.YCBV_FAR), P(rays_tmp), stream)),
+                ('raw2outputs_kernel S=64 (coarse composite, writes weights)', n * (S_ * 16 + S_ * 4 + 12 + S_ * 4 + 20),
+                 lambda: L.nsr_raw2outputs(P(raw0), P(z0), P(d3), 3, n, S_, 0, P(outs['rgb0']), P(outs['disp0']), P(outs['acc0']), P(w0), None, stream)),
+                ('resample_merge_kernel 64+128 (sample_pdf + sort + z_std)', n * (S_ * 4 + S_ * 4 + T_ * 4 + 4),
+                 lambda: L.nsr_resample_merge(P(z0), P(w0), n, S_, N_IMPORTANCE, None, P(zf), None, P(outs['zstd']), stream)),
+                ('raw2outputs_kernel S=192 (fine composite)', n * (T_ * 16 + T_ * 4 + 12 + 20),
+                 lambda: L.nsr_raw2outputs(P(rawf), P(zf), P(d3), 3, n, T_, 0, P(outs['rgb']), P(outs['disp']), P(outs['acc']), None, None, stream)),
+                ('to8b_kernel (RH:14)', n * 15,
+                 lambda: L.nsr_to8b(P(outs['rgb']), n * 3, P(rgb8), stream)),
+            ]
+            stages = []
+            for name, nbytes, fn in stage_defs:
+                ms = time_stage(fn)
+                stages.append({'kernel': name, 'ms': ms, 'algorithmic_bytes': nbytes, 'gb_per_s': nbytes / (ms * 1e-3) / 1e9,
+                               'frac_of_hbm_peak': nbytes / (ms * 1e-3) / 1e9 / hbm})
+            stages.append({'kernel': 'nerf_mlp_kernel fine (192 samples/ray)', 'ms': k_ms, 'algorithmic_tflops': achieved, 'frac_of_tensor_peak': achieved / peak})
+            # CPU baseline: the oracle port on this box's host cores, bounded sample
+            rate, cores, times = cpu_render_rate(4096, 2)
+            cpu_base = {'value': rate, 'unit': 'rays/s', 'cores': cores, 'kind': 'port',
+                        'sample': f'2 passes over 4096 rays of the same image (chunk=512, netchunk=65536, fp32 torch CPU, {cores} of {os.cpu_count()} threads = fastest tried, {sum(times):.1f} s)'}
 
     if world > 1:
         dist.barrier()
@@ -401,7 +476,7 @@ def run_ours(args):
                     'api': 'render(H, W, K, chunk, rays=<pinned host [2,N,3] -> cuda>, **render_kwargs_test) + D2H of rgb/disp/acc'},
             'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_base,
             'flop_per_ray': FLOP_PER_RAY, 'tflops_device_resident': value * FLOP_PER_RAY / 1e12,
-            'tensor_flop_issued_per_algorithmic_flop': 3, 'fast_fp16_mode': fast, 'mixed_f8_mode': mixed, 'fwd_bwd': fwd_bwd,
+            'tensor_flop_issued_per_algorithmic_flop': 3, 'fast_fp16_mode': fast, 'mixed_f8_mode': mixed, 'fwd_bwd': fwd_bwd, 'train_step': train, 'stages': stages,
         }))
 
 

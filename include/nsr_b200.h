@@ -42,7 +42,8 @@ extern "C" {
 
 #define NSR_FLAG_MIXED_F8 16u  /* MLP products of the first three layers as the fp16 hi/lo split, of the later layers as one fp16
                                   MMA plus the two residual products in e4m3 (kind::f8f6f4, double rate): 2.25 instead of 3
-                                  tensor-core passes per product; stays inside the 1e-3 bar ("precision").
+                                  tensor-core passes per product; inside the 1e-3 bar on the fitted scene (3.7e-4) but not on
+                                  every network (2.6e-3 on 3x-scaled random ones): opt-in ("precision").
                                   Forward only; NSR_FLAG_FAST_FP16 wins if both are set. */
 
 /* network geometry this library is specialised for (RN:261-278, CFG): D=8, W=256, skips=[4],
@@ -159,6 +160,40 @@ int nsr_render_rays_backward(const float* rays, const float* z_vals, const float
  */
 int nsr_make_rays(int H, int W, const float* K_host, const float* c2w_host, float near_, float far_, float* rays_out,
                   void* stream);
+
+/* The same from a c2w that lives on the DEVICE (rows ld_c2w >= 4 floats apart: a [3,4] or the top of a [4,4] matrix), e.g. the
+ * pose sampler's output (LL:63-72): the pose never visits the host. */
+int nsr_make_rays_dev(int H, int W, const float* K_host, const float* c2w_dev, int ld_c2w, float near_, float far_,
+                      float* rays_out, void* stream);
+
+/* RH:14 to8b: out[i] = uint8(255 * clip(x[i], 0, 1)) (fp32 product, truncation), n_values floats -> n_values bytes.  Replaces
+ * the host-side conversion in front of imageio.imwrite (RN:200-206, RN:245-250): an image leaves the GPU as H*W*3 bytes. */
+int nsr_to8b(const float* x, int64_t n_values, uint8_t* out, void* stream);
+
+/*
+ * Pull dL/d(ray_batch) [n,11] back through get_rays (RH:156-165) and the view-direction normalisation (RN:97) to the camera
+ * pose: d_c2w [12] (device, row-major 3x4; = or += with accumulate != 0).  Replaces the get_rays part of the tape behind
+ *   dLdpsi = torch.autograd.grad(batch_rays, categorical_prob, grad_outputs=dLdray)                     (RN:179-181)
+ * -- the caller chains d_c2w through the 8-float pose sampler.  rays / d_rays: [n,11] as produced by nsr_make_rays and
+ * nsr_render_rays_backward.  pixel_idx = NULL: the rays are the whole H*W image in row-major order; else int32 [n] pixel index
+ * (row*W + column) of each ray.  workspace: nsr_c2w_grad_workspace_bytes() bytes, 8-byte aligned.  Deterministic (no atomics).
+ */
+size_t nsr_c2w_grad_workspace_bytes(void);
+int nsr_rays_grad_to_c2w(int H, int W, const float* K_host, const float* rays, const float* d_rays, const int32_t* pixel_idx,
+                         int64_t n_rays, float* d_c2w, int accumulate, void* workspace, void* stream);
+
+/*
+ * One image, forward: ray generation (host OR device c2w; exactly one non-NULL) -> nsr_render_rays_forward over all H*W rays ->
+ * to8b.  Replaces one iteration of render_path's loop (RN:229-250: render(H, W, K, c2w=...) + to8b).  Outputs (NULL = not
+ * wanted): rgb8 [H,W,3] uint8, rgb_map [H*W,3], disp_map, acc_map, rgb0, disp0, acc0, z_std [H*W].  The packed rays [H*W,11]
+ * are left at the head of the workspace (256-byte aligned, nsr_render_image_workspace_bytes()).
+ */
+size_t nsr_render_image_workspace_bytes(int H, int W, int n_samples, int n_importance);
+int nsr_render_image_forward(int H, int W, const float* K_host, const float* c2w_host, const float* c2w_dev, int ld_c2w,
+                             float near_, float far_, const void* packed_coarse, const void* packed_fine, int n_samples,
+                             int n_importance, uint32_t flags, uint8_t* rgb8, float* rgb_map, float* disp_map, float* acc_map,
+                             float* rgb0, float* disp0, float* acc0, float* z_std, void* workspace, size_t workspace_bytes,
+                             void* stream);
 
 /* Number of kernels this library has launched since load (all threads); used by bench.py's gpu_launches. */
 uint64_t nsr_launch_count(void);

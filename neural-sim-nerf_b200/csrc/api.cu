@@ -236,4 +236,62 @@ int nsr_make_rays(int H, int W, const float* K_host, const float* c2w_host, floa
   return launch_make_rays(H, W, K_host, c2w_host, near_, far_, rays_out, static_cast<cudaStream_t>(stream));
 }
 
+int nsr_make_rays_dev(int H, int W, const float* K_host, const float* c2w_dev, int ld_c2w, float near_, float far_, float* rays_out,
+                      void* stream) {
+  NSR_REQUIRE(H > 0 && W > 0 && K_host && c2w_dev && rays_out && ld_c2w >= 4, "nsr_make_rays_dev: bad argument");
+  return launch_make_rays_dev(H, W, K_host, c2w_dev, ld_c2w, near_, far_, rays_out, static_cast<cudaStream_t>(stream));
+}
+
+int nsr_to8b(const float* x, int64_t n_values, uint8_t* out, void* stream) {
+  NSR_REQUIRE(n_values >= 0, "nsr_to8b: bad size");
+  if (n_values == 0) return NSR_OK;
+  NSR_REQUIRE(x && out, "nsr_to8b: null argument");
+  return launch_to8b(x, n_values, out, static_cast<cudaStream_t>(stream));
+}
+
+size_t nsr_c2w_grad_workspace_bytes(void) { return c2w_grad_workspace_bytes(); }
+
+int nsr_rays_grad_to_c2w(int H, int W, const float* K_host, const float* rays, const float* d_rays, const int32_t* pixel_idx,
+                         int64_t n_rays, float* d_c2w, int accumulate, void* workspace, void* stream) {
+  NSR_REQUIRE(H > 0 && W > 0 && K_host && d_c2w && workspace && n_rays >= 0, "nsr_rays_grad_to_c2w: bad argument");
+  NSR_REQUIRE(n_rays == 0 || (rays && d_rays), "nsr_rays_grad_to_c2w: null rays / d_rays");
+  NSR_REQUIRE(pixel_idx != nullptr || n_rays == int64_t(H) * W, "nsr_rays_grad_to_c2w: without pixel_idx the rays must be the whole image in row-major order");
+  NSR_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 7) == 0, "nsr_rays_grad_to_c2w: workspace must be 8-byte aligned");
+  return launch_c2w_grad(W, K_host, rays, d_rays, pixel_idx, n_rays, d_c2w, accumulate, static_cast<double*>(workspace),
+                         static_cast<cudaStream_t>(stream));
+}
+
+// workspace layout: rays [H*W,11] | rgb [H*W,3] (used when rgb8 is wanted without rgb_map) | nsr_render_rays_forward's workspace
+size_t nsr_render_image_workspace_bytes(int H, int W, int S, int Ni) {
+  const int64_t n = int64_t(H) * W;
+  return align_up(size_t(n) * 44, 256) + align_up(size_t(n) * 12, 256) + nsr_render_workspace_bytes(n, S, Ni);
+}
+
+int nsr_render_image_forward(int H, int W, const float* K_host, const float* c2w_host, const float* c2w_dev, int ld_c2w, float near_,
+                             float far_, const void* packed_coarse, const void* packed_fine, int S, int Ni, uint32_t flags,
+                             uint8_t* rgb8, float* rgb_map, float* disp_map, float* acc_map, float* rgb0, float* disp0, float* acc0,
+                             float* z_std, void* workspace, size_t workspace_bytes, void* stream) {
+  NSR_REQUIRE(H > 0 && W > 0 && K_host, "nsr_render_image_forward: bad camera");
+  NSR_REQUIRE((c2w_host != nullptr) != (c2w_dev != nullptr), "nsr_render_image_forward: give exactly one of c2w_host / c2w_dev");
+  NSR_REQUIRE(workspace && workspace_bytes >= nsr_render_image_workspace_bytes(H, W, S, Ni), "nsr_render_image_forward: workspace too small");
+  NSR_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "nsr_render_image_forward: workspace must be 256-byte aligned");
+  const int64_t n = int64_t(H) * W;
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  float* rays = reinterpret_cast<float*>(ws);
+  ws += align_up(size_t(n) * 44, 256);
+  float* rgb_tmp = reinterpret_cast<float*>(ws);
+  ws += align_up(size_t(n) * 12, 256);
+  int rc;
+  if (c2w_host) rc = nsr_make_rays(H, W, K_host, c2w_host, near_, far_, rays, stream);
+  else rc = nsr_make_rays_dev(H, W, K_host, c2w_dev, ld_c2w, near_, far_, rays, stream);
+  if (rc) return rc;
+  float* rgb = rgb_map ? rgb_map : (rgb8 ? rgb_tmp : nullptr);
+  rc = nsr_render_rays_forward(rays, n, packed_coarse, packed_fine, S, Ni, flags, nullptr, nullptr, rgb, disp_map, acc_map, rgb0, disp0,
+                               acc0, z_std, nullptr, nullptr, nullptr, ws, workspace_bytes - size_t(ws - static_cast<uint8_t*>(workspace)),
+                               stream);
+  if (rc) return rc;
+  if (rgb8) return nsr_to8b(rgb, n * 3, rgb8, stream);      // RN:246: to8b(rgbs[-1]) -> HWC uint8
+  return NSR_OK;
+}
+
 }  // extern "C"

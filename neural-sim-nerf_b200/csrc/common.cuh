@@ -113,6 +113,13 @@ int launch_resample_merge(const float* z, const float* w, int64_t n, int S, int 
                           float* z_samples, float* z_std, cudaStream_t st);
 int launch_make_rays(int H, int W, const float* K9, const float* c2w12, float near_, float far_, float* rays,
                      cudaStream_t st);
+// image_stage.cu
+int launch_to8b(const float* x, int64_t n, uint8_t* out, cudaStream_t st);
+int launch_make_rays_dev(int H, int W, const float* K9, const float* c2w_dev, int ld_c2w, float near_, float far_, float* rays,
+                         cudaStream_t st);
+int launch_c2w_grad(int W, const float* K9, const float* rays, const float* d_rays, const int32_t* pixel_idx, int64_t n,
+                    float* d_c2w, int accumulate, double* partials, cudaStream_t st);
+size_t c2w_grad_workspace_bytes();
 // mlp_forward.cu
 int launch_pack_net(const float* const* weights, const float* const* biases, void* packed, cudaStream_t st);
 int launch_mlp_forward(const float* rays, const float* z_or_pts, int64_t n, int S, const void* packed, uint32_t flags,

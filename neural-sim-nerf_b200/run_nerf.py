@@ -528,23 +528,192 @@ def _imwrite(filename, rgb8):
         Image.fromarray(rgb8).save(filename)
 
 
+def to8b_device(x):
+    """RH:14 on the device: float tensor -> uint8 tensor of the same shape (255*clip(x,0,1), truncated)."""
+    x = _f32c(x, 'x')
+    out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    check(lib().nsr_to8b(ptr(x), x.numel(), ptr(out), _stream()), 'nsr_to8b')
+    return out
+
+
+def _K9(K):
+    return np.ascontiguousarray(np.asarray([[float(K[r][c]) for c in range(3)] for r in range(3)], dtype=np.float32))
+
+
+def _image_path_ok(kw):
+    """Can render(H, W, K, c2w=..., **kw) go through the one-call image entry?  (what MAIN:109-114 + create_nerf's
+    render_kwargs_test amount to: use_viewdirs, no NDC, deterministic sampling, scalar bounds)"""
+    return (kw.get('use_viewdirs', False) and not kw.get('ndc', True) and kw.get('c2w_staticcam') is None
+            and not kw.get('perturb', 0.) and not kw.get('raw_noise_std', 0.) and not kw.get('retraw', False)
+            and not torch.is_tensor(kw.get('near', 0.)) and not torch.is_tensor(kw.get('far', 1.))
+            and kw.get('network_fn') is not None)
+
+
+def render_image(H, W, K, c2w, want=('rgb8', 'rgb_map', 'disp_map'), **kw):
+    """One image through nsr_render_image_forward: ray generation (c2w on the host or on the device), coarse + fine pass,
+    compositing and to8b in one C call; returns {name: device tensor} for the names in `want`
+    ('rgb8' [H,W,3] uint8, 'rgb_map' [H,W,3], 'disp_map', 'acc_map', 'rgb0', 'disp0', 'acc0', 'z_std' [H,W]) plus
+    'rays' [H*W,11] (a view into the call's workspace).  `kw` = the reference's render_kwargs (RN:318-338 + near/far)."""
+    if not _image_path_ok(kw):
+        raise NotImplementedError('render_image covers use_viewdirs=True, ndc=False, perturb=0, raw_noise_std=0, scalar near/far')
+    L = lib()
+    net_c, net_f = kw['network_fn'], kw.get('network_fine')
+    S, Ni = int(kw['N_samples']), int(kw.get('N_importance', 0))
+    flags = (FLAG_LINDISP if kw.get('lindisp', False) else 0) | (FLAG_WHITE_BKGD if kw.get('white_bkgd', False) else 0) | _prec_flag()
+    pc = packed_weights(net_c)
+    pf = packed_weights(net_f) if (net_f is not None and Ni > 0) else None
+    dev = pc.device
+    n = H * W
+    shapes = {'rgb8': ((H, W, 3), torch.uint8), 'rgb_map': ((H, W, 3), torch.float32), 'rgb0': ((H, W, 3), torch.float32)}
+    out = {}
+    for name in want:
+        if name not in ('rgb8', 'rgb_map', 'disp_map', 'acc_map', 'rgb0', 'disp0', 'acc0', 'z_std'):
+            raise ValueError(f'render_image: unknown output {name!r}')
+        if Ni == 0 and name in ('rgb0', 'disp0', 'acc0', 'z_std'):
+            raise ValueError(f'render_image: {name!r} needs N_importance > 0')
+        shape, dt = shapes.get(name, ((H, W), torch.float32))
+        out[name] = torch.empty(shape, dtype=dt, device=dev)
+    ws_bytes = L.nsr_render_image_workspace_bytes(H, W, S, Ni)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    Kh = _K9(K)
+    c2w_host = c2w_dev = None
+    ld = 4
+    keep = None
+    if torch.is_tensor(c2w) and c2w.is_cuda:
+        c = c2w.detach()
+        if c.dtype != torch.float32 or c.stride(-1) != 1 or c.stride(0) < 4:
+            c = c.float().contiguous()
+        keep, c2w_dev, ld = c, ptr(c), c.stride(0)
+    else:
+        c = c2w.detach().float().numpy() if torch.is_tensor(c2w) else np.asarray(c2w, dtype=np.float32)
+        keep = np.ascontiguousarray(c[:3, :4], dtype=np.float32)
+        c2w_host = keep.ctypes.data_as(ctypes.c_void_p)
+    g = lambda k: ptr(out.get(k))
+    check(L.nsr_render_image_forward(H, W, Kh.ctypes.data_as(ctypes.c_void_p), c2w_host, c2w_dev, ld, float(kw['near']), float(kw['far']),
+                                     ptr(pc), ptr(pf), S, Ni, flags, g('rgb8'), g('rgb_map'), g('disp_map'), g('acc_map'), g('rgb0'),
+                                     g('disp0'), g('acc0'), g('z_std'), ptr(ws), ws_bytes, _stream()), 'nsr_render_image_forward')
+    del keep
+    out['rays'] = ws[:n * 44].view(torch.float32).view(n, 11)
+    return out
+
+
+def rays_grad_to_c2w(H, W, K, rays, d_rays, pixel_idx=None):
+    """dL/d(ray_batch) [n,11] -> dL/dc2w [3,4] in closed form (nsr_rays_grad_to_c2w): the get_rays (RH:156-165) + RN:97 part
+    of `torch.autograd.grad(batch_rays, categorical_prob, grad_outputs=dLdray)` (RN:179-181)."""
+    L = lib()
+    rays, d_rays = _f32c(rays, 'rays'), _f32c(d_rays, 'd_rays')
+    n = rays.shape[0]
+    if pixel_idx is not None:
+        pixel_idx = pixel_idx.to(device=rays.device, dtype=torch.int32).contiguous()
+    ws = torch.empty(L.nsr_c2w_grad_workspace_bytes(), dtype=torch.uint8, device=rays.device)
+    out = torch.empty(3, 4, dtype=torch.float32, device=rays.device)
+    Kh = _K9(K)
+    check(L.nsr_rays_grad_to_c2w(H, W, Kh.ctypes.data_as(ctypes.c_void_p), ptr(rays), ptr(d_rays), ptr(pixel_idx), n, ptr(out), 0,
+                                 ptr(ws), _stream()), 'nsr_rays_grad_to_c2w')
+    return out
+
+
+def render_image_grad(H, W, K, c2w, g_rgb, **kw):
+    """One image forward + backward for the pose path (RN:148-181 for all H*W rays at once): returns (rgb_map [H,W,3],
+    dL/dc2w [3,4]) given g_rgb = dL/drgb_map [H*W,3].  No autograd graph is built: rays come from the device-resident c2w,
+    the fine pass is back-propagated by nsr_render_rays_backward and dL/d(ray_batch) is folded to the pose in closed form."""
+    if not _image_path_ok(kw):
+        raise NotImplementedError('render_image_grad covers use_viewdirs=True, ndc=False, perturb=0, raw_noise_std=0, scalar near/far')
+    if PRECISION == 'fp16':
+        raise NotImplementedError("backward is not built for NSR_PRECISION='fp16'")
+    L = lib()
+    net_c, net_f = kw['network_fn'], kw.get('network_fine')
+    S, Ni = int(kw['N_samples']), int(kw.get('N_importance', 0))
+    flags = (FLAG_LINDISP if kw.get('lindisp', False) else 0) | (FLAG_WHITE_BKGD if kw.get('white_bkgd', False) else 0)
+    pc = packed_weights(net_c)
+    pf = packed_weights(net_f) if (net_f is not None and Ni > 0) else None
+    dev = pc.device
+    c = c2w.detach().to(device=dev, dtype=torch.float32)[:3, :4].contiguous()
+    rays = torch.empty(H * W, 11, dtype=torch.float32, device=dev)
+    Kh = _K9(K)
+    check(L.nsr_make_rays_dev(H, W, Kh.ctypes.data_as(ctypes.c_void_p), ptr(c), 4, float(kw['near']), float(kw['far']), ptr(rays), _stream()),
+          'nsr_make_rays_dev')
+    cfg = dict(pc=pc, pf=pf, S=S, Ni=Ni, flags=flags, t_rand=None, u=None, retraw=False)
+    with torch.no_grad():
+        outs, saved = _forward_impl(rays, cfg, keep_for_backward=True)
+        g = g_rgb.detach().to(device=dev, dtype=torch.float32).reshape(-1, 3).contiguous()
+        d_rays, _ = _RenderRaysFn._one_pass(rays, saved[0], saved[1], pf if pf is not None else pc, flags & FLAG_WHITE_BKGD, g, False)
+        d_c2w = rays_grad_to_c2w(H, W, K, rays, d_rays)
+    return outs[0].view(H, W, 3), d_c2w
+
+
+class _AsyncImageWriter:
+    """Pinned staging buffers + events: the D2H copy and the PNG encode of image i overlap the kernels of image i+1
+    (SURVEY §8f N3)."""
+
+    def __init__(self, depth=2):
+        self.depth, self.slots, self.pending = depth, {}, []
+
+    def _pinned(self, key, t, slot):
+        k = (key, tuple(t.shape), t.dtype, slot)
+        if k not in self.slots:
+            self.slots[k] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+        return self.slots[k]
+
+    def submit(self, index, tensors, on_ready):
+        """tensors: {name: device tensor}; on_ready(index, {name: numpy}) runs once the copies have landed."""
+        slot = index % self.depth
+        while len(self.pending) >= self.depth:
+            self._retire()
+        host = {}
+        for name, t in tensors.items():
+            h = self._pinned(name, t, slot)
+            h.copy_(t, non_blocking=True)
+            host[name] = h
+        ev = torch.cuda.Event()
+        ev.record()
+        self.pending.append((index, host, ev, on_ready))
+
+    def _retire(self):
+        index, host, ev, on_ready = self.pending.pop(0)
+        ev.synchronize()
+        on_ready(index, {k: v.numpy().copy() for k, v in host.items()})
+
+    def drain(self):
+        while self.pending:
+            self._retire()
+
+
 def render_path(categorical_prob, render_poses, hwf, K, chunk, render_kwargs, gt_imgs=None, savedir=None, object_id=2,
                 render_factor=0):
-    """RN:213-255: render every pose under no_grad, optionally write <savedir>/<object_id>/NNN.png.  One kernel
-    sequence per image (rays are generated on the device from c2w, RH:156-165 fused with RN:91-112)."""
+    """RN:213-255: render every pose under no_grad, optionally write <savedir>/<object_id>/NNN.png.  One C call per
+    image (nsr_render_image_forward: rays from c2w, both passes, to8b on the device); the device->host copies and the
+    PNG encode of an image overlap the kernels of the next one."""
     H, W, focal = hwf
     if render_factor != 0:                                         # RN:217-221
         H, W, focal = H // render_factor, W // render_factor, focal / render_factor
-    rgbs, disps = [], []
+    n_img = len(render_poses)
+    rgbs, disps = [None] * n_img, [None] * n_img
     if savedir is not None:
         os.makedirs(os.path.join(savedir, str(object_id)), exist_ok=True)
+
+    def on_ready(i, host):
+        rgbs[i], disps[i] = host['rgb_map'], host['disp_map']
+        if savedir is not None:
+            _imwrite(os.path.join(savedir, str(object_id), '{:03d}.png'.format(i)), host['rgb8'])       # RN:245-250
+
+    fast = _image_path_ok(render_kwargs)
+    writer = _AsyncImageWriter()
     with torch.no_grad():
+        if fast and torch.is_tensor(render_poses) and not render_poses.is_cuda:
+            render_poses = render_poses.float()
         for i, c2w in enumerate(render_poses):
-            rgb, disp, acc, _ = render(H, W, K, chunk=chunk, c2w=c2w[:3, :4], **render_kwargs)    # RN:233
-            rgbs.append(rgb.cpu().numpy())
-            disps.append(disp.cpu().numpy())
-            if savedir is not None:
-                _imwrite(os.path.join(savedir, str(object_id), '{:03d}.png'.format(i)), to8b(rgbs[-1]))   # RN:245-250
+            if fast:
+                want = ('rgb8', 'rgb_map', 'disp_map') if savedir is not None else ('rgb_map', 'disp_map')
+                out = render_image(H, W, K, c2w[:3, :4], want=want, **render_kwargs)
+                out.pop('rays')
+            else:
+                rgb, disp, acc, _ = render(H, W, K, chunk=chunk, c2w=c2w[:3, :4], **render_kwargs)    # RN:233
+                out = {'rgb_map': rgb, 'disp_map': disp}
+                if savedir is not None:
+                    out['rgb8'] = to8b_device(rgb)
+            writer.submit(i, out, on_ready)
+        writer.drain()
     return np.stack(rgbs, 0), np.stack(disps, 0)
 
 
@@ -554,29 +723,48 @@ def render_path_grad(categorical_prob, render_poses, hwf, K, chunk, grad_E, rend
 
     The reference returns one dL/dpsi per `chunk` rays and its caller averages them all (MAIN:191), i.e. the estimator is
     sum_over_chunks(g_chunk) / (n_images * n_chunks).  Gradients add over rays, so the whole image's gradient equals
-    sum_over_chunks(g_chunk); one entry per image, divided by n_chunks = ceil(H*W/chunk), leaves that mean unchanged."""
+    sum_over_chunks(g_chunk); one entry per image, divided by n_chunks = ceil(H*W/chunk), leaves that mean unchanged.
+
+    Per image: render_image_grad (no autograd tape over rays: dL/d(ray_batch) is folded to dL/dc2w [3,4] on the device in
+    closed form), then ONE autograd.grad of the 12 pose entries w.r.t. categorical_prob through the pose sampler's graph
+    (RN:179-181).  Render arguments outside the image path's envelope take the general autograd route (same numbers)."""
     H, W, focal = hwf
     if render_factor != 0:
         H, W, focal = H // render_factor, W // render_factor, focal / render_factor
-    rgbs, dLdpsis = [], []
+    n_img = min(len(render_poses), len(grad_E))                                                 # RN:142
+    rgbs, dLdpsis = [None] * n_img, []
     n_chunks = max(1, math.ceil(H * W / chunk))
-    for i_pose, c2w in enumerate(render_poses):
-        if i_pose >= len(grad_E):
-            break                                                                               # RN:142
-        pose = c2w[:3, :4]
-        rays_o, rays_d = get_rays(H, W, K, pose)                                                # RN:148 (graph-attached to psi)
-        g = grad_E[i_pose]['grad_E'][0]
-        g = (g if torch.is_tensor(g) else torch.as_tensor(g)).to(rays_d.device).permute(1, 2, 0).reshape(-1, 3).float()   # RN:154-155
-        batch_rays = torch.stack([rays_o.reshape(-1, 3), rays_d.reshape(-1, 3)], 0)             # RN:163, all rays at once
-        rgb_p, _, _, _ = render(H, W, K, chunk=max(chunk, H * W), rays=batch_rays, retraw=True, **render_kwargs)   # RN:168-170
-        dLdray = torch.autograd.grad(rgb_p, batch_rays, grad_outputs=g, retain_graph=True)      # RN:177-178
-        dLdpsi = torch.autograd.grad(batch_rays, categorical_prob, grad_outputs=dLdray, retain_graph=True)       # RN:179-181
-        dLdpsis.append((dLdpsi[0] / n_chunks).cpu().detach())
-        rgbs.append(rgb_p.detach().reshape(H, W, 3).cpu().numpy())
+    fast = _image_path_ok(render_kwargs) and PRECISION != 'fp16'
+    if savedir is not None:
+        os.makedirs(os.path.join(savedir, str(object_id), 'withgrad'), exist_ok=True)
+
+    def on_ready(i, host):
+        rgbs[i] = host['rgb_map']
         if savedir is not None:
-            os.makedirs(os.path.join(savedir, str(object_id), 'withgrad'), exist_ok=True)
-            _imwrite(os.path.join(savedir, str(object_id), 'withgrad', '{:03d}.png'.format(i_pose)), to8b(rgbs[-1]))   # RN:200-206
-    return np.stack(rgbs, 0), dLdpsis
+            _imwrite(os.path.join(savedir, str(object_id), 'withgrad', '{:03d}.png'.format(i)), host['rgb8'])   # RN:200-206
+
+    writer = _AsyncImageWriter()
+    for i_pose in range(n_img):
+        pose = render_poses[i_pose][:3, :4]
+        g = grad_E[i_pose]['grad_E'][0]
+        g = (g if torch.is_tensor(g) else torch.as_tensor(g)).to(device).permute(1, 2, 0).reshape(-1, 3).float()   # RN:154-155
+        if fast and pose.is_cuda:
+            rgb, d_c2w = render_image_grad(H, W, K, pose, g, **render_kwargs)                  # RN:148-178
+            dLdpsi = torch.autograd.grad(pose, categorical_prob, grad_outputs=d_c2w.to(pose.dtype), retain_graph=True)   # RN:179-181
+        else:
+            rays_o, rays_d = get_rays(H, W, K, pose)                                            # RN:148 (graph-attached to psi)
+            batch_rays = torch.stack([rays_o.reshape(-1, 3), rays_d.reshape(-1, 3)], 0)         # RN:163, all rays at once
+            rgb_p, _, _, _ = render(H, W, K, chunk=max(chunk, H * W), rays=batch_rays, retraw=True, **render_kwargs)   # RN:168-170
+            dLdray = torch.autograd.grad(rgb_p, batch_rays, grad_outputs=g, retain_graph=True)  # RN:177-178
+            dLdpsi = torch.autograd.grad(batch_rays, categorical_prob, grad_outputs=dLdray, retain_graph=True)       # RN:179-181
+            rgb = rgb_p.detach().reshape(H, W, 3)
+        dLdpsis.append(dLdpsi[0] / n_chunks)
+        out = {'rgb_map': rgb}
+        if savedir is not None:
+            out['rgb8'] = to8b_device(rgb)
+        writer.submit(i_pose, out, on_ready)
+    writer.drain()
+    return np.stack(rgbs, 0), [d.cpu().detach() for d in dLdpsis]
 
 
 def install(reference_module, loops=False):

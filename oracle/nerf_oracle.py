@@ -232,6 +232,21 @@ def render(H, W, K, sd_coarse, sd_fine, chunk=512, rays=None, c2w=None, near=0.,
     return [out[k] for k in keys] + [{k: v for k, v in out.items() if k not in keys}]
 
 
+def to8b(x):
+    """RH:14."""
+    return (255 * np.clip(x, 0, 1)).astype(np.uint8)
+
+
+def rays_grad_to_c2w(H, W, K, c2w, d_packed, near=0., far=1.):
+    """What autograd computes for RN:179-181 restricted to the pose: the pull-back of a cotangent on the packed rays
+    [H*W,11] (RN:106-112) through RN:97 and get_rays (RH:156-165) to c2w [3,4]."""
+    c = torch.as_tensor(c2w, dtype=torch.float32)[:3, :4].clone().requires_grad_(True)
+    ro, rd = get_rays(H, W, K, c)
+    packed = pack_rays(ro, rd, near, far)
+    g, = torch.autograd.grad(packed, c, grad_outputs=torch.as_tensor(d_packed, dtype=torch.float32))
+    return g
+
+
 # --------------------------------------------------------------------------
 # helpers shared by tests / bench (not part of the reference)
 # --------------------------------------------------------------------------

@@ -78,3 +78,34 @@ def test_ndc_rays_matches_the_reference_bit_for_bit():
     a = nsr.ndc_rays(400, 300, 555.0, 1.0, ro, rd)
     b = RH.ndc_rays(400, 300, 555.0, 1.0, ro, rd)
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+def test_c2w_gradient_closed_form_is_what_autograd_computes():
+    """The formula nsr_rays_grad_to_c2w implements (include/nsr_b200.h): g_d = dL/dd + (g_v - v (v.g_v)) / |d|,
+    dL/dR = sum_rays g_d dirs^T, dL/dt = sum_rays dL/do -- against autograd through get_rays + RN:97 (oracle)."""
+    import numpy as np
+    import torch
+    import nerf_oracle as O
+    H, W = 7, 9
+    K = [[50.0, 0, 4.2], [0, 48.0, 3.1], [0, 0, 1]]
+    c2w = O.pose_spherical(70., 33., 1.3)[:3, :4]
+    g = torch.randn(H * W, 11, generator=torch.Generator().manual_seed(5))
+    ref = O.rays_grad_to_c2w(H, W, K, c2w, g)
+    ro, rd = O.get_rays(H, W, K, c2w)
+    rays = O.pack_rays(ro, rd, 0., 1.).double()
+    gd_ = g.double()
+    jj, ii = np.meshgrid(np.arange(H), np.arange(W), indexing='ij')
+    dirs = torch.from_numpy(np.stack([(ii - K[0][2]) / K[0][0], -(jj - K[1][2]) / K[1][1], -np.ones_like(ii, dtype=np.float64)], -1)).reshape(-1, 3)
+    d = rays[:, 3:6]
+    inv = 1.0 / d.norm(dim=-1, keepdim=True)
+    v = d * inv
+    gd = gd_[:, 3:6] + (gd_[:, 8:11] - v * (v * gd_[:, 8:11]).sum(-1, keepdim=True)) * inv
+    got = torch.cat([gd.t() @ dirs, gd_[:, 0:3].sum(0)[:, None]], 1)
+    assert torch.allclose(got.float(), ref, rtol=1e-4, atol=1e-5)
+
+
+def test_oracle_to8b():
+    import numpy as np
+    import nerf_oracle as O
+    x = np.array([-1.0, 0.0, 0.5, 1.0, 2.0, 0.999, 1 / 255, 254.9999 / 255], dtype=np.float32)
+    assert O.to8b(x).tolist() == [0, 0, 127, 255, 255, 254, 1, 254]

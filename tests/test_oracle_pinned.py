@@ -141,3 +141,24 @@ def test_oracle_autograd_vs_live_reference_tape(wfit):
     assert (g_or - g_ref).abs().max() <= 1e-5 * g_ref.abs().max()
     for name, p in fine.named_parameters():
         assert (sf[name].grad - p.grad).abs().max() <= 1e-5 * max(1e-12, p.grad.abs().max()), name
+
+
+@pytest.mark.skipif(not ref_import.available(), reason='reference tree only exists in the build container')
+def test_oracle_image_stage_vs_live_reference():
+    """to8b (RH:14) and the pose pull-back of RN:179-181: autograd.grad(batch_rays, <pose>, grad_outputs=dLdray) with the
+    reference's own get_rays (RH:156-165) and the normalisation inside its render() (RN:97) against the oracle's."""
+    RN, RH = ref_import.load()
+    torch.autograd.set_detect_anomaly(False)
+    x = np.random.RandomState(0).uniform(-0.3, 1.3, size=(50, 3)).astype(np.float32)
+    assert np.array_equal(RH.to8b(x), O.to8b(x))
+    H, W = 12, 10
+    K = [[60.0, 0, 4.5], [0, 61.0, 6.5], [0, 0, 1]]
+    c2w = O.pose_spherical(80., 40., 1.05)[:3, :4].clone().requires_grad_(True)
+    ro, rd = RH.get_rays(H, W, torch.tensor(K), c2w)
+    ro, rd = ro.reshape(-1, 3), rd.reshape(-1, 3)
+    vd = rd / torch.norm(rd, dim=-1, keepdim=True)                      # RN:97
+    g = torch.randn(H * W, 11, generator=torch.Generator().manual_seed(3))
+    loss = (ro * g[:, 0:3]).sum() + (rd * g[:, 3:6]).sum() + (vd * g[:, 8:11]).sum()
+    ref, = torch.autograd.grad(loss, c2w)
+    mine = O.rays_grad_to_c2w(H, W, K, c2w.detach(), g)
+    assert torch.allclose(mine, ref, rtol=1e-5, atol=1e-6)

@@ -16,6 +16,11 @@ bench)
 benchref)
   timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.txt 2> gpurun_out/bench_ref.err
   cat gpurun_out/bench_ref.txt ;;
+bench[248])
+  N=${what#bench}
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 \
+      bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_n$N.txt 2> gpurun_out/bench_n$N.err
+  echo "bench$N exit $?" >> gpurun_out/bench_n$N.err; cat gpurun_out/bench_n$N.txt; tail -3 gpurun_out/bench_n$N.err ;;
 launches)
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 2 --warmup 1 --profile > gpurun_out/launches.log 2>&1
