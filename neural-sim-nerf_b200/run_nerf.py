@@ -767,6 +767,54 @@ def render_path_grad(categorical_prob, render_poses, hwf, K, chunk, grad_E, rend
     return np.stack(rgbs, 0), [d.cpu().detach() for d in dLdpsis]
 
 
+def create_nerf(args):
+    """RN:257-340: build the coarse (+ fine) network, the Adam optimiser and the two render-kwargs dictionaries from the
+    reference's argparse namespace, and resume from the newest `<basedir>/<expname>/*.tar` (or args.ft_path) unless
+    args.no_reload.  Checkpoint keys as the reference writes them (RN:725-731): global_step, network_fn_state_dict,
+    network_fine_state_dict, optimizer_state_dict.  Returns (render_kwargs_train, render_kwargs_test, start, grad_vars,
+    optimizer).  Host-side plumbing only; geometries other than the one the kernels are built for are refused here."""
+    _, input_ch = get_embedder(args.multires, args.i_embed)
+    if not args.use_viewdirs:
+        raise NotImplementedError('use_viewdirs=False is not built (CFG:8 sets use_viewdirs=True)')
+    _, input_ch_views = get_embedder(args.multires_views, args.i_embed)
+    geometry = dict(input_ch=input_ch, input_ch_views=input_ch_views, skips=[4], use_viewdirs=True,
+                    output_ch=5 if args.N_importance > 0 else 4)
+    nets = [NeRF(D=args.netdepth, W=args.netwidth, **geometry).to(device)]
+    if args.N_importance > 0:
+        nets.append(NeRF(D=args.netdepth_fine, W=args.netwidth_fine, **geometry).to(device))
+    if torch.cuda.is_available():
+        for m in nets:
+            _net_tensors(m)                       # refuse unsupported depths / widths / multires up front
+    grad_vars = [p for m in nets for p in m.parameters()]
+    optimizer = torch.optim.Adam(params=grad_vars, lr=args.lrate, betas=(0.9, 0.999))
+    start = 0
+    ft = getattr(args, 'ft_path', None)
+    if ft is not None and ft != 'None':
+        found = [ft]
+    else:
+        run_dir = os.path.join(args.basedir, args.expname)
+        found = [os.path.join(run_dir, f) for f in sorted(os.listdir(run_dir)) if 'tar' in f]
+    print('Found ckpts', found)
+    if found and not args.no_reload:
+        print('Reloading from', found[-1])
+        ckpt = torch.load(found[-1], map_location=device, weights_only=False)
+        start = ckpt['global_step']
+        optimizer.load_state_dict(ckpt['optimizer_state_dict'])
+        nets[0].load_state_dict(ckpt['network_fn_state_dict'])
+        if len(nets) > 1:
+            nets[1].load_state_dict(ckpt['network_fine_state_dict'])
+    query = lambda inputs, viewdirs, network_fn: run_network(inputs, viewdirs, network_fn, netchunk=args.netchunk)   # RN:281-284
+    train = dict(network_query_fn=query, perturb=args.perturb, N_importance=args.N_importance,
+                 network_fine=nets[1] if len(nets) > 1 else None, N_samples=args.N_samples, network_fn=nets[0],
+                 use_viewdirs=args.use_viewdirs, white_bkgd=args.white_bkgd, raw_noise_std=args.raw_noise_std)
+    if args.dataset_type != 'llff' or args.no_ndc:                                               # RN:328-331
+        print('Not ndc!')
+        train['ndc'] = False
+        train['lindisp'] = args.lindisp
+    test = dict(train, perturb=False, raw_noise_std=0.)                                          # RN:333-335
+    return train, test, start, grad_vars, optimizer
+
+
 def install(reference_module, loops=False):
     """Monkey-patch a loaded reference `utils.run_nerf_noscale` module so its callers
     (render_path RN:233, render_path_grad RN:168, MAIN:128/184) run on this renderer.  With loops=True the two image

@@ -109,3 +109,65 @@ def test_oracle_to8b():
     import nerf_oracle as O
     x = np.array([-1.0, 0.0, 0.5, 1.0, 2.0, 0.999, 1 / 255, 254.9999 / 255], dtype=np.float32)
     assert O.to8b(x).tolist() == [0, 0, 127, 255, 255, 254, 1, 254]
+
+
+def _nerf_args(tmp_path, **over):
+    from argparse import Namespace
+    a = dict(multires=10, multires_views=4, i_embed=0, use_viewdirs=True, N_importance=128, N_samples=64, netdepth=8, netwidth=256,
+             netdepth_fine=8, netwidth_fine=256, netchunk=65536, lrate=5e-4, basedir=str(tmp_path), expname='obj2', ft_path=None,
+             no_reload=False, perturb=1., white_bkgd=False, raw_noise_std=0., dataset_type='blender', no_ndc=False, lindisp=False)
+    a.update(over)
+    return Namespace(**a)
+
+
+def test_create_nerf_builds_and_resumes_reference_checkpoints(tmp_path):
+    """RN:257-340: kwargs dictionaries, optimiser, and resume from a .tar with the reference's keys (RN:725-731)."""
+    import os
+    import torch
+    import neural_sim_nerf_b200 as nsr
+    os.makedirs(tmp_path / 'obj2')
+    train, test, start, grad_vars, opt = nsr.create_nerf(_nerf_args(tmp_path))
+    assert start == 0 and len(grad_vars) == 48 and isinstance(opt, torch.optim.Adam)
+    assert sum(p.numel() for p in grad_vars) == 2 * 595844                       # SURVEY a-7
+    assert train['perturb'] == 1. and test['perturb'] is False and test['raw_noise_std'] == 0.
+    assert train['ndc'] is False and train['N_samples'] == 64 and train['network_fine'] is not train['network_fn']
+    assert set(train) == {'network_query_fn', 'perturb', 'N_importance', 'network_fine', 'N_samples', 'network_fn', 'use_viewdirs',
+                          'white_bkgd', 'raw_noise_std', 'ndc', 'lindisp'}
+    # a checkpoint as the reference's train loop writes it
+    with torch.no_grad():
+        for p in grad_vars:
+            p.add_(0.25)
+    torch.save({'global_step': 1234, 'network_fn_state_dict': train['network_fn'].state_dict(),
+                'network_fine_state_dict': train['network_fine'].state_dict(), 'optimizer_state_dict': opt.state_dict()},
+               tmp_path / 'obj2' / '001234.tar')
+    train2, _, start2, grad_vars2, _ = nsr.create_nerf(_nerf_args(tmp_path))
+    assert start2 == 1234
+    for a, b in zip(grad_vars, grad_vars2):
+        assert torch.equal(a.detach().cpu(), b.detach().cpu())
+    _, _, start3, _, _ = nsr.create_nerf(_nerf_args(tmp_path, no_reload=True))
+    assert start3 == 0
+    # llff + ndc keeps render()'s ndc default (RN:328), coarse-only has no fine network
+    tr, _, _, gv, _ = nsr.create_nerf(_nerf_args(tmp_path, dataset_type='llff', N_importance=0, no_reload=True))
+    assert 'ndc' not in tr and tr['network_fine'] is None and len(gv) == 24
+
+
+def test_create_nerf_matches_live_reference(tmp_path):
+    """Same parameter names / shapes and kwargs keys as the unmodified reference's create_nerf."""
+    import os
+    import pytest
+    import ref_import
+    if not ref_import.available():
+        pytest.skip('reference tree only exists in the build container')
+    import neural_sim_nerf_b200 as nsr
+    RN, _ = ref_import.load()
+    os.makedirs(tmp_path / 'obj2')
+    ref = RN.create_nerf(_nerf_args(tmp_path, no_reload=True))
+    mine = nsr.create_nerf(_nerf_args(tmp_path, no_reload=True))
+    assert set(ref[0]) == set(mine[0]) and set(ref[1]) == set(mine[1])
+    for k in ('perturb', 'N_importance', 'N_samples', 'use_viewdirs', 'white_bkgd', 'raw_noise_std', 'ndc', 'lindisp'):
+        assert ref[0][k] == mine[0][k] and ref[1][k] == mine[1][k], k
+    for net in ('network_fn', 'network_fine'):
+        a, b = ref[0][net].state_dict(), mine[0][net].state_dict()
+        assert list(a) == list(b) and all(a[k].shape == b[k].shape for k in a)
+    assert ref[2] == mine[2] == 0 and len(ref[3]) == len(mine[3])
+    assert ref[4].defaults['lr'] == mine[4].defaults['lr'] and ref[4].defaults['betas'] == mine[4].defaults['betas']
