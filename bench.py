@@ -414,7 +414,30 @@ def run_ours(args):
             train = {'workload': 'one Adam step of both networks on N_rand=1024 rays, 64+128 samples, loss = mse(rgb) + mse(rgb0) (RN:643-716) through render() + autograd + torch.optim.Adam',
                      'ms_per_step': tr_ms, 'rays_per_s': n_rand / (tr_ms * 1e-3), 'steps_per_s': 1e3 / tr_ms,
                      'kernels_per_step': (L.nsr_launch_count() - launches_t0) / (t_steps + 3)}
-            del tnets, opt
+            # the same iteration as ONE C call (nsr_train_step: forward, loss, both backward passes, Adam, re-pack; device Philox draws)
+            fnets = [copy.deepcopy(m) for m in nets]
+            fopt = torch.optim.Adam([p_ for m in fnets for p_ in m.parameters()], lr=5e-4, betas=(0.9, 0.999))
+            fkw = dict(tkw, network_fn=fnets[0], network_fine=fnets[1])
+
+            def fused_step(s):
+                sel = torch.randint(0, n, (n_rand,), device=dev, generator=gen)
+                r = rays_dev[s % len(rays_dev)][sel]
+                return nsr.train_step(torch.stack([r[:, 0:3], r[:, 3:6]], 0), target, fopt, **fkw)
+
+            launches_f0 = L.nsr_launch_count()
+            for s in range(3):
+                fused_step(s)
+            torch.cuda.synchronize()
+            e0.record()
+            for s in range(t_steps):
+                fused_step(s)
+            e1.record()
+            torch.cuda.synchronize()
+            fu_ms = e0.elapsed_time(e1) / t_steps
+            train['fused'] = {'api': 'train_step(batch_rays, target_s, optimizer, **render_kwargs_train) -> nsr_train_step', 'ms_per_step': fu_ms,
+                              'rays_per_s': n_rand / (fu_ms * 1e-3), 'steps_per_s': 1e3 / fu_ms,
+                              'kernels_per_step': (L.nsr_launch_count() - launches_f0) / (t_steps + 3)}
+            del tnets, opt, fnets, fopt
             # per-stage table: the HBM-bound ray-stage kernels, each timed alone (CUDA events, 20 launches back to back)
             hbm = peaks.get('hbm_gbs', 6650.0)
 

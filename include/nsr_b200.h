@@ -195,6 +195,38 @@ int nsr_render_image_forward(int H, int W, const float* K_host, const float* c2w
                              float* rgb0, float* disp0, float* acc0, float* z_std, void* workspace, size_t workspace_bytes,
                              void* stream);
 
+/*
+ * Counter-based random numbers (Philox4x32-10): out[i] ~ U[0,1), a pure function of (seed, stream_id, i).  What the training
+ * kwargs draw with torch.rand for the stratified jitter (RN:455, t_rand [n,S]) and the inverse-CDF samples (RH:211, u [n,Ni]).
+ */
+int nsr_random_uniform(uint64_t seed, uint32_t stream_id, float* out, int64_t count, void* stream);
+
+/* raw[p][3] += std * N(0,1) for p < n_points (RN:365-366 raw_noise_std regularisation), N(0,1) from (seed, stream_id, p). */
+int nsr_add_sigma_noise(uint64_t seed, uint32_t stream_id, float* raw, int64_t n_points, float std, void* stream);
+
+/*
+ * One optimisation step of the NeRF training loop, RN:691-707, entirely on the device:
+ *   render(rays) with the training kwargs (perturb: stratified depths + random inverse-CDF draws; raw_noise_std) ->
+ *   loss = img2mse(rgb, target) + img2mse(rgb0, target) -> backward to the parameters of both networks (the fine one through
+ *   rgb, the coarse one through rgb0; z_samples detached, RN:475) -> Adam (torch.optim.Adam, RN:287: no weight decay) ->
+ *   re-pack the operand blobs.  The learning-rate schedule (RN:710-715) stays with the caller: pass this step's `lr`.
+ *   nsr_train_net: HOST arrays of 24 DEVICE pointers each -- 12 weights in nsr_pack_net order, then the 12 biases -- for the
+ *   parameters and Adam's exp_avg / exp_avg_sq, plus the network's packed blob (updated in place).  fine = NULL: the coarse
+ *   network also evaluates the fine pass (RN:481).  step: 1-based Adam step count.  losses_out: device [2] = img_loss, img_loss0.
+ *   rgb_out (may be NULL): [n,3].  Random tensors are functions of (seed, element index): streams 0 t_rand, 1 u, 2/3 sigma noise.
+ */
+typedef struct nsr_train_net {
+  float* const* params;
+  float* const* exp_avg;
+  float* const* exp_avg_sq;
+  void* packed;
+} nsr_train_net;
+size_t nsr_train_workspace_bytes(int64_t n_rays, int n_samples, int n_importance);
+int nsr_train_step(const float* rays, const float* target, int64_t n_rays, const nsr_train_net* coarse, const nsr_train_net* fine,
+                   int n_samples, int n_importance, uint32_t flags, int perturb, float raw_noise_std, uint64_t seed, float lr,
+                   float beta1, float beta2, float eps, int64_t step, float* losses_out, float* rgb_out, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
 /* Number of kernels this library has launched since load (all threads); used by bench.py's gpu_launches. */
 uint64_t nsr_launch_count(void);
 

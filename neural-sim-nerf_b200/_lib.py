@@ -46,7 +46,18 @@ _SIGNATURES = {
     'nsr_render_image_forward': (c_int, [c_int, c_int, c_vp, c_vp, c_f32p, c_int, ctypes.c_float, ctypes.c_float, c_vp, c_vp,
                                          c_int, c_int, c_u32, c_vp, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p,
                                          c_vp, c_size, c_vp]),
+    'nsr_random_uniform': (c_int, [ctypes.c_uint64, c_u32, c_f32p, c_i64, c_vp]),
+    'nsr_add_sigma_noise': (c_int, [ctypes.c_uint64, c_u32, c_f32p, c_i64, ctypes.c_float, c_vp]),
+    'nsr_train_workspace_bytes': (c_size, [c_i64, c_int, c_int]),
+    'nsr_train_step': (c_int, [c_f32p, c_f32p, c_i64, c_vp, c_vp, c_int, c_int, c_u32, c_int, ctypes.c_float, ctypes.c_uint64,
+                               ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, c_i64, c_f32p, c_f32p, c_vp, c_size, c_vp]),
 }
+
+
+class TrainNet(ctypes.Structure):
+    """struct nsr_train_net (include/nsr_b200.h)."""
+    _fields_ = [('params', c_vp), ('exp_avg', c_vp), ('exp_avg_sq', c_vp), ('packed', c_vp)]
+
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -294,4 +294,148 @@ int nsr_render_image_forward(int H, int W, const float* K_host, const float* c2w
   return NSR_OK;
 }
 
+// ----------------------------------------------------------------------------- one optimisation step (RN:643-716)
+static const int kParamRows[NSR_NET_NUM_TENSORS] = {256, 256, 256, 256, 256, 256, 256, 256, 128, 256, 1, 3};
+static const int kParamCols[NSR_NET_NUM_TENSORS] = {63, 256, 256, 256, 256, 319, 256, 256, 283, 256, 256, 128};
+static const size_t kNetParams = 595844;      // SURVEY a-7
+static const size_t kNetParamsPadded = 595968;  // multiple of 64 floats
+
+int nsr_random_uniform(uint64_t seed, uint32_t stream_id, float* out, int64_t count, void* stream) {
+  NSR_REQUIRE(count >= 0 && (count == 0 || out), "nsr_random_uniform: bad argument");
+  return launch_uniform(seed, stream_id, out, count, static_cast<cudaStream_t>(stream));
+}
+
+int nsr_add_sigma_noise(uint64_t seed, uint32_t stream_id, float* raw, int64_t n_points, float std, void* stream) {
+  NSR_REQUIRE(n_points >= 0 && (n_points == 0 || raw), "nsr_add_sigma_noise: bad argument");
+  NSR_REQUIRE((reinterpret_cast<uintptr_t>(raw) & 15) == 0, "nsr_add_sigma_noise: raw must be 16-byte aligned");
+  return launch_sigma_noise(seed, stream_id, raw, n_points, std, static_cast<cudaStream_t>(stream));
+}
+
+// workspace layout (each block padded to 256 B):
+//   forward workspace (nsr_render_workspace_bytes) | t_rand [n,S] | u [n,Ni] | rgb [n,3] | rgb0 [n,3] | d_rgb [n,3] | d_rgb0 [n,3] |
+//   d_rays [n,11] | backward workspace (n, T) | dump (n, T) | gradients 2 x 595 968 floats
+size_t nsr_train_workspace_bytes(int64_t n, int S, int Ni) {
+  const int T = S + Ni;
+  size_t b = nsr_render_workspace_bytes(n, S, Ni);
+  b += align_up(size_t(n) * S * 4, 256) + align_up(size_t(n) * (Ni > 0 ? Ni : 1) * 4, 256);
+  b += 4 * align_up(size_t(n) * 12, 256) + align_up(size_t(n) * 44, 256);
+  b += nsr_render_backward_workspace_bytes(n, T);
+  b += align_up(nsr_mlp_dump_bytes(n, T), 256);
+  b += 2 * kNetParamsPadded * 4;
+  return b;
+}
+
+int nsr_train_step(const float* rays, const float* target, int64_t n, const nsr_train_net* coarse, const nsr_train_net* fine, int S, int Ni,
+                   uint32_t flags, int perturb, float raw_noise_std, uint64_t seed, float lr, float beta1, float beta2, float eps,
+                   int64_t step, float* losses_out, float* rgb_out, void* workspace, size_t workspace_bytes, void* stream) {
+  NSR_REQUIRE(n > 0 && S >= 2 && Ni >= 0 && step >= 1, "nsr_train_step: bad sizes (n_rays=%lld, step=%lld)", (long long)n, (long long)step);
+  NSR_REQUIRE(Ni == 0 || S >= 3, "nsr_train_step: hierarchical sampling needs n_samples >= 3");
+  NSR_REQUIRE(rays && target && coarse && losses_out, "nsr_train_step: null argument");
+  NSR_REQUIRE(workspace && workspace_bytes >= nsr_train_workspace_bytes(n, S, Ni), "nsr_train_step: workspace too small");
+  NSR_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "nsr_train_step: workspace must be 256-byte aligned");
+  if (fine != nullptr && Ni == 0) fine = nullptr;   // RN:272: no fine pass, the fine network is never evaluated
+  const nsr_train_net* nets[2] = {coarse, fine};
+  for (int k = 0; k < 2; ++k) {
+    if (!nets[k]) continue;
+    NSR_REQUIRE(nets[k]->params && nets[k]->exp_avg && nets[k]->exp_avg_sq && nets[k]->packed, "nsr_train_step: null network field");
+    for (int i = 0; i < 2 * NSR_NET_NUM_TENSORS; ++i)
+      NSR_REQUIRE(nets[k]->params[i] && nets[k]->exp_avg[i] && nets[k]->exp_avg_sq[i], "nsr_train_step: null tensor %d", i);
+    NSR_REQUIRE((reinterpret_cast<uintptr_t>(nets[k]->packed) & 127) == 0, "nsr_train_step: packed blob must be 128-byte aligned");
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int T = S + Ni;
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  auto carve = [&](size_t bytes) {
+    uint8_t* p = ws;
+    ws += align_up(bytes, 256);
+    return p;
+  };
+  const size_t fwd_bytes = nsr_render_workspace_bytes(n, S, Ni);
+  uint8_t* fwd = carve(fwd_bytes);
+  float* z0 = reinterpret_cast<float*>(fwd);                                      // layout of nsr_render_workspace_bytes
+  float* w0 = reinterpret_cast<float*>(fwd + align_up(size_t(n) * S * 4, 256));
+  float* raw0 = reinterpret_cast<float*>(fwd + 2 * align_up(size_t(n) * S * 4, 256));
+  float* z1 = reinterpret_cast<float*>(fwd + 2 * align_up(size_t(n) * S * 4, 256) + align_up(size_t(n) * S * 16, 256));
+  float* raw1 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(z1) + align_up(size_t(n) * T * 4, 256));
+  float* t_rand = reinterpret_cast<float*>(carve(size_t(n) * S * 4));
+  float* u = reinterpret_cast<float*>(carve(size_t(n) * (Ni > 0 ? Ni : 1) * 4));
+  float* rgb = reinterpret_cast<float*>(carve(size_t(n) * 12));
+  float* rgb0 = reinterpret_cast<float*>(carve(size_t(n) * 12));
+  float* d_rgb = reinterpret_cast<float*>(carve(size_t(n) * 12));
+  float* d_rgb0 = reinterpret_cast<float*>(carve(size_t(n) * 12));
+  float* d_rays = reinterpret_cast<float*>(carve(size_t(n) * 44));
+  const size_t bwd_bytes = nsr_render_backward_workspace_bytes(n, T);
+  void* bwd = carve(bwd_bytes);
+  void* dump = carve(nsr_mlp_dump_bytes(n, T));
+  float* grads = reinterpret_cast<float*>(carve(2 * kNetParamsPadded * 4));
+  if (rgb_out) rgb = rgb_out;
+
+  // gradient tensors of both networks inside the flat buffer, reference shapes
+  float* dW[2][NSR_NET_NUM_TENSORS];
+  float* dB[2][NSR_NET_NUM_TENSORS];
+  for (int k = 0; k < 2; ++k) {
+    float* g = grads + k * kNetParamsPadded;
+    for (int i = 0; i < NSR_NET_NUM_TENSORS; ++i) {
+      dW[k][i] = g;
+      g += size_t(kParamRows[i]) * kParamCols[i];
+    }
+    for (int i = 0; i < NSR_NET_NUM_TENSORS; ++i) {
+      dB[k][i] = g;
+      g += kParamRows[i];
+    }
+  }
+  const uint32_t cflags = flags & NSR_FLAG_WHITE_BKGD;
+  const uint32_t zflags = flags & NSR_FLAG_LINDISP;
+  const void* pc = coarse->packed;
+  const void* pl = fine ? fine->packed : coarse->packed;   // network of the last pass (RN:481)
+  const int last = fine ? 1 : 0;
+  int rc;
+  // ---- forward (RN:390-501 with perturb / raw_noise_std as the training kwargs set them)
+  if (perturb) {
+    if ((rc = launch_uniform(seed, 0u, t_rand, n * int64_t(S), st))) return rc;                                   // RN:455
+    if (Ni > 0 && (rc = launch_uniform(seed, 1u, u, n * int64_t(Ni), st))) return rc;                             // RH:211
+  }
+  if ((rc = launch_coarse_z(rays, n, S, zflags, perturb ? t_rand : nullptr, z0, st))) return rc;
+  if ((rc = launch_mlp_forward(rays, z0, n, S, pc, 0, raw0, st))) return rc;
+  if (raw_noise_std > 0.f && (rc = launch_sigma_noise(seed, 2u, raw0, n * int64_t(S), raw_noise_std, st))) return rc;  // RN:365-366
+  if ((rc = launch_raw2outputs(raw0, z0, rays + 3, 11, n, S, cflags, Ni > 0 ? rgb0 : rgb, nullptr, nullptr, w0, nullptr, st))) return rc;
+  if (Ni > 0) {
+    if ((rc = launch_resample_merge(z0, w0, n, S, Ni, perturb ? u : nullptr, z1, nullptr, nullptr, st))) return rc;
+    if ((rc = launch_mlp_forward(rays, z1, n, T, pl, 0, raw1, st))) return rc;
+    if (raw_noise_std > 0.f && (rc = launch_sigma_noise(seed, 3u, raw1, n * int64_t(T), raw_noise_std, st))) return rc;
+    if ((rc = launch_raw2outputs(raw1, z1, rays + 3, 11, n, T, cflags, rgb, nullptr, nullptr, nullptr, nullptr, st))) return rc;
+  }
+  // ---- loss = img2mse(rgb, target) [+ img2mse(rgb0, target)]  (RN:696-704) and its gradient
+  if ((rc = launch_mse_grad(rgb, target, n * 3, d_rgb, losses_out, st))) return rc;
+  if (Ni > 0) {
+    if ((rc = launch_mse_grad(rgb0, target, n * 3, d_rgb0, losses_out + 1, st))) return rc;
+  } else {
+    cudaMemsetAsync(losses_out + 1, 0, 4, st);
+  }
+  // ---- loss.backward() (RN:705): the last pass through rgb, the coarse pass through rgb0
+  cudaMemsetAsync(grads, 0, 2 * kNetParamsPadded * 4, st);
+  if ((rc = nsr_render_rays_backward(rays, Ni > 0 ? z1 : z0, Ni > 0 ? raw1 : raw0, n, Ni > 0 ? T : S, pl, cflags, d_rgb, d_rays, dump, dW[last],
+                                     dB[last], bwd, bwd_bytes, stream))) return rc;
+  if (Ni > 0 && (rc = nsr_render_rays_backward(rays, z0, raw0, n, S, pc, cflags, d_rgb0, d_rays, dump, dW[0], dB[0], bwd, bwd_bytes, stream))) return rc;
+  // ---- optimizer.step() (RN:707)
+  AdamJobs jobs;
+  jobs.count = 0;
+  for (int k = 0; k < 2; ++k) {
+    if (!nets[k]) continue;
+    for (int i = 0; i < 2 * NSR_NET_NUM_TENSORS; ++i) {
+      const int t = i % NSR_NET_NUM_TENSORS;
+      const bool is_w = i < NSR_NET_NUM_TENSORS;
+      jobs.j[jobs.count++] = AdamJob{nets[k]->params[i], is_w ? dW[k][t] : dB[k][t], nets[k]->exp_avg[i], nets[k]->exp_avg_sq[i],
+                                     is_w ? kParamRows[t] * kParamCols[t] : kParamRows[t]};
+    }
+  }
+  if ((rc = launch_adam(jobs, beta1, beta2, lr, eps, step, st))) return rc;
+  // ---- the kernels read packed operands: re-pack what changed
+  for (int k = 0; k < 2; ++k) {
+    if (!nets[k]) continue;
+    if ((rc = launch_pack_net(nets[k]->params, nets[k]->params + NSR_NET_NUM_TENSORS, nets[k]->packed, st))) return rc;
+  }
+  return NSR_OK;
+}
+
 }  // extern "C"

@@ -120,6 +120,22 @@ int launch_make_rays_dev(int H, int W, const float* K9, const float* c2w_dev, in
 int launch_c2w_grad(int W, const float* K9, const float* rays, const float* d_rays, const int32_t* pixel_idx, int64_t n,
                     float* d_c2w, int accumulate, double* partials, cudaStream_t st);
 size_t c2w_grad_workspace_bytes();
+// train_stage.cu
+struct AdamJob {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  int n;
+};
+struct AdamJobs {
+  AdamJob j[2 * 2 * NSR_NET_NUM_TENSORS];
+  int count;
+};
+int launch_uniform(uint64_t seed, uint32_t stream, float* out, int64_t count, cudaStream_t st);
+int launch_sigma_noise(uint64_t seed, uint32_t stream, float* raw, int64_t n_points, float std, cudaStream_t st);
+int launch_mse_grad(const float* x, const float* y, int64_t count, float* d_x, float* loss, cudaStream_t st);
+int launch_adam(const AdamJobs& jobs, float beta1, float beta2, float lr, float eps, int64_t step, cudaStream_t st);
 // mlp_forward.cu
 int launch_pack_net(const float* const* weights, const float* const* biases, void* packed, cudaStream_t st);
 int launch_mlp_forward(const float* rays, const float* z_or_pts, int64_t n, int S, const void* packed, uint32_t flags,

@@ -815,6 +815,104 @@ def create_nerf(args):
     return train, test, start, grad_vars, optimizer
 
 
+# ----------------------------------------------------------------------------- RN:691-707
+_train_cache = weakref.WeakKeyDictionary()      # optimizer -> cached pointer tables
+
+
+def _adam_state(optimizer, p):
+    st = optimizer.state[p]
+    if len(st) == 0:                                        # as torch.optim.Adam initialises it lazily
+        st['step'] = torch.tensor(0.0, dtype=torch.float32)
+        st['exp_avg'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+        st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+    return st
+
+
+def train_step(batch_rays, target_s, optimizer, near=0., far=1., seed=None, **kw):
+    """The body of the reference's training iteration, RN:691-707, as ONE call of nsr_train_step:
+
+        rgb, disp, acc, extras = render(H, W, K, chunk, rays=batch_rays, retraw=True, **render_kwargs_train)
+        optimizer.zero_grad(); loss = img2mse(rgb, target_s) + img2mse(extras['rgb0'], target_s); loss.backward(); optimizer.step()
+
+    batch_rays [2,n,3] = (rays_o, rays_d) and target_s [n,3] as RN:679-689 build them; `kw` = render_kwargs_train (+ near / far).
+    `optimizer` is the torch.optim.Adam create_nerf returned: its exp_avg / exp_avg_sq / step state is what the kernel updates,
+    so optimizer.state_dict() checkpoints stay in the reference's format (RN:725-731).  Random draws (perturb, raw_noise_std)
+    come from the device Philox generator: `seed` (default torch.initial_seed()) and the Adam step count address them.
+    Returns {'loss', 'img_loss', 'img_loss0', 'psnr', 'rgb'} as device tensors (no host synchronisation).  The learning-rate
+    decay (RN:710-715) is the caller's, through optimizer.param_groups as in the reference."""
+    if not isinstance(optimizer, torch.optim.Adam):
+        raise NotImplementedError('train_step drives torch.optim.Adam (RN:287)')
+    net_c, net_f = kw['network_fn'], kw.get('network_fine')
+    S, Ni = int(kw['N_samples']), int(kw.get('N_importance', 0))
+    if Ni == 0:
+        net_f = None
+    if not kw.get('use_viewdirs', False) or kw.get('ndc', True):
+        raise NotImplementedError('train_step covers use_viewdirs=True, ndc=False')
+    if len(optimizer.param_groups) != 1:
+        raise NotImplementedError('train_step expects the single parameter group of RN:287')
+    grp = optimizer.param_groups[0]
+    if grp.get('weight_decay', 0) != 0 or grp.get('amsgrad', False) or grp.get('maximize', False):
+        raise NotImplementedError('train_step implements plain Adam (no weight decay / amsgrad / maximize), as RN:287 configures it')
+    nets = [net_c] + ([net_f] if net_f is not None else [])
+    params = [p for m in nets for p in _params_of(m)]
+    known = {id(p) for p in grp['params']}
+    if any(id(p) not in known for p in params):
+        raise ValueError('the optimizer does not own the parameters of network_fn / network_fine')
+    L = lib()
+    blobs = [packed_weights(m) for m in nets]
+    key = tuple((p.data_ptr(), id(optimizer.state[p].get('exp_avg'))) for p in params) + tuple(b.data_ptr() for b in blobs)
+    hit = _train_cache.get(optimizer)
+    if hit is None or hit['key'] != key:
+        tables, structs = [], []
+        for m, blob in zip(nets, blobs):
+            ps = _params_of(m)
+            for p in ps:
+                if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                    raise _lib.NsrError('network parameters must be contiguous fp32 CUDA tensors (no CPU fallback)')
+            sts = [_adam_state(optimizer, p) for p in ps]
+            arr = lambda ts: (ctypes.c_void_p * 24)(*[t.data_ptr() for t in ts])
+            t3 = (arr(ps), arr([s_['exp_avg'] for s_ in sts]), arr([s_['exp_avg_sq'] for s_ in sts]))
+            tables.append(t3)
+            structs.append(_lib.TrainNet(ctypes.cast(t3[0], ctypes.c_void_p), ctypes.cast(t3[1], ctypes.c_void_p),
+                                         ctypes.cast(t3[2], ctypes.c_void_p), ctypes.c_void_p(blob.data_ptr())))
+        key = tuple((p.data_ptr(), id(optimizer.state[p].get('exp_avg'))) for p in params) + tuple(b.data_ptr() for b in blobs)
+        hit = {'key': key, 'tables': tables, 'structs': structs, 'ws': None}
+        _train_cache[optimizer] = hit
+    rays_o, rays_d = batch_rays[0], batch_rays[1]
+    with torch.no_grad():
+        rays_d = _f32c(rays_d, 'batch_rays').reshape(-1, 3)
+        rays_o = _f32c(rays_o, 'batch_rays').reshape(-1, 3)
+        n = rays_d.shape[0]
+        vd = rays_d / torch.norm(rays_d, dim=-1, keepdim=True)                                   # RN:97
+        bounds = torch.tensor([float(near), float(far)], dtype=torch.float32, device=rays_d.device).expand(n, 2)
+        rays = torch.cat([rays_o, rays_d, bounds, vd], -1).contiguous()                          # RN:106-112
+        target = _f32c(target_s, 'target_s').reshape(-1, 3)
+    if target.shape[0] != n:
+        raise ValueError(f'target_s {tuple(target_s.shape)} does not match batch_rays {tuple(batch_rays.shape)}')
+    step = int(optimizer.state[params[0]]['step']) + 1
+    base = torch.initial_seed() if seed is None else int(seed)
+    call_seed = (base * 0x9E3779B97F4A7C15 + step) & 0xFFFFFFFFFFFFFFFF
+    ws_bytes = L.nsr_train_workspace_bytes(n, S, Ni)
+    if hit['ws'] is None or hit['ws'].numel() < ws_bytes:
+        hit['ws'] = torch.empty(ws_bytes, dtype=torch.uint8, device=rays.device)
+    losses = torch.empty(2, dtype=torch.float32, device=rays.device)
+    rgb = torch.empty(n, 3, dtype=torch.float32, device=rays.device)
+    flags = (FLAG_LINDISP if kw.get('lindisp', False) else 0) | (FLAG_WHITE_BKGD if kw.get('white_bkgd', False) else 0)
+    b1, b2 = grp['betas']
+    structs = hit['structs']
+    check(L.nsr_train_step(ptr(rays), ptr(target), n, ctypes.byref(structs[0]), ctypes.byref(structs[1]) if len(structs) > 1 else None,
+                           S, Ni, flags, 1 if kw.get('perturb', 0.) else 0, float(kw.get('raw_noise_std', 0.)), call_seed,
+                           float(grp['lr']), float(b1), float(b2), float(grp['eps']), step, ptr(losses), ptr(rgb),
+                           ptr(hit['ws']), ws_bytes, _stream()), 'nsr_train_step')
+    for p in params:                                            # what optimizer.step() does to the bookkeeping
+        optimizer.state[p]['step'] += 1
+        torch.autograd.graph.increment_version(p)
+    for m, blob in zip(nets, blobs):                            # the blobs were re-packed in place: keep the cache in step
+        ps = _params_of(m)
+        _pack_cache[m] = (tuple((p.data_ptr(), p._version, p.device.index) for p in ps), blob)
+    return {'loss': losses[0] + losses[1], 'img_loss': losses[0], 'img_loss0': losses[1], 'psnr': mse2psnr(losses[0:1])[0], 'rgb': rgb}
+
+
 def install(reference_module, loops=False):
     """Monkey-patch a loaded reference `utils.run_nerf_noscale` module so its callers
     (render_path RN:233, render_path_grad RN:168, MAIN:128/184) run on this renderer.  With loops=True the two image

@@ -247,6 +247,33 @@ def rays_grad_to_c2w(H, W, K, c2w, d_packed, near=0., far=1.):
     return g
 
 
+def philox4x32_10(counter, key):
+    """Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11; the Random123 library's
+    philox4x32 with 10 rounds) on numpy uint32 arrays: counter [...,4], key [...,2] -> [...,4].  Not part of the reference
+    (which draws with torch.rand / torch.randn, RN:455, RH:211, RN:366): it is the checker of the device generator that
+    replaces those draws in nsr_train_step, pinned by Random123's published known-answer vectors (tests/test_host_logic.py)."""
+    c = [np.asarray(counter[..., i], dtype=np.uint64) for i in range(4)]
+    k0 = np.asarray(key[..., 0], dtype=np.uint64)
+    k1 = np.asarray(key[..., 1], dtype=np.uint64)
+    M0, M1, W0, W1, MASK = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0x9E3779B9), np.uint64(0xBB67AE85), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & MASK, p1 >> np.uint64(32), p1 & MASK
+        c = [hi1 ^ c[1] ^ k0, lo1, hi0 ^ c[3] ^ k1, lo0]
+        k0, k1 = (k0 + W0) & MASK, (k1 + W1) & MASK
+    return np.stack(c, -1).astype(np.uint32)
+
+
+def philox_uniform(seed, stream, count):
+    """The device generator's addressing (include/nsr_b200.h nsr_random_uniform): element 4q+j = component j of
+    philox(counter = (q lo, q hi, stream, 0), key = (seed lo, seed hi)), mapped to [0,1) as (x >> 8) * 2^-24."""
+    q = np.arange((count + 3) // 4, dtype=np.uint64)
+    ctr = np.stack([q & np.uint64(0xFFFFFFFF), q >> np.uint64(32), np.full_like(q, stream), np.zeros_like(q)], -1)
+    key = np.broadcast_to(np.array([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], dtype=np.uint64), (len(q), 2))
+    r = philox4x32_10(ctr, key).reshape(-1)[:count]
+    return ((r >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)).astype(np.float32)
+
+
 # --------------------------------------------------------------------------
 # helpers shared by tests / bench (not part of the reference)
 # --------------------------------------------------------------------------

@@ -171,3 +171,19 @@ def test_create_nerf_matches_live_reference(tmp_path):
         assert list(a) == list(b) and all(a[k].shape == b[k].shape for k in a)
     assert ref[2] == mine[2] == 0 and len(ref[3]) == len(mine[3])
     assert ref[4].defaults['lr'] == mine[4].defaults['lr'] and ref[4].defaults['betas'] == mine[4].defaults['betas']
+
+
+def test_philox_known_answers():
+    """Random123's known-answer vectors for philox4x32-10 (kat_vectors): pins the oracle generator the GPU one is checked against."""
+    import numpy as np
+    import nerf_oracle as O
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = O.philox4x32_10(np.array([ctr], dtype=np.uint64), np.array([key], dtype=np.uint64))[0]
+        assert tuple(int(x) for x in got) == want
+    u = O.philox_uniform(1234, 1, 10001)
+    assert u.dtype == np.float32 and u.shape == (10001,) and 0.0 <= u.min() and u.max() < 1.0
+    assert abs(float(u.mean()) - 0.5) < 0.01
+    assert np.array_equal(u[:37], O.philox_uniform(1234, 1, 37))            # addressable by index: a prefix is a prefix
