@@ -92,7 +92,16 @@ __device__ int layer_shift(const NetPtrs& p, int step, float* red) {
   const int count = step == 0 ? 256 * 63 : (step == 5 ? 256 * 319 : (step == 9 ? 128 * 283 : 65536));
   const float* w = p.w[tensor];
   float m = 0.f;
-  for (int i = threadIdx.x; i < count; i += blockDim.x) m = fmaxf(m, fabsf(w[i]));
+  if ((reinterpret_cast<uintptr_t>(w) & 15) == 0) {   // every count is a multiple of 4
+    const float4* w4 = reinterpret_cast<const float4*>(w);
+#pragma unroll 4
+    for (int i = threadIdx.x; i < count / 4; i += blockDim.x) {
+      const float4 v = w4[i];
+      m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+  } else {
+    for (int i = threadIdx.x; i < count; i += blockDim.x) m = fmaxf(m, fabsf(w[i]));
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   __syncthreads();
@@ -116,7 +125,7 @@ __global__ void pack_net_kernel(NetPtrs p, uint8_t* __restrict__ out) {
     __half* hi = reinterpret_cast<__half*>(out + size_t(c) * CHUNK_PAIR_BYTES);
     __half* lo = reinterpret_cast<__half*>(out + size_t(c) * CHUNK_PAIR_BYTES + CHUNK_BYTES);
     for (int e = threadIdx.x; e < CHUNK_ROWS * CHUNK_K; e += blockDim.x) {
-      const int nl = e / CHUNK_K, kl = e % CHUNK_K;
+      const int kl = e / CHUNK_ROWS, nl = e % CHUNK_ROWS;   // consecutive threads: consecutive n = contiguous in the source row
       const int n = nh * 128 + nl, k = kc * 64 + kl;
       float v = 0.f;
       switch (bstep) {
@@ -173,7 +182,7 @@ __global__ void pack_net_kernel(NetPtrs p, uint8_t* __restrict__ out) {
         lo[chunk_off(nl, kl) >> 1] = __float2half_rn(v - __half2float(h));
       }
     }
-  } else {  // fp32 tail
+  } else if (c == MIX_CHUNK0 + NUM_CHUNKS) {  // fp32 tail
     float* t = reinterpret_cast<float*>(out + WEIGHT_BYTES);
     for (int i = threadIdx.x; i < TAIL_FLOATS; i += blockDim.x) {
       float v = 0.f;
@@ -192,13 +201,13 @@ __global__ void pack_net_kernel(NetPtrs p, uint8_t* __restrict__ out) {
         if (j == 0) v = p.b[10][0];
         else if (j < 4) v = p.b[11][j - 1];
       }
-      t[i] = v;
+      if (i < TAIL_MIXSCALE || i >= TAIL_MIXSCALE + NUM_STEPS) t[i] = v;   // the scales are written by the blocks below
     }
+  } else if (c < MIX_CHUNK0 + NUM_CHUNKS + 1 + NUM_STEPS) {  // one block per GEMM step: 2^-b of its mixed-precision chunks
+    const int step = c - (MIX_CHUNK0 + NUM_CHUNKS + 1);
     __shared__ float s_red[8];
-    for (int step = 0; step < NUM_STEPS; ++step) {
-      const int b = layer_shift(p, step, s_red);
-      if (threadIdx.x == 0) t[TAIL_MIXSCALE + step] = exp2f(float(-b));
-    }
+    const int b = layer_shift(p, step, s_red);
+    if (threadIdx.x == 0) reinterpret_cast<float*>(out + WEIGHT_BYTES)[TAIL_MIXSCALE + step] = exp2f(float(-b));
   }
 }
 
@@ -208,7 +217,7 @@ int launch_pack_net(const float* const* weights, const float* const* biases, voi
     p.w[i] = weights[i];
     p.b[i] = biases[i];
   }
-  pack_net_kernel<<<2 * NUM_CHUNKS + NUM_BWD_CHUNKS + 1, 256, 0, st>>>(p, static_cast<uint8_t*>(packed));
+  pack_net_kernel<<<2 * NUM_CHUNKS + NUM_BWD_CHUNKS + 1 + NUM_STEPS, 256, 0, st>>>(p, static_cast<uint8_t*>(packed));
   count_launch();
   return check_launch("pack_net_kernel");
 }

@@ -122,38 +122,103 @@ struct SJobs {
   SJob j[SK_NUM_JOBS];
 };
 
+// One block = 256 threads walking whole 128-point tiles in 16-byte units (8 consecutive features of one point).  Inside a tile
+// an array is (128/8) row blocks of W units each (unit index inside a row block = feature group * 8 + row % 8), so thread t of a
+// warp reads 16 bytes next to its neighbours' (512 B per warp) and -- W being 128 or 256 -- always meets the same feature group
+// t % W / 8: its 8 x n_out partial sums stay in registers over all tiles, are folded over the 8 rows of a feature group with
+// shuffles, over the warps through shared memory, and leave the block as one atomicAdd per output element.
 __global__ void __launch_bounds__(256) wgrad_skinny_kernel(const uint8_t* __restrict__ dump, const float* __restrict__ d_raw,
                                                            long long n_points, SJobs jobs, int n_tiles, const float* gscale) {
   const SJob job = jobs.j[blockIdx.y];
-  const int c = threadIdx.x;
-  float acc[3] = {0.f, 0.f, 0.f}, csum[3] = {0.f, 0.f, 0.f};
+  const int t = threadIdx.x;
+  const int W = job.w;                       // 128 or 256
+  const int within = t % W;                  // unit inside a row block: constant per thread
+  const int fg = within >> 3, rlow = within & 7;
+  const int rb0 = t / W, rb_step = 256 / W;  // row blocks this thread visits: rb0, rb0 + rb_step, ...
+  float acc[3][8];
+  float csum[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[j][q] = 0.f;
   float scale = __uint_as_float(__float_as_uint(*gscale) & 0x7f800000u);
   if (!(scale > 0.f) || !(scale < 3.0e38f)) scale = 1.f;
+  const bool has_coef = job.coef_col >= 0;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    for (int r = 0; r < 128; ++r) {
-      const long long p = (long long)tile * 128 + r;
+    const uint8_t* base = dump + job.x_off + size_t(tile) * (size_t(128) * W * 2);
+#pragma unroll 4
+    for (int rb = rb0; rb < 16; rb += rb_step) {
+      const uint4 u = *reinterpret_cast<const uint4*>(base + (size_t(rb) * W + within) * 16);
       float co[3] = {1.f, 0.f, 0.f};
-      if (job.coef_col >= 0) {
+      if (has_coef) {
+        const long long p = (long long)tile * 128 + rb * 8 + rlow;
+        float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p < n_points) d = reinterpret_cast<const float4*>(d_raw)[p];
+        if (job.coef_col == 0) {          // rgb head: the three colour columns of dL/draw
+          co[0] = d.x;
+          co[1] = d.y;
+          co[2] = d.z;
+        } else {                          // alpha head: the sigma column
+          co[0] = d.w;
+        }
+        if (fg == 0) {
 #pragma unroll
-        for (int j = 0; j < 3; ++j) co[j] = (j < job.n_out && p < n_points) ? d_raw[p * 4 + job.coef_col + j] : 0.f;
+          for (int j = 0; j < 3; ++j) csum[j] += co[j];
+        }
       }
-      if (c < job.w) {
-        const __half x = *reinterpret_cast<const __half*>(dump + job.x_off + dump_blocked_off(tile, r, job.w, c >> 3) + (c & 7) * 2);
-        const float xf = __half2float(x);
+      const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-        for (int j = 0; j < 3; ++j) acc[j] = fmaf(co[j], xf, acc[j]);
-      }
-      if (c == 0 && job.out_coef != nullptr) {
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w4[q]));
 #pragma unroll
-        for (int j = 0; j < 3; ++j) csum[j] += co[j];
+        for (int j = 0; j < 3; ++j) {
+          acc[j][2 * q] = fmaf(co[j], f.x, acc[j][2 * q]);
+          acc[j][2 * q + 1] = fmaf(co[j], f.y, acc[j][2 * q + 1]);
+        }
       }
     }
   }
-  const float mul = (job.coef_col >= 0) ? 1.f : scale;
-  if (c < job.w)
-    for (int j = 0; j < job.n_out; ++j) atomicAdd(job.out + size_t(j) * job.ld + c, acc[j] * mul);
-  if (c == 0 && job.out_coef != nullptr)
-    for (int j = 0; j < job.n_out; ++j) atomicAdd(job.out_coef + j, csum[j]);
+  // fold the 8 rows of a feature group (adjacent lanes), then the warps that share it
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float v = acc[j][q];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      acc[j][q] = v;
+    }
+    float c = csum[j];
+    c += __shfl_xor_sync(0xffffffffu, c, 1);
+    c += __shfl_xor_sync(0xffffffffu, c, 2);
+    c += __shfl_xor_sync(0xffffffffu, c, 4);
+    csum[j] = c;
+  }
+  __shared__ float red[2][3][256];          // [row-block parity for W = 128][out row][feature]
+  if (rlow == 0) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) red[rb0][j][fg * 8 + q] = acc[j][q];
+  }
+  __shared__ float cred[2][3];
+  if (within == 0) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) cred[rb0][j] = csum[j];
+  }
+  __syncthreads();
+  const float mul = has_coef ? 1.f : scale;
+  if (t < W) {
+    for (int j = 0; j < job.n_out; ++j) {
+      float v = red[0][j][t];
+      if (W == 128) v += red[1][j][t];
+      atomicAdd(job.out + size_t(j) * job.ld + t, v * mul);
+    }
+  }
+  if (t == 0 && job.out_coef != nullptr) {
+    for (int j = 0; j < job.n_out; ++j) atomicAdd(job.out_coef + j, cred[0][j] + (W == 128 ? cred[1][j] : 0.f));
+  }
 }
 
 int launch_weight_grads(const void* dump_v, const float* d_raw, int64_t n_points, const float* gscale, float* const* dW,
@@ -196,7 +261,7 @@ int launch_weight_grads(const void* dump_v, const float* d_raw, int64_t n_points
   s.j[k++] = SJob{(unsigned long long)dump_off_gf(P), 256, -1, 1, dB[9], 256, nullptr};
   s.j[k++] = SJob{(unsigned long long)dump_off_h(P, 7), 256, 3, 1, dW[10], 256, dB[10]};                                   // alpha_linear: sigma column
   s.j[k++] = SJob{(unsigned long long)dump_off_hv(P), 128, 0, 3, dW[11], 128, dB[11]};                                     // rgb_linear: rgb columns
-  wgrad_skinny_kernel<<<dim3(24, SK_NUM_JOBS), 256, 0, st>>>(dump, d_raw, (long long)n_points, s, n_tiles, gscale);
+  wgrad_skinny_kernel<<<dim3(n_tiles < 74 ? n_tiles : 74, SK_NUM_JOBS), 256, 0, st>>>(dump, d_raw, (long long)n_points, s, n_tiles, gscale);
   count_launch();
   return check_launch("wgrad_skinny_kernel");
 }

@@ -106,9 +106,12 @@ def test_train_step_equals_autograd_and_torch_adam(nsr, wfit):
         (img_loss + img_loss0).backward()
         opt_a.step()
         out = nsr.train_step(br, tgt, opt_b, **train_kwargs(nets_b))
-        assert abs(float(out['img_loss']) - float(img_loss)) <= 1e-6 * max(1.0, float(img_loss))
-        assert abs(float(out['img_loss0']) - float(img_loss0)) <= 1e-6 * max(1.0, float(img_loss0))
-        assert torch.allclose(out['rgb'], rgb.detach(), atol=1e-6)
+        assert abs(float(out['img_loss']) - float(img_loss)) <= 1e-5 * max(1.0, float(img_loss))
+        assert abs(float(out['img_loss0']) - float(img_loss0)) <= 1e-5 * max(1.0, float(img_loss0))
+        if it == 0:
+            assert torch.equal(out['rgb'], rgb.detach())                # identical parameters, identical kernels
+        else:
+            assert torch.allclose(out['rgb'], rgb.detach(), atol=5e-4)   # parameters differ by summation order of the weight gradients
         assert float(out['psnr']) == pytest.approx(float(nsr.mse2psnr(img_loss.detach())), rel=1e-5)
     moved = 0.0
     for (na, pa), (nb, pb), p0 in zip(nets_a[0].named_parameters(), nets_b[0].named_parameters(), start[:24]):
