@@ -284,6 +284,49 @@ def run_ours(args):
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     e2e_value = world * n * args.steps / (ms_e2e * 1e-3)
 
+    # ------------------------------------------------------------- BASELINE configs 3 / 4: forward + backward to the pose, all ranks
+    # per step and rank: one image forward (z / raw kept), nsr_render_rays_backward from a fixed dL/drgb, closed-form fold to dL/dc2w
+    # [3,4], then the path's only collective: an all-reduce of the 12 pose-gradient floats (dist.py; MAIN:191's mean over images)
+    T = N_SAMPLES + N_IMPORTANCE
+    bws_bytes = L.nsr_render_backward_workspace_bytes(n, T)
+    bws = torch.empty(bws_bytes, dtype=torch.uint8, device=dev)
+    g_rgb = torch.randn(n, 3, device=dev, generator=torch.Generator(device=dev).manual_seed(rank))
+    d_rays = new(n, 11)
+    zsave, rawsave = new(n, T), new(n, T, 4)
+    d_c2w = new(12)
+    relu_mask = torch.empty(L.nsr_relu_mask_bytes(n, T), dtype=torch.uint8, device=dev)    # 272 B per sample point: 8.4 GB per image
+    cws = torch.empty(L.nsr_c2w_grad_workspace_bytes(), dtype=torch.uint8, device=dev)
+    Kf = (ctypes.c_float * 9)(*[float(v) for row in O.YCBV_K_400 for v in row])
+
+    def step_pose_grad(s):
+        r = rays_dev[s % len(rays_dev)]
+        rc = L.nsr_render_rays_forward_ex(P(r), n, P(pc), P(pf), N_SAMPLES, N_IMPORTANCE, 0, None, None, P(outs['rgb']), P(outs['disp']),
+                                          P(outs['acc']), P(outs['rgb0']), P(outs['disp0']), P(outs['acc0']), P(outs['zstd']), P(rawsave),
+                                          P(zsave), None, P(relu_mask), P(ws), ws_bytes, stream)
+        rc = rc or L.nsr_render_rays_backward_ex(P(r), P(zsave), P(rawsave), n, T, P(pf), 0, P(g_rgb), P(d_rays), None, None, None,
+                                                 P(relu_mask), P(bws), bws_bytes, stream)
+        rc = rc or L.nsr_rays_grad_to_c2w(H, W, Kf, P(r), P(d_rays), None, n, P(d_c2w), 0, P(cws), stream)
+        if rc != 0:
+            raise RuntimeError(L.nsr_last_error().decode())
+        if world > 1:
+            dist.all_reduce(d_c2w, op=dist.ReduceOp.SUM)
+
+    for s in range(2):
+        step_pose_grad(s)
+    barrier()
+    e0.record()
+    for s in range(args.steps):
+        step_pose_grad(args.warmup + s)
+    e1.record()
+    barrier()
+    ms_pg = max_over_ranks(e0.elapsed_time(e1))
+    pose_grad = {'workload': 'BASELINE config 3/4: per rank and step one 400x400 image forward (saving one bit per ReLU, 272 B/point) + backward '
+                             'dL/d(rays) without recompute -> dL/dc2w (closed form) + all-reduce of the 12 pose-gradient floats over the ranks',
+                 'rays_per_s': world * n * args.steps / (ms_pg * 1e-3), 'ms_per_step': ms_pg / args.steps,
+                 'collective': 'ncclAllReduce(SUM) of 48 bytes per step' if world > 1 else 'none (1 rank)',
+                 'algorithmic_tflops': world * n * args.steps * (64 + 192 + 192) * FLOP_PER_POINT / (ms_pg * 1e-3) / 1e12}
+    del bws, zsave, rawsave, d_rays, relu_mask
+
     # ------------------------------------------------------------- roofline of the dominant kernel (fine-pass MLP)
     roofline = cpu_base = fast = mixed = fwd_bwd = stages = train = None
     if rank == 0:
@@ -376,7 +419,7 @@ def run_ours(args):
             e1.record()
             torch.cuda.synchronize()
             fb_ms = e0.elapsed_time(e1) / args.steps
-            fwd_bwd = {'workload': 'BASELINE config 3: forward + backward dL/d(rays) from dL/d(rgb_map), 160000 rays, 64+128 samples (fine pass recomputed in the backward kernel)',
+            fwd_bwd = {'workload': 'BASELINE config 3 on the recompute route (no extra memory): forward + backward dL/d(rays) from dL/d(rgb_map), 160000 rays, 64+128 samples (fine pass recomputed in the backward kernel)',
                        'rays_per_s': n / (fb_ms * 1e-3), 'ms_per_step': fb_ms, 'algorithmic_flop_per_ray': (64 + 192 + 192) * FLOP_PER_POINT,
                        'algorithmic_tflops': n * (64 + 192 + 192) * FLOP_PER_POINT / (fb_ms * 1e-3) / 1e12}
             del bws, zsave, rawsave
@@ -499,7 +542,7 @@ def run_ours(args):
                     'api': 'render(H, W, K, chunk, rays=<pinned host [2,N,3] -> cuda>, **render_kwargs_test) + D2H of rgb/disp/acc'},
             'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_base,
             'flop_per_ray': FLOP_PER_RAY, 'tflops_device_resident': value * FLOP_PER_RAY / 1e12,
-            'tensor_flop_issued_per_algorithmic_flop': 3, 'fast_fp16_mode': fast, 'mixed_f8_mode': mixed, 'fwd_bwd': fwd_bwd, 'train_step': train, 'stages': stages,
+            'tensor_flop_issued_per_algorithmic_flop': 3, 'fast_fp16_mode': fast, 'mixed_f8_mode': mixed, 'fwd_bwd': fwd_bwd, 'pose_grad': pose_grad, 'train_step': train, 'stages': stages,
         }))
 
 

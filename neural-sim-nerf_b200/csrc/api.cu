@@ -147,11 +147,23 @@ size_t nsr_render_workspace_bytes(int64_t n, int S, int Ni) {
   return b;
 }
 
+size_t nsr_relu_mask_bytes(int64_t n_rays, int n_total_samples) { return relu_mask_bytes(n_rays * int64_t(n_total_samples)); }
+
 int nsr_render_rays_forward(const float* rays, int64_t n, const void* packed_coarse, const void* packed_fine, int S,
                             int Ni, uint32_t flags, const float* t_rand, const float* u, float* rgb_map, float* disp_map,
                             float* acc_map, float* rgb0, float* disp0, float* acc0, float* z_std, float* raw,
                             float* z_vals_out, float* weights_out, void* workspace, size_t workspace_bytes, void* stream) {
+  return nsr_render_rays_forward_ex(rays, n, packed_coarse, packed_fine, S, Ni, flags, t_rand, u, rgb_map, disp_map, acc_map, rgb0, disp0,
+                                    acc0, z_std, raw, z_vals_out, weights_out, nullptr, workspace, workspace_bytes, stream);
+}
+
+int nsr_render_rays_forward_ex(const float* rays, int64_t n, const void* packed_coarse, const void* packed_fine, int S,
+                               int Ni, uint32_t flags, const float* t_rand, const float* u, float* rgb_map, float* disp_map,
+                               float* acc_map, float* rgb0, float* disp0, float* acc0, float* z_std, float* raw,
+                               float* z_vals_out, float* weights_out, void* relu_mask, void* workspace, size_t workspace_bytes,
+                               void* stream) {
   NSR_REQUIRE(n >= 0 && S >= 2 && Ni >= 0, "nsr_render_rays_forward: bad sizes (needs at least 2 samples per ray)");
+  NSR_REQUIRE(relu_mask == nullptr || (reinterpret_cast<uintptr_t>(relu_mask) & 15) == 0, "nsr_render_rays_forward: relu_mask must be 16-byte aligned");
   if (n == 0) return NSR_OK;
   NSR_REQUIRE(rays && packed_coarse, "nsr_render_rays_forward: null rays / weights");
   NSR_REQUIRE(workspace && workspace_bytes >= nsr_render_workspace_bytes(n, S, Ni), "nsr_render_rays_forward: workspace too small");
@@ -173,8 +185,9 @@ int nsr_render_rays_forward(const float* rays, int64_t n, const void* packed_coa
   const uint32_t mflags = flags & (NSR_FLAG_FAST_FP16 | NSR_FLAG_MIXED_F8);
   int rc;
 
+  uint32_t* mask = static_cast<uint32_t*>(relu_mask);      // sign bits of the LAST pass: the only one that carries gradient to the rays
   if ((rc = launch_coarse_z(rays, n, S, flags, t_rand, z0, st))) return rc;                          // RN:439-461
-  if ((rc = launch_mlp_forward(rays, z0, n, S, packed_coarse, mflags, raw0, st))) return rc;              // RN:463-466
+  if ((rc = launch_mlp_forward(rays, z0, n, S, packed_coarse, mflags, raw0, st, Ni == 0 ? mask : nullptr))) return rc;   // RN:463-466
   if (Ni == 0) {
     if ((rc = launch_raw2outputs(raw0, z0, rays + 3, 11, n, S, cflags, rgb_map, disp_map, acc_map, weights_out, nullptr, st))) return rc;
     if (raw) cudaMemcpyAsync(raw, raw0, size_t(n) * S * 16, cudaMemcpyDeviceToDevice, st);
@@ -185,7 +198,7 @@ int nsr_render_rays_forward(const float* rays, int64_t n, const void* packed_coa
   float* zf = z_vals_out ? z_vals_out : z1;
   if ((rc = launch_resample_merge(z0, w0, n, S, Ni, u, zf, nullptr, z_std, st))) return rc;          // RN:473-477, 495
   float* rawf = raw ? raw : raw1;
-  if ((rc = launch_mlp_forward(rays, zf, n, T, packed_fine ? packed_fine : packed_coarse, mflags, rawf, st))) return rc;  // RN:478-483
+  if ((rc = launch_mlp_forward(rays, zf, n, T, packed_fine ? packed_fine : packed_coarse, mflags, rawf, st, mask))) return rc;  // RN:478-483
   if ((rc = launch_raw2outputs(rawf, zf, rays + 3, 11, n, T, cflags, rgb_map, disp_map, acc_map, weights_out, nullptr, st))) return rc;  // RN:485
   return NSR_OK;
 }
@@ -200,7 +213,16 @@ size_t nsr_mlp_dump_bytes(int64_t n_rays, int n_total_samples) { return mlp_dump
 int nsr_render_rays_backward(const float* rays, const float* z_vals, const float* raw, int64_t n, int T, const void* packed_net,
                              uint32_t flags, const float* d_rgb_map, float* d_rays, void* dump, float* const* dW,
                              float* const* dB, void* workspace, size_t workspace_bytes, void* stream) {
+  return nsr_render_rays_backward_ex(rays, z_vals, raw, n, T, packed_net, flags, d_rgb_map, d_rays, dump, dW, dB, nullptr, workspace,
+                                     workspace_bytes, stream);
+}
+
+int nsr_render_rays_backward_ex(const float* rays, const float* z_vals, const float* raw, int64_t n, int T, const void* packed_net,
+                                uint32_t flags, const float* d_rgb_map, float* d_rays, void* dump, float* const* dW,
+                                float* const* dB, const void* relu_mask, void* workspace, size_t workspace_bytes, void* stream) {
   NSR_REQUIRE(n >= 0 && T > 0, "nsr_render_rays_backward: bad sizes");
+  NSR_REQUIRE(relu_mask == nullptr || dW == nullptr, "nsr_render_rays_backward: parameter gradients need the recompute path (relu_mask = NULL)");
+  NSR_REQUIRE(relu_mask == nullptr || (reinterpret_cast<uintptr_t>(relu_mask) & 15) == 0, "nsr_render_rays_backward: relu_mask must be 16-byte aligned");
   if (n == 0) return NSR_OK;
   NSR_REQUIRE(rays && z_vals && raw && packed_net && d_rgb_map && d_rays, "nsr_render_rays_backward: null argument");
   NSR_REQUIRE(workspace && workspace_bytes >= nsr_render_backward_workspace_bytes(n, T), "nsr_render_rays_backward: workspace too small");
@@ -225,7 +247,8 @@ int nsr_render_rays_backward(const float* rays, const float* z_vals, const float
   if (dW) cudaMemsetAsync(gmax, 0, 4, st);
   if ((rc = launch_raw2outputs_backward(raw, z_vals, rays, n, T, flags & NSR_FLAG_WHITE_BKGD, d_rgb_map, d_raw, d_dnorm,
                                         dW ? gmax : nullptr, st))) return rc;
-  if ((rc = launch_mlp_backward(rays, z_vals, n, T, packed_net, d_raw, d_pts, dW ? dump : nullptr, gmax, st))) return rc;
+  if ((rc = launch_mlp_backward(rays, z_vals, n, T, packed_net, d_raw, d_pts, dW ? dump : nullptr, gmax, st,
+                                static_cast<const uint32_t*>(relu_mask)))) return rc;
   if ((rc = launch_ray_grad_reduce(rays, z_vals, d_pts, d_dnorm, n, T, d_rays, st))) return rc;
   if (dW) return launch_weight_grads(dump, d_raw, n * int64_t(T), gmax, dW, dB, st);
   return NSR_OK;
@@ -297,7 +320,6 @@ int nsr_render_image_forward(int H, int W, const float* K_host, const float* c2w
 // ----------------------------------------------------------------------------- one optimisation step (RN:643-716)
 static const int kParamRows[NSR_NET_NUM_TENSORS] = {256, 256, 256, 256, 256, 256, 256, 256, 128, 256, 1, 3};
 static const int kParamCols[NSR_NET_NUM_TENSORS] = {63, 256, 256, 256, 256, 319, 256, 256, 283, 256, 256, 128};
-static const size_t kNetParams = 595844;      // SURVEY a-7
 static const size_t kNetParamsPadded = 595968;  // multiple of 64 floats
 
 int nsr_random_uniform(uint64_t seed, uint32_t stream_id, float* out, int64_t count, void* stream) {

@@ -74,6 +74,17 @@ __host__ __device__ constexpr int bstep_n_halves(int b) { return bstep_is_side(b
 __host__ __device__ constexpr int bstep_k_chunks(int b) { return b <= 1 ? 2 : 4; }
 __host__ __device__ constexpr int bstep_side_n(int b) { return b == 0 ? 32 : 64; }
 
+// ----------------------------------------------------------------------------- saved ReLU sign bits (pose-gradient backward)
+// With relu_mask != NULL the forward kernel stores one bit per ReLU output (is the fp16-rounded activation non-zero?) of the
+// eight 256-wide layers and of the 128-wide views layer: 2176 bits = 272 B per point instead of ~5 KB of activations.  The
+// backward kernel then skips its forward recompute (GEMM steps 0..9) altogether.  Per 128-point tile: 68 words x 128 rows of
+// u32, word (l*8 + w) = columns [32w, 32w+32) of layer l (w < 8), word 64 + w = columns [32w, 32w+32) of the views layer
+// (w < 4); inside a word bit j = column 2j, bit 16 + j = column 2j + 1 (the packed fp16 pair order of the operand words).
+constexpr int MASK_WORDS = 8 * 8 + 4;                   // per point
+constexpr int MASK_TILE_WORDS = MASK_WORDS * 128;       // 8704
+constexpr int MASK_TILE_BYTES = MASK_TILE_WORDS * 4;    // 34,816
+__host__ __device__ inline size_t relu_mask_bytes(int64_t n_points) { return size_t((n_points + 127) / 128) * MASK_TILE_BYTES; }
+
 // ----------------------------------------------------------------------------- backward "dump" (operands of dL/dMLP, RN:691-707)
 // With dump != NULL the backward kernel writes, for P = 128 * tiles points, every weight layer's input activations
 // and pre-activation gradients as fp16, one array after the other:
@@ -139,10 +150,10 @@ int launch_adam(const AdamJobs& jobs, float beta1, float beta2, float lr, float 
 // mlp_forward.cu
 int launch_pack_net(const float* const* weights, const float* const* biases, void* packed, cudaStream_t st);
 int launch_mlp_forward(const float* rays, const float* z_or_pts, int64_t n, int S, const void* packed, uint32_t flags,
-                       float* raw, cudaStream_t st);
+                       float* raw, cudaStream_t st, uint32_t* relu_mask = nullptr);
 // mlp_backward.cu: d_raw [n,S,4] -> d_pts [n,S,8] = (dL/dpoint[3], 0, dL/dviewdir[3], 0) per sample
 int launch_mlp_backward(const float* rays, const float* z, int64_t n, int S, const void* packed, const float* d_raw,
-                        float* d_pts, void* dump, const float* gscale, cudaStream_t st);
+                        float* d_pts, void* dump, const float* gscale, cudaStream_t st, const uint32_t* relu_mask = nullptr);
 // wgrad.cu: dL/dW, dL/db of one network pass from the dump; accumulates (atomicAdd) into dW[12], dB[12] (fp32, reference shapes)
 int launch_weight_grads(const void* dump, const float* d_raw, int64_t n_points, const float* gscale, float* const* dW,
                         float* const* dB, cudaStream_t st);

@@ -20,14 +20,20 @@ namespace nsr {
 constexpr int BWD_STAGES = 4;
 constexpr int B_ENC_BYTES = 128 * 64 * 2, B_DIR_BYTES = 128 * 32 * 2;
 constexpr int B_OFF_ENC_HI = 0, B_OFF_DIR_HI = B_ENC_BYTES, B_OFF_ENC_LO = B_ENC_BYTES + B_DIR_BYTES, B_OFF_DIR_LO = 2 * B_ENC_BYTES + B_DIR_BYTES;
-constexpr int B_SM_INBUF = 0;
-constexpr int B_SM_RING = 2 * (B_ENC_BYTES + B_DIR_BYTES);
-constexpr int B_SM_TAIL = B_SM_RING + BWD_STAGES * CHUNK_PAIR_BYTES;
-constexpr int B_SM_XCH = B_SM_TAIL + TAIL_BYTES;                 // [128] x 2 float4
-constexpr int B_SM_MASK = B_SM_XCH + 128 * 32;                   // [8 layers][8 words][128 rows] u32: ReLU sign bits
-constexpr int B_SM_BAR = B_SM_MASK + 8 * 8 * 128 * 4;
-constexpr int B_SM_TOTAL = B_SM_BAR + 256;
-static_assert(B_SM_TOTAL <= 227 * 1024, "backward kernel shared memory");
+// MASKED = the forward pass saved the ReLU sign bits (common.cuh MASK_*): no forward recompute, so no encoding buffers; the
+// space holds two mask tiles instead (the next tile's bits are bulk-copied in while this one computes).
+template <bool MASKED>
+struct BCfg {
+  static constexpr int SM_INBUF = 0;
+  static constexpr int SM_RING = MASKED ? 0 : 2 * (B_ENC_BYTES + B_DIR_BYTES);
+  static constexpr int SM_TAIL = SM_RING + BWD_STAGES * CHUNK_PAIR_BYTES;
+  static constexpr int SM_XCH = SM_TAIL + TAIL_BYTES;            // [128] x 2 float4
+  static constexpr int SM_MASK = SM_XCH + 128 * 32;              // recompute: [8 layers][8 words][128 rows] u32; MASKED: 2 x [68][128]
+  static constexpr int SM_BAR = SM_MASK + (MASKED ? 2 * MASK_TILE_BYTES : 8 * 8 * 128 * 4);
+  static constexpr int SM_TOTAL = SM_BAR + 256;
+  static_assert(SM_TOTAL <= 227 * 1024, "backward kernel shared memory");
+  static_assert(SM_MASK % 16 == 0, "bulk-copy destination alignment");
+};
 constexpr int NUM_GSTEPS = NUM_STEPS + NUM_BSTEPS;               // 22
 
 struct BwdArgs {
@@ -39,6 +45,7 @@ struct BwdArgs {
   int64_t n_points;
   int S;
   int num_tiles;
+  const uint32_t* relu_mask;  // MASKED kernel: sign bits written by the forward pass, [tile][68][128] u32
   uint8_t* dump;        // optional: fp16 activations / pre-activation gradients of every layer (common.cuh), for dL/dMLP
   const float* gscale;  // with dump: one power-of-two scale for ALL rows (max |dL/draw| of the batch), device scalar
   unsigned long long* trace;  // debug (NSR_TRACE_FILE_BWD): clock64 stamps of CTA 0's first tiles, [tile][gstep][16]
@@ -59,15 +66,6 @@ __device__ __forceinline__ void dump64(uint8_t* arr, int tile, int row, int W, i
 __device__ __forceinline__ bool gstep_is_side(int g) { return g == 9 || (g >= 10 && bstep_is_side(g - 10)); }
 __device__ __forceinline__ int gstep_k_chunks(int g) { return g < 10 ? step_k_chunks(g) : bstep_k_chunks(g - 10); }
 __device__ __forceinline__ int gstep_side_n(int g) { return g == 9 ? 128 : bstep_side_n(g - 10); }
-
-// sign bits of 32 freshly rounded activations (16 packed fp16 pairs, all >= 0): bit j <- low half of pair j,
-// bit 16 + j <- high half
-__device__ __forceinline__ uint32_t sign_bits(const uint32_t* H) {
-  uint32_t m = 0;
-#pragma unroll
-  for (int j = 0; j < 16; ++j) m |= __vcmpne2(H[j], 0u) & (0x00010001u << j);
-  return m;
-}
 
 // forward-recompute epilogue of 32 columns: bias + ReLU + hi/lo split (+ sign bits)
 __device__ __forceinline__ uint32_t fwd32(const uint32_t (&u)[32], const float* bias, bool relu, uint32_t* H, uint32_t* L) {
@@ -135,19 +133,24 @@ __device__ __forceinline__ void enc_backward32(const uint32_t (&u)[32], const fl
   }
 }
 
+template <bool MASKED>
 __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a) {
+  using C = BCfg<MASKED>;
+  constexpr int G0 = MASKED ? 10 : 0;          // first GEMM step of a tile
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sRing = smem + B_SM_RING;
-  const float* sTail = reinterpret_cast<const float*>(smem + B_SM_TAIL);
-  float4* sXch = reinterpret_cast<float4*>(smem + B_SM_XCH);
-  uint32_t* sMask = reinterpret_cast<uint32_t*>(smem + B_SM_MASK);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + B_SM_BAR);
+  uint8_t* sRing = smem + C::SM_RING;
+  const float* sTail = reinterpret_cast<const float*>(smem + C::SM_TAIL);
+  float4* sXch = reinterpret_cast<float4*>(smem + C::SM_XCH);
+  uint32_t* sMask = reinterpret_cast<uint32_t*>(smem + C::SM_MASK);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::SM_BAR);
   uint64_t* empty = full + BWD_STAGES;
   uint64_t* acc_ready = empty + BWD_STAGES;
   uint64_t* a_ready = acc_ready + 2;
   uint64_t* enc_ready = a_ready + 2;
   uint64_t* enc_free = enc_ready + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(enc_free + 2);
+  uint64_t* mask_full = enc_free + 2;          // [2] MASKED: producer (tx bytes) -> epilogue
+  uint64_t* mask_free = mask_full + 2;         // [2] MASKED: epilogue (256) -> producer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mask_free + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const size_t P = size_t(a.num_tiles) * 128;  // rows of the optional dump
@@ -162,12 +165,14 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
       mbar_init(&a_ready[h], EPI_THREADS);
       mbar_init(&enc_ready[h], ENC_THREADS);
       mbar_init(&enc_free[h], 1);
+      mbar_init(&mask_full[h], 1);
+      mbar_init(&mask_free[h], EPI_THREADS);
     }
     fence_mbar_init();
   }
   if (warp == MMA_WARP) tmem_alloc(tmem_slot, 512);
   for (int i = tid; i < TAIL_FLOATS; i += MLP_THREADS)
-    reinterpret_cast<float*>(smem + B_SM_TAIL)[i] = reinterpret_cast<const float*>(a.packed + WEIGHT_BYTES)[i];
+    reinterpret_cast<float*>(smem + C::SM_TAIL)[i] = reinterpret_cast<const float*>(a.packed + WEIGHT_BYTES)[i];
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -175,10 +180,20 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
   if (warp == PROD_WARP) {
     // ===================================================================== weight producer: forward chunks then backward chunks
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
+      uint32_t stage = 0, phase = 0, tl = 0;
       bool first_lap = true;
-      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-        for (int c = 0; c < NUM_CHUNKS + NUM_BWD_CHUNKS; ++c) {
+      auto fetch_mask = [&](int tile, uint32_t t) {   // tile's sign bits -> buffer t & 1 (its t/2-th use)
+        const uint32_t b = t & 1;
+        if (t >= 2) mbar_wait(&mask_free[b], ((t >> 1) - 1) & 1);
+        mbar_arrive_expect_tx(&mask_full[b], MASK_TILE_BYTES);
+        bulk_g2s(smem + C::SM_MASK + b * MASK_TILE_BYTES, reinterpret_cast<const uint8_t*>(a.relu_mask) + size_t(tile) * MASK_TILE_BYTES,
+                 MASK_TILE_BYTES, &mask_full[b]);
+      };
+      if (MASKED && int(blockIdx.x) < a.num_tiles) fetch_mask(blockIdx.x, 0);
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++tl) {
+        for (int c = MASKED ? NUM_CHUNKS : 0; c < NUM_CHUNKS + NUM_BWD_CHUNKS; ++c) {
+          // the next tile's bits: a few chunks in, when the tile before this one has long released the other buffer
+          if (MASKED && c == NUM_CHUNKS + 8 && tile + int(gridDim.x) < a.num_tiles) fetch_mask(tile + gridDim.x, tl + 1);
           if (!first_lap) mbar_wait(&empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full[stage], CHUNK_PAIR_BYTES);
           bulk_g2s(sRing + stage * CHUNK_PAIR_BYTES, a.packed + size_t(c) * CHUNK_PAIR_BYTES, CHUNK_PAIR_BYTES, &full[stage]);
@@ -195,15 +210,15 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
     const bool leader = elect_one();
     constexpr uint32_t HI_B = sdesc_hi(1024), HI_DIR = sdesc_hi(512);
     const uint32_t ring_lo = sdesc_lo(smem_u32(sRing), 128);
-    const uint32_t inbuf = smem_u32(smem + B_SM_INBUF);
+    const uint32_t inbuf = smem_u32(smem + C::SM_INBUF);
     const uint32_t enc_hi = sdesc_lo(inbuf + B_OFF_ENC_HI, 128), enc_lo = sdesc_lo(inbuf + B_OFF_ENC_LO, 128);
     const uint32_t dir_hi = sdesc_lo(inbuf + B_OFF_DIR_HI, 128), dir_lo = sdesc_lo(inbuf + B_OFF_DIR_LO, 128);
     uint32_t stage = 0, phase = 0, tl = 0;
     Waiter w_a[2], w_enc[2];
     bool ready = false;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++tl) {
-      w_enc[0].wait(&enc_ready[0]);
-      for (int g = 0; g < NUM_GSTEPS; ++g) {
+      if (!MASKED) w_enc[0].wait(&enc_ready[0]);
+      for (int g = G0; g < NUM_GSTEPS; ++g) {
         if (g == 9) w_enc[1].wait(&enc_ready[1]);
         const bool side = gstep_is_side(g);
         const int nk = gstep_k_chunks(g);
@@ -284,8 +299,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
     const int er = tid - ENC_WARP0 * 32;
     uint32_t tl = 0;
     Waiter w_free[2];
-    uint8_t* inbuf = smem + B_SM_INBUF;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++tl) {
+    uint8_t* inbuf = smem + C::SM_INBUF;
+    for (int tile = blockIdx.x; !MASKED && tile < a.num_tiles; tile += gridDim.x, ++tl) {
       float x[2][3], vd[2][3];
 #pragma unroll
       for (int rr = 0; rr < 2; ++rr) {
@@ -375,12 +390,15 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
     const int col0 = ch * 64;
     const uint32_t tlane = uint32_t((warp & 3) * 32) << 16;
     Waiter w_acc[2];
-    mbar_arrive(&a_ready[0]);
-    mbar_arrive(&a_ready[1]);
+    if (!MASKED) {   // initial credits (MASKED: the first arrival is the dL/dh_views operand written at the top of every tile)
+      mbar_arrive(&a_ready[0]);
+      mbar_arrive(&a_ready[1]);
+    }
     // sign-bit words of this thread: layer l, accumulator half h, 32-column group q  ->  sMask[(l*8 + h*4 + ch*2 + q)*128 + row]
     uint32_t* my_mask = sMask + (ch * 2) * 128 + row;
     uint32_t tl = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++tl) {
+      if (MASKED) my_mask = sMask + (tl & 1) * MASK_TILE_WORDS + (ch * 2) * 128 + row;
       const int64_t p = int64_t(tile) * 128 + row;
       float x[3] = {0.f, 0.f, 0.f}, vd[3] = {0.f, 0.f, 0.f};
       float4 gr = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -406,7 +424,40 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
       gr.w *= inv;
       float dx[3] = {0.f, 0.f, 0.f}, dv[3] = {0.f, 0.f, 0.f};
 
-      for (int g = 0; g < NUM_GSTEPS; ++g) {
+      if (MASKED) {
+        // ---------------------------------------------------- dL/dh_views = W_rgb^T dL/drgb_raw . [h_views > 0] (RH:117, RH:115 backwards)
+        // from the saved sign bits: the operand of the first two backward steps, written without any GEMM.  Every MMA of the previous
+        // tile retired before this thread left its last step (it waited on that step's accumulator), so A may be overwritten.
+        mbar_wait(&mask_full[tl & 1], (tl >> 1) & 1);
+        const float4* wr = reinterpret_cast<const float4*>(sTail + TAIL_WRGB) + col0;
+        const uint32_t mv0 = my_mask[64 * 128], mv1 = my_mask[65 * 128];
+        uint32_t H[32], L[32];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float gg[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int c = (q < 2) ? 2 * j + q : 32 + 2 * j + (q - 2);
+            const uint32_t word = (q < 2) ? mv0 : mv1;
+            const uint32_t bit = (q & 1) ? (0x10000u << j) : (1u << j);
+            const float4 w = wr[c];
+            gg[q] = (word & bit) ? (gr.x * w.x + gr.y * w.y + gr.z * w.z) : 0.f;
+          }
+          split2<true>(gg[0], gg[1], H[j], L[j]);
+          split2<true>(gg[2], gg[3], H[16 + j], L[16 + j]);
+        }
+        tc_fence_after_sync();
+        tmem_st16(tlane + TM_AHI + col0 / 2, *reinterpret_cast<const uint32_t(*)[16]>(&H[0]));
+        tmem_st16(tlane + TM_AHI + col0 / 2 + 16, *reinterpret_cast<const uint32_t(*)[16]>(&H[16]));
+        tmem_st16(tlane + TM_ALO + col0 / 2, *reinterpret_cast<const uint32_t(*)[16]>(&L[0]));
+        tmem_st16(tlane + TM_ALO + col0 / 2 + 16, *reinterpret_cast<const uint32_t(*)[16]>(&L[16]));
+        tmem_st_wait();
+        tc_fence_before_sync();
+        mbar_arrive(&a_ready[0]);
+        mbar_arrive(&a_ready[1]);
+      }
+
+      for (int g = G0; g < NUM_GSTEPS; ++g) {
         if (!gstep_is_side(g)) {
           // ------------------------------------------------ full step: both accumulator halves -> next A operand
           const bool fwd = g < 10;
@@ -529,7 +580,9 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
           // ------------------------------------------------ backward side step (ACC1): gradient w.r.t. an encoding
           w_acc[1].wait(&acc_ready[1]);
           tc_fence_after_sync();
-          mbar_arrive(&a_ready[0]);  // A is only read by this step
+          // (MASKED: the tile's last step hands nothing on -- the next arrival is the next tile's dL/dh_views operand)
+          const bool hand_on = !(MASKED && g == NUM_GSTEPS - 1);
+          if (hand_on) mbar_arrive(&a_ready[0]);  // A is only read by this step
           // ACC1 is copied to registers and handed back at once: the sin/cos Jacobian below takes thousands of cycles and
           // must not hold up the next step's second half
           uint32_t u[32];
@@ -539,7 +592,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
             tmem_ld_wait();
           }
           tc_fence_before_sync();
-          mbar_arrive(&a_ready[1]);
+          if (hand_on) mbar_arrive(&a_ready[1]);
           if (mine) {
             if (g == 10) enc_backward32<0, 27, 4>(u, vd, dv);
             else if (ch == 0) enc_backward32<0, 63, 10>(u, x, dx);    // dL/d(xyz encoding), 63 channels: 32 per column half
@@ -547,6 +600,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
           }
         }
       }
+      if (MASKED) mbar_arrive(&mask_free[tl & 1]);   // this tile's sign bits are no longer needed
       // ---- the two column halves of a row meet in shared memory; the ch == 0 thread writes d_pts[p]
       if (ch == 1) {
         sXch[2 * row] = make_float4(dx[0], dx[1], dx[2], 0.f);
@@ -569,12 +623,17 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
 size_t mlp_dump_bytes(int64_t n_points) { return dump_total(size_t((n_points + 127) / 128) * 128); }
 
 int launch_mlp_backward(const float* rays, const float* z, int64_t n, int S, const void* packed, const float* d_raw, float* d_pts,
-                        void* dump, const float* gscale, cudaStream_t st) {
+                        void* dump, const float* gscale, cudaStream_t st, const uint32_t* relu_mask) {
   const int64_t n_points = n * S;
   if (n_points == 0) return NSR_OK;
   int num_sms = 0;
   if (int rc = current_device_sms(&num_sms)) return rc;
-  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(&nerf_mlp_bwd_kernel), B_SM_TOTAL)) return rc;
+  if (relu_mask != nullptr && dump != nullptr) {
+    set_error("mlp_backward: the saved-sign-bit path carries no activations, parameter gradients need the recompute path");
+    return NSR_E_INVALID;
+  }
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(&nerf_mlp_bwd_kernel<false>), BCfg<false>::SM_TOTAL)) return rc;
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(&nerf_mlp_bwd_kernel<true>), BCfg<true>::SM_TOTAL)) return rc;
   BwdArgs a;
   a.rays = rays;
   a.z = z;
@@ -584,15 +643,16 @@ int launch_mlp_backward(const float* rays, const float* z, int64_t n, int S, con
   a.n_points = n_points;
   a.S = S;
   a.num_tiles = int((n_points + 127) / 128);
+  a.relu_mask = relu_mask;
   a.dump = static_cast<uint8_t*>(dump);
   a.gscale = dump != nullptr ? gscale : nullptr;
   a.trace = nullptr;
   const char* trace_file = getenv("NSR_TRACE_FILE_BWD");  // debug only: synchronous, dumps CTA 0's timeline
-  if (trace_file != nullptr && a.num_tiles >= 3 * num_sms) {
+  if (trace_file != nullptr && a.num_tiles >= 3 * num_sms && relu_mask == nullptr) {
     const size_t nb = 3 * 22 * 16 * sizeof(unsigned long long);
     cudaMalloc(&a.trace, nb);
     cudaMemset(a.trace, 0, nb);
-    nerf_mlp_bwd_kernel<<<num_sms, MLP_THREADS, B_SM_TOTAL, st>>>(a);
+    nerf_mlp_bwd_kernel<false><<<num_sms, MLP_THREADS, BCfg<false>::SM_TOTAL, st>>>(a);
     cudaStreamSynchronize(st);
     unsigned long long host[3 * 22 * 16];
     cudaMemcpy(host, a.trace, nb, cudaMemcpyDeviceToHost);
@@ -610,7 +670,8 @@ int launch_mlp_backward(const float* rays, const float* z, int64_t n, int S, con
     return check_launch("nerf_mlp_bwd_kernel");
   }
   const int grid = a.num_tiles < num_sms ? a.num_tiles : num_sms;
-  nerf_mlp_bwd_kernel<<<grid, MLP_THREADS, B_SM_TOTAL, st>>>(a);
+  if (relu_mask != nullptr) nerf_mlp_bwd_kernel<true><<<grid, MLP_THREADS, BCfg<true>::SM_TOTAL, st>>>(a);
+  else nerf_mlp_bwd_kernel<false><<<grid, MLP_THREADS, BCfg<false>::SM_TOTAL, st>>>(a);
   count_launch();
   return check_launch("nerf_mlp_bwd_kernel");
 }

@@ -41,6 +41,15 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_
   }
 }
 
+// sign bits of 32 freshly rounded activations (16 packed fp16 pairs, all >= 0): bit j <- low half of pair j,
+// bit 16 + j <- high half
+__device__ __forceinline__ uint32_t sign_bits(const uint32_t* H) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) m |= __vcmpne2(H[j], 0u) & (0x00010001u << j);
+  return m;
+}
+
 struct Waiter {  // one per (thread, barrier): parity follows the number of completed waits
   uint32_t n = 0;
   __device__ __forceinline__ void wait(uint64_t* bar) {

@@ -258,6 +258,7 @@ struct MlpArgs {
   int S;
   uint32_t flags;
   int num_tiles;
+  uint32_t* relu_mask;        // optional: sign bits of every ReLU output for the backward pass (common.cuh MASK_*)
   unsigned long long* trace;  // debug (NSR_TRACE_FILE): clock64 stamps of CTA 0's first tiles, [tile][step][16]
 };
 
@@ -558,6 +559,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++tl) {
       const int64_t p = int64_t(tile) * 128 + row;
       float sigma = 0.f;
+      uint32_t* mrow = a.relu_mask != nullptr ? a.relu_mask + size_t(tile) * MASK_TILE_WORDS + (ch * 2) * 128 + row : nullptr;
       for (int step = 0; step < 9; ++step) {
         const float* bias = sTail + TAIL_BIAS + step * 256 + col0;
         const float* walpha = (step == 7) ? sTail + TAIL_WALPHA + col0 : nullptr;
@@ -608,6 +610,10 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
           tmem_ld_wait();
           convert(u0, u1, 0);
         }
+        if (mrow != nullptr && step < 8) {
+          mrow[(step * 8 + 0) * 128] = sign_bits(H);
+          mrow[(step * 8 + 1) * 128] = sign_bits(H + 16);
+        }
         // ---- every MMA of this step has retired: the old activations may be overwritten
         if (tid == 0) NSR_TR(tl, step, 9);
         w_acc[1].wait(&acc_ready[1]);
@@ -624,6 +630,10 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
           tmem_ld_wait();
           convert(u0, u1, 1);
         }
+        if (mrow != nullptr && step < 8) {
+          mrow[(step * 8 + 4) * 128] = sign_bits(H);
+          mrow[(step * 8 + 5) * 128] = sign_bits(H + 16);
+        }
         store(1);
         mbar_arrive(&a_ready[1]);
         if (tid == 0) NSR_TR(tl, step, 12);
@@ -635,6 +645,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
       // the MMA warp must have consumed the previous a_ready[0] phase first -- it has once step 9 was issued.)
       mbar_arrive(&a_ready[0]);
       float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+      uint32_t mv0 = 0u, mv1 = 0u;   // sign bits of this thread's 2 x 32 views-layer columns
       {
         const float* bias = sTail + TAIL_BIAS + 9 * 256 + col0;
         const float4* wr = reinterpret_cast<const float4*>(sTail + TAIL_WRGB) + col0;
@@ -655,6 +666,12 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
             const float h0 = fmaxf(kMixed ? fmaf(__uint_as_float(u0[4 * j + q]), sc9, bb0[q]) : __uint_as_float(u0[4 * j + q]) + bb0[q], 0.f);
             const float h1 = fmaxf(kMixed ? fmaf(__uint_as_float(u1[4 * j + q]), sc9, bb1[q]) : __uint_as_float(u1[4 * j + q]) + bb1[q], 0.f);
             const float4 w0 = wr[4 * j + q], w1 = wr[32 + 4 * j + q];
+            {
+              const int cc = 4 * j + q;                       // column inside the 32-column word
+              const int bit = (cc & 1) ? 16 + (cc >> 1) : (cc >> 1);
+              mv0 |= (h0 > 0.f ? 1u : 0u) << bit;
+              mv1 |= (h1 > 0.f ? 1u : 0u) << bit;
+            }
             r0 = fmaf(h0, w0.x, r0);
             r1 = fmaf(h0, w0.y, r1);
             r2 = fmaf(h0, w0.z, r2);
@@ -663,6 +680,10 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
             r2 = fmaf(h1, w1.z, r2);
           }
         }
+      }
+      if (mrow != nullptr) {
+        mrow[(64 + 0) * 128] = mv0;
+        mrow[(64 + 1) * 128] = mv1;
       }
       // ---- the two column halves of a row meet in shared memory; the ch == 0 thread writes raw[p]
       if (ch == 1) sXch[row] = make_float4(r0, r1, r2, sigma);
@@ -695,7 +716,7 @@ static int launch_by_flags(const MlpArgs& a, int grid, uint32_t flags, cudaStrea
 }
 
 int launch_mlp_forward(const float* rays, const float* z_or_pts, int64_t n, int S, const void* packed, uint32_t flags,
-                       float* raw, cudaStream_t st) {
+                       float* raw, cudaStream_t st, uint32_t* relu_mask) {
   const int64_t n_points = n * S;
   if (n_points == 0) return NSR_OK;
   if (n_points > (int64_t(1) << 31) * 64) {
@@ -713,6 +734,7 @@ int launch_mlp_forward(const float* rays, const float* z_or_pts, int64_t n, int 
   a.S = S;
   a.flags = flags;
   a.num_tiles = int((n_points + 127) / 128);
+  a.relu_mask = relu_mask;
   a.trace = nullptr;
   const int grid = a.num_tiles < num_sms ? a.num_tiles : num_sms;
   const char* trace_file = getenv("NSR_TRACE_FILE");  // debug only: synchronous, dumps CTA 0's timeline

@@ -293,9 +293,20 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
     return dict(zip(keys, outs))
 
 
-def _forward_impl(rays, cfg, keep_for_backward):
-    """One call of nsr_render_rays_forward.  Returns (outputs tuple, saved) with saved = (z_vals [n,T], raw [n,T,4],
-    z0 [n,S], raw0 [n,S,4]) of the last and (when N_importance > 0) the coarse pass, or Nones."""
+# Pose-gradient passes (no parameter gradient wanted) keep one bit per ReLU of the last network pass -- 272 B per sample point --
+# so that the backward kernel skips its forward recompute (DESIGN.md "backward").  NSR_SAVE_RELU_MASK=0 turns it off; it is
+# also skipped when the bits would not fit comfortably in the free device memory (the recompute path needs no extra memory).
+SAVE_RELU_MASK = os.environ.get('NSR_SAVE_RELU_MASK', '1') != '0'
+
+
+def _mask_fits(n_bytes, dev):
+    free, _ = torch.cuda.mem_get_info(dev)
+    return n_bytes <= free // 2
+
+
+def _forward_impl(rays, cfg, keep_for_backward, save_mask=False):
+    """One call of nsr_render_rays_forward(_ex).  Returns (outputs tuple, saved) with saved = (z_vals [n,T], raw [n,T,4],
+    z0 [n,S], raw0 [n,S,4], relu_mask) of the last and (when N_importance > 0) the coarse pass, or Nones."""
     L = lib()
     n, dev = rays.shape[0], rays.device
     S, Ni = cfg['S'], cfg['Ni']
@@ -309,9 +320,14 @@ def _forward_impl(rays, cfg, keep_for_backward):
     zv = new(n, T) if keep_for_backward else None
     ws_bytes = L.nsr_render_workspace_bytes(n, S, Ni)
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
-    check(L.nsr_render_rays_forward(ptr(rays), n, ptr(cfg['pc']), ptr(cfg['pf']), S, Ni, cfg['flags'], ptr(cfg['t_rand']), ptr(cfg['u']),
-                                    ptr(rgb), ptr(disp), ptr(acc), ptr(rgb0), ptr(disp0), ptr(acc0), ptr(zstd),
-                                    ptr(raw), ptr(zv), None, ptr(ws), ws_bytes, _stream()), 'nsr_render_rays_forward')
+    mask = None
+    if save_mask and keep_for_backward and SAVE_RELU_MASK and n > 0:
+        mb = L.nsr_relu_mask_bytes(n, T)
+        if _mask_fits(mb, dev):
+            mask = torch.empty(mb, dtype=torch.uint8, device=dev)
+    check(L.nsr_render_rays_forward_ex(ptr(rays), n, ptr(cfg['pc']), ptr(cfg['pf']), S, Ni, cfg['flags'], ptr(cfg['t_rand']), ptr(cfg['u']),
+                                       ptr(rgb), ptr(disp), ptr(acc), ptr(rgb0), ptr(disp0), ptr(acc0), ptr(zstd),
+                                       ptr(raw), ptr(zv), None, ptr(mask), ptr(ws), ws_bytes, _stream()), 'nsr_render_rays_forward')
     z0 = raw0 = None
     if keep_for_backward and Ni > 0:
         # the coarse pass's depths and raw outputs sit at the head of the workspace (include/nsr_b200.h layout: z0 | w0 | raw0 | ...)
@@ -320,7 +336,7 @@ def _forward_impl(rays, cfg, keep_for_backward):
         z0 = ws[o_z0:o_z0 + n * S * 4].view(torch.float32).view(n, S).clone()
         raw0 = ws[o_raw0:o_raw0 + n * S * 16].view(torch.float32).view(n, S, 4).clone()
     outs = [rgb, disp, acc] + ([rgb0, disp0, acc0, zstd] if Ni > 0 else []) + ([raw] if cfg['retraw'] else [])
-    return tuple(outs), (zv, raw, z0, raw0)
+    return tuple(outs), (zv, raw, z0, raw0, mask)
 
 
 def _params_of(net):
@@ -336,8 +352,10 @@ class _RenderRaysFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, ray_batch, cfg, *params):
         rays = ray_batch.detach().to(torch.float32).contiguous()
-        outs, saved = _forward_impl(rays, cfg, keep_for_backward=True)
-        ctx.save_for_backward(rays, *[t for t in saved if t is not None])
+        pose_only = not any(torch.is_tensor(p) and p.requires_grad for p in params)     # RN:168-181: no dL/dMLP wanted
+        outs, saved = _forward_impl(rays, cfg, keep_for_backward=True, save_mask=pose_only)
+        ctx.relu_mask = saved[4]
+        ctx.save_for_backward(rays, *[t for t in saved[:4] if t is not None])
         ctx.have_coarse = saved[2] is not None
         ctx.cfg = cfg
         ctx.in_dtype = ray_batch.dtype
@@ -347,7 +365,7 @@ class _RenderRaysFn(torch.autograd.Function):
         return outs
 
     @staticmethod
-    def _one_pass(rays, zv, raw, net_blob, flags, g, want_dump):
+    def _one_pass(rays, zv, raw, net_blob, flags, g, want_dump, relu_mask=None):
         L = lib()
         n, T = zv.shape
         d_rays = torch.empty(n, 11, dtype=torch.float32, device=rays.device)
@@ -361,8 +379,10 @@ class _RenderRaysFn(torch.autograd.Function):
                     [torch.zeros(s[0], dtype=torch.float32, device=rays.device) for s in shapes]
             dWp = (ctypes.c_void_p * 12)(*[t.data_ptr() for t in grads[:12]])
             dBp = (ctypes.c_void_p * 12)(*[t.data_ptr() for t in grads[12:]])
-        check(L.nsr_render_rays_backward(ptr(rays), ptr(zv), ptr(raw), n, T, ptr(net_blob), flags, ptr(g), ptr(d_rays), ptr(dump),
-                                         dWp, dBp, ptr(ws), ws_bytes, _stream()), 'nsr_render_rays_backward')
+        if want_dump:
+            relu_mask = None                     # parameter gradients need the activations: recompute path
+        check(L.nsr_render_rays_backward_ex(ptr(rays), ptr(zv), ptr(raw), n, T, ptr(net_blob), flags, ptr(g), ptr(d_rays), ptr(dump),
+                                            dWp, dBp, ptr(relu_mask), ptr(ws), ws_bytes, _stream()), 'nsr_render_rays_backward')
         return d_rays, grads
 
     @staticmethod
@@ -384,7 +404,7 @@ class _RenderRaysFn(torch.autograd.Function):
         if d_rgb is not None:
             blob = cfg['pc'] if fine_is_coarse else cfg['pf']
             want = need_c if fine_is_coarse else need_f
-            dr, gr = _RenderRaysFn._one_pass(rays, zv, raw, blob, wflag, d_rgb.detach().float().contiguous(), want)
+            dr, gr = _RenderRaysFn._one_pass(rays, zv, raw, blob, wflag, d_rgb.detach().float().contiguous(), want, ctx.relu_mask)
             d_rays = dr
             if fine_is_coarse:
                 g_c = gr
@@ -635,9 +655,9 @@ def render_image_grad(H, W, K, c2w, g_rgb, **kw):
           'nsr_make_rays_dev')
     cfg = dict(pc=pc, pf=pf, S=S, Ni=Ni, flags=flags, t_rand=None, u=None, retraw=False)
     with torch.no_grad():
-        outs, saved = _forward_impl(rays, cfg, keep_for_backward=True)
+        outs, saved = _forward_impl(rays, cfg, keep_for_backward=True, save_mask=True)
         g = g_rgb.detach().to(device=dev, dtype=torch.float32).reshape(-1, 3).contiguous()
-        d_rays, _ = _RenderRaysFn._one_pass(rays, saved[0], saved[1], pf if pf is not None else pc, flags & FLAG_WHITE_BKGD, g, False)
+        d_rays, _ = _RenderRaysFn._one_pass(rays, saved[0], saved[1], pf if pf is not None else pc, flags & FLAG_WHITE_BKGD, g, False, saved[4])
         d_c2w = rays_grad_to_c2w(H, W, K, rays, d_rays)
     return outs[0].view(H, W, 3), d_c2w
 

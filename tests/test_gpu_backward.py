@@ -172,3 +172,73 @@ def test_parameter_gradients_many_samples_no_resampling(nsr, wfit):
         except AssertionError as e:
             failures.append(str(e))
     assert not failures, failures
+
+
+@pytest.mark.parametrize('n_side,S,Ni', [(17, 64, 128), (3, 64, 128), (9, 64, 0), (11, 16, 40)])
+def test_saved_sign_bits_backward_equals_recompute(nsr, nets, n_side, S, Ni):
+    """nsr_render_rays_forward_ex saves one bit per ReLU; nsr_render_rays_backward_ex with those bits (no forward recompute,
+    12 instead of 22 GEMM steps) must return what the recompute route returns."""
+    import ctypes
+    L = nsr.lib()
+    rays = camera_rays(n_side, 22.5).cuda()
+    n, T = rays.shape[0], S + Ni
+    pc, pf = nsr.packed_weights(nets[0]), nsr.packed_weights(nets[1])
+    P = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+    new = lambda *s: torch.empty(*s, device='cuda')
+    rgb, raw, zv = new(n, 3), new(n, T, 4), new(n, T)
+    ws = torch.empty(L.nsr_render_workspace_bytes(n, S, Ni), dtype=torch.uint8, device='cuda')
+    mask = torch.full((L.nsr_relu_mask_bytes(n, T),), 0xAA, dtype=torch.uint8, device='cuda')
+    assert mask.numel() == ((n * T + 127) // 128) * 68 * 128 * 4
+    rc = L.nsr_render_rays_forward_ex(P(rays), n, P(pc), P(pf), S, Ni, 0, None, None, P(rgb), None, None, None, None, None, None, P(raw), P(zv),
+                                      None, P(mask), P(ws), ws.numel(), None)
+    assert rc == 0, L.nsr_last_error()
+    g = torch.randn(n, 3, device='cuda', generator=torch.Generator(device='cuda').manual_seed(3))
+    bws = torch.empty(L.nsr_render_backward_workspace_bytes(n, T), dtype=torch.uint8, device='cuda')
+    net = pf if Ni > 0 else pc
+    d_ref, d_got = new(n, 11), new(n, 11)
+    assert L.nsr_render_rays_backward_ex(P(rays), P(zv), P(raw), n, T, P(net), 0, P(g), P(d_ref), None, None, None, None, P(bws), bws.numel(), None) == 0
+    assert L.nsr_render_rays_backward_ex(P(rays), P(zv), P(raw), n, T, P(net), 0, P(g), P(d_got), None, None, None, P(mask), P(bws), bws.numel(), None) == 0, L.nsr_last_error()
+    torch.cuda.synchronize()
+    scale = float(d_ref.abs().max())
+    err = float((d_got - d_ref).abs().max())
+    print(f'saved-bits vs recompute (n={n}, S={S}, Ni={Ni}): max|ref| {scale:.3e}, max diff {err:.3e}, bit-equal {torch.equal(d_got, d_ref)}')
+    assert scale > 0 and err <= 1e-6 * scale
+    # the bits themselves: a fitted network has both live and dead units
+    words = mask.view(torch.int32)
+    assert int((words != 0).sum()) > 0 and int((words != -1).sum()) > 0
+    # parameter gradients need activations: refused on the saved-bits route
+    dump = torch.empty(L.nsr_mlp_dump_bytes(n, T), dtype=torch.uint8, device='cuda')
+    gw = [torch.zeros(s, device='cuda') for s in nsr.run_nerf._EXPECTED_SHAPES]
+    gb = [torch.zeros(s[0], device='cuda') for s in nsr.run_nerf._EXPECTED_SHAPES]
+    dWp = (ctypes.c_void_p * 12)(*[t.data_ptr() for t in gw])
+    dBp = (ctypes.c_void_p * 12)(*[t.data_ptr() for t in gb])
+    assert L.nsr_render_rays_backward_ex(P(rays), P(zv), P(raw), n, T, P(net), 0, P(g), P(d_got), P(dump), dWp, dBp, P(mask), P(bws), bws.numel(), None) == -1
+
+
+def test_pose_only_autograd_takes_the_saved_bits_route(nsr, wfit, nets):
+    """With frozen networks (nothing but the rays asks for gradient) render_rays keeps the sign bits and the backward skips the
+    recompute; same gradient as with NSR_SAVE_RELU_MASK=0 and as the oracle's autograd."""
+    import copy
+    frozen = [copy.deepcopy(m).requires_grad_(False) for m in nets]
+    rays = camera_rays(12, 202.5)
+    g = torch.randn(rays.shape[0], 3, generator=torch.Generator().manual_seed(5))
+    grads = {}
+    launches = {}
+    nsr.packed_weights(frozen[0]), nsr.packed_weights(frozen[1])      # pack outside the counted region
+    for save in (True, False):
+        nsr.run_nerf.SAVE_RELU_MASK = save
+        try:
+            r = rays.cuda().requires_grad_(True)
+            before = nsr.lib().nsr_launch_count()
+            out = nsr.render_rays(r, frozen[0], None, 64, N_importance=128, network_fine=frozen[1])
+            (grads[save],) = torch.autograd.grad(out['rgb_map'], r, grad_outputs=g.cuda())
+            launches[save] = nsr.lib().nsr_launch_count() - before
+        finally:
+            nsr.run_nerf.SAVE_RELU_MASK = True
+    assert launches[True] == launches[False]
+    scale = float(grads[False].abs().max())
+    assert float((grads[True] - grads[False]).abs().max()) <= 1e-6 * scale
+    r_cpu = rays.clone().requires_grad_(True)
+    ref = O.render_rays(r_cpu, wfit[0], wfit[1], 64, 128)
+    (ref_grad,) = torch.autograd.grad(ref['rgb_map'], r_cpu, grad_outputs=g)
+    check_grad(grads[True][:, 0:6], ref_grad[:, 0:6], 'dL/d rays (saved sign bits)')
