@@ -33,5 +33,17 @@ ncubwd)
   timeout 1500 ncu --set full --clock-control none --import-source on -k regex:nerf_mlp_bwd -s 1 -c 1 -f -o gpurun_out/prof_bwd \
       python tools/trace_bwd_plain.py > gpurun_out/ncu_bwd.log 2>&1
   echo "ncubwd exit $?" >> gpurun_out/ncu_bwd.log; tail -3 gpurun_out/ncu_bwd.log ;;
+bilevel)
+  timeout 600 python tools/bilevel_stub.py --epochs 3 --K 8 > gpurun_out/bilevel_n1.txt 2> gpurun_out/bilevel_n1.err
+  echo "bilevel exit $?" >> gpurun_out/bilevel_n1.err; cat gpurun_out/bilevel_n1.txt; tail -3 gpurun_out/bilevel_n1.err ;;
+bilevel[248])
+  N=${what#bilevel}
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29519 \
+      tools/bilevel_stub.py --epochs 3 --K 8 > gpurun_out/bilevel_n$N.txt 2> gpurun_out/bilevel_n$N.err
+  echo "bilevel$N exit $?" >> gpurun_out/bilevel_n$N.err; cat gpurun_out/bilevel_n$N.txt; tail -3 gpurun_out/bilevel_n$N.err ;;
+ncubwdm)
+  timeout 1500 ncu --set full --clock-control none --import-source on -k regex:nerf_mlp_bwd -s 1 -c 1 -f -o gpurun_out/prof_bwd_masked \
+      python tools/trace_bwd_masked.py > gpurun_out/ncu_bwd_masked.log 2>&1
+  echo "ncubwdm exit $?" >> gpurun_out/ncu_bwd_masked.log; tail -3 gpurun_out/ncu_bwd_masked.log ;;
 esac
 done
