@@ -1,6 +1,7 @@
 // C ABI of libnsr_b200 (include/nsr_b200.h): argument checking, error strings, and the
 // forward orchestration of render_rays (RN:390-501) over the kernels in ray_stage.cu / mlp_forward.cu.
 #include <atomic>
+#include <mutex>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -53,6 +54,8 @@ int ensure_dynamic_smem(const void* func, int bytes) {
   struct Entry { const void* f; int dev; };
   static Entry done[256];
   static int n_done = 0;
+  static std::mutex mu;                       // host threads driving different devices may get here together
+  std::lock_guard<std::mutex> lock(mu);
   int dev = 0;
   cudaGetDevice(&dev);
   for (int i = 0; i < n_done; ++i)
