@@ -302,7 +302,7 @@ def run_ours(args):
         r = rays_dev[s % len(rays_dev)]
         rc = L.nsr_render_rays_forward_ex(P(r), n, P(pc), P(pf), N_SAMPLES, N_IMPORTANCE, 0, None, None, P(outs['rgb']), P(outs['disp']),
                                           P(outs['acc']), P(outs['rgb0']), P(outs['disp0']), P(outs['acc0']), P(outs['zstd']), P(rawsave),
-                                          P(zsave), None, P(relu_mask), P(ws), ws_bytes, stream)
+                                          P(zsave), None, P(relu_mask), None, P(ws), ws_bytes, stream)
         rc = rc or L.nsr_render_rays_backward_ex(P(r), P(zsave), P(rawsave), n, T, P(pf), 0, P(g_rgb), P(d_rays), None, None, None,
                                                  P(relu_mask), P(bws), bws_bytes, stream)
         rc = rc or L.nsr_rays_grad_to_c2w(H, W, Kf, P(r), P(d_rays), None, n, P(d_c2w), 0, P(cws), stream)

@@ -136,13 +136,16 @@ int nsr_render_rays_forward(const float* rays, int64_t n_rays, const void* packe
  * receives one bit per ReLU output of the LAST network pass (2176 bits = 272 B per sample point; nothing else of the
  * activations is kept).  Handing it to nsr_render_rays_backward_ex lets the backward pass skip its forward recompute
  * (10 of its 22 GEMM steps): the pose-gradient route of RN:168-181 for callers that can spare 272 B per point.
+ * dump_out (NULL, or nsr_mlp_dump_bytes() bytes, 128-byte aligned; needs relu_mask and the default precision): the last pass also
+ * writes every layer's input activations as fp16 (the operand half of the weight-gradient dump), so that a backward call with
+ * BOTH relu_mask and dump can produce dL/dW, dL/db without recomputing the forward pass either (what nsr_train_step does).
  */
 size_t nsr_relu_mask_bytes(int64_t n_rays, int n_total_samples);
 int nsr_render_rays_forward_ex(const float* rays, int64_t n_rays, const void* packed_coarse, const void* packed_fine,
                                int n_samples, int n_importance, uint32_t flags, const float* t_rand, const float* u,
                                float* rgb_map, float* disp_map, float* acc_map, float* rgb0, float* disp0, float* acc0,
                                float* z_std, float* raw, float* z_vals_out, float* weights_out, void* relu_mask,
-                               void* workspace, size_t workspace_bytes, void* stream);
+                               void* dump_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Bytes of scratch nsr_render_rays_backward needs for n rays of T = n_samples + n_importance depths. */
 size_t nsr_render_backward_workspace_bytes(int64_t n_rays, int n_total_samples);
@@ -167,9 +170,9 @@ int nsr_render_rays_backward(const float* rays, const float* z_vals, const float
                              const void* packed_net, uint32_t flags, const float* d_rgb_map, float* d_rays, void* dump,
                              float* const* dW, float* const* dB, void* workspace, size_t workspace_bytes, void* stream);
 
-/* The same, reading the ReLU sign bits nsr_render_rays_forward_ex saved for this pass (relu_mask != NULL: no recompute; dW / dB /
- * dump must then be NULL -- parameter gradients need the activations, i.e. the recompute path).  relu_mask = NULL: identical to
- * nsr_render_rays_backward. */
+/* The same, reading the ReLU sign bits nsr_render_rays_forward_ex saved for this pass (relu_mask != NULL: no recompute).  With
+ * relu_mask AND dW / dB, `dump` must be the buffer that forward call filled through dump_out (activations); this call adds the
+ * gradients to it.  relu_mask = NULL: identical to nsr_render_rays_backward (everything recomputed). */
 int nsr_render_rays_backward_ex(const float* rays, const float* z_vals, const float* raw, int64_t n_rays, int n_total_samples,
                                 const void* packed_net, uint32_t flags, const float* d_rgb_map, float* d_rays, void* dump,
                                 float* const* dW, float* const* dB, const void* relu_mask, void* workspace,

@@ -37,7 +37,7 @@ _SIGNATURES = {
     'nsr_relu_mask_bytes': (c_size, [c_i64, c_int]),
     'nsr_render_rays_forward_ex': (c_int, [c_f32p, c_i64, c_vp, c_vp, c_int, c_int, c_u32, c_f32p, c_f32p,
                                            c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p,
-                                           c_vp, c_vp, c_size, c_vp]),
+                                           c_vp, c_vp, c_vp, c_size, c_vp]),
     'nsr_render_rays_backward_ex': (c_int, [c_f32p, c_f32p, c_f32p, c_i64, c_int, c_vp, c_u32, c_f32p, c_f32p, c_vp, c_vp, c_vp, c_vp,
                                             c_vp, c_size, c_vp]),
     'nsr_render_backward_workspace_bytes': (c_size, [c_i64, c_int]),

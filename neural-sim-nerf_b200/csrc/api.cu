@@ -157,16 +157,19 @@ int nsr_render_rays_forward(const float* rays, int64_t n, const void* packed_coa
                             float* acc_map, float* rgb0, float* disp0, float* acc0, float* z_std, float* raw,
                             float* z_vals_out, float* weights_out, void* workspace, size_t workspace_bytes, void* stream) {
   return nsr_render_rays_forward_ex(rays, n, packed_coarse, packed_fine, S, Ni, flags, t_rand, u, rgb_map, disp_map, acc_map, rgb0, disp0,
-                                    acc0, z_std, raw, z_vals_out, weights_out, nullptr, workspace, workspace_bytes, stream);
+                                    acc0, z_std, raw, z_vals_out, weights_out, nullptr, nullptr, workspace, workspace_bytes, stream);
 }
 
 int nsr_render_rays_forward_ex(const float* rays, int64_t n, const void* packed_coarse, const void* packed_fine, int S,
                                int Ni, uint32_t flags, const float* t_rand, const float* u, float* rgb_map, float* disp_map,
                                float* acc_map, float* rgb0, float* disp0, float* acc0, float* z_std, float* raw,
-                               float* z_vals_out, float* weights_out, void* relu_mask, void* workspace, size_t workspace_bytes,
-                               void* stream) {
+                               float* z_vals_out, float* weights_out, void* relu_mask, void* dump_out, void* workspace,
+                               size_t workspace_bytes, void* stream) {
   NSR_REQUIRE(n >= 0 && S >= 2 && Ni >= 0, "nsr_render_rays_forward: bad sizes (needs at least 2 samples per ray)");
   NSR_REQUIRE(relu_mask == nullptr || (reinterpret_cast<uintptr_t>(relu_mask) & 15) == 0, "nsr_render_rays_forward: relu_mask must be 16-byte aligned");
+  NSR_REQUIRE(dump_out == nullptr || relu_mask != nullptr, "nsr_render_rays_forward: dump_out goes with relu_mask (the backward pass needs both)");
+  NSR_REQUIRE(dump_out == nullptr || (reinterpret_cast<uintptr_t>(dump_out) & 127) == 0, "nsr_render_rays_forward: dump_out must be 128-byte aligned");
+  NSR_REQUIRE(dump_out == nullptr || !(flags & (NSR_FLAG_FAST_FP16 | NSR_FLAG_MIXED_F8)), "nsr_render_rays_forward: dump_out needs the default precision");
   if (n == 0) return NSR_OK;
   NSR_REQUIRE(rays && packed_coarse, "nsr_render_rays_forward: null rays / weights");
   NSR_REQUIRE(workspace && workspace_bytes >= nsr_render_workspace_bytes(n, S, Ni), "nsr_render_rays_forward: workspace too small");
@@ -190,7 +193,7 @@ int nsr_render_rays_forward_ex(const float* rays, int64_t n, const void* packed_
 
   uint32_t* mask = static_cast<uint32_t*>(relu_mask);      // sign bits of the LAST pass: the only one that carries gradient to the rays
   if ((rc = launch_coarse_z(rays, n, S, flags, t_rand, z0, st))) return rc;                          // RN:439-461
-  if ((rc = launch_mlp_forward(rays, z0, n, S, packed_coarse, mflags, raw0, st, Ni == 0 ? mask : nullptr))) return rc;   // RN:463-466
+  if ((rc = launch_mlp_forward(rays, z0, n, S, packed_coarse, mflags, raw0, st, Ni == 0 ? mask : nullptr, Ni == 0 ? dump_out : nullptr))) return rc;   // RN:463-466
   if (Ni == 0) {
     if ((rc = launch_raw2outputs(raw0, z0, rays + 3, 11, n, S, cflags, rgb_map, disp_map, acc_map, weights_out, nullptr, st))) return rc;
     if (raw) cudaMemcpyAsync(raw, raw0, size_t(n) * S * 16, cudaMemcpyDeviceToDevice, st);
@@ -201,7 +204,7 @@ int nsr_render_rays_forward_ex(const float* rays, int64_t n, const void* packed_
   float* zf = z_vals_out ? z_vals_out : z1;
   if ((rc = launch_resample_merge(z0, w0, n, S, Ni, u, zf, nullptr, z_std, st))) return rc;          // RN:473-477, 495
   float* rawf = raw ? raw : raw1;
-  if ((rc = launch_mlp_forward(rays, zf, n, T, packed_fine ? packed_fine : packed_coarse, mflags, rawf, st, mask))) return rc;  // RN:478-483
+  if ((rc = launch_mlp_forward(rays, zf, n, T, packed_fine ? packed_fine : packed_coarse, mflags, rawf, st, mask, dump_out))) return rc;  // RN:478-483
   if ((rc = launch_raw2outputs(rawf, zf, rays + 3, 11, n, T, cflags, rgb_map, disp_map, acc_map, weights_out, nullptr, st))) return rc;  // RN:485
   return NSR_OK;
 }
@@ -224,7 +227,6 @@ int nsr_render_rays_backward_ex(const float* rays, const float* z_vals, const fl
                                 uint32_t flags, const float* d_rgb_map, float* d_rays, void* dump, float* const* dW,
                                 float* const* dB, const void* relu_mask, void* workspace, size_t workspace_bytes, void* stream) {
   NSR_REQUIRE(n >= 0 && T > 0, "nsr_render_rays_backward: bad sizes");
-  NSR_REQUIRE(relu_mask == nullptr || dW == nullptr, "nsr_render_rays_backward: parameter gradients need the recompute path (relu_mask = NULL)");
   NSR_REQUIRE(relu_mask == nullptr || (reinterpret_cast<uintptr_t>(relu_mask) & 15) == 0, "nsr_render_rays_backward: relu_mask must be 16-byte aligned");
   if (n == 0) return NSR_OK;
   NSR_REQUIRE(rays && z_vals && raw && packed_net && d_rgb_map && d_rays, "nsr_render_rays_backward: null argument");
@@ -338,14 +340,17 @@ int nsr_add_sigma_noise(uint64_t seed, uint32_t stream_id, float* raw, int64_t n
 
 // workspace layout (each block padded to 256 B):
 //   forward workspace (nsr_render_workspace_bytes) | t_rand [n,S] | u [n,Ni] | rgb [n,3] | rgb0 [n,3] | d_rgb [n,3] | d_rgb0 [n,3] |
-//   d_rays [n,11] | backward workspace (n, T) | dump (n, T) | gradients 2 x 595 968 floats
+//   d_rays [n,11] | backward workspace (n, T) | dump + sign bits of the last pass (n, T) | (Ni > 0) dump + sign bits of the coarse pass
+//   (n, S) | gradients 2 x 595 968 floats.  Both forward passes write their activations (fp16) and ReLU sign bits, so neither backward
+//   pass recomputes anything.
 size_t nsr_train_workspace_bytes(int64_t n, int S, int Ni) {
   const int T = S + Ni;
   size_t b = nsr_render_workspace_bytes(n, S, Ni);
   b += align_up(size_t(n) * S * 4, 256) + align_up(size_t(n) * (Ni > 0 ? Ni : 1) * 4, 256);
   b += 4 * align_up(size_t(n) * 12, 256) + align_up(size_t(n) * 44, 256);
   b += nsr_render_backward_workspace_bytes(n, T);
-  b += align_up(nsr_mlp_dump_bytes(n, T), 256);
+  b += align_up(nsr_mlp_dump_bytes(n, T), 256) + align_up(nsr_relu_mask_bytes(n, T), 256);
+  if (Ni > 0) b += align_up(nsr_mlp_dump_bytes(n, S), 256) + align_up(nsr_relu_mask_bytes(n, S), 256);
   b += 2 * kNetParamsPadded * 4;
   return b;
 }
@@ -392,6 +397,9 @@ int nsr_train_step(const float* rays, const float* target, int64_t n, const nsr_
   const size_t bwd_bytes = nsr_render_backward_workspace_bytes(n, T);
   void* bwd = carve(bwd_bytes);
   void* dump = carve(nsr_mlp_dump_bytes(n, T));
+  uint32_t* bits = reinterpret_cast<uint32_t*>(carve(nsr_relu_mask_bytes(n, T)));
+  void* dump0 = Ni > 0 ? carve(nsr_mlp_dump_bytes(n, S)) : nullptr;
+  uint32_t* bits0 = Ni > 0 ? reinterpret_cast<uint32_t*>(carve(nsr_relu_mask_bytes(n, S))) : nullptr;
   float* grads = reinterpret_cast<float*>(carve(2 * kNetParamsPadded * 4));
   if (rgb_out) rgb = rgb_out;
 
@@ -421,12 +429,12 @@ int nsr_train_step(const float* rays, const float* target, int64_t n, const nsr_
     if (Ni > 0 && (rc = launch_uniform(seed, 1u, u, n * int64_t(Ni), st))) return rc;                             // RH:211
   }
   if ((rc = launch_coarse_z(rays, n, S, zflags, perturb ? t_rand : nullptr, z0, st))) return rc;
-  if ((rc = launch_mlp_forward(rays, z0, n, S, pc, 0, raw0, st))) return rc;
+  if ((rc = launch_mlp_forward(rays, z0, n, S, pc, 0, raw0, st, Ni > 0 ? bits0 : bits, Ni > 0 ? dump0 : dump))) return rc;
   if (raw_noise_std > 0.f && (rc = launch_sigma_noise(seed, 2u, raw0, n * int64_t(S), raw_noise_std, st))) return rc;  // RN:365-366
   if ((rc = launch_raw2outputs(raw0, z0, rays + 3, 11, n, S, cflags, Ni > 0 ? rgb0 : rgb, nullptr, nullptr, w0, nullptr, st))) return rc;
   if (Ni > 0) {
     if ((rc = launch_resample_merge(z0, w0, n, S, Ni, perturb ? u : nullptr, z1, nullptr, nullptr, st))) return rc;
-    if ((rc = launch_mlp_forward(rays, z1, n, T, pl, 0, raw1, st))) return rc;
+    if ((rc = launch_mlp_forward(rays, z1, n, T, pl, 0, raw1, st, bits, dump))) return rc;
     if (raw_noise_std > 0.f && (rc = launch_sigma_noise(seed, 3u, raw1, n * int64_t(T), raw_noise_std, st))) return rc;
     if ((rc = launch_raw2outputs(raw1, z1, rays + 3, 11, n, T, cflags, rgb, nullptr, nullptr, nullptr, nullptr, st))) return rc;
   }
@@ -439,9 +447,10 @@ int nsr_train_step(const float* rays, const float* target, int64_t n, const nsr_
   }
   // ---- loss.backward() (RN:705): the last pass through rgb, the coarse pass through rgb0
   cudaMemsetAsync(grads, 0, 2 * kNetParamsPadded * 4, st);
-  if ((rc = nsr_render_rays_backward(rays, Ni > 0 ? z1 : z0, Ni > 0 ? raw1 : raw0, n, Ni > 0 ? T : S, pl, cflags, d_rgb, d_rays, dump, dW[last],
-                                     dB[last], bwd, bwd_bytes, stream))) return rc;
-  if (Ni > 0 && (rc = nsr_render_rays_backward(rays, z0, raw0, n, S, pc, cflags, d_rgb0, d_rays, dump, dW[0], dB[0], bwd, bwd_bytes, stream))) return rc;
+  if ((rc = nsr_render_rays_backward_ex(rays, Ni > 0 ? z1 : z0, Ni > 0 ? raw1 : raw0, n, Ni > 0 ? T : S, pl, cflags, d_rgb, d_rays, dump, dW[last],
+                                        dB[last], bits, bwd, bwd_bytes, stream))) return rc;
+  if (Ni > 0 && (rc = nsr_render_rays_backward_ex(rays, z0, raw0, n, S, pc, cflags, d_rgb0, d_rays, dump0, dW[0], dB[0], bits0, bwd, bwd_bytes,
+                                                  stream))) return rc;
   // ---- optimizer.step() (RN:707)
   AdamJobs jobs;
   jobs.count = 0;

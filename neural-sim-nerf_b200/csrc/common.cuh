@@ -150,7 +150,7 @@ int launch_adam(const AdamJobs& jobs, float beta1, float beta2, float lr, float 
 // mlp_forward.cu
 int launch_pack_net(const float* const* weights, const float* const* biases, void* packed, cudaStream_t st);
 int launch_mlp_forward(const float* rays, const float* z_or_pts, int64_t n, int S, const void* packed, uint32_t flags,
-                       float* raw, cudaStream_t st, uint32_t* relu_mask = nullptr);
+                       float* raw, cudaStream_t st, uint32_t* relu_mask = nullptr, void* dump = nullptr);
 // mlp_backward.cu: d_raw [n,S,4] -> d_pts [n,S,8] = (dL/dpoint[3], 0, dL/dviewdir[3], 0) per sample
 int launch_mlp_backward(const float* rays, const float* z, int64_t n, int S, const void* packed, const float* d_raw,
                         float* d_pts, void* dump, const float* gscale, cudaStream_t st, const uint32_t* relu_mask = nullptr);

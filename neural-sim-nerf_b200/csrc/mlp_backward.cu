@@ -51,13 +51,6 @@ struct BwdArgs {
   unsigned long long* trace;  // debug (NSR_TRACE_FILE_BWD): clock64 stamps of CTA 0's first tiles, [tile][gstep][16]
 };
 
-// 64 consecutive features (32 packed fp16 words) of tile-row `row` at feature `col` of a blocked [P, W] dump array
-__device__ __forceinline__ void dump64(uint8_t* arr, int tile, int row, int W, int col, const uint32_t* H) {
-  uint8_t* dst = arr + dump_blocked_off(tile, row, W, col >> 3);
-#pragma unroll
-  for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(dst + q * 128) = make_uint4(H[4 * q], H[4 * q + 1], H[4 * q + 2], H[4 * q + 3]);
-}
-
 #define NSR_TRB(tl, g, slot)                                                                              \
   do {                                                                                                  \
     if (a.trace != nullptr && blockIdx.x == 0 && (tl) < 3) a.trace[((tl) * 22 + (g)) * 16 + (slot)] = clock64(); \
@@ -446,6 +439,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
           split2<true>(gg[0], gg[1], H[j], L[j]);
           split2<true>(gg[2], gg[3], H[16 + j], L[16 + j]);
         }
+        if (a.dump != nullptr) dump64(a.dump + dump_off_gv(P), tile, row, 128, col0, H);   // the activations were dumped by the forward pass
         tc_fence_after_sync();
         tmem_st16(tlane + TM_AHI + col0 / 2, *reinterpret_cast<const uint32_t(*)[16]>(&H[0]));
         tmem_st16(tlane + TM_AHI + col0 / 2 + 16, *reinterpret_cast<const uint32_t(*)[16]>(&H[16]));
@@ -628,10 +622,8 @@ int launch_mlp_backward(const float* rays, const float* z, int64_t n, int S, con
   if (n_points == 0) return NSR_OK;
   int num_sms = 0;
   if (int rc = current_device_sms(&num_sms)) return rc;
-  if (relu_mask != nullptr && dump != nullptr) {
-    set_error("mlp_backward: the saved-sign-bit path carries no activations, parameter gradients need the recompute path");
-    return NSR_E_INVALID;
-  }
+  // relu_mask with dump: the forward pass (launch_mlp_forward with relu_mask AND dump) already wrote the activation half of the
+  // dump (EX, EV, H0..H7, F, HV); this pass adds the gradient half (GV, GF, G0..G7)
   if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(&nerf_mlp_bwd_kernel<false>), BCfg<false>::SM_TOTAL)) return rc;
   if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(&nerf_mlp_bwd_kernel<true>), BCfg<true>::SM_TOTAL)) return rc;
   BwdArgs a;

@@ -50,6 +50,13 @@ __device__ __forceinline__ uint32_t sign_bits(const uint32_t* H) {
   return m;
 }
 
+// 64 consecutive features (32 packed fp16 words) of tile-row `row` at feature `col` of a blocked [P, W] dump array
+__device__ __forceinline__ void dump64(uint8_t* arr, int tile, int row, int W, int col, const uint32_t* H) {
+  uint8_t* dst = arr + dump_blocked_off(tile, row, W, col >> 3);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(dst + q * 128) = make_uint4(H[4 * q], H[4 * q + 1], H[4 * q + 2], H[4 * q + 3]);
+}
+
 struct Waiter {  // one per (thread, barrier): parity follows the number of completed waits
   uint32_t n = 0;
   __device__ __forceinline__ void wait(uint64_t* bar) {

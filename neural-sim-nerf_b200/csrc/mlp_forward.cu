@@ -259,6 +259,7 @@ struct MlpArgs {
   uint32_t flags;
   int num_tiles;
   uint32_t* relu_mask;        // optional: sign bits of every ReLU output for the backward pass (common.cuh MASK_*)
+  uint8_t* dump;              // optional: the activation half of the weight-gradient dump (common.cuh): EX, EV, H0..H7, F, HV as fp16
   unsigned long long* trace;  // debug (NSR_TRACE_FILE): clock64 stamps of CTA 0's first tiles, [tile][step][16]
 };
 
@@ -286,6 +287,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(enc_free + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const size_t dumpP = size_t(a.num_tiles) * 128;   // rows of the optional dump
 
   if (tid == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -508,6 +510,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
           for (int q = 0; q < 4; ++q) split2<kSplit>(e[8 * g + 2 * q], e[8 * g + 2 * q + 1], h[q], l[q]);
           st_a8(inbuf + C::OFF_ENC_HI, 1024, row, g, h[0], h[1], h[2], h[3]);
           if (kSplit) st_a8(inbuf + C::OFF_ENC_LO, 1024, row, g, l[0], l[1], l[2], l[3]);
+          if (a.dump != nullptr)
+            *reinterpret_cast<uint4*>(a.dump + dump_off_ex(dumpP) + dump_blocked_off(tile, row, 64, g)) = make_uint4(h[0], h[1], h[2], h[3]);
         }
       }
       fence_proxy_async_smem();
@@ -539,6 +543,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
           for (int q = 0; q < 4; ++q) split2<kSplit>(v[8 * g + 2 * q], v[8 * g + 2 * q + 1], h[q], l[q]);
           st_a8(inbuf + C::OFF_DIR_HI, 512, row, g, h[0], h[1], h[2], h[3]);
           if (kSplit) st_a8(inbuf + C::OFF_DIR_LO, 512, row, g, l[0], l[1], l[2], l[3]);
+          if (a.dump != nullptr)
+            *reinterpret_cast<uint4*>(a.dump + dump_off_ev(dumpP) + dump_blocked_off(tile, row, 32, g)) = make_uint4(h[0], h[1], h[2], h[3]);
         }
       }
       fence_proxy_async_smem();
@@ -614,6 +620,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
           mrow[(step * 8 + 0) * 128] = sign_bits(H);
           mrow[(step * 8 + 1) * 128] = sign_bits(H + 16);
         }
+        if (a.dump != nullptr) dump64(a.dump + dump_off_h(dumpP, step), tile, row, 256, col0, H);       // step 8: F
         // ---- every MMA of this step has retired: the old activations may be overwritten
         if (tid == 0) NSR_TR(tl, step, 9);
         w_acc[1].wait(&acc_ready[1]);
@@ -634,6 +641,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
           mrow[(step * 8 + 4) * 128] = sign_bits(H);
           mrow[(step * 8 + 5) * 128] = sign_bits(H + 16);
         }
+        if (a.dump != nullptr) dump64(a.dump + dump_off_h(dumpP, step), tile, row, 256, 128 + col0, H);
         store(1);
         mbar_arrive(&a_ready[1]);
         if (tid == 0) NSR_TR(tl, step, 12);
@@ -646,6 +654,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
       mbar_arrive(&a_ready[0]);
       float r0 = 0.f, r1 = 0.f, r2 = 0.f;
       uint32_t mv0 = 0u, mv1 = 0u;   // sign bits of this thread's 2 x 32 views-layer columns
+      uint32_t HV[32];               // the same columns as packed fp16 (only kept for the dump)
       {
         const float* bias = sTail + TAIL_BIAS + 9 * 256 + col0;
         const float4* wr = reinterpret_cast<const float4*>(sTail + TAIL_WRGB) + col0;
@@ -661,11 +670,14 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
         for (int j = 0; j < 8; ++j) {
           const float4 b0 = *reinterpret_cast<const float4*>(bias + 4 * j), b1 = *reinterpret_cast<const float4*>(bias + 32 + 4 * j);
           const float bb0[4] = {b0.x, b0.y, b0.z, b0.w}, bb1[4] = {b1.x, b1.y, b1.z, b1.w};
+          float hq0[4], hq1[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float h0 = fmaxf(kMixed ? fmaf(__uint_as_float(u0[4 * j + q]), sc9, bb0[q]) : __uint_as_float(u0[4 * j + q]) + bb0[q], 0.f);
             const float h1 = fmaxf(kMixed ? fmaf(__uint_as_float(u1[4 * j + q]), sc9, bb1[q]) : __uint_as_float(u1[4 * j + q]) + bb1[q], 0.f);
             const float4 w0 = wr[4 * j + q], w1 = wr[32 + 4 * j + q];
+            hq0[q] = h0;
+            hq1[q] = h1;
             {
               const int cc = 4 * j + q;                       // column inside the 32-column word
               const int bit = (cc & 1) ? 16 + (cc >> 1) : (cc >> 1);
@@ -679,8 +691,13 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
             r1 = fmaf(h1, w1.y, r1);
             r2 = fmaf(h1, w1.z, r2);
           }
+          HV[2 * j] = pack_f16x2(hq0[0], hq0[1]);
+          HV[2 * j + 1] = pack_f16x2(hq0[2], hq0[3]);
+          HV[16 + 2 * j] = pack_f16x2(hq1[0], hq1[1]);
+          HV[16 + 2 * j + 1] = pack_f16x2(hq1[2], hq1[3]);
         }
       }
+      if (a.dump != nullptr) dump64(a.dump + dump_off_hv(dumpP), tile, row, 128, col0, HV);
       if (mrow != nullptr) {
         mrow[(64 + 0) * 128] = mv0;
         mrow[(64 + 1) * 128] = mv1;
@@ -716,7 +733,7 @@ static int launch_by_flags(const MlpArgs& a, int grid, uint32_t flags, cudaStrea
 }
 
 int launch_mlp_forward(const float* rays, const float* z_or_pts, int64_t n, int S, const void* packed, uint32_t flags,
-                       float* raw, cudaStream_t st, uint32_t* relu_mask) {
+                       float* raw, cudaStream_t st, uint32_t* relu_mask, void* dump) {
   const int64_t n_points = n * S;
   if (n_points == 0) return NSR_OK;
   if (n_points > (int64_t(1) << 31) * 64) {
@@ -735,6 +752,7 @@ int launch_mlp_forward(const float* rays, const float* z_or_pts, int64_t n, int 
   a.flags = flags;
   a.num_tiles = int((n_points + 127) / 128);
   a.relu_mask = relu_mask;
+  a.dump = static_cast<uint8_t*>(dump);
   a.trace = nullptr;
   const int grid = a.num_tiles < num_sms ? a.num_tiles : num_sms;
   const char* trace_file = getenv("NSR_TRACE_FILE");  // debug only: synchronous, dumps CTA 0's timeline

@@ -327,7 +327,7 @@ def _forward_impl(rays, cfg, keep_for_backward, save_mask=False):
             mask = torch.empty(mb, dtype=torch.uint8, device=dev)
     check(L.nsr_render_rays_forward_ex(ptr(rays), n, ptr(cfg['pc']), ptr(cfg['pf']), S, Ni, cfg['flags'], ptr(cfg['t_rand']), ptr(cfg['u']),
                                        ptr(rgb), ptr(disp), ptr(acc), ptr(rgb0), ptr(disp0), ptr(acc0), ptr(zstd),
-                                       ptr(raw), ptr(zv), None, ptr(mask), ptr(ws), ws_bytes, _stream()), 'nsr_render_rays_forward')
+                                       ptr(raw), ptr(zv), None, ptr(mask), None, ptr(ws), ws_bytes, _stream()), 'nsr_render_rays_forward')
     z0 = raw0 = None
     if keep_for_backward and Ni > 0:
         # the coarse pass's depths and raw outputs sit at the head of the workspace (include/nsr_b200.h layout: z0 | w0 | raw0 | ...)

@@ -190,7 +190,7 @@ def test_saved_sign_bits_backward_equals_recompute(nsr, nets, n_side, S, Ni):
     mask = torch.full((L.nsr_relu_mask_bytes(n, T),), 0xAA, dtype=torch.uint8, device='cuda')
     assert mask.numel() == ((n * T + 127) // 128) * 68 * 128 * 4
     rc = L.nsr_render_rays_forward_ex(P(rays), n, P(pc), P(pf), S, Ni, 0, None, None, P(rgb), None, None, None, None, None, None, P(raw), P(zv),
-                                      None, P(mask), P(ws), ws.numel(), None)
+                                      None, P(mask), None, P(ws), ws.numel(), None)
     assert rc == 0, L.nsr_last_error()
     g = torch.randn(n, 3, device='cuda', generator=torch.Generator(device='cuda').manual_seed(3))
     bws = torch.empty(L.nsr_render_backward_workspace_bytes(n, T), dtype=torch.uint8, device='cuda')
@@ -206,13 +206,37 @@ def test_saved_sign_bits_backward_equals_recompute(nsr, nets, n_side, S, Ni):
     # the bits themselves: a fitted network has both live and dead units
     words = mask.view(torch.int32)
     assert int((words != 0).sum()) > 0 and int((words != -1).sum()) > 0
-    # parameter gradients need activations: refused on the saved-bits route
-    dump = torch.empty(L.nsr_mlp_dump_bytes(n, T), dtype=torch.uint8, device='cuda')
-    gw = [torch.zeros(s, device='cuda') for s in nsr.run_nerf._EXPECTED_SHAPES]
-    gb = [torch.zeros(s[0], device='cuda') for s in nsr.run_nerf._EXPECTED_SHAPES]
-    dWp = (ctypes.c_void_p * 12)(*[t.data_ptr() for t in gw])
-    dBp = (ctypes.c_void_p * 12)(*[t.data_ptr() for t in gb])
-    assert L.nsr_render_rays_backward_ex(P(rays), P(zv), P(raw), n, T, P(net), 0, P(g), P(d_got), P(dump), dWp, dBp, P(mask), P(bws), bws.numel(), None) == -1
+    # parameter gradients without recompute: the forward pass also dumps the activations (dump_out), the backward pass adds the
+    # gradients to the same buffer; dL/dW, dL/db against the recompute route (whose backward kernel fills the whole dump itself)
+    def param_grads(use_saved):
+        dump = torch.empty(L.nsr_mlp_dump_bytes(n, T), dtype=torch.uint8, device='cuda')
+        if use_saved:
+            m2 = torch.empty_like(mask)
+            rc = L.nsr_render_rays_forward_ex(P(rays), n, P(pc), P(pf), S, Ni, 0, None, None, P(rgb), None, None, None, None, None, None, P(raw),
+                                              P(zv), None, P(m2), P(dump), P(ws), ws.numel(), None)
+            assert rc == 0, L.nsr_last_error()
+            assert torch.equal(m2, mask)
+        gw = [torch.zeros(s_, device='cuda') for s_ in nsr.run_nerf._EXPECTED_SHAPES]
+        gb = [torch.zeros(s_[0], device='cuda') for s_ in nsr.run_nerf._EXPECTED_SHAPES]
+        dWp = (ctypes.c_void_p * 12)(*[t.data_ptr() for t in gw])
+        dBp = (ctypes.c_void_p * 12)(*[t.data_ptr() for t in gb])
+        d = new(n, 11)
+        rc = L.nsr_render_rays_backward_ex(P(rays), P(zv), P(raw), n, T, P(net), 0, P(g), P(d), P(dump), dWp, dBp, P(mask) if use_saved else None,
+                                           P(bws), bws.numel(), None)
+        assert rc == 0, L.nsr_last_error()
+        torch.cuda.synchronize()
+        return d, gw, gb
+    d_a, gw_a, gb_a = param_grads(False)
+    d_b, gw_b, gb_b = param_grads(True)
+    assert float((d_a - d_b).abs().max()) <= 1e-6 * float(d_a.abs().max())
+    for i, (x, y) in enumerate(list(zip(gw_a, gw_b)) + list(zip(gb_a, gb_b))):
+        sc = float(x.abs().max())
+        assert sc > 0, i
+        assert float((x - y).abs().max()) <= 1e-4 * sc, (i, float((x - y).abs().max()), sc)   # split-K atomics: summation order differs run to run
+    with pytest.raises(AssertionError):     # dump_out without relu_mask is refused
+        rc = L.nsr_render_rays_forward_ex(P(rays), n, P(pc), P(pf), S, Ni, 0, None, None, P(rgb), None, None, None, None, None, None, P(raw), P(zv),
+                                          None, None, P(mask), P(ws), ws.numel(), None)
+        assert rc == 0
 
 
 def test_pose_only_autograd_takes_the_saved_bits_route(nsr, wfit, nets):
