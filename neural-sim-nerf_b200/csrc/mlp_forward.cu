@@ -269,7 +269,9 @@ struct MlpArgs {
   } while (0)
 
 // ----------------------------------------------------------------------------- the kernel
-template <int SPLIT>
+// SAVE: also write the ReLU sign bits (a.relu_mask) and, when a.dump != NULL, the activation half of the weight-gradient dump
+// for the backward pass.  A separate instantiation, so the plain render kernel carries none of that code.
+template <int SPLIT, bool SAVE>
 __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
   using C = Cfg<SPLIT>;
   constexpr bool kSplit = C::kSplit;
@@ -350,13 +352,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
         const int nk = step_k_chunks(step);
         const int nhs = step_n_halves(step);
         bool waited1 = false;
-        long long w_cycles = 0, w_count = 0;
         if (lane == 0) NSR_TR(tl, step, 0);
-        if (lane == 0 && a.trace != nullptr && blockIdx.x == 0 && tl < 4) {
-          unsigned long long gt;
-          asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
-          a.trace[(tl * 10 + step) * 16 + 7] = gt;
-        }
         w_a[0].wait(&a_ready[0]);  // A[K 0..127] of this step written, ACC0 drained
         if (lane == 0) NSR_TR(tl, step, 1);
         if (step == 9) {           // the single 128-wide half of step 9 accumulates in ACC1
@@ -379,16 +375,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
               tc_fence_after_sync();
               waited1 = true;
             }
-            if (!ready) {
-              if (a.trace != nullptr) {  // debug: cycles this step spent waiting for weights
-                const long long t0 = clock64();
-                mbar_wait(&full[stage], phase);
-                w_cycles += clock64() - t0;
-                ++w_count;
-              } else {
-                mbar_wait(&full[stage], phase);
-              }
-            }
+            if (!ready) mbar_wait(&full[stage], phase);
             // descriptors: only the start-address field moves (16-byte units): +16 per k-step of 16 elements
             const uint32_t bh = ring_lo + stage * (C::STAGE_BYTES >> 4), bl = bh + (CHUNK_BYTES >> 4);
             const uint32_t acc0 = kc != 0;  // first MMA of a half overwrites the accumulator
@@ -446,10 +433,6 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
         }
         if (!waited1) w_a[1].wait(&a_ready[1]);  // keep the parity in step (cannot happen with this network)
         if (lane == 0) NSR_TR(tl, step, 4);
-        if (lane == 0 && a.trace != nullptr && blockIdx.x == 0 && tl < 4) {
-          a.trace[(tl * 10 + step) * 16 + 5] = w_cycles;
-          a.trace[(tl * 10 + step) * 16 + 6] = w_count;
-        }
         if (step == 5 && leader) umma_commit(&enc_free[0]);  // last reader of the xyz encoding
       }
       if (leader) umma_commit(&enc_free[1]);
@@ -510,7 +493,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
           for (int q = 0; q < 4; ++q) split2<kSplit>(e[8 * g + 2 * q], e[8 * g + 2 * q + 1], h[q], l[q]);
           st_a8(inbuf + C::OFF_ENC_HI, 1024, row, g, h[0], h[1], h[2], h[3]);
           if (kSplit) st_a8(inbuf + C::OFF_ENC_LO, 1024, row, g, l[0], l[1], l[2], l[3]);
-          if (a.dump != nullptr)
+          if (SAVE && a.dump != nullptr)
             *reinterpret_cast<uint4*>(a.dump + dump_off_ex(dumpP) + dump_blocked_off(tile, row, 64, g)) = make_uint4(h[0], h[1], h[2], h[3]);
         }
       }
@@ -543,7 +526,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
           for (int q = 0; q < 4; ++q) split2<kSplit>(v[8 * g + 2 * q], v[8 * g + 2 * q + 1], h[q], l[q]);
           st_a8(inbuf + C::OFF_DIR_HI, 512, row, g, h[0], h[1], h[2], h[3]);
           if (kSplit) st_a8(inbuf + C::OFF_DIR_LO, 512, row, g, l[0], l[1], l[2], l[3]);
-          if (a.dump != nullptr)
+          if (SAVE && a.dump != nullptr)
             *reinterpret_cast<uint4*>(a.dump + dump_off_ev(dumpP) + dump_blocked_off(tile, row, 32, g)) = make_uint4(h[0], h[1], h[2], h[3]);
         }
       }
@@ -565,7 +548,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++tl) {
       const int64_t p = int64_t(tile) * 128 + row;
       float sigma = 0.f;
-      uint32_t* mrow = a.relu_mask != nullptr ? a.relu_mask + size_t(tile) * MASK_TILE_WORDS + (ch * 2) * 128 + row : nullptr;
+      uint32_t* mrow = (SAVE && a.relu_mask != nullptr) ? a.relu_mask + size_t(tile) * MASK_TILE_WORDS + (ch * 2) * 128 + row : nullptr;
       for (int step = 0; step < 9; ++step) {
         const float* bias = sTail + TAIL_BIAS + step * 256 + col0;
         const float* walpha = (step == 7) ? sTail + TAIL_WALPHA + col0 : nullptr;
@@ -616,11 +599,11 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
           tmem_ld_wait();
           convert(u0, u1, 0);
         }
-        if (mrow != nullptr && step < 8) {
+        if (SAVE && mrow != nullptr && step < 8) {
           mrow[(step * 8 + 0) * 128] = sign_bits(H);
           mrow[(step * 8 + 1) * 128] = sign_bits(H + 16);
         }
-        if (a.dump != nullptr) dump64(a.dump + dump_off_h(dumpP, step), tile, row, 256, col0, H);       // step 8: F
+        if (SAVE && a.dump != nullptr) dump64(a.dump + dump_off_h(dumpP, step), tile, row, 256, col0, H);       // step 8: F
         // ---- every MMA of this step has retired: the old activations may be overwritten
         if (tid == 0) NSR_TR(tl, step, 9);
         w_acc[1].wait(&acc_ready[1]);
@@ -637,11 +620,11 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
           tmem_ld_wait();
           convert(u0, u1, 1);
         }
-        if (mrow != nullptr && step < 8) {
+        if (SAVE && mrow != nullptr && step < 8) {
           mrow[(step * 8 + 4) * 128] = sign_bits(H);
           mrow[(step * 8 + 5) * 128] = sign_bits(H + 16);
         }
-        if (a.dump != nullptr) dump64(a.dump + dump_off_h(dumpP, step), tile, row, 256, 128 + col0, H);
+        if (SAVE && a.dump != nullptr) dump64(a.dump + dump_off_h(dumpP, step), tile, row, 256, 128 + col0, H);
         store(1);
         mbar_arrive(&a_ready[1]);
         if (tid == 0) NSR_TR(tl, step, 12);
@@ -670,15 +653,15 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
         for (int j = 0; j < 8; ++j) {
           const float4 b0 = *reinterpret_cast<const float4*>(bias + 4 * j), b1 = *reinterpret_cast<const float4*>(bias + 32 + 4 * j);
           const float bb0[4] = {b0.x, b0.y, b0.z, b0.w}, bb1[4] = {b1.x, b1.y, b1.z, b1.w};
-          float hq0[4], hq1[4];
+          float hq0[4] = {0.f, 0.f, 0.f, 0.f}, hq1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float h0 = fmaxf(kMixed ? fmaf(__uint_as_float(u0[4 * j + q]), sc9, bb0[q]) : __uint_as_float(u0[4 * j + q]) + bb0[q], 0.f);
             const float h1 = fmaxf(kMixed ? fmaf(__uint_as_float(u1[4 * j + q]), sc9, bb1[q]) : __uint_as_float(u1[4 * j + q]) + bb1[q], 0.f);
             const float4 w0 = wr[4 * j + q], w1 = wr[32 + 4 * j + q];
-            hq0[q] = h0;
-            hq1[q] = h1;
-            {
+            if (SAVE) {
+              hq0[q] = h0;
+              hq1[q] = h1;
               const int cc = 4 * j + q;                       // column inside the 32-column word
               const int bit = (cc & 1) ? 16 + (cc >> 1) : (cc >> 1);
               mv0 |= (h0 > 0.f ? 1u : 0u) << bit;
@@ -691,14 +674,16 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
             r1 = fmaf(h1, w1.y, r1);
             r2 = fmaf(h1, w1.z, r2);
           }
-          HV[2 * j] = pack_f16x2(hq0[0], hq0[1]);
-          HV[2 * j + 1] = pack_f16x2(hq0[2], hq0[3]);
-          HV[16 + 2 * j] = pack_f16x2(hq1[0], hq1[1]);
-          HV[16 + 2 * j + 1] = pack_f16x2(hq1[2], hq1[3]);
+          if (SAVE) {
+            HV[2 * j] = pack_f16x2(hq0[0], hq0[1]);
+            HV[2 * j + 1] = pack_f16x2(hq0[2], hq0[3]);
+            HV[16 + 2 * j] = pack_f16x2(hq1[0], hq1[1]);
+            HV[16 + 2 * j + 1] = pack_f16x2(hq1[2], hq1[3]);
+          }
         }
       }
-      if (a.dump != nullptr) dump64(a.dump + dump_off_hv(dumpP), tile, row, 128, col0, HV);
-      if (mrow != nullptr) {
+      if (SAVE && a.dump != nullptr) dump64(a.dump + dump_off_hv(dumpP), tile, row, 128, col0, HV);
+      if (SAVE && mrow != nullptr) {
         mrow[(64 + 0) * 128] = mv0;
         mrow[(64 + 1) * 128] = mv1;
       }
@@ -718,18 +703,25 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
   if (warp == MMA_WARP) tmem_dealloc(0u, 512);
 }
 
-template <int SPLIT>
+template <int SPLIT, bool SAVE>
 static int launch_variant(const MlpArgs& a, int grid, cudaStream_t st) {
-  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(&nerf_mlp_kernel<SPLIT>), Cfg<SPLIT>::SM_TOTAL)) return rc;
-  nerf_mlp_kernel<SPLIT><<<grid, MLP_THREADS, Cfg<SPLIT>::SM_TOTAL, st>>>(a);
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(&nerf_mlp_kernel<SPLIT, SAVE>), Cfg<SPLIT>::SM_TOTAL)) return rc;
+  nerf_mlp_kernel<SPLIT, SAVE><<<grid, MLP_THREADS, Cfg<SPLIT>::SM_TOTAL, st>>>(a);
   count_launch();
   return check_launch("nerf_mlp_kernel");
 }
 
 static int launch_by_flags(const MlpArgs& a, int grid, uint32_t flags, cudaStream_t st) {
-  if (flags & NSR_FLAG_FAST_FP16) return launch_variant<1>(a, grid, st);
-  if (flags & NSR_FLAG_MIXED_F8) return launch_variant<2>(a, grid, st);
-  return launch_variant<3>(a, grid, st);
+  if (a.relu_mask != nullptr || a.dump != nullptr) {
+    if (flags & (NSR_FLAG_FAST_FP16 | NSR_FLAG_MIXED_F8)) {
+      set_error("mlp_forward: sign bits / activations are saved for the backward pass, which is built for the default precision only");
+      return NSR_E_INVALID;
+    }
+    return launch_variant<3, true>(a, grid, st);
+  }
+  if (flags & NSR_FLAG_FAST_FP16) return launch_variant<1, false>(a, grid, st);
+  if (flags & NSR_FLAG_MIXED_F8) return launch_variant<2, false>(a, grid, st);
+  return launch_variant<3, false>(a, grid, st);
 }
 
 int launch_mlp_forward(const float* rays, const float* z_or_pts, int64_t n, int S, const void* packed, uint32_t flags,

