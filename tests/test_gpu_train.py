@@ -113,6 +113,10 @@ def test_train_step_equals_autograd_and_torch_adam(nsr, wfit):
         else:
             assert torch.allclose(out['rgb'], rgb.detach(), atol=5e-4)   # parameters differ by summation order of the weight gradients
         assert float(out['psnr']) == pytest.approx(float(nsr.mse2psnr(img_loss.detach())), rel=1e-5)
+        if it == 0:     # identical parameters so far: the gradients both routes fed to Adam agree to rounding
+            for pa, pb in zip([p for m in nets_a for p in m.parameters()], [p for m in nets_b for p in m.parameters()]):
+                assert max_rel(opt_b.state[pb]['exp_avg'], opt_a.state[pa]['exp_avg']) <= 2e-3
+                assert max_rel(opt_b.state[pb]['exp_avg_sq'], opt_a.state[pa]['exp_avg_sq']) <= 4e-3
     moved = 0.0
     for (na, pa), (nb, pb), p0 in zip(nets_a[0].named_parameters(), nets_b[0].named_parameters(), start[:24]):
         # the weight-gradient kernels add split-K partial sums with atomics: the two routes agree to rounding, and an Adam update is
@@ -130,8 +134,9 @@ def test_train_step_equals_autograd_and_torch_adam(nsr, wfit):
     assert set(sa) == set(sb)
     for k in sa:
         assert float(sb[k]['step']) == 3.0 == float(sa[k]['step'])
-        assert max_rel(sb[k]['exp_avg'], sa[k]['exp_avg']) <= 2e-3
-        assert max_rel(sb[k]['exp_avg_sq'], sa[k]['exp_avg_sq']) <= 2e-3
+        # two independent three-step trajectories of a sharp-edged scene: the moments stay close, not identical
+        assert max_rel(sb[k]['exp_avg'], sa[k]['exp_avg']) <= 5e-2
+        assert max_rel(sb[k]['exp_avg_sq'], sa[k]['exp_avg_sq']) <= 1e-1
 
 
 def test_train_step_keeps_the_packed_weights_in_step(nsr, wfit):
