@@ -354,7 +354,7 @@ def run_ours(args):
         peak = peaks.get('bf16_tflops_sustained', peaks['bf16_tflops'])
         roofline = {'bound': 'tensor', 'kernel': 'nerf_mlp_kernel (fine pass, 192 samples/ray)', 'achieved': achieved, 'peak': peak,
                     'unit': 'TFLOP/s', 'frac': achieved / peak,
-                    'traffic': 584553728, 'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this launch (profiles/r01_v9_ncu_fine_mlp_summary.csv); the launch writes raw [n,192,4] = 491.5 MB and reads depths + rays + weights = 132 MB', 'peak_source': f'{how} bf16_tflops_sustained (kernel timed back to back)',
+                    'traffic': 583430656, 'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this launch (profiles/r01_v10_ncu_fine_mlp_summary.csv); the launch writes raw [n,192,4] = 491.5 MB and reads depths + rays + weights = 132 MB', 'peak_source': f'{how} bf16_tflops_sustained (kernel timed back to back)',
                     'ms_per_launch': k_ms, 'algorithmic_flop_per_launch': flops}
         if world == 1:          # side legs only at N=1 (the scaling runs stay short; cpu_baseline is an N=1 figure)
             # informational: the opt-in single-pass fp16 mode (NOT parity-valid, see DESIGN.md "precision")

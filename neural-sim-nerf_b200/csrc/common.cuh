@@ -69,6 +69,35 @@ __host__ __device__ constexpr int step_n_halves(int s) { return s == 9 ? 1 : 2; 
 __host__ __device__ constexpr int step_k_chunks(int s) { return s == 0 ? 1 : ((s == 5 || s == 9) ? 5 : 4); }
 // mixed mode: does chunk (step, kc) carry fp8 correction tiles (else the fp16 hi/lo split)?
 __host__ __device__ constexpr bool mix_chunk_is_f8(int s, int kc) { return s >= MIX_X3_STEPS && !(s == 5 && kc == 0) && !(s == 9 && kc == 4); }
+// Issue order of a step's weight chunks.  Packed order is [half 0: kc 0..nk-1][half 1: kc 0..nk-1]; the kernels CONSUME a
+// two-half step as  (h0, K early) (h1, K early) (h0, K late) (h1, K late), where "early" are the k0 chunks whose A operand is
+// complete with the first half of the previous step's epilogue (an encoding, or activations 0..127) and "late" the ones that
+// need its second half (activations 128..255).  That way the tensor pipe always has 2 x k0 chunks of work that do not depend
+// on the epilogue still in flight, and the epilogue of accumulator 0 runs under (h1, K late).  Slot i -> (half, kc).
+__host__ __device__ constexpr int step_k_early(int s) { return s == 0 ? 1 : (s == 5 ? 3 : 2); }
+__host__ __device__ inline void issue_slot(int nk, int k0, int halves, int i, int& nh, int& kc) {
+  if (halves == 1) {
+    nh = 0;
+    kc = i;
+    return;
+  }
+  const int k1 = nk - k0;
+  if (i < k0) {
+    nh = 0;
+    kc = i;
+  } else if (i < 2 * k0) {
+    nh = 1;
+    kc = i - k0;
+  } else if (i < 2 * k0 + k1) {
+    nh = 0;
+    kc = k0 + (i - 2 * k0);
+  } else {
+    nh = 1;
+    kc = k0 + (i - 2 * k0 - k1);
+  }
+}
+// slot after which accumulator half 0 of a two-half step is complete
+__host__ __device__ inline int last_slot_half0(int nk, int k0) { return (nk - k0) > 0 ? 2 * k0 + (nk - k0) - 1 : k0 - 1; }
 __host__ __device__ constexpr bool bstep_is_side(int b) { return b == 0 || b == 5 || b == 11; }
 __host__ __device__ constexpr int bstep_n_halves(int b) { return bstep_is_side(b) ? 1 : 2; }
 __host__ __device__ constexpr int bstep_k_chunks(int b) { return b <= 1 ? 2 : 4; }

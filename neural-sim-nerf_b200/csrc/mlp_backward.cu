@@ -59,6 +59,7 @@ struct BwdArgs {
 __device__ __forceinline__ bool gstep_is_side(int g) { return g == 9 || (g >= 10 && bstep_is_side(g - 10)); }
 __device__ __forceinline__ int gstep_k_chunks(int g) { return g < 10 ? step_k_chunks(g) : bstep_k_chunks(g - 10); }
 __device__ __forceinline__ int gstep_side_n(int g) { return g == 9 ? 128 : bstep_side_n(g - 10); }
+__device__ __forceinline__ int gstep_k_early(int g) { return g < 10 ? step_k_early(g) : 2; }   // common.cuh issue_slot
 
 // forward-recompute epilogue of 32 columns: bias + ReLU + hi/lo split (+ sign bits)
 __device__ __forceinline__ uint32_t fwd32(const uint32_t (&u)[32], const float* bias, bool relu, uint32_t* H, uint32_t* L) {
@@ -184,17 +185,24 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
       };
       if (MASKED && int(blockIdx.x) < a.num_tiles) fetch_mask(blockIdx.x, 0);
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++tl) {
-        for (int c = MASKED ? NUM_CHUNKS : 0; c < NUM_CHUNKS + NUM_BWD_CHUNKS; ++c) {
-          // the next tile's bits: a few chunks in, when the tile before this one has long released the other buffer
-          if (MASKED && c == NUM_CHUNKS + 8 && tile + int(gridDim.x) < a.num_tiles) fetch_mask(tile + gridDim.x, tl + 1);
-          if (!first_lap) mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], CHUNK_PAIR_BYTES);
-          bulk_g2s(sRing + stage * CHUNK_PAIR_BYTES, a.packed + size_t(c) * CHUNK_PAIR_BYTES, CHUNK_PAIR_BYTES, &full[stage]);
-          if (++stage == BWD_STAGES) {
-            stage = 0;
-            phase ^= 1;
-            first_lap = false;
+        int base = MASKED ? NUM_CHUNKS : 0;        // first packed chunk of the step
+        for (int g = G0; g < NUM_GSTEPS; ++g) {
+          const int nk = gstep_k_chunks(g), nhs = gstep_is_side(g) ? 1 : 2;
+          for (int i = 0; i < nk * nhs; ++i) {       // in the order the MMA warp consumes them (common.cuh issue_slot)
+            // the next tile's bits: a few chunks in, when the tile before this one has long released the other buffer
+            if (MASKED && g == 12 && i == 0 && tile + int(gridDim.x) < a.num_tiles) fetch_mask(tile + gridDim.x, tl + 1);
+            int nh, kc;
+            issue_slot(nk, gstep_k_early(g), nhs, i, nh, kc);
+            if (!first_lap) mbar_wait(&empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full[stage], CHUNK_PAIR_BYTES);
+            bulk_g2s(sRing + stage * CHUNK_PAIR_BYTES, a.packed + size_t(base + nh * nk + kc) * CHUNK_PAIR_BYTES, CHUNK_PAIR_BYTES, &full[stage]);
+            if (++stage == BWD_STAGES) {
+              stage = 0;
+              phase ^= 1;
+              first_lap = false;
+            }
           }
+          base += nk * nhs;
         }
       }
     }
@@ -226,9 +234,12 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
           waited1 = true;
         }
         tc_fence_after_sync();
-        for (int nh = 0; nh < nhs; ++nh) {
-          const uint32_t acc = (side || nh == 1) ? TM_ACC1 : TM_ACC0;
-          for (int kc = 0; kc < nk; ++kc) {
+        const int k_early = gstep_k_early(g), slot_h0 = side ? -1 : last_slot_half0(nk, k_early);
+        for (int slot = 0; slot < nk * nhs; ++slot) {
+          {
+            int nh, kc;
+            issue_slot(nk, k_early, nhs, slot, nh, kc);
+            const uint32_t acc = (side || nh == 1) ? TM_ACC1 : TM_ACC0;
             int src = 1, ak = kc;
             if ((g == 0 || g == 5) && kc == 0) src = 0;
             else if (g == 9 && kc == 4) src = 2;
@@ -279,7 +290,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
             }
             ready = mbar_try_wait(&full[stage], phase);
           }
-          if (leader) umma_commit(&acc_ready[side ? 1 : nh]);
+          if (slot == slot_h0 && leader) umma_commit(&acc_ready[0]);
+          if (slot == nk * nhs - 1 && leader) umma_commit(&acc_ready[1]);
         }
         if (!waited1) w_a[1].wait(&a_ready[1]);
         if (lane == 0) NSR_TRB(tl, g, 4);
@@ -488,9 +500,14 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
                               : a.dump + (fwd ? dump_off_h(P, g) : (g == 11 ? dump_off_gf(P) : dump_off_g(P, mlayer)));
           if (dump_arr != nullptr) dump64(dump_arr, tile, row, 256, col0, H);
           if (tid == 0) NSR_TRB(tl, g, 9);
-          w_acc[1].wait(&acc_ready[1]);
-          if (tid == 0) NSR_TRB(tl, g, 10);
-          tc_fence_after_sync();
+          // The chunks that read A[K 0..127] are issued before accumulator 0's last ones (common.cuh issue_slot) and retired with it,
+          // so the first operand half can be overwritten while half 1 is still in the tensor pipe -- except in step 11, whose K is
+          // 128 wide: both of its halves read A[K 0..127] and accumulator 1's chunks come after accumulator 0 is complete.
+          const bool early_store = g != 11;
+          if (!early_store) {
+            w_acc[1].wait(&acc_ready[1]);
+            tc_fence_after_sync();
+          }
           tmem_st16(tlane + TM_AHI + col0 / 2, *reinterpret_cast<const uint32_t(*)[16]>(&H[0]));
           tmem_st16(tlane + TM_AHI + col0 / 2 + 16, *reinterpret_cast<const uint32_t(*)[16]>(&H[16]));
           tmem_st16(tlane + TM_ALO + col0 / 2, *reinterpret_cast<const uint32_t(*)[16]>(&L[0]));
@@ -499,6 +516,11 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
           tc_fence_before_sync();
           mbar_arrive(&a_ready[0]);
           if (tid == 0) NSR_TRB(tl, g, 11);
+          if (early_store) {
+            w_acc[1].wait(&acc_ready[1]);
+            tc_fence_after_sync();
+          }
+          if (tid == 0) NSR_TRB(tl, g, 10);
           {
             uint32_t u0[32], u1[32];
             tmem_ld32(tlane + TM_ACC1 + col0, u0);

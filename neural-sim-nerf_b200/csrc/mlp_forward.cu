@@ -318,16 +318,22 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
       uint32_t stage = 0, phase = 0;
       bool first_lap = true;
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-        for (int c = 0; c < NUM_CHUNKS; ++c) {
-          if (!first_lap) mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
-          bulk_g2s(sRing + stage * C::STAGE_BYTES, a.packed + size_t(c + (kMixed ? MIX_CHUNK0 : 0)) * CHUNK_PAIR_BYTES, C::STAGE_BYTES,
-                   &full[stage]);
-          if (++stage == C::STAGES) {
-            stage = 0;
-            phase ^= 1;
-            first_lap = false;
+        int base = kMixed ? MIX_CHUNK0 : 0;          // first packed chunk of the step
+        for (int step = 0; step < NUM_STEPS; ++step) {
+          const int nk = step_k_chunks(step), nhs = step_n_halves(step);
+          for (int i = 0; i < nk * nhs; ++i) {         // in the order the MMA warp consumes them (common.cuh issue_slot)
+            int nh, kc;
+            issue_slot(nk, step_k_early(step), nhs, i, nh, kc);
+            if (!first_lap) mbar_wait(&empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
+            bulk_g2s(sRing + stage * C::STAGE_BYTES, a.packed + size_t(base + nh * nk + kc) * CHUNK_PAIR_BYTES, C::STAGE_BYTES, &full[stage]);
+            if (++stage == C::STAGES) {
+              stage = 0;
+              phase ^= 1;
+              first_lap = false;
+            }
           }
+          base += nk * nhs;
         }
       }
     }
@@ -360,9 +366,12 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
           waited1 = true;
         }
         tc_fence_after_sync();
-        for (int nh = 0; nh < nhs; ++nh) {
-          const uint32_t acc = (step == 9 || nh == 1) ? TM_ACC1 : TM_ACC0;
-          for (int kc = 0; kc < nk; ++kc) {
+        const int k_early = step_k_early(step), slot_h0 = nhs == 2 ? last_slot_half0(nk, k_early) : -1;
+        for (int slot = 0; slot < nk * nhs; ++slot) {
+          {
+            int nh, kc;
+            issue_slot(nk, k_early, nhs, slot, nh, kc);
+            const uint32_t acc = (step == 9 || nh == 1) ? TM_ACC1 : TM_ACC0;
             // ---- A source of this K chunk: 0 = xyz encoding, 1 = TMEM activations, 2 = view-dir encoding
             int src = 1, ak = kc;
             if ((step == 0 || step == 5) && kc == 0) src = 0;
@@ -429,7 +438,10 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
             // probe the next stage AFTER queueing this chunk's MMAs: the probe's latency then overlaps their execution
             ready = mbar_try_wait(&full[stage], phase);
           }
-          if (leader) umma_commit(&acc_ready[(step == 9) ? 1 : nh]);
+          // accumulator 0 is complete after its late-K chunks (every MMA that read A[K 0..127] has been issued before them: the
+          // commit covers those too); accumulator 1 (and the single half of step 9) with the step's last chunk
+          if (slot == slot_h0 && leader) umma_commit(&acc_ready[0]);
+          if (slot == nk * nhs - 1 && leader) umma_commit(&acc_ready[1]);
         }
         if (!waited1) w_a[1].wait(&a_ready[1]);  // keep the parity in step (cannot happen with this network)
         if (lane == 0) NSR_TR(tl, step, 4);
@@ -604,14 +616,16 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
           mrow[(step * 8 + 1) * 128] = sign_bits(H + 16);
         }
         if (SAVE && a.dump != nullptr) dump64(a.dump + dump_off_h(dumpP, step), tile, row, 256, col0, H);       // step 8: F
-        // ---- every MMA of this step has retired: the old activations may be overwritten
+        // ---- the chunks that read A[K 0..127] were issued before accumulator 0's last ones (common.cuh issue_slot), so they
+        // retired with it: the first half of the activations may be overwritten now, while half 1 is still in the tensor pipe
         if (tid == 0) NSR_TR(tl, step, 9);
-        w_acc[1].wait(&acc_ready[1]);
-        if (tid == 0) NSR_TR(tl, step, 10);
-        tc_fence_after_sync();
         store(0);
         mbar_arrive(&a_ready[0]);
         if (tid == 0) NSR_TR(tl, step, 11);
+        // ---- every MMA of this step has retired
+        w_acc[1].wait(&acc_ready[1]);
+        if (tid == 0) NSR_TR(tl, step, 10);
+        tc_fence_after_sync();
         // ---- second half: drain ACC1 straight into the operands for K 128..255
         {
           uint32_t u0[32], u1[32];

@@ -1,7 +1,7 @@
 """Debug: dump CTA 0's per-step timeline of the MLP kernel (NSR_TRACE_FILE) for the precision modes given as flags
 on the command line (default: 0 = fp16x3, 16 = mixed), then print per-step intervals.
 slots: MMA warp 0 step start | 1 a_ready[0] seen | 2 before / 3 after the a_ready[1] wait | 4 step issued
-       epilogue 8 acc_ready[0] seen | 9 ACC0 converted | 10 acc_ready[1] seen | 11 first half stored | 12 second half stored"""
+       epilogue 8 acc_ready[0] seen | 9 ACC0 converted | 11 first half stored | 10 acc_ready[1] seen | 12 second half stored"""
 import ctypes, os, sys
 sys.path.insert(0, '.'); sys.path.insert(0, 'oracle')
 OUT = 'gpurun_out/trace.txt'
@@ -41,5 +41,4 @@ for b in blocks[len(modes):]:
         f = lambda a, b_: (s[b_] - s[a]) if (s[a] and s[b_]) else -1
         print(f'{r[1]:4d} | {f(0,1):6d} {f(1,2):6d} {f(2,3):6d} {f(3,4):6d} | {f(0,8):6d} {f(8,9):6d} {f(9,10):6d} {f(10,11):6d} {f(11,12):6d} | {nxt - s[0] if nxt else -1:6d} | {s[5]:6d} {s[6]:3d}')
     t0 = b['rows'][10][2]; t3 = b['rows'][30][2]
-    g0 = b['rows'][10][2 + 7]; g3 = b['rows'][30][2 + 7]
-    print('cycles per tile (tiles 1..2 average):', (t3 - t0) / 2, ' SM clock MHz:', (t3 - t0) / (g3 - g0) * 1e3)
+    print('cycles per tile (tiles 1..2 average):', (t3 - t0) / 2)
