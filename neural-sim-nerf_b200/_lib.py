@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libnsr_b200.so')
+LIB_PATH = os.environ.get('NSR_LIB_PATH') or os.path.join(_HERE, 'libnsr_b200.so')   # NSR_LIB_PATH: A/B runs of two builds (tools/)
 
 _lib = None
 
