@@ -259,6 +259,8 @@ struct MlpArgs {
   uint32_t flags;
   int num_tiles;
   uint32_t* relu_mask;        // optional: sign bits of every ReLU output for the backward pass (common.cuh MASK_*)
+  int experiment;             // debug (NSR_EXPERIMENT): 1 = the producer re-arms the ring without copying after its first lap
+                              // (wrong results; isolates the cost of streaming the weights from L2)
   uint8_t* dump;              // optional: the activation half of the weight-gradient dump (common.cuh): EX, EV, H0..H7, F, HV as fp16
   unsigned long long* trace;  // debug (NSR_TRACE_FILE): clock64 stamps of CTA 0's first tiles, [tile][step][16]
 };
@@ -325,8 +327,12 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
             int nh, kc;
             issue_slot(nk, step_k_early(step), nhs, i, nh, kc);
             if (!first_lap) mbar_wait(&empty[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
-            bulk_g2s(sRing + stage * C::STAGE_BYTES, a.packed + size_t(base + nh * nk + kc) * CHUNK_PAIR_BYTES, C::STAGE_BYTES, &full[stage]);
+            if (a.experiment == 1 && !first_lap) {
+              mbar_arrive(&full[stage]);
+            } else {
+              mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
+              bulk_g2s(sRing + stage * C::STAGE_BYTES, a.packed + size_t(base + nh * nk + kc) * CHUNK_PAIR_BYTES, C::STAGE_BYTES, &full[stage]);
+            }
             if (++stage == C::STAGES) {
               stage = 0;
               phase ^= 1;
@@ -760,6 +766,8 @@ int launch_mlp_forward(const float* rays, const float* z_or_pts, int64_t n, int 
   a.relu_mask = relu_mask;
   a.dump = static_cast<uint8_t*>(dump);
   a.trace = nullptr;
+  const char* experiment = getenv("NSR_EXPERIMENT");
+  a.experiment = experiment != nullptr ? atoi(experiment) : 0;
   const int grid = a.num_tiles < num_sms ? a.num_tiles : num_sms;
   const char* trace_file = getenv("NSR_TRACE_FILE");  // debug only: synchronous, dumps CTA 0's timeline
   if (trace_file != nullptr && a.num_tiles >= 4 * grid) {
