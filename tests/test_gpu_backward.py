@@ -266,3 +266,45 @@ def test_pose_only_autograd_takes_the_saved_bits_route(nsr, wfit, nets):
     ref = O.render_rays(r_cpu, wfit[0], wfit[1], 64, 128)
     (ref_grad,) = torch.autograd.grad(ref['rgb_map'], r_cpu, grad_outputs=g)
     check_grad(grads[True][:, 0:6], ref_grad[:, 0:6], 'dL/d rays (saved sign bits)')
+
+
+def test_full_size_backward_properties(nsr, nets):
+    """BASELINE config 3 at full size (160 000 rays, 64+128 samples), through size-independent properties: the saved-bits and the
+    recompute routes agree, the backward is linear in dL/drgb (a power-of-two multiple is exact), rays whose dL/drgb is zero get a
+    zero gradient, near/far get none, and everything is finite."""
+    import ctypes
+    L = nsr.lib()
+    H = W = 400
+    S, Ni = 64, 128
+    T = S + Ni
+    rays = nsr.make_rays(H, W, O.YCBV_K_400, O.pose_spherical(90., 67.5 - 180., 1.01)[:3, :4], O.YCBV_NEAR, O.YCBV_FAR)
+    n = rays.shape[0]
+    pc, pf = nsr.packed_weights(nets[0]), nsr.packed_weights(nets[1])
+    P = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+    new = lambda *s: torch.empty(*s, device='cuda')
+    rgb, raw, zv = new(n, 3), new(n, T, 4), new(n, T)
+    ws = torch.empty(L.nsr_render_workspace_bytes(n, S, Ni), dtype=torch.uint8, device='cuda')
+    mask = torch.empty(L.nsr_relu_mask_bytes(n, T), dtype=torch.uint8, device='cuda')
+    assert L.nsr_render_rays_forward_ex(P(rays), n, P(pc), P(pf), S, Ni, 0, None, None, P(rgb), None, None, None, None, None, None, P(raw), P(zv),
+                                        None, P(mask), None, P(ws), ws.numel(), None) == 0, L.nsr_last_error()
+    g = torch.randn(n, 3, device='cuda', generator=torch.Generator(device='cuda').manual_seed(9))
+    g[::7] = 0.0
+    bws = torch.empty(L.nsr_render_backward_workspace_bytes(n, T), dtype=torch.uint8, device='cuda')
+
+    def bwd(gg, m):
+        d = new(n, 11)
+        assert L.nsr_render_rays_backward_ex(P(rays), P(zv), P(raw), n, T, P(pf), 0, P(gg), P(d), None, None, None, P(m), P(bws), bws.numel(), None) == 0
+        torch.cuda.synchronize()
+        return d
+    d_saved, d_rec = bwd(g, mask), bwd(g, None)
+    assert bool(torch.isfinite(d_saved).all())
+    scale = float(d_rec.abs().max())
+    assert scale > 0 and float((d_saved - d_rec).abs().max()) <= 2e-6 * scale
+    assert torch.equal(bwd(g * 4.0, mask), d_saved * 4.0)            # per-row power-of-two scaling: exact
+    assert float(d_saved[::7].abs().max()) == 0.0 and float(d_saved[:, 6:8].abs().max()) == 0.0
+    hit = rgb.sum(-1) > 0.05
+    assert float(d_saved[hit].abs().max()) > 0 and int(hit.sum()) > 1000
+    # closed-form pose pull-back of the full image: deterministic, finite, and it responds to the gradient
+    c1 = nsr.rays_grad_to_c2w(H, W, O.YCBV_K_400, rays, d_saved)
+    assert torch.equal(c1, nsr.rays_grad_to_c2w(H, W, O.YCBV_K_400, rays, d_saved)) and bool(torch.isfinite(c1).all())
+    assert float(c1.abs().max()) > 0
