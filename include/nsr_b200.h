@@ -220,6 +220,18 @@ int nsr_render_image_forward(int H, int W, const float* K_host, const float* c2w
                              void* stream);
 
 /*
+ * One image, forward + backward to the pose: what one iteration of render_path_grad's loop (RN:141-194) computes for ALL rays of the
+ * image at once -- rays from the device-resident c2w (RN:148), render (RN:168-170, saving one bit per ReLU), the backward of RN:177-178
+ * from d_rgb_map [H*W,3] (= grad_E permuted to HWC, RN:154-155) without recompute, and the get_rays part of RN:179-181 in closed form.
+ * Outputs: rgb_map [H*W,3] (may be NULL), d_c2w [12] device (= or += with accumulate != 0).  No autograd tape, one call, no host sync.
+ */
+size_t nsr_render_image_grad_workspace_bytes(int H, int W, int n_samples, int n_importance);
+int nsr_render_image_grad(int H, int W, const float* K_host, const float* c2w_dev, int ld_c2w, float near_, float far_,
+                          const void* packed_coarse, const void* packed_fine, int n_samples, int n_importance, uint32_t flags,
+                          const float* d_rgb_map, float* rgb_map, float* d_c2w, int accumulate, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
+/*
  * Counter-based random numbers (Philox4x32-10): out[i] ~ U[0,1), a pure function of (seed, stream_id, i).  What the training
  * kwargs draw with torch.rand for the stratified jitter (RN:455, t_rand [n,S]) and the inverse-CDF samples (RH:211, u [n,Ni]).
  */

@@ -52,6 +52,9 @@ _SIGNATURES = {
     'nsr_render_image_forward': (c_int, [c_int, c_int, c_vp, c_vp, c_f32p, c_int, ctypes.c_float, ctypes.c_float, c_vp, c_vp,
                                          c_int, c_int, c_u32, c_vp, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p,
                                          c_vp, c_size, c_vp]),
+    'nsr_render_image_grad_workspace_bytes': (c_size, [c_int, c_int, c_int, c_int]),
+    'nsr_render_image_grad': (c_int, [c_int, c_int, c_vp, c_f32p, c_int, ctypes.c_float, ctypes.c_float, c_vp, c_vp, c_int, c_int, c_u32,
+                                      c_f32p, c_f32p, c_f32p, c_int, c_vp, c_size, c_vp]),
     'nsr_random_uniform': (c_int, [ctypes.c_uint64, c_u32, c_f32p, c_i64, c_vp]),
     'nsr_add_sigma_noise': (c_int, [ctypes.c_uint64, c_u32, c_f32p, c_i64, ctypes.c_float, c_vp]),
     'nsr_train_workspace_bytes': (c_size, [c_i64, c_int, c_int]),

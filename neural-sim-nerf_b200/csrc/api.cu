@@ -322,6 +322,51 @@ int nsr_render_image_forward(int H, int W, const float* K_host, const float* c2w
   return NSR_OK;
 }
 
+// workspace layout: rays [n,11] | z [n,T] | raw [n,T,4] | d_rays [n,11] | rgb [n,3] (when rgb_map is NULL) | c2w-gradient partials |
+//   ReLU sign bits (n, T) | forward workspace | backward workspace
+size_t nsr_render_image_grad_workspace_bytes(int H, int W, int S, int Ni) {
+  const int64_t n = int64_t(H) * W;
+  const int T = S + Ni;
+  return align_up(size_t(n) * 44, 256) + align_up(size_t(n) * T * 4, 256) + align_up(size_t(n) * T * 16, 256) + align_up(size_t(n) * 44, 256) +
+         align_up(size_t(n) * 12, 256) + align_up(nsr_c2w_grad_workspace_bytes(), 256) + align_up(nsr_relu_mask_bytes(n, T), 256) +
+         nsr_render_workspace_bytes(n, S, Ni) + nsr_render_backward_workspace_bytes(n, T);
+}
+
+int nsr_render_image_grad(int H, int W, const float* K_host, const float* c2w_dev, int ld_c2w, float near_, float far_,
+                          const void* packed_coarse, const void* packed_fine, int S, int Ni, uint32_t flags, const float* d_rgb_map,
+                          float* rgb_map, float* d_c2w, int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+  NSR_REQUIRE(H > 0 && W > 0 && K_host && c2w_dev && ld_c2w >= 4 && d_rgb_map && d_c2w, "nsr_render_image_grad: bad argument");
+  NSR_REQUIRE(!(flags & (NSR_FLAG_FAST_FP16 | NSR_FLAG_MIXED_F8)), "nsr_render_image_grad: gradient passes run the default precision");
+  NSR_REQUIRE(workspace && workspace_bytes >= nsr_render_image_grad_workspace_bytes(H, W, S, Ni), "nsr_render_image_grad: workspace too small");
+  NSR_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "nsr_render_image_grad: workspace must be 256-byte aligned");
+  const int64_t n = int64_t(H) * W;
+  const int T = S + Ni;
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  auto carve = [&](size_t bytes) {
+    uint8_t* p = ws;
+    ws += align_up(bytes, 256);
+    return p;
+  };
+  float* rays = reinterpret_cast<float*>(carve(size_t(n) * 44));
+  float* zv = reinterpret_cast<float*>(carve(size_t(n) * T * 4));
+  float* raw = reinterpret_cast<float*>(carve(size_t(n) * T * 16));
+  float* d_rays = reinterpret_cast<float*>(carve(size_t(n) * 44));
+  float* rgb_tmp = reinterpret_cast<float*>(carve(size_t(n) * 12));
+  void* cws = carve(nsr_c2w_grad_workspace_bytes());
+  void* bits = carve(nsr_relu_mask_bytes(n, T));
+  const size_t fwd_bytes = nsr_render_workspace_bytes(n, S, Ni), bwd_bytes = nsr_render_backward_workspace_bytes(n, T);
+  void* fwd = carve(fwd_bytes);
+  void* bwd = carve(bwd_bytes);
+  int rc;
+  if ((rc = nsr_make_rays_dev(H, W, K_host, c2w_dev, ld_c2w, near_, far_, rays, stream))) return rc;                       // RN:148
+  if ((rc = nsr_render_rays_forward_ex(rays, n, packed_coarse, packed_fine, S, Ni, flags, nullptr, nullptr, rgb_map ? rgb_map : rgb_tmp, nullptr,
+                                       nullptr, nullptr, nullptr, nullptr, nullptr, raw, zv, nullptr, bits, nullptr, fwd, fwd_bytes, stream))) return rc;   // RN:168-170
+  const void* last = (Ni > 0 && packed_fine) ? packed_fine : packed_coarse;
+  if ((rc = nsr_render_rays_backward_ex(rays, zv, raw, n, Ni > 0 ? T : S, last, flags & NSR_FLAG_WHITE_BKGD, d_rgb_map, d_rays, nullptr, nullptr,
+                                        nullptr, bits, bwd, bwd_bytes, stream))) return rc;                                                                 // RN:177-178
+  return nsr_rays_grad_to_c2w(H, W, K_host, rays, d_rays, nullptr, n, d_c2w, accumulate, cws, stream);                                                      // RN:179-181
+}
+
 // ----------------------------------------------------------------------------- one optimisation step (RN:643-716)
 static const int kParamRows[NSR_NET_NUM_TENSORS] = {256, 256, 256, 256, 256, 256, 256, 256, 128, 256, 1, 3};
 static const int kParamCols[NSR_NET_NUM_TENSORS] = {63, 256, 256, 256, 256, 319, 256, 256, 283, 256, 256, 128};

@@ -649,15 +649,27 @@ def render_image_grad(H, W, K, c2w, g_rgb, **kw):
     pf = packed_weights(net_f) if (net_f is not None and Ni > 0) else None
     dev = pc.device
     c = c2w.detach().to(device=dev, dtype=torch.float32)[:3, :4].contiguous()
-    rays = torch.empty(H * W, 11, dtype=torch.float32, device=dev)
     Kh = _K9(K)
+    g = g_rgb.detach().to(device=dev, dtype=torch.float32).reshape(-1, 3).contiguous()
+    if g.shape[0] != H * W:
+        raise ValueError(f'g_rgb {tuple(g_rgb.shape)} does not match a {H}x{W} image')
+    ws_bytes = L.nsr_render_image_grad_workspace_bytes(H, W, S, Ni)
+    if SAVE_RELU_MASK and _mask_fits(ws_bytes, dev):
+        # one C call: rays, both passes (saving the ReLU sign bits), backward without recompute, closed-form dL/dc2w
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        rgb = torch.empty(H * W, 3, dtype=torch.float32, device=dev)
+        d_c2w = torch.empty(3, 4, dtype=torch.float32, device=dev)
+        check(L.nsr_render_image_grad(H, W, Kh.ctypes.data_as(ctypes.c_void_p), ptr(c), 4, float(kw['near']), float(kw['far']), ptr(pc), ptr(pf),
+                                      S, Ni, flags, ptr(g), ptr(rgb), ptr(d_c2w), 0, ptr(ws), ws_bytes, _stream()), 'nsr_render_image_grad')
+        return rgb.view(H, W, 3), d_c2w
+    # the recompute route, stage by stage (no extra memory for the sign bits)
+    rays = torch.empty(H * W, 11, dtype=torch.float32, device=dev)
     check(L.nsr_make_rays_dev(H, W, Kh.ctypes.data_as(ctypes.c_void_p), ptr(c), 4, float(kw['near']), float(kw['far']), ptr(rays), _stream()),
           'nsr_make_rays_dev')
     cfg = dict(pc=pc, pf=pf, S=S, Ni=Ni, flags=flags, t_rand=None, u=None, retraw=False)
     with torch.no_grad():
-        outs, saved = _forward_impl(rays, cfg, keep_for_backward=True, save_mask=True)
-        g = g_rgb.detach().to(device=dev, dtype=torch.float32).reshape(-1, 3).contiguous()
-        d_rays, _ = _RenderRaysFn._one_pass(rays, saved[0], saved[1], pf if pf is not None else pc, flags & FLAG_WHITE_BKGD, g, False, saved[4])
+        outs, saved = _forward_impl(rays, cfg, keep_for_backward=True, save_mask=False)
+        d_rays, _ = _RenderRaysFn._one_pass(rays, saved[0], saved[1], pf if pf is not None else pc, flags & FLAG_WHITE_BKGD, g, False, None)
         d_c2w = rays_grad_to_c2w(H, W, K, rays, d_rays)
     return outs[0].view(H, W, 3), d_c2w
 

@@ -176,3 +176,27 @@ def test_render_path_pipelined_many_images(nsr, nets, tmp_path):
         png = np.asarray(Image.open(tmp_path / '7' / f'{i:03d}.png'))
         assert np.array_equal(png, O.to8b(ref)), i
     assert not np.array_equal(imgs[0], imgs[1])
+
+
+def test_render_image_grad_routes_agree(nsr, nets):
+    """nsr_render_image_grad (one C call, saved sign bits) against the staged recompute route it falls back to when the bits do
+    not fit in memory; non-square image, white background."""
+    H, W = 24, 18
+    K = [[70.0, 0, 8.5], [0, 70.0, 12.5], [0, 0, 1]]
+    pose = O.pose_spherical(88., 112.5 - 180., 1.01)[:3, :4].cuda()
+    g = torch.randn(H * W, 3, generator=torch.Generator().manual_seed(12)).cuda() * 1e-2
+    kw = kwargs(nets, white_bkgd=True)
+    out = {}
+    for save in (True, False):
+        nsr.run_nerf.SAVE_RELU_MASK = save
+        try:
+            before = nsr.lib().nsr_launch_count()
+            out[save] = nsr.render_image_grad(H, W, K, pose, g, **kw)
+            torch.cuda.synchronize()
+        finally:
+            nsr.run_nerf.SAVE_RELU_MASK = True
+    assert torch.equal(out[True][0], out[False][0])
+    scale = float(out[False][1].abs().max())
+    assert scale > 0 and float((out[True][1] - out[False][1]).abs().max()) <= 1e-5 * scale
+    with pytest.raises(ValueError):
+        nsr.render_image_grad(H, W, K, pose, g[:-1], **kw)
