@@ -44,7 +44,7 @@ class MomentumPsi:
         self.lr, self.momentum, self.v = lr, momentum, None
 
     def update(self, params, grads):
-        params, grads = np.array(params, dtype=np.float32), np.array(grads, dtype=np.float32)
+        params, grads = params.detach().cpu().numpy().astype(np.float32), grads.detach().cpu().numpy().astype(np.float32)
         self.v = (np.zeros_like(params) if self.v is None else self.momentum * self.v) - self.lr * grads
         return torch.tensor(params + self.v)
 
