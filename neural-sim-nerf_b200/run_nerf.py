@@ -304,9 +304,10 @@ def _mask_fits(n_bytes, dev):
     return n_bytes <= free // 2
 
 
-def _forward_impl(rays, cfg, keep_for_backward, save_mask=False):
+def _forward_impl(rays, cfg, keep_for_backward, save_mask=False, save_dump=False):
     """One call of nsr_render_rays_forward(_ex).  Returns (outputs tuple, saved) with saved = (z_vals [n,T], raw [n,T,4],
-    z0 [n,S], raw0 [n,S,4], relu_mask) of the last and (when N_importance > 0) the coarse pass, or Nones."""
+    z0 [n,S], raw0 [n,S,4], relu_mask, dump) of the last and (when N_importance > 0) the coarse pass, or Nones.
+    save_dump (training batches): the last pass also writes its activations for the weight-gradient GEMMs (~5 KB per point)."""
     L = lib()
     n, dev = rays.shape[0], rays.device
     S, Ni = cfg['S'], cfg['Ni']
@@ -320,14 +321,17 @@ def _forward_impl(rays, cfg, keep_for_backward, save_mask=False):
     zv = new(n, T) if keep_for_backward else None
     ws_bytes = L.nsr_render_workspace_bytes(n, S, Ni)
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
-    mask = None
-    if save_mask and keep_for_backward and SAVE_RELU_MASK and n > 0:
+    mask = dump = None
+    if (save_mask or save_dump) and keep_for_backward and SAVE_RELU_MASK and n > 0 and not (cfg['flags'] & (FLAG_FAST_FP16 | FLAG_MIXED_F8)):
         mb = L.nsr_relu_mask_bytes(n, T)
-        if _mask_fits(mb, dev):
+        db = L.nsr_mlp_dump_bytes(n, T) if save_dump else 0
+        if _mask_fits(mb + db, dev):
             mask = torch.empty(mb, dtype=torch.uint8, device=dev)
+            if save_dump:
+                dump = torch.empty(db, dtype=torch.uint8, device=dev)
     check(L.nsr_render_rays_forward_ex(ptr(rays), n, ptr(cfg['pc']), ptr(cfg['pf']), S, Ni, cfg['flags'], ptr(cfg['t_rand']), ptr(cfg['u']),
                                        ptr(rgb), ptr(disp), ptr(acc), ptr(rgb0), ptr(disp0), ptr(acc0), ptr(zstd),
-                                       ptr(raw), ptr(zv), None, ptr(mask), None, ptr(ws), ws_bytes, _stream()), 'nsr_render_rays_forward')
+                                       ptr(raw), ptr(zv), None, ptr(mask), ptr(dump), ptr(ws), ws_bytes, _stream()), 'nsr_render_rays_forward')
     z0 = raw0 = None
     if keep_for_backward and Ni > 0:
         # the coarse pass's depths and raw outputs sit at the head of the workspace (include/nsr_b200.h layout: z0 | w0 | raw0 | ...)
@@ -336,7 +340,7 @@ def _forward_impl(rays, cfg, keep_for_backward, save_mask=False):
         z0 = ws[o_z0:o_z0 + n * S * 4].view(torch.float32).view(n, S).clone()
         raw0 = ws[o_raw0:o_raw0 + n * S * 16].view(torch.float32).view(n, S, 4).clone()
     outs = [rgb, disp, acc] + ([rgb0, disp0, acc0, zstd] if Ni > 0 else []) + ([raw] if cfg['retraw'] else [])
-    return tuple(outs), (zv, raw, z0, raw0, mask)
+    return tuple(outs), (zv, raw, z0, raw0, mask, dump)
 
 
 def _params_of(net):
@@ -353,8 +357,10 @@ class _RenderRaysFn(torch.autograd.Function):
     def forward(ctx, ray_batch, cfg, *params):
         rays = ray_batch.detach().to(torch.float32).contiguous()
         pose_only = not any(torch.is_tensor(p) and p.requires_grad for p in params)     # RN:168-181: no dL/dMLP wanted
-        outs, saved = _forward_impl(rays, cfg, keep_for_backward=True, save_mask=pose_only)
-        ctx.relu_mask = saved[4]
+        # pose path: keep the ReLU sign bits; training batches: the activations of the last pass too -- either way the backward
+        # kernel of that pass recomputes nothing (whole images with parameter gradients do not fit: _mask_fits decides)
+        outs, saved = _forward_impl(rays, cfg, keep_for_backward=True, save_mask=True, save_dump=not pose_only)
+        ctx.relu_mask, ctx.dump = saved[4], saved[5]
         ctx.save_for_backward(rays, *[t for t in saved[:4] if t is not None])
         ctx.have_coarse = saved[2] is not None
         ctx.cfg = cfg
@@ -365,7 +371,7 @@ class _RenderRaysFn(torch.autograd.Function):
         return outs
 
     @staticmethod
-    def _one_pass(rays, zv, raw, net_blob, flags, g, want_dump, relu_mask=None):
+    def _one_pass(rays, zv, raw, net_blob, flags, g, want_dump, relu_mask=None, fwd_dump=None):
         L = lib()
         n, T = zv.shape
         d_rays = torch.empty(n, 11, dtype=torch.float32, device=rays.device)
@@ -373,14 +379,14 @@ class _RenderRaysFn(torch.autograd.Function):
         ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=rays.device)
         dump = grads = dWp = dBp = None
         if want_dump:   # parameter gradients: the kernels ADD this pass's dL/dW, dL/db into zero-initialised fp32 tensors
-            dump = torch.empty(L.nsr_mlp_dump_bytes(n, T), dtype=torch.uint8, device=rays.device)
+            dump = fwd_dump if fwd_dump is not None else torch.empty(L.nsr_mlp_dump_bytes(n, T), dtype=torch.uint8, device=rays.device)
             shapes = _EXPECTED_SHAPES
             grads = [torch.zeros(s, dtype=torch.float32, device=rays.device) for s in shapes] + \
                     [torch.zeros(s[0], dtype=torch.float32, device=rays.device) for s in shapes]
             dWp = (ctypes.c_void_p * 12)(*[t.data_ptr() for t in grads[:12]])
             dBp = (ctypes.c_void_p * 12)(*[t.data_ptr() for t in grads[12:]])
-        if want_dump:
-            relu_mask = None                     # parameter gradients need the activations: recompute path
+        if want_dump and fwd_dump is None:
+            relu_mask = None                     # parameter gradients need the activations: recompute them unless the forward pass dumped them
         check(L.nsr_render_rays_backward_ex(ptr(rays), ptr(zv), ptr(raw), n, T, ptr(net_blob), flags, ptr(g), ptr(d_rays), ptr(dump),
                                             dWp, dBp, ptr(relu_mask), ptr(ws), ws_bytes, _stream()), 'nsr_render_rays_backward')
         return d_rays, grads
@@ -404,7 +410,8 @@ class _RenderRaysFn(torch.autograd.Function):
         if d_rgb is not None:
             blob = cfg['pc'] if fine_is_coarse else cfg['pf']
             want = need_c if fine_is_coarse else need_f
-            dr, gr = _RenderRaysFn._one_pass(rays, zv, raw, blob, wflag, d_rgb.detach().float().contiguous(), want, ctx.relu_mask)
+            dr, gr = _RenderRaysFn._one_pass(rays, zv, raw, blob, wflag, d_rgb.detach().float().contiguous(), want, ctx.relu_mask,
+                                             ctx.dump if (want and ctx.relu_mask is not None) else None)
             d_rays = dr
             if fine_is_coarse:
                 g_c = gr
