@@ -299,9 +299,21 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
 SAVE_RELU_MASK = os.environ.get('NSR_SAVE_RELU_MASK', '1') != '0'
 
 
+_fit_cache = {}          # device index -> (monotonic time of the query, bytes that fit)
+
+
 def _mask_fits(n_bytes, dev):
-    free, _ = torch.cuda.mem_get_info(dev)
-    return n_bytes <= free // 2
+    """Is there comfortably room for n_bytes more?  cudaMemGetInfo costs milliseconds, so one answer serves for two seconds
+    (the allocations themselves are guarded: an out-of-memory error falls back to the recompute route)."""
+    import time
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    now = time.monotonic()
+    hit = _fit_cache.get(idx)
+    if hit is None or now - hit[0] > 2.0:
+        free, _ = torch.cuda.mem_get_info(idx)
+        hit = (now, free // 2)
+        _fit_cache[idx] = hit
+    return n_bytes <= hit[1]
 
 
 def _forward_impl(rays, cfg, keep_for_backward, save_mask=False, save_dump=False):
@@ -326,9 +338,12 @@ def _forward_impl(rays, cfg, keep_for_backward, save_mask=False, save_dump=False
         mb = L.nsr_relu_mask_bytes(n, T)
         db = L.nsr_mlp_dump_bytes(n, T) if save_dump else 0
         if _mask_fits(mb + db, dev):
-            mask = torch.empty(mb, dtype=torch.uint8, device=dev)
-            if save_dump:
-                dump = torch.empty(db, dtype=torch.uint8, device=dev)
+            try:
+                mask = torch.empty(mb, dtype=torch.uint8, device=dev)
+                if save_dump:
+                    dump = torch.empty(db, dtype=torch.uint8, device=dev)
+            except torch.cuda.OutOfMemoryError:
+                mask = dump = None               # the recompute route needs neither
     check(L.nsr_render_rays_forward_ex(ptr(rays), n, ptr(cfg['pc']), ptr(cfg['pf']), S, Ni, cfg['flags'], ptr(cfg['t_rand']), ptr(cfg['u']),
                                        ptr(rgb), ptr(disp), ptr(acc), ptr(rgb0), ptr(disp0), ptr(acc0), ptr(zstd),
                                        ptr(raw), ptr(zv), None, ptr(mask), ptr(dump), ptr(ws), ws_bytes, _stream()), 'nsr_render_rays_forward')
