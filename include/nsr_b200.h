@@ -263,6 +263,12 @@ int nsr_train_step(const float* rays, const float* target, int64_t n_rays, const
                    float beta1, float beta2, float eps, int64_t step, float* losses_out, float* rgb_out, void* workspace,
                    size_t workspace_bytes, void* stream);
 
+/* Introspection (host only, no GPU): the order in which the MLP kernels consume the weight chunks of forward GEMM step `step`
+ * (0..7 pts_linears, 8 feature_linear, 9 views_linears): slot i -> (accumulator half, K chunk).  Returns the number of slots
+ * (halves x K chunks), or a negative error code.  Two-half steps run (h0, K early) (h1, K early) (h0, K late) (h1, K late), see
+ * DESIGN.md "Pipeline". */
+int nsr_chunk_issue_order(int step, int* half_out, int* kc_out, int capacity);
+
 /* Number of kernels this library has launched since load (all threads); used by bench.py's gpu_launches. */
 uint64_t nsr_launch_count(void);
 

@@ -23,6 +23,7 @@ _SIGNATURES = {
     'nsr_version': (c_int, []),
     'nsr_last_error': (ctypes.c_char_p, []),
     'nsr_launch_count': (ctypes.c_uint64, []),
+    'nsr_chunk_issue_order': (c_int, [c_int, c_vp, c_vp, c_int]),
     'nsr_packed_net_bytes': (c_size, []),
     'nsr_pack_net': (c_int, [c_vp, c_vp, c_vp, c_vp]),
     'nsr_mlp_forward': (c_int, [c_f32p, c_f32p, c_i64, c_int, c_vp, c_u32, c_f32p, c_vp]),

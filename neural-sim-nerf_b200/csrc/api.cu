@@ -88,6 +88,14 @@ const char* nsr_last_error(void) { return g_err; }
 
 uint64_t nsr_launch_count(void) { return g_launches.load(); }
 
+int nsr_chunk_issue_order(int step, int* half_out, int* kc_out, int capacity) {
+  NSR_REQUIRE(step >= 0 && step < NUM_STEPS && half_out && kc_out, "nsr_chunk_issue_order: bad argument");
+  const int nk = step_k_chunks(step), nhs = step_n_halves(step);
+  NSR_REQUIRE(capacity >= nk * nhs, "nsr_chunk_issue_order: capacity %d < %d", capacity, nk * nhs);
+  for (int i = 0; i < nk * nhs; ++i) issue_slot(nk, step_k_early(step), nhs, i, half_out[i], kc_out[i]);
+  return nk * nhs;
+}
+
 size_t nsr_packed_net_bytes(void) { return PACKED_BYTES; }
 
 int nsr_pack_net(const float* const* weights, const float* const* biases, void* packed_out, void* stream) {

@@ -66,3 +66,37 @@ def test_sass_is_blackwell_native(built_lib):
     sass = subprocess.run([cuobjdump, '-sass', built_lib], capture_output=True, text=True).stdout
     for mnemonic in ('UTCHMMA', 'UTCQMMA', 'LDTM', 'UBLKCP'):
         assert mnemonic in sass, mnemonic
+
+
+def test_chunk_issue_order_invariants(built_lib):
+    """The schedule both MLP kernels rely on (DESIGN.md "Pipeline"): every (half, K chunk) of a step exactly once; in a two-half
+    step all chunks whose A operand is ready early -- an encoding, or activations 0..127 -- come before any late one (so the first
+    operand half may be overwritten as soon as accumulator 0 is complete), and accumulator 0's last chunk precedes accumulator 1's."""
+    import neural_sim_nerf_b200 as nsr
+    L = nsr.lib()
+    k_chunks = [1, 4, 4, 4, 4, 5, 4, 4, 4, 5]
+    halves = [2] * 9 + [1]
+    early = [1, 2, 2, 2, 2, 3, 2, 2, 2, None]
+    total = 0
+    for step in range(10):
+        h = (ctypes.c_int * 16)()
+        k = (ctypes.c_int * 16)()
+        n = L.nsr_chunk_issue_order(step, h, k, 16)
+        assert n == k_chunks[step] * halves[step]
+        total += n
+        slots = [(h[i], k[i]) for i in range(n)]
+        assert sorted(slots) == [(a, b) for a in range(halves[step]) for b in range(k_chunks[step])]
+        if halves[step] == 2:
+            is_late = [kc >= early[step] for _, kc in slots]
+            assert is_late == sorted(is_late), (step, slots)            # every early chunk before every late one
+            last0 = max(i for i, (a, _) in enumerate(slots) if a == 0)
+            last1 = max(i for i, (a, _) in enumerate(slots) if a == 1)
+            assert last0 < last1 == n - 1
+            first_late = is_late.index(True) if True in is_late else n
+            assert all(a == 0 for a, _ in slots[:early[step]]) and all(a == 1 for a, _ in slots[early[step]:2 * early[step]])
+            assert first_late == 2 * early[step] or first_late == n
+        else:
+            assert slots == [(0, b) for b in range(k_chunks[step])]
+    assert total == 73                                                     # NUM_CHUNKS
+    assert L.nsr_chunk_issue_order(10, (ctypes.c_int * 16)(), (ctypes.c_int * 16)(), 16) == -1
+    assert L.nsr_chunk_issue_order(1, (ctypes.c_int * 16)(), (ctypes.c_int * 16)(), 3) == -1
