@@ -513,8 +513,17 @@ def ndc_rays(H, W, focal, near, rays_o, rays_d):
 
 
 def make_rays(H, W, K, c2w, near, far):
-    """get_rays + viewdir normalisation + packing (RH:156-165, RN:91-112) in one kernel -> [H*W,11]."""
-    Kh = np.ascontiguousarray(np.asarray([[float(K[r][c]) for c in range(3)] for r in range(3)], dtype=np.float32))
+    """get_rays + viewdir normalisation + packing (RH:156-165, RN:91-112) in one kernel -> [H*W,11].  A pose that already lives
+    on the GPU (the device pose sampler's output) is read there (nsr_make_rays_dev): no device->host copy, no synchronisation."""
+    Kh = _K9(K)
+    if torch.is_tensor(c2w) and c2w.is_cuda:
+        c = c2w.detach()
+        if c.dtype != torch.float32 or c.dim() != 2 or c.stride(-1) != 1 or c.stride(0) < 4 or c.shape[0] < 3 or c.shape[1] < 4:
+            c = c.float()[:3, :4].contiguous()
+        rays = torch.empty(H * W, 11, dtype=torch.float32, device=c.device)
+        check(lib().nsr_make_rays_dev(H, W, Kh.ctypes.data_as(ctypes.c_void_p), ptr(c), c.stride(0), float(near), float(far), ptr(rays), _stream()),
+              'nsr_make_rays_dev')
+        return rays
     c = c2w.detach().float().cpu().numpy() if torch.is_tensor(c2w) else np.asarray(c2w, dtype=np.float32)
     ch = np.ascontiguousarray(c[:3, :4], dtype=np.float32)
     rays = torch.empty(H * W, 11, dtype=torch.float32, device=device)

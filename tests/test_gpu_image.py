@@ -75,6 +75,9 @@ def test_make_rays_dev_equals_host_variant(nsr):
         assert torch.equal(out, host)
     ro, rd = O.get_rays(H, W, O.YCBV_K_400, pose44[:3, :4])
     assert torch.allclose(host.cpu(), O.pack_rays(ro, rd, 0.3, 1.9), rtol=0, atol=1e-6)
+    # the mirror picks the device variant for poses that live on the GPU (a [3,4] view of a [4,4] matrix, a double-precision pose)
+    assert torch.equal(nsr.make_rays(H, W, O.YCBV_K_400, pose44.cuda()[:3, :4], 0.3, 1.9), host)
+    assert torch.equal(nsr.make_rays(H, W, O.YCBV_K_400, pose44.double().cuda(), 0.3, 1.9), host)
 
 
 @pytest.mark.parametrize('H,W', [(20, 20), (33, 47), (400, 400)])
