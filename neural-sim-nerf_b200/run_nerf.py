@@ -685,9 +685,14 @@ def render_image_grad(H, W, K, c2w, g_rgb, **kw):
     if g.shape[0] != H * W:
         raise ValueError(f'g_rgb {tuple(g_rgb.shape)} does not match a {H}x{W} image')
     ws_bytes = L.nsr_render_image_grad_workspace_bytes(H, W, S, Ni)
+    ws = None
     if SAVE_RELU_MASK and _mask_fits(ws_bytes, dev):
+        try:
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        except torch.cuda.OutOfMemoryError:
+            ws = None                            # the staged recompute route below needs far less
+    if ws is not None:
         # one C call: rays, both passes (saving the ReLU sign bits), backward without recompute, closed-form dL/dc2w
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         rgb = torch.empty(H * W, 3, dtype=torch.float32, device=dev)
         d_c2w = torch.empty(3, 4, dtype=torch.float32, device=dev)
         check(L.nsr_render_image_grad(H, W, Kh.ctypes.data_as(ctypes.c_void_p), ptr(c), 4, float(kw['near']), float(kw['far']), ptr(pc), ptr(pf),
