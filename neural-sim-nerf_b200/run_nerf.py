@@ -19,7 +19,7 @@ import weakref
 import numpy as np
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
+import torch.nn.functional as F  # noqa: F401  (RN:6 star-exports it: `from utils.run_nerf_noscale import *` users may rely on `F`)
 
 from . import _lib
 from ._lib import FLAG_FAST_FP16, FLAG_LINDISP, FLAG_MIXED_F8, FLAG_PTS_INPUT, FLAG_WHITE_BKGD, check, lib, ptr
