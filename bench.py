@@ -246,6 +246,17 @@ def run_ours(args):
     launches = L.nsr_launch_count() - launches0
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
+    # two-tier evaluation: control words of the last step's coarse / fine pass (left in the workspace)
+    off = (ctypes.c_size_t * 8)()
+    L.nsr_render_workspace_layout(n, N_SAMPLES, N_IMPORTANCE, off, 8)
+    import numpy as np
+    c0, c1 = (ws[o:o + 16].view(torch.int32).cpu().numpy().astype(np.int64) & 0xFFFFFFFF for o in (off[5], off[6]))
+    as_float = lambda u: float(np.array([u], dtype=np.uint32).view(np.float32)[0])
+    two_tier = {'coarse_active_fraction': float(c0[0]) / (n * N_SAMPLES), 'fine_active_fraction': float(c1[0]) / (n * T),
+                'coarse_max_dsigma_on_active': as_float(c0[1]), 'fine_max_dsigma_on_active': as_float(c1[1]),
+                'fine_pass_forced_dense': int(c1[2]), 'dense_re_evaluations': int(c0[3]) + int(c1[3]),
+                'note': 'tier 1 (1 fp16 MMA per product, steps 0-7 + alpha head, every point) certifies sigma <= -4 => weight exactly 0; tier 2 = fp16x3 on the '
+                        'active points only; maps bit-identical to the dense evaluation (tests/test_gpu_two_tier.py)'}
     value = world * n * args.steps / (ms_total * 1e-3)
     if args.profile:      # under ncu: device-resident steps only
         if world > 1:
@@ -302,9 +313,9 @@ def run_ours(args):
         r = rays_dev[s % len(rays_dev)]
         rc = L.nsr_render_rays_forward_ex(P(r), n, P(pc), P(pf), N_SAMPLES, N_IMPORTANCE, 0, None, None, P(outs['rgb']), P(outs['disp']),
                                           P(outs['acc']), P(outs['rgb0']), P(outs['disp0']), P(outs['acc0']), P(outs['zstd']), P(rawsave),
-                                          P(zsave), None, P(relu_mask), None, P(ws), ws_bytes, stream)
+                                          P(zsave), None, P(relu_mask), None, None, P(ws), ws_bytes, stream)
         rc = rc or L.nsr_render_rays_backward_ex(P(r), P(zsave), P(rawsave), n, T, P(pf), 0, P(g_rgb), P(d_rays), None, None, None,
-                                                 P(relu_mask), P(bws), bws_bytes, stream)
+                                                 P(relu_mask), None, P(bws), bws_bytes, stream)
         rc = rc or L.nsr_rays_grad_to_c2w(H, W, Kf, P(r), P(d_rays), None, n, P(d_c2w), 0, P(cws), stream)
         if rc != 0:
             raise RuntimeError(L.nsr_last_error().decode())
@@ -357,6 +368,18 @@ def run_ours(args):
                     'traffic': 583430656, 'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this launch (profiles/r01_v10_ncu_fine_mlp_summary.csv); the launch writes raw [n,192,4] = 491.5 MB and reads depths + rays + weights = 132 MB', 'peak_source': f'{how} bf16_tflops_sustained (kernel timed back to back)',
                     'ms_per_launch': k_ms, 'algorithmic_flop_per_launch': flops}
         if world == 1:          # side legs only at N=1 (the scaling runs stay short; cpu_baseline is an N=1 figure)
+            # every point through fp16x3 (NSR_FLAG_DENSE): what round 1 measured as the default
+            DENSE = 32
+            for _ in range(2):
+                step_device(0, DENSE)
+            torch.cuda.synchronize()
+            e0.record()
+            for s in range(args.steps):
+                step_device(s, DENSE)
+            e1.record()
+            torch.cuda.synchronize()
+            dense_ms = e0.elapsed_time(e1) / args.steps
+            two_tier['dense_fp16x3'] = {'rays_per_s_device_resident': n / (dense_ms * 1e-3), 'ms_per_step': dense_ms}
             # informational: the opt-in single-pass fp16 mode (NOT parity-valid, see DESIGN.md "precision")
             FAST = 8
             for _ in range(2):
@@ -542,7 +565,7 @@ def run_ours(args):
                     'api': 'render(H, W, K, chunk, rays=<pinned host [2,N,3] -> cuda>, **render_kwargs_test) + D2H of rgb/disp/acc'},
             'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_base,
             'flop_per_ray': FLOP_PER_RAY, 'tflops_device_resident': value * FLOP_PER_RAY / 1e12,
-            'tensor_flop_issued_per_algorithmic_flop': 3, 'fast_fp16_mode': fast, 'mixed_f8_mode': mixed, 'fwd_bwd': fwd_bwd, 'pose_grad': pose_grad, 'train_step': train, 'stages': stages,
+            'tensor_flop_issued_per_algorithmic_flop': 3, 'two_tier': two_tier, 'fast_fp16_mode': fast, 'mixed_f8_mode': mixed, 'fwd_bwd': fwd_bwd, 'pose_grad': pose_grad, 'train_step': train, 'stages': stages,
         }))
 
 

@@ -46,6 +46,9 @@ extern "C" {
                                   every network (2.6e-3 on 3x-scaled random ones): opt-in ("precision").
                                   Forward only; NSR_FLAG_FAST_FP16 wins if both are set. */
 
+#define NSR_FLAG_DENSE 32u     /* evaluate EVERY sample point with the default fp16 hi/lo arithmetic.  Without it the render entry points
+                                  use the two-tier evaluation ("active set", below) wherever its outputs are bit-identical. */
+
 /* network geometry this library is specialised for (RN:261-278, CFG): D=8, W=256, skips=[4],
  * multires=10 (63 ch), multires_views=4 (27 ch), use_viewdirs=True. */
 #define NSR_NET_NUM_TENSORS 12 /* pts_linears.0-7, views_linears.0, feature_linear, alpha_linear, rgb_linear */
@@ -110,9 +113,11 @@ int nsr_resample_merge(const float* z_coarse, const float* weights, int64_t n_ra
                        const float* u, float* z_fine, float* z_samples, float* z_std, void* stream);
 
 /* Bytes of scratch nsr_render_rays_forward needs for n rays.  Layout (each block padded to 256 bytes), left valid
- * after the call: z0 [n,S] | weights0 [n,S] | raw0 [n,S,4] | z_fine [n,S+Ni] | raw_fine [n,S+Ni,4] -- the coarse pass's
- * depths and raw outputs are what a backward through rgb0 needs. */
+ * after the call: z0 [n,S] | weights0 [n,S] | raw0 [n,S,4] | z_fine [n,S+Ni] | raw_fine [n,S+Ni,4] | active set of the coarse pass |
+ * active set of the fine pass -- the coarse pass's depths and raw outputs are what a backward through rgb0 needs.
+ * nsr_render_workspace_layout writes the 7 block offsets and the total (8 values, same order) to offsets_out and returns 8. */
 size_t nsr_render_workspace_bytes(int64_t n_rays, int n_samples, int n_importance);
+int nsr_render_workspace_layout(int64_t n_rays, int n_samples, int n_importance, size_t* offsets_out, int capacity);
 
 /*
  * The whole per-ray renderer, forward.  Replaces RN:390-501 render_rays (perturb = 0 unless
@@ -139,13 +144,38 @@ int nsr_render_rays_forward(const float* rays, int64_t n_rays, const void* packe
  * dump_out (NULL, or nsr_mlp_dump_bytes() bytes, 128-byte aligned; needs relu_mask and the default precision): the last pass also
  * writes every layer's input activations as fp16 (the operand half of the weight-gradient dump), so that a backward call with
  * BOTH relu_mask and dump can produce dL/dW, dL/db without recomputing the forward pass either (what nsr_train_step does).
+ *
+ * Two-tier evaluation and the ACTIVE SET.  RN:356 computes alpha = 1 - exp(-relu(sigma) dist): a sample point with sigma <= 0 has
+ * alpha == 0 and weight == 0 EXACTLY, so neither its colour nor the value of its sigma reaches any output of raw2outputs (RN:343-387)
+ * or any gradient.  Unless NSR_FLAG_DENSE (or an opt-in precision flag, or dump_out) is given, each network pass therefore runs as
+ *   tier 1  every point, ONE fp16 MMA per product, pts_linears.0-7 + alpha head only -> sigma~; points with sigma~ <= -tau
+ *           (default 4.0; |sigma~ - sigma| is ~1e-2 there and <= 0.53 anywhere on the fitted test scene) are certified empty;
+ *   tier 2  the remaining points (the "active set", a compacted index list) with the default error-compensated arithmetic: bit for
+ *           bit what the dense pass computes for them, since every row of an MMA tile is independent of the others;
+ *   verify  tier 2 records max |sigma~ - sigma| over the active points; above verify_max (default 1.0) a third launch re-evaluates
+ *           EVERY point densely (it exits immediately otherwise).  A coarse pass whose active fraction exceeds force_fraction
+ *           (default 0.30), or that failed its verification, makes the fine pass skip tier 1 and run densely.
+ * All decisions are taken on the device (no host synchronisation).  Every map output (rgb/disp/acc/weights/z_std) is bit-identical
+ * to the dense evaluation; only `raw` differs: certified-empty points hold (0, 0, 0, sigma~).  Hence `raw` and `relu_mask` (whose
+ * tile order follows the active list) are only produced by the two-tier route when the caller passes `active_set`, a buffer of
+ * nsr_active_set_bytes(n_rays, n_total_samples) bytes (256-byte aligned) describing the LAST pass: 16 u32 of control words
+ * [0] number of active points, [1] float bits of max |sigma~ - sigma|, [2] "dense: tier 1 skipped", [3] "dense: verification
+ * failed", padded to 256 B, then int32 point indices (ray * T + sample).  nsr_render_rays_backward_ex takes the same buffer and
+ * back-propagates the active points only (dL/draw is exactly 0 at every other point).  active_set = NULL with raw / relu_mask
+ * requested: dense evaluation, as before.
  */
 size_t nsr_relu_mask_bytes(int64_t n_rays, int n_total_samples);
+size_t nsr_active_set_bytes(int64_t n_rays, int n_total_samples);
 int nsr_render_rays_forward_ex(const float* rays, int64_t n_rays, const void* packed_coarse, const void* packed_fine,
                                int n_samples, int n_importance, uint32_t flags, const float* t_rand, const float* u,
                                float* rgb_map, float* disp_map, float* acc_map, float* rgb0, float* disp0, float* acc0,
                                float* z_std, float* raw, float* z_vals_out, float* weights_out, void* relu_mask,
-                               void* dump_out, void* workspace, size_t workspace_bytes, void* stream);
+                               void* dump_out, void* active_set, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Knobs of the two-tier evaluation (process-wide; change them only while no work is being enqueued).  enabled = 0 makes every
+ * pass dense.  Requires tau > verify_max >= 0.  nsr_get_two_tier: any pointer may be NULL. */
+int nsr_set_two_tier(int enabled, float tau, float verify_max, float force_fraction);
+int nsr_get_two_tier(int* enabled, float* tau, float* verify_max, float* force_fraction);
 
 /* Bytes of scratch nsr_render_rays_backward needs for n rays of T = n_samples + n_importance depths. */
 size_t nsr_render_backward_workspace_bytes(int64_t n_rays, int n_total_samples);
@@ -172,10 +202,12 @@ int nsr_render_rays_backward(const float* rays, const float* z_vals, const float
 
 /* The same, reading the ReLU sign bits nsr_render_rays_forward_ex saved for this pass (relu_mask != NULL: no recompute).  With
  * relu_mask AND dW / dB, `dump` must be the buffer that forward call filled through dump_out (activations); this call adds the
- * gradients to it.  relu_mask = NULL: identical to nsr_render_rays_backward (everything recomputed). */
+ * gradients to it.  relu_mask = NULL: identical to nsr_render_rays_backward (everything recomputed).
+ * active_set (NULL, or the buffer that forward call filled): back-propagate the active points only -- same dL/d(rays), since
+ * dL/draw == 0 exactly at every certified-empty point; needs dW = dB = dump = NULL. */
 int nsr_render_rays_backward_ex(const float* rays, const float* z_vals, const float* raw, int64_t n_rays, int n_total_samples,
                                 const void* packed_net, uint32_t flags, const float* d_rgb_map, float* d_rays, void* dump,
-                                float* const* dW, float* const* dB, const void* relu_mask, void* workspace,
+                                float* const* dW, float* const* dB, const void* relu_mask, const void* active_set, void* workspace,
                                 size_t workspace_bytes, void* stream);
 
 /*

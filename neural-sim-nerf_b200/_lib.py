@@ -38,9 +38,13 @@ _SIGNATURES = {
     'nsr_relu_mask_bytes': (c_size, [c_i64, c_int]),
     'nsr_render_rays_forward_ex': (c_int, [c_f32p, c_i64, c_vp, c_vp, c_int, c_int, c_u32, c_f32p, c_f32p,
                                            c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p,
-                                           c_vp, c_vp, c_vp, c_size, c_vp]),
-    'nsr_render_rays_backward_ex': (c_int, [c_f32p, c_f32p, c_f32p, c_i64, c_int, c_vp, c_u32, c_f32p, c_f32p, c_vp, c_vp, c_vp, c_vp,
+                                           c_vp, c_vp, c_vp, c_vp, c_size, c_vp]),
+    'nsr_render_rays_backward_ex': (c_int, [c_f32p, c_f32p, c_f32p, c_i64, c_int, c_vp, c_u32, c_f32p, c_f32p, c_vp, c_vp, c_vp, c_vp, c_vp,
                                             c_vp, c_size, c_vp]),
+    'nsr_active_set_bytes': (c_size, [c_i64, c_int]),
+    'nsr_render_workspace_layout': (c_int, [c_i64, c_int, c_int, c_vp, c_int]),
+    'nsr_set_two_tier': (c_int, [c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float]),
+    'nsr_get_two_tier': (c_int, [c_vp, c_vp, c_vp, c_vp]),
     'nsr_render_backward_workspace_bytes': (c_size, [c_i64, c_int]),
     'nsr_mlp_dump_bytes': (c_size, [c_i64, c_int]),
     'nsr_render_rays_backward': (c_int, [c_f32p, c_f32p, c_f32p, c_i64, c_int, c_vp, c_u32, c_f32p, c_f32p, c_vp, c_vp, c_vp, c_vp, c_size, c_vp]),
@@ -76,6 +80,7 @@ FLAG_WHITE_BKGD = 2
 FLAG_PTS_INPUT = 4
 FLAG_FAST_FP16 = 8
 FLAG_MIXED_F8 = 16
+FLAG_DENSE = 32
 
 
 class NsrError(RuntimeError):

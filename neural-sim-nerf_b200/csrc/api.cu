@@ -68,6 +68,37 @@ int ensure_dynamic_smem(const void* func, int bytes) {
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// two-tier evaluation knobs (process-wide; set them before launching work, not concurrently with it)
+static TwoTierParams g_two_tier = {4.0f, 1.0f, 0.30f};
+static bool g_two_tier_enabled = true;
+const TwoTierParams& two_tier_params() { return g_two_tier; }
+
+// byte offsets of the blocks inside nsr_render_rays_forward's workspace
+struct FwdLayout {
+  size_t z0, w0, raw0, z1, raw1, as0, as1, total;
+};
+static FwdLayout fwd_layout(int64_t n, int S, int Ni) {
+  const size_t T = size_t(S) + size_t(Ni);
+  FwdLayout L;
+  size_t b = 0;
+  L.z0 = b;
+  b += align_up(size_t(n) * S * 4, 256);
+  L.w0 = b;
+  b += align_up(size_t(n) * S * 4, 256);
+  L.raw0 = b;
+  b += align_up(size_t(n) * S * 16, 256);
+  L.z1 = b;
+  b += align_up(size_t(n) * T * 4, 256);
+  L.raw1 = b;
+  b += align_up(size_t(n) * T * 16, 256);
+  L.as0 = b;
+  b += n > 0 ? align_up(active_set_bytes(n * int64_t(S)), 256) : 0;
+  L.as1 = b;
+  b += n > 0 ? align_up(active_set_bytes(n * int64_t(T)), 256) : 0;
+  L.total = b;
+  return L;
+}
+
 }  // namespace nsr
 
 using namespace nsr;
@@ -146,16 +177,33 @@ int nsr_resample_merge(const float* z_coarse, const float* weights, int64_t n_ra
                                static_cast<cudaStream_t>(stream));
 }
 
-// workspace layout: z0 [n,S] | w0 [n,S] | raw0 [n,S,4] | z1 [n,T] | raw1 [n,T,4]   (T = S + Ni)
-size_t nsr_render_workspace_bytes(int64_t n, int S, int Ni) {
-  const size_t T = size_t(S) + size_t(Ni);
-  size_t b = 0;
-  b += align_up(size_t(n) * S * 4, 256);
-  b += align_up(size_t(n) * S * 4, 256);
-  b += align_up(size_t(n) * S * 16, 256);
-  b += align_up(size_t(n) * T * 4, 256);
-  b += align_up(size_t(n) * T * 16, 256);
-  return b;
+// workspace layout: z0 [n,S] | w0 [n,S] | raw0 [n,S,4] | z1 [n,T] | raw1 [n,T,4] | active set of the coarse pass | of the fine pass
+size_t nsr_render_workspace_bytes(int64_t n, int S, int Ni) { return fwd_layout(n, S, Ni).total; }
+
+int nsr_render_workspace_layout(int64_t n, int S, int Ni, size_t* offsets_out, int capacity) {
+  NSR_REQUIRE(n >= 0 && S > 0 && Ni >= 0 && offsets_out && capacity >= 8, "nsr_render_workspace_layout: bad argument (capacity >= 8)");
+  const FwdLayout L = fwd_layout(n, S, Ni);
+  const size_t v[8] = {L.z0, L.w0, L.raw0, L.z1, L.raw1, L.as0, L.as1, L.total};
+  for (int i = 0; i < 8; ++i) offsets_out[i] = v[i];
+  return 8;
+}
+
+size_t nsr_active_set_bytes(int64_t n_rays, int n_total_samples) { return active_set_bytes(n_rays * int64_t(n_total_samples)); }
+
+int nsr_set_two_tier(int enabled, float tau, float verify_max, float force_fraction) {
+  NSR_REQUIRE(tau > 0.f && verify_max >= 0.f && verify_max < tau && force_fraction >= 0.f,
+              "nsr_set_two_tier: need tau > verify_max >= 0 and force_fraction >= 0");
+  g_two_tier_enabled = enabled != 0;
+  g_two_tier = TwoTierParams{tau, verify_max, force_fraction};
+  return NSR_OK;
+}
+
+int nsr_get_two_tier(int* enabled, float* tau, float* verify_max, float* force_fraction) {
+  if (enabled) *enabled = g_two_tier_enabled ? 1 : 0;
+  if (tau) *tau = g_two_tier.tau;
+  if (verify_max) *verify_max = g_two_tier.verify_max;
+  if (force_fraction) *force_fraction = g_two_tier.force_frac;
+  return NSR_OK;
 }
 
 size_t nsr_relu_mask_bytes(int64_t n_rays, int n_total_samples) { return relu_mask_bytes(n_rays * int64_t(n_total_samples)); }
@@ -165,14 +213,24 @@ int nsr_render_rays_forward(const float* rays, int64_t n, const void* packed_coa
                             float* acc_map, float* rgb0, float* disp0, float* acc0, float* z_std, float* raw,
                             float* z_vals_out, float* weights_out, void* workspace, size_t workspace_bytes, void* stream) {
   return nsr_render_rays_forward_ex(rays, n, packed_coarse, packed_fine, S, Ni, flags, t_rand, u, rgb_map, disp_map, acc_map, rgb0, disp0,
-                                    acc0, z_std, raw, z_vals_out, weights_out, nullptr, nullptr, workspace, workspace_bytes, stream);
+                                    acc0, z_std, raw, z_vals_out, weights_out, nullptr, nullptr, nullptr, workspace, workspace_bytes, stream);
+}
+
+// One network pass over (n, S) points into raw: dense fp16x3 (as = NULL), or tier 1 -> tier 2 -> conditional re-evaluation.
+static int mlp_pass(const float* rays, const float* z, int64_t n, int S, const void* packed, uint32_t mflags, float* raw, cudaStream_t st,
+                    uint32_t* mask, void* dump, void* as) {
+  if (as == nullptr) return launch_mlp_forward(rays, z, n, S, packed, mflags, raw, st, mask, dump);
+  int rc;
+  if ((rc = launch_mlp_forward(rays, z, n, S, packed, 0, raw, st, nullptr, nullptr, AS_ROLE_TIER1, as))) return rc;
+  if ((rc = launch_mlp_forward(rays, z, n, S, packed, 0, raw, st, mask, nullptr, AS_ROLE_TIER2, as))) return rc;
+  return launch_mlp_forward(rays, z, n, S, packed, 0, raw, st, mask, nullptr, AS_ROLE_REDO, as);
 }
 
 int nsr_render_rays_forward_ex(const float* rays, int64_t n, const void* packed_coarse, const void* packed_fine, int S,
                                int Ni, uint32_t flags, const float* t_rand, const float* u, float* rgb_map, float* disp_map,
                                float* acc_map, float* rgb0, float* disp0, float* acc0, float* z_std, float* raw,
-                               float* z_vals_out, float* weights_out, void* relu_mask, void* dump_out, void* workspace,
-                               size_t workspace_bytes, void* stream) {
+                               float* z_vals_out, float* weights_out, void* relu_mask, void* dump_out, void* active_set,
+                               void* workspace, size_t workspace_bytes, void* stream) {
   NSR_REQUIRE(n >= 0 && S >= 2 && Ni >= 0, "nsr_render_rays_forward: bad sizes (needs at least 2 samples per ray)");
   NSR_REQUIRE(relu_mask == nullptr || (reinterpret_cast<uintptr_t>(relu_mask) & 15) == 0, "nsr_render_rays_forward: relu_mask must be 16-byte aligned");
   NSR_REQUIRE(dump_out == nullptr || relu_mask != nullptr, "nsr_render_rays_forward: dump_out goes with relu_mask (the backward pass needs both)");
@@ -183,25 +241,40 @@ int nsr_render_rays_forward_ex(const float* rays, int64_t n, const void* packed_
   NSR_REQUIRE(workspace && workspace_bytes >= nsr_render_workspace_bytes(n, S, Ni), "nsr_render_rays_forward: workspace too small");
   NSR_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "nsr_render_rays_forward: workspace must be 256-byte aligned");
   NSR_REQUIRE(Ni == 0 || S >= 3, "nsr_render_rays_forward: hierarchical sampling needs n_samples >= 3");
+  NSR_REQUIRE(active_set == nullptr || (reinterpret_cast<uintptr_t>(active_set) & 255) == 0, "nsr_render_rays_forward: active_set must be 256-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int T = S + Ni;
   uint8_t* ws = static_cast<uint8_t*>(workspace);
-  float* z0 = reinterpret_cast<float*>(ws);
-  ws += align_up(size_t(n) * S * 4, 256);
-  float* w0 = reinterpret_cast<float*>(ws);
-  ws += align_up(size_t(n) * S * 4, 256);
-  float* raw0 = reinterpret_cast<float*>(ws);
-  ws += align_up(size_t(n) * S * 16, 256);
-  float* z1 = reinterpret_cast<float*>(ws);
-  ws += align_up(size_t(n) * T * 4, 256);
-  float* raw1 = reinterpret_cast<float*>(ws);
+  const FwdLayout lay = fwd_layout(n, S, Ni);
+  float* z0 = reinterpret_cast<float*>(ws + lay.z0);
+  float* w0 = reinterpret_cast<float*>(ws + lay.w0);
+  float* raw0 = reinterpret_cast<float*>(ws + lay.raw0);
+  float* z1 = reinterpret_cast<float*>(ws + lay.z1);
+  float* raw1 = reinterpret_cast<float*>(ws + lay.raw1);
   const uint32_t cflags = flags & NSR_FLAG_WHITE_BKGD;
   const uint32_t mflags = flags & (NSR_FLAG_FAST_FP16 | NSR_FLAG_MIXED_F8);
   int rc;
+  // Two-tier evaluation (common.cuh "active set"): same outputs as the dense fp16x3 passes, bit for bit, except that `raw` keeps
+  // (0, 0, 0, sigma~) for the certified-empty points -- so a caller that wants raw (or the sign bits, whose order follows the
+  // active list) must say it knows by passing an active_set buffer.
+  const bool two_tier = g_two_tier_enabled && !(flags & (NSR_FLAG_FAST_FP16 | NSR_FLAG_MIXED_F8 | NSR_FLAG_DENSE)) && dump_out == nullptr &&
+                        ((raw == nullptr && relu_mask == nullptr) || active_set != nullptr) && n * int64_t(T) < (int64_t(1) << 31);
+    void* as0 = two_tier ? ws + lay.as0 : nullptr;                                     // coarse pass (when it is not the last one)
+  void* as_last = two_tier ? (active_set ? active_set : static_cast<void*>(ws + (Ni > 0 ? lay.as1 : lay.as0))) : nullptr;
+  if (active_set != nullptr && !two_tier) {
+    // the caller will hand this buffer to the backward pass: mark it "everything, in order"
+    const uint32_t dense_ctrl[AS_CTRL_WORDS] = {0u, 0u, 1u, 0u};
+    if (cudaMemcpyAsync(active_set, dense_ctrl, sizeof(dense_ctrl), cudaMemcpyHostToDevice, st) != cudaSuccess) return check_launch("active_set init");
+  }
+  if (two_tier) {
+    if (cudaMemsetAsync(Ni > 0 ? as0 : as_last, 0, AS_CTRL_BYTES, st) != cudaSuccess) return check_launch("active_set init");
+    if (Ni > 0 && cudaMemsetAsync(as_last, 0, AS_CTRL_BYTES, st) != cudaSuccess) return check_launch("active_set init");
+  }
 
   uint32_t* mask = static_cast<uint32_t*>(relu_mask);      // sign bits of the LAST pass: the only one that carries gradient to the rays
   if ((rc = launch_coarse_z(rays, n, S, flags, t_rand, z0, st))) return rc;                          // RN:439-461
-  if ((rc = launch_mlp_forward(rays, z0, n, S, packed_coarse, mflags, raw0, st, Ni == 0 ? mask : nullptr, Ni == 0 ? dump_out : nullptr))) return rc;   // RN:463-466
+  if ((rc = mlp_pass(rays, z0, n, S, packed_coarse, mflags, raw0, st, Ni == 0 ? mask : nullptr, Ni == 0 ? dump_out : nullptr,
+                     Ni == 0 ? as_last : as0))) return rc;                                            // RN:463-466
   if (Ni == 0) {
     if ((rc = launch_raw2outputs(raw0, z0, rays + 3, 11, n, S, cflags, rgb_map, disp_map, acc_map, weights_out, nullptr, st))) return rc;
     if (raw) cudaMemcpyAsync(raw, raw0, size_t(n) * S * 16, cudaMemcpyDeviceToDevice, st);
@@ -210,9 +283,11 @@ int nsr_render_rays_forward_ex(const float* rays, int64_t n, const void* packed_
   }
   if ((rc = launch_raw2outputs(raw0, z0, rays + 3, 11, n, S, cflags, rgb0, disp0, acc0, w0, nullptr, st))) return rc;  // RN:467
   float* zf = z_vals_out ? z_vals_out : z1;
-  if ((rc = launch_resample_merge(z0, w0, n, S, Ni, u, zf, nullptr, z_std, st))) return rc;          // RN:473-477, 495
+  const uint32_t force_count = uint32_t(double(g_two_tier.force_frac) * double(n) * double(S));
+  if ((rc = launch_resample_merge(z0, w0, n, S, Ni, u, zf, nullptr, z_std, st, static_cast<const uint32_t*>(as0),
+                                  static_cast<uint32_t*>(as_last), force_count))) return rc;        // RN:473-477, 495
   float* rawf = raw ? raw : raw1;
-  if ((rc = launch_mlp_forward(rays, zf, n, T, packed_fine ? packed_fine : packed_coarse, mflags, rawf, st, mask, dump_out))) return rc;  // RN:478-483
+  if ((rc = mlp_pass(rays, zf, n, T, packed_fine ? packed_fine : packed_coarse, mflags, rawf, st, mask, dump_out, as_last))) return rc;  // RN:478-483
   if ((rc = launch_raw2outputs(rawf, zf, rays + 3, 11, n, T, cflags, rgb_map, disp_map, acc_map, weights_out, nullptr, st))) return rc;  // RN:485
   return NSR_OK;
 }
@@ -227,13 +302,14 @@ size_t nsr_mlp_dump_bytes(int64_t n_rays, int n_total_samples) { return mlp_dump
 int nsr_render_rays_backward(const float* rays, const float* z_vals, const float* raw, int64_t n, int T, const void* packed_net,
                              uint32_t flags, const float* d_rgb_map, float* d_rays, void* dump, float* const* dW,
                              float* const* dB, void* workspace, size_t workspace_bytes, void* stream) {
-  return nsr_render_rays_backward_ex(rays, z_vals, raw, n, T, packed_net, flags, d_rgb_map, d_rays, dump, dW, dB, nullptr, workspace,
+  return nsr_render_rays_backward_ex(rays, z_vals, raw, n, T, packed_net, flags, d_rgb_map, d_rays, dump, dW, dB, nullptr, nullptr, workspace,
                                      workspace_bytes, stream);
 }
 
 int nsr_render_rays_backward_ex(const float* rays, const float* z_vals, const float* raw, int64_t n, int T, const void* packed_net,
                                 uint32_t flags, const float* d_rgb_map, float* d_rays, void* dump, float* const* dW,
-                                float* const* dB, const void* relu_mask, void* workspace, size_t workspace_bytes, void* stream) {
+                                float* const* dB, const void* relu_mask, const void* active_set, void* workspace, size_t workspace_bytes,
+                                void* stream) {
   NSR_REQUIRE(n >= 0 && T > 0, "nsr_render_rays_backward: bad sizes");
   NSR_REQUIRE(relu_mask == nullptr || (reinterpret_cast<uintptr_t>(relu_mask) & 15) == 0, "nsr_render_rays_backward: relu_mask must be 16-byte aligned");
   if (n == 0) return NSR_OK;
@@ -247,6 +323,8 @@ int nsr_render_rays_backward_ex(const float* rays, const float* z_vals, const fl
   if (dW)
     for (int i = 0; i < NSR_NET_NUM_TENSORS; ++i) NSR_REQUIRE(dW[i] && dB[i], "nsr_render_rays_backward: gradient tensor %d is null", i);
   NSR_REQUIRE(dump == nullptr || (reinterpret_cast<uintptr_t>(dump) & 127) == 0, "nsr_render_rays_backward: dump must be 128-byte aligned");
+  NSR_REQUIRE(active_set == nullptr || (dW == nullptr && dump == nullptr), "nsr_render_rays_backward: the active-set route gives dL/d(rays) only");
+  NSR_REQUIRE(active_set == nullptr || (reinterpret_cast<uintptr_t>(active_set) & 255) == 0, "nsr_render_rays_backward: active_set must be 256-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   float* d_raw = reinterpret_cast<float*>(ws);
@@ -260,8 +338,10 @@ int nsr_render_rays_backward_ex(const float* rays, const float* z_vals, const fl
   if (dW) cudaMemsetAsync(gmax, 0, 4, st);
   if ((rc = launch_raw2outputs_backward(raw, z_vals, rays, n, T, flags & NSR_FLAG_WHITE_BKGD, d_rgb_map, d_raw, d_dnorm,
                                         dW ? gmax : nullptr, st))) return rc;
+  // active set: only its points are back-propagated (dL/draw is exactly 0 everywhere else: alpha == 0 there), the rest stays 0
+  if (active_set != nullptr && cudaMemsetAsync(d_pts, 0, size_t(n) * T * 32, st) != cudaSuccess) return check_launch("d_pts memset");
   if ((rc = launch_mlp_backward(rays, z_vals, n, T, packed_net, d_raw, d_pts, dW ? dump : nullptr, gmax, st,
-                                static_cast<const uint32_t*>(relu_mask)))) return rc;
+                                static_cast<const uint32_t*>(relu_mask), active_set))) return rc;
   if ((rc = launch_ray_grad_reduce(rays, z_vals, d_pts, d_dnorm, n, T, d_rays, st))) return rc;
   if (dW) return launch_weight_grads(dump, d_raw, n * int64_t(T), gmax, dW, dB, st);
   return NSR_OK;
@@ -337,7 +417,7 @@ size_t nsr_render_image_grad_workspace_bytes(int H, int W, int S, int Ni) {
   const int T = S + Ni;
   return align_up(size_t(n) * 44, 256) + align_up(size_t(n) * T * 4, 256) + align_up(size_t(n) * T * 16, 256) + align_up(size_t(n) * 44, 256) +
          align_up(size_t(n) * 12, 256) + align_up(nsr_c2w_grad_workspace_bytes(), 256) + align_up(nsr_relu_mask_bytes(n, T), 256) +
-         nsr_render_workspace_bytes(n, S, Ni) + nsr_render_backward_workspace_bytes(n, T);
+         align_up(nsr_active_set_bytes(n, T), 256) + nsr_render_workspace_bytes(n, S, Ni) + nsr_render_backward_workspace_bytes(n, T);
 }
 
 int nsr_render_image_grad(int H, int W, const float* K_host, const float* c2w_dev, int ld_c2w, float near_, float far_,
@@ -362,16 +442,17 @@ int nsr_render_image_grad(int H, int W, const float* K_host, const float* c2w_de
   float* rgb_tmp = reinterpret_cast<float*>(carve(size_t(n) * 12));
   void* cws = carve(nsr_c2w_grad_workspace_bytes());
   void* bits = carve(nsr_relu_mask_bytes(n, T));
+  void* aset = carve(nsr_active_set_bytes(n, T));
   const size_t fwd_bytes = nsr_render_workspace_bytes(n, S, Ni), bwd_bytes = nsr_render_backward_workspace_bytes(n, T);
   void* fwd = carve(fwd_bytes);
   void* bwd = carve(bwd_bytes);
   int rc;
   if ((rc = nsr_make_rays_dev(H, W, K_host, c2w_dev, ld_c2w, near_, far_, rays, stream))) return rc;                       // RN:148
   if ((rc = nsr_render_rays_forward_ex(rays, n, packed_coarse, packed_fine, S, Ni, flags, nullptr, nullptr, rgb_map ? rgb_map : rgb_tmp, nullptr,
-                                       nullptr, nullptr, nullptr, nullptr, nullptr, raw, zv, nullptr, bits, nullptr, fwd, fwd_bytes, stream))) return rc;   // RN:168-170
+                                       nullptr, nullptr, nullptr, nullptr, nullptr, raw, zv, nullptr, bits, nullptr, aset, fwd, fwd_bytes, stream))) return rc;   // RN:168-170
   const void* last = (Ni > 0 && packed_fine) ? packed_fine : packed_coarse;
   if ((rc = nsr_render_rays_backward_ex(rays, zv, raw, n, Ni > 0 ? T : S, last, flags & NSR_FLAG_WHITE_BKGD, d_rgb_map, d_rays, nullptr, nullptr,
-                                        nullptr, bits, bwd, bwd_bytes, stream))) return rc;                                                                 // RN:177-178
+                                        nullptr, bits, aset, bwd, bwd_bytes, stream))) return rc;                                                           // RN:177-178
   return nsr_rays_grad_to_c2w(H, W, K_host, rays, d_rays, nullptr, n, d_c2w, accumulate, cws, stream);                                                      // RN:179-181
 }
 
@@ -501,8 +582,8 @@ int nsr_train_step(const float* rays, const float* target, int64_t n, const nsr_
   // ---- loss.backward() (RN:705): the last pass through rgb, the coarse pass through rgb0
   cudaMemsetAsync(grads, 0, 2 * kNetParamsPadded * 4, st);
   if ((rc = nsr_render_rays_backward_ex(rays, Ni > 0 ? z1 : z0, Ni > 0 ? raw1 : raw0, n, Ni > 0 ? T : S, pl, cflags, d_rgb, d_rays, dump, dW[last],
-                                        dB[last], bits, bwd, bwd_bytes, stream))) return rc;
-  if (Ni > 0 && (rc = nsr_render_rays_backward_ex(rays, z0, raw0, n, S, pc, cflags, d_rgb0, d_rays, dump0, dW[0], dB[0], bits0, bwd, bwd_bytes,
+                                        dB[last], bits, nullptr, bwd, bwd_bytes, stream))) return rc;
+  if (Ni > 0 && (rc = nsr_render_rays_backward_ex(rays, z0, raw0, n, S, pc, cflags, d_rgb0, d_rays, dump0, dW[0], dB[0], bits0, nullptr, bwd, bwd_bytes,
                                                   stream))) return rc;
   // ---- optimizer.step() (RN:707)
   AdamJobs jobs;

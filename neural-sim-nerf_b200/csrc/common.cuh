@@ -114,12 +114,40 @@ constexpr int MASK_TILE_WORDS = MASK_WORDS * 128;       // 8704
 constexpr int MASK_TILE_BYTES = MASK_TILE_WORDS * 4;    // 34,816
 __host__ __device__ inline size_t relu_mask_bytes(int64_t n_points) { return size_t((n_points + 127) / 128) * MASK_TILE_BYTES; }
 
+// ----------------------------------------------------------------------------- active set (two-tier evaluation, DESIGN.md "precision")
+// A sample point whose density is certainly <= 0 has alpha == 0 exactly (RN:356: 1 - exp(-relu(sigma) dist)), so its weight is
+// exactly 0 and neither its colour nor the value of its sigma reach any output of raw2outputs (RN:343-387) or any gradient.
+// Tier 1 evaluates EVERY point with one fp16 MMA per product through pts_linears.0-7 and the alpha head only (sigma~); points with
+// sigma~ <= -tau are certified empty (|sigma~ - sigma| is orders of magnitude below tau, and that is verified at run time on the
+// points that do get both evaluations); the others -- the "active set", a compacted list of point indices -- are evaluated again
+// with the default error-compensated arithmetic (tier 2), bit for bit what the dense fp16x3 pass computes for them.
+//   ctrl block (16 x u32, zeroed by the host before the pass):
+constexpr int AS_COUNT = 0;        // number of active points (atomic counter of the tier-1 kernel)
+constexpr int AS_VMAX = 1;         // max |sigma~ - sigma| over the active points as float bits (atomicMax; NaN / inf sort above)
+constexpr int AS_FORCE_DENSE = 2;  // set before the pass (from the coarse pass's active fraction): skip tier 1, evaluate everything
+constexpr int AS_DENSE_FINAL = 3;  // set by the re-evaluation kernel: verification failed, every point was re-evaluated densely
+constexpr int AS_CTRL_WORDS = 16;
+constexpr int AS_CTRL_BYTES = 256; // one ctrl block, padded
+//   active set buffer handed across the C ABI (nsr_active_set_bytes): [ctrl, 256 B][list: int32 per point]
+__host__ __device__ inline size_t active_set_bytes(int64_t n_points) { return AS_CTRL_BYTES + size_t(n_points) * 4; }
+struct TwoTierParams {
+  float tau;            // certified empty: sigma~ <= -tau
+  float verify_max;     // tier 2 must not move any active point's sigma by more than this, else everything is re-evaluated
+  float force_frac;     // coarse active fraction above which the fine pass skips tier 1
+};
+const TwoTierParams& two_tier_params();
+// role of an MLP launch with respect to the active set
+enum : int { AS_ROLE_PLAIN = 0, AS_ROLE_TIER1 = 1, AS_ROLE_TIER2 = 2, AS_ROLE_REDO = 3 };
+
 // ----------------------------------------------------------------------------- backward "dump" (operands of dL/dMLP, RN:691-707)
 // With dump != NULL the backward kernel writes, for P = 128 * tiles points, every weight layer's input activations
 // and pre-activation gradients as fp16, one array after the other:
 //   EX [P,64] xyz encoding | EV [P,32] view-dir encoding | H0..H7 [P,256] post-ReLU | F [P,256] feature |
 //   HV [P,128] views hidden | GV [P,128] dL/d(views pre-act) | GF [P,256] dL/dfeature | G0..G7 [P,256] dL/d(pts_linears.l pre-act)
-// (gradients divided by one power-of-two `gscale`).  Each array is stored tile by tile (128 points) in the UMMA
+// (gradients divided by one power-of-two `gscale`), and then the fp16 RESIDUALS of all of them (x - fp16(x)) in the same order,
+// dump_lo(P) bytes further on: the weight-gradient GEMMs run the same error-compensated product as the forward pass
+// (G_hi H_hi + G_lo H_hi + G_hi H_lo), which keeps dL/dW within 1e-3 of fp32 autograd (single fp16 operands: 1.4e-3 on the first
+// layers of the fine network).  Each array is stored tile by tile (128 points) in the UMMA
 // MN-major no-swizzle canonical layout, i.e. 8x8 blocks [8 points][8 features] of 128 contiguous bytes, feature blocks
 // adjacent, point blocks (W/8)*128 bytes apart, so the weight-gradient kernel can feed slices of it to tcgen05.mma
 // as BOTH operands of dW = G^T H with the points as the K dimension -- no transposition anywhere.
@@ -130,7 +158,8 @@ __host__ __device__ inline size_t dump_off_hv(size_t P) { return dump_off_h(P, 9
 __host__ __device__ inline size_t dump_off_gv(size_t P) { return dump_off_hv(P) + P * 256; }
 __host__ __device__ inline size_t dump_off_gf(size_t P) { return dump_off_gv(P) + P * 256; }
 __host__ __device__ inline size_t dump_off_g(size_t P, int l) { return dump_off_gf(P) + P * 512 + size_t(l) * P * 512; }
-__host__ __device__ inline size_t dump_total(size_t P) { return dump_off_g(P, 8); }
+__host__ __device__ inline size_t dump_lo(size_t P) { return dump_off_g(P, 8); }        // offset of the residual copy of every array
+__host__ __device__ inline size_t dump_total(size_t P) { return 2 * dump_lo(P); }
 // byte offset inside a [P, W] array of the 16-byte group (tile, row, feature group fg = feature / 8)
 __host__ __device__ inline size_t dump_blocked_off(int tile, int row, int W, int fg) {
   return size_t(tile) * (size_t(128) * W * 2) + size_t(row >> 3) * (W / 8) * 128 + size_t(fg) * 128 + size_t(row & 7) * 16;
@@ -150,7 +179,8 @@ int launch_raw2outputs(const float* raw, const float* z, const float* rays_d, in
 int launch_sample_pdf(const float* bins, const float* weights, int64_t n, int B, int N, const float* u, float* out,
                       cudaStream_t st);
 int launch_resample_merge(const float* z, const float* w, int64_t n, int S, int Ni, const float* u, float* z_fine,
-                          float* z_samples, float* z_std, cudaStream_t st);
+                          float* z_samples, float* z_std, cudaStream_t st, const uint32_t* ctrl_coarse = nullptr,
+                          uint32_t* ctrl_fine = nullptr, uint32_t force_count = 0);
 int launch_make_rays(int H, int W, const float* K9, const float* c2w12, float near_, float far_, float* rays,
                      cudaStream_t st);
 // image_stage.cu
@@ -179,10 +209,12 @@ int launch_adam(const AdamJobs& jobs, float beta1, float beta2, float lr, float 
 // mlp_forward.cu
 int launch_pack_net(const float* const* weights, const float* const* biases, void* packed, cudaStream_t st);
 int launch_mlp_forward(const float* rays, const float* z_or_pts, int64_t n, int S, const void* packed, uint32_t flags,
-                       float* raw, cudaStream_t st, uint32_t* relu_mask = nullptr, void* dump = nullptr);
+                       float* raw, cudaStream_t st, uint32_t* relu_mask = nullptr, void* dump = nullptr, int role = AS_ROLE_PLAIN,
+                       void* active_set = nullptr);
 // mlp_backward.cu: d_raw [n,S,4] -> d_pts [n,S,8] = (dL/dpoint[3], 0, dL/dviewdir[3], 0) per sample
 int launch_mlp_backward(const float* rays, const float* z, int64_t n, int S, const void* packed, const float* d_raw,
-                        float* d_pts, void* dump, const float* gscale, cudaStream_t st, const uint32_t* relu_mask = nullptr);
+                        float* d_pts, void* dump, const float* gscale, cudaStream_t st, const uint32_t* relu_mask = nullptr,
+                        const void* active_set = nullptr);
 // wgrad.cu: dL/dW, dL/db of one network pass from the dump; accumulates (atomicAdd) into dW[12], dB[12] (fp32, reference shapes)
 int launch_weight_grads(const void* dump, const float* d_raw, int64_t n_points, const float* gscale, float* const* dW,
                         float* const* dB, cudaStream_t st);

@@ -49,6 +49,11 @@ struct BwdArgs {
   uint8_t* dump;        // optional: fp16 activations / pre-activation gradients of every layer (common.cuh), for dL/dMLP
   const float* gscale;  // with dump: one power-of-two scale for ALL rows (max |dL/draw| of the batch), device scalar
   unsigned long long* trace;  // debug (NSR_TRACE_FILE_BWD): clock64 stamps of CTA 0's first tiles, [tile][gstep][16]
+  // active set of the forward pass (common.cuh): only its points carry gradient (every other point has dL/draw == 0 exactly, so its
+  // dL/dpoint is 0 and the caller pre-zeroes d_pts); tile t of this launch = entries [128 t, 128 t + 128) of the list, which is also
+  // how the forward pass indexed the sign bits it saved.  NULL: every point, in order.
+  const uint32_t* ctrl;
+  const int32_t* list;
 };
 
 #define NSR_TRB(tl, g, slot)                                                                              \
@@ -147,7 +152,21 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mask_free + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const size_t P = size_t(a.num_tiles) * 128;  // rows of the optional dump
+  const size_t P = size_t(a.num_tiles) * 128;  // rows of the optional dump (dense launches only)
+  int num_tiles = a.num_tiles;
+  int n_act = 0;
+  bool use_list = false;
+  if (a.ctrl != nullptr && !(a.ctrl[AS_FORCE_DENSE] | a.ctrl[AS_DENSE_FINAL])) {
+    use_list = true;
+    n_act = int(a.ctrl[AS_COUNT]);
+    num_tiles = (n_act + 127) >> 7;
+    if (num_tiles == 0) return;
+  }
+  auto point_of = [&](int tile, int row) -> int64_t {
+    const int64_t q = int64_t(tile) * 128 + row;
+    if (use_list) return q < n_act ? int64_t(a.list[q]) : int64_t(-1);
+    return q < a.n_points ? q : int64_t(-1);
+  };
 
   if (tid == 0) {
     for (int s = 0; s < BWD_STAGES; ++s) {
@@ -183,14 +202,14 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
         bulk_g2s(smem + C::SM_MASK + b * MASK_TILE_BYTES, reinterpret_cast<const uint8_t*>(a.relu_mask) + size_t(tile) * MASK_TILE_BYTES,
                  MASK_TILE_BYTES, &mask_full[b]);
       };
-      if (MASKED && int(blockIdx.x) < a.num_tiles) fetch_mask(blockIdx.x, 0);
-      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++tl) {
+      if (MASKED && int(blockIdx.x) < num_tiles) fetch_mask(blockIdx.x, 0);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
         int base = MASKED ? NUM_CHUNKS : 0;        // first packed chunk of the step
         for (int g = G0; g < NUM_GSTEPS; ++g) {
           const int nk = gstep_k_chunks(g), nhs = gstep_is_side(g) ? 1 : 2;
           for (int i = 0; i < nk * nhs; ++i) {       // in the order the MMA warp consumes them (common.cuh issue_slot)
             // the next tile's bits: a few chunks in, when the tile before this one has long released the other buffer
-            if (MASKED && g == 12 && i == 0 && tile + int(gridDim.x) < a.num_tiles) fetch_mask(tile + gridDim.x, tl + 1);
+            if (MASKED && g == 12 && i == 0 && tile + int(gridDim.x) < num_tiles) fetch_mask(tile + gridDim.x, tl + 1);
             int nh, kc;
             issue_slot(nk, gstep_k_early(g), nhs, i, nh, kc);
             if (!first_lap) mbar_wait(&empty[stage], phase ^ 1);
@@ -217,7 +236,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
     uint32_t stage = 0, phase = 0, tl = 0;
     Waiter w_a[2], w_enc[2];
     bool ready = false;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++tl) {
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
       if (!MASKED) w_enc[0].wait(&enc_ready[0]);
       for (int g = G0; g < NUM_GSTEPS; ++g) {
         if (g == 9) w_enc[1].wait(&enc_ready[1]);
@@ -305,14 +324,14 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
     uint32_t tl = 0;
     Waiter w_free[2];
     uint8_t* inbuf = smem + C::SM_INBUF;
-    for (int tile = blockIdx.x; !MASKED && tile < a.num_tiles; tile += gridDim.x, ++tl) {
+    for (int tile = blockIdx.x; !MASKED && tile < num_tiles; tile += gridDim.x, ++tl) {
       float x[2][3], vd[2][3];
 #pragma unroll
       for (int rr = 0; rr < 2; ++rr) {
-        const int64_t p = int64_t(tile) * 128 + er + rr * 64;
+        const int64_t p = point_of(tile, er + rr * 64);
 #pragma unroll
         for (int d = 0; d < 3; ++d) x[rr][d] = vd[rr][d] = 0.f;
-        if (p < a.n_points) {
+        if (p >= 0) {
           const float* rp = a.rays + (p / a.S) * 11;
           const float z = a.z[p];
 #pragma unroll
@@ -348,8 +367,11 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
           for (int q = 0; q < 4; ++q) split2<true>(e[8 * gq + 2 * q], e[8 * gq + 2 * q + 1], h[q], l[q]);
           st_a8(inbuf + B_OFF_ENC_HI, 1024, row, gq, h[0], h[1], h[2], h[3]);
           st_a8(inbuf + B_OFF_ENC_LO, 1024, row, gq, l[0], l[1], l[2], l[3]);
-          if (a.dump != nullptr)
-            *reinterpret_cast<uint4*>(a.dump + dump_off_ex(P) + dump_blocked_off(tile, row, 64, gq)) = make_uint4(h[0], h[1], h[2], h[3]);
+          if (a.dump != nullptr) {
+            uint8_t* d = a.dump + dump_off_ex(P) + dump_blocked_off(tile, row, 64, gq);
+            *reinterpret_cast<uint4*>(d) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(d + dump_lo(P)) = make_uint4(l[0], l[1], l[2], l[3]);
+          }
         }
       }
       fence_proxy_async_smem();
@@ -381,8 +403,11 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
           for (int q = 0; q < 4; ++q) split2<true>(v[8 * gq + 2 * q], v[8 * gq + 2 * q + 1], h[q], l[q]);
           st_a8(inbuf + B_OFF_DIR_HI, 512, row, gq, h[0], h[1], h[2], h[3]);
           st_a8(inbuf + B_OFF_DIR_LO, 512, row, gq, l[0], l[1], l[2], l[3]);
-          if (a.dump != nullptr)
-            *reinterpret_cast<uint4*>(a.dump + dump_off_ev(P) + dump_blocked_off(tile, row, 32, gq)) = make_uint4(h[0], h[1], h[2], h[3]);
+          if (a.dump != nullptr) {
+            uint8_t* d = a.dump + dump_off_ev(P) + dump_blocked_off(tile, row, 32, gq);
+            *reinterpret_cast<uint4*>(d) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(d + dump_lo(P)) = make_uint4(l[0], l[1], l[2], l[3]);
+          }
         }
       }
       fence_proxy_async_smem();
@@ -402,12 +427,12 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
     // sign-bit words of this thread: layer l, accumulator half h, 32-column group q  ->  sMask[(l*8 + h*4 + ch*2 + q)*128 + row]
     uint32_t* my_mask = sMask + (ch * 2) * 128 + row;
     uint32_t tl = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++tl) {
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
       if (MASKED) my_mask = sMask + (tl & 1) * MASK_TILE_WORDS + (ch * 2) * 128 + row;
-      const int64_t p = int64_t(tile) * 128 + row;
+      const int64_t p = point_of(tile, row);
       float x[3] = {0.f, 0.f, 0.f}, vd[3] = {0.f, 0.f, 0.f};
       float4 gr = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (p < a.n_points) {
+      if (p >= 0) {
         const float* rp = a.rays + (p / a.S) * 11;
         const float z = a.z[p];
 #pragma unroll
@@ -451,7 +476,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
           split2<true>(gg[0], gg[1], H[j], L[j]);
           split2<true>(gg[2], gg[3], H[16 + j], L[16 + j]);
         }
-        if (a.dump != nullptr) dump64(a.dump + dump_off_gv(P), tile, row, 128, col0, H);   // the activations were dumped by the forward pass
+        if (a.dump != nullptr) dump64_hl(a.dump + dump_off_gv(P), dump_lo(P), tile, row, 128, col0, H, L);   // the activations were dumped by the forward pass
         tc_fence_after_sync();
         tmem_st16(tlane + TM_AHI + col0 / 2, *reinterpret_cast<const uint32_t(*)[16]>(&H[0]));
         tmem_st16(tlane + TM_AHI + col0 / 2 + 16, *reinterpret_cast<const uint32_t(*)[16]>(&H[16]));
@@ -498,7 +523,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
           // forward step g writes H_g (g = 8: F); backward steps write GF (g = 11) or G_l of the layer whose ReLU gated them
           uint8_t* dump_arr = a.dump == nullptr ? nullptr
                               : a.dump + (fwd ? dump_off_h(P, g) : (g == 11 ? dump_off_gf(P) : dump_off_g(P, mlayer)));
-          if (dump_arr != nullptr) dump64(dump_arr, tile, row, 256, col0, H);
+          if (dump_arr != nullptr) dump64_hl(dump_arr, dump_lo(P), tile, row, 256, col0, H, L);
           if (tid == 0) NSR_TRB(tl, g, 9);
           // The chunks that read A[K 0..127] are issued before accumulator 0's last ones (common.cuh issue_slot) and retired with it,
           // so the first operand half can be overwritten while half 1 is still in the tensor pipe -- except in step 11, whose K is
@@ -540,7 +565,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
               bwd32(u1, m1, mlayer >= 0, extra ? extra + 160 : nullptr, gr.w, H + 16, L + 16);
             }
           }
-          if (dump_arr != nullptr) dump64(dump_arr, tile, row, 256, 128 + col0, H);
+          if (dump_arr != nullptr) dump64_hl(dump_arr, dump_lo(P), tile, row, 256, 128 + col0, H, L);
           tmem_st16(tlane + TM_AHI + 64 + col0 / 2, *reinterpret_cast<const uint32_t(*)[16]>(&H[0]));
           tmem_st16(tlane + TM_AHI + 64 + col0 / 2 + 16, *reinterpret_cast<const uint32_t(*)[16]>(&H[16]));
           tmem_st16(tlane + TM_ALO + 64 + col0 / 2, *reinterpret_cast<const uint32_t(*)[16]>(&L[0]));
@@ -555,7 +580,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
           tc_fence_after_sync();
           const float* bias = sTail + TAIL_BIAS + 9 * 256 + col0;
           const float4* wr = reinterpret_cast<const float4*>(sTail + TAIL_WRGB) + col0;
-          uint32_t H[32], L[32], HV[32];
+          uint32_t H[32], L[32], HV[32], HVL[32];
           {
             uint32_t u0[32], u1[32];
             tmem_ld32(tlane + TM_ACC1 + col0, u0);
@@ -576,13 +601,13 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
               }
               split2<true>(gg[0], gg[1], H[j], L[j]);
               split2<true>(gg[2], gg[3], H[16 + j], L[16 + j]);
-              HV[j] = pack_f16x2(hh[0], hh[1]);
-              HV[16 + j] = pack_f16x2(hh[2], hh[3]);
+              split2<true>(hh[0], hh[1], HV[j], HVL[j]);
+              split2<true>(hh[2], hh[3], HV[16 + j], HVL[16 + j]);
             }
           }
           if (a.dump != nullptr) {
-            dump64(a.dump + dump_off_hv(P), tile, row, 128, col0, HV);
-            dump64(a.dump + dump_off_gv(P), tile, row, 128, col0, H);
+            dump64_hl(a.dump + dump_off_hv(P), dump_lo(P), tile, row, 128, col0, HV, HVL);
+            dump64_hl(a.dump + dump_off_gv(P), dump_lo(P), tile, row, 128, col0, H, L);
           }
           tmem_st16(tlane + TM_AHI + col0 / 2, *reinterpret_cast<const uint32_t(*)[16]>(&H[0]));
           tmem_st16(tlane + TM_AHI + col0 / 2 + 16, *reinterpret_cast<const uint32_t(*)[16]>(&H[16]));
@@ -623,7 +648,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
         sXch[2 * row + 1] = make_float4(dv[0], dv[1], dv[2], 0.f);
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (ch == 0 && p < a.n_points) {
+      if (ch == 0 && p >= 0) {
         const float4 o0 = sXch[2 * row], o1 = sXch[2 * row + 1];
         float4* out = reinterpret_cast<float4*>(a.d_pts) + 2 * p;
         out[0] = make_float4((dx[0] + o0.x) * scale, (dx[1] + o0.y) * scale, (dx[2] + o0.z) * scale, 0.f);
@@ -639,7 +664,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_bwd_kernel(BwdArgs a)
 size_t mlp_dump_bytes(int64_t n_points) { return dump_total(size_t((n_points + 127) / 128) * 128); }
 
 int launch_mlp_backward(const float* rays, const float* z, int64_t n, int S, const void* packed, const float* d_raw, float* d_pts,
-                        void* dump, const float* gscale, cudaStream_t st, const uint32_t* relu_mask) {
+                        void* dump, const float* gscale, cudaStream_t st, const uint32_t* relu_mask, const void* active_set) {
   const int64_t n_points = n * S;
   if (n_points == 0) return NSR_OK;
   int num_sms = 0;
@@ -661,6 +686,17 @@ int launch_mlp_backward(const float* rays, const float* z, int64_t n, int S, con
   a.dump = static_cast<uint8_t*>(dump);
   a.gscale = dump != nullptr ? gscale : nullptr;
   a.trace = nullptr;
+  a.ctrl = nullptr;
+  a.list = nullptr;
+  if (active_set != nullptr) {
+    if (dump != nullptr || n_points >= (int64_t(1) << 31)) {
+      set_error("mlp_backward: the active-set route computes dL/d(rays) only (no parameter-gradient dump)");
+      return NSR_E_INVALID;
+    }
+    a.ctrl = static_cast<const uint32_t*>(active_set);
+    a.list = reinterpret_cast<const int32_t*>(static_cast<const uint8_t*>(active_set) + AS_CTRL_BYTES);
+  }
+#ifdef NSR_DEBUG_HOOKS
   const char* trace_file = getenv("NSR_TRACE_FILE_BWD");  // debug only: synchronous, dumps CTA 0's timeline
   if (trace_file != nullptr && a.num_tiles >= 3 * num_sms && relu_mask == nullptr) {
     const size_t nb = 3 * 22 * 16 * sizeof(unsigned long long);
@@ -683,6 +719,7 @@ int launch_mlp_backward(const float* rays, const float* z, int64_t n, int S, con
     count_launch();
     return check_launch("nerf_mlp_bwd_kernel");
   }
+#endif
   const int grid = a.num_tiles < num_sms ? a.num_tiles : num_sms;
   if (relu_mask != nullptr) nerf_mlp_bwd_kernel<true><<<grid, MLP_THREADS, BCfg<true>::SM_TOTAL, st>>>(a);
   else nerf_mlp_bwd_kernel<false><<<grid, MLP_THREADS, BCfg<false>::SM_TOTAL, st>>>(a);

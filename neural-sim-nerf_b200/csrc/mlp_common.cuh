@@ -57,6 +57,12 @@ __device__ __forceinline__ void dump64(uint8_t* arr, int tile, int row, int W, i
   for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(dst + q * 128) = make_uint4(H[4 * q], H[4 * q + 1], H[4 * q + 2], H[4 * q + 3]);
 }
 
+// the same for an operand pair: hi words into the array, residual words into its copy `lo_off` bytes further on
+__device__ __forceinline__ void dump64_hl(uint8_t* arr, size_t lo_off, int tile, int row, int W, int col, const uint32_t* H, const uint32_t* L) {
+  dump64(arr, tile, row, W, col, H);
+  dump64(arr + lo_off, tile, row, W, col, L);
+}
+
 struct Waiter {  // one per (thread, barrier): parity follows the number of completed waits
   uint32_t n = 0;
   __device__ __forceinline__ void wait(uint64_t* bar) {

@@ -16,16 +16,26 @@
 // (three MMAs per k-step into the same fp32 accumulator; the dropped x_lo.W_lo term is ~2^-22).
 // SPLIT=1 (NSR_FLAG_FAST_FP16) issues only the first term.
 //
-// Pipeline.  For step s the MMA warp issues the N=0..127 half (all K) then the N=128..255 half; the
-// epilogue drains ACC0 while the second half is still being multiplied, keeps the rounded result in
-// registers until every MMA that reads the old activations has retired, then overwrites AHI/ALO[K 0..127];
-// the next step's first K half starts as soon as that store lands, while ACC1 is being drained.
-// Encoder warps prepare tile i+1's encodings during tile i.
+// Pipeline.  A two-half step consumes its weight chunks as (h0, K early) (h1, K early) (h0, K late) (h1, K late)
+// (common.cuh issue_slot): "early" chunks need only the first half of the previous step's epilogue (an encoding, or
+// activations 0..127), so the tensor pipe always holds work that does not depend on the epilogue still in flight;
+// accumulator 0 completes three quarters into the step and its epilogue -- which may overwrite A[K 0..127] at once,
+// every chunk that read it having been issued before accumulator 0's last ones -- runs under (h1, K late);
+// accumulator 1's epilogue runs under the next step's early chunks.  Encoder warps prepare tile i+1's encodings
+// during tile i.
 //
-// Warp roles: 0-3 epilogue (TMEM lane quadrant = warp), 4-5 encoders, 6 MMA issuer, 7 weight producer.
+// Warp roles (384 threads, mlp_common.cuh): 0-7 epilogue (warp w drains TMEM lane quadrant w & 3, columns
+// [64 (w >> 2), +64) of each accumulator half), 8-9 encoders (two rows per thread), 10 MMA issuer (the whole warp runs
+// the uniform control flow, one elected lane issues), 11 weight producer (one lane drives the TMA engine).
+//
+// Two-tier evaluation (common.cuh "active set"): the CLASSIFY instantiation is tier 1 -- one fp16 MMA per product through
+// pts_linears.0-7 and the alpha head only, writes sigma~ and appends every point that is not certainly empty to the active
+// list; the default instantiation run over that list is tier 2 (rows of a tile are then arbitrary points: every row of
+// the tile is independent, so a point's result does not depend on which tile it lands in).
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <cuda_fp8.h>
 
@@ -263,6 +273,12 @@ struct MlpArgs {
                               // (wrong results; isolates the cost of streaming the weights from L2)
   uint8_t* dump;              // optional: the activation half of the weight-gradient dump (common.cuh): EX, EV, H0..H7, F, HV as fp16
   unsigned long long* trace;  // debug (NSR_TRACE_FILE): clock64 stamps of CTA 0's first tiles, [tile][step][16]
+  // two-tier evaluation (common.cuh "active set"); ctrl == NULL: plain dense launch
+  uint32_t* ctrl;             // control block of this pass
+  int32_t* list;              // active point indices (tier 1 appends, tier 2 reads)
+  int role;                   // AS_ROLE_*
+  float tau;                  // tier 1: a point with sigma~ <= -tau is certified empty
+  uint32_t verify_bits;       // re-evaluation launch: runs iff ctrl[AS_VMAX] > verify_bits
 };
 
 #define NSR_TR(tl, step, slot)                                                                         \
@@ -273,11 +289,40 @@ struct MlpArgs {
 // ----------------------------------------------------------------------------- the kernel
 // SAVE: also write the ReLU sign bits (a.relu_mask) and, when a.dump != NULL, the activation half of the weight-gradient dump
 // for the backward pass.  A separate instantiation, so the plain render kernel carries none of that code.
-template <int SPLIT, bool SAVE>
+// CLASSIFY: tier 1 of the two-tier evaluation (SPLIT = 1 only): GEMM steps 0..7 + alpha head, sigma~ and the active list out.
+template <int SPLIT, bool SAVE, bool CLASSIFY>
 __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
   using C = Cfg<SPLIT>;
   constexpr bool kSplit = C::kSplit;
   constexpr bool kMixed = C::kMixed;
+  constexpr int kSteps = CLASSIFY ? 8 : NUM_STEPS;   // GEMM steps per tile
+  static_assert(!CLASSIFY || (SPLIT == 1 && !SAVE), "tier 1 is the single-pass fp16 arithmetic, nothing saved");
+  // ---- role with respect to the active set: every thread of every CTA takes the same decision from the control block, which no
+  // kernel of this launch's role modifies in the words read here
+  int num_tiles = a.num_tiles;
+  int n_act = 0;
+  bool use_list = false;
+  if (a.ctrl != nullptr) {
+    const uint32_t force = a.ctrl[AS_FORCE_DENSE];
+    if (a.role == AS_ROLE_TIER1) {
+      if (force) return;
+    } else if (a.role == AS_ROLE_TIER2) {
+      if (!force) {
+        use_list = true;
+        n_act = int(a.ctrl[AS_COUNT]);
+        num_tiles = (n_act + 127) >> 7;
+        if (num_tiles == 0) return;
+      }
+    } else if (a.role == AS_ROLE_REDO) {
+      if (force || !(a.ctrl[AS_VMAX] > a.verify_bits)) return;
+    }
+  }
+  // point index of (tile, row), or -1 for the padding rows of the last tile
+  auto point_of = [&](int tile, int row) -> int64_t {
+    const int64_t q = int64_t(tile) * 128 + row;
+    if (use_list) return q < n_act ? int64_t(a.list[q]) : int64_t(-1);
+    return q < a.n_points ? q : int64_t(-1);
+  };
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sRing = smem + C::SM_RING;
   const float* sTail = reinterpret_cast<const float*>(smem + C::SM_TAIL);
@@ -291,7 +336,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(enc_free + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const size_t dumpP = size_t(a.num_tiles) * 128;   // rows of the optional dump
+  const size_t dumpP = size_t(a.num_tiles) * 128;   // (dump: dense launches only)   // rows of the optional dump
 
   if (tid == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -319,9 +364,9 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       bool first_lap = true;
-      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int base = kMixed ? MIX_CHUNK0 : 0;          // first packed chunk of the step
-        for (int step = 0; step < NUM_STEPS; ++step) {
+        for (int step = 0; step < kSteps; ++step) {
           const int nk = step_k_chunks(step), nhs = step_n_halves(step);
           for (int i = 0; i < nk * nhs; ++i) {         // in the order the MMA warp consumes them (common.cuh issue_slot)
             int nh, kc;
@@ -357,9 +402,9 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
     uint32_t stage = 0, phase = 0, tl = 0;
     Waiter w_a[2], w_enc[2];
     bool ready = false;  // result of an early try_wait on full[stage]
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++tl) {
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
       w_enc[0].wait(&enc_ready[0]);
-      for (int step = 0; step < NUM_STEPS; ++step) {
+      for (int step = 0; step < kSteps; ++step) {
         if (step == 9) w_enc[1].wait(&enc_ready[1]);
         const int nk = step_k_chunks(step);
         const int nhs = step_n_halves(step);
@@ -453,7 +498,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
         if (lane == 0) NSR_TR(tl, step, 4);
         if (step == 5 && leader) umma_commit(&enc_free[0]);  // last reader of the xyz encoding
       }
-      if (leader) umma_commit(&enc_free[1]);
+      if (!CLASSIFY && leader) umma_commit(&enc_free[1]);
     }
   } else if (warp >= ENC_WARP0) {
     // ===================================================================== encoders (2 warps, 2 rows per thread):
@@ -462,14 +507,14 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
     uint32_t tl = 0;
     Waiter w_free[2];
     uint8_t* inbuf = smem + C::SM_INBUF;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++tl) {
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
       float x[2][3], vd[2][3];
 #pragma unroll
       for (int rr = 0; rr < 2; ++rr) {
-        const int64_t p = int64_t(tile) * 128 + er + rr * 64;
+        const int64_t p = point_of(tile, er + rr * 64);
 #pragma unroll
         for (int d = 0; d < 3; ++d) x[rr][d] = vd[rr][d] = 0.f;
-        if (p < a.n_points) {
+        if (p >= 0) {
           const int64_t ray = p / a.S;
           const float* rp = a.rays + ray * 11;
           if (a.flags & NSR_FLAG_PTS_INPUT) {
@@ -511,12 +556,16 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
           for (int q = 0; q < 4; ++q) split2<kSplit>(e[8 * g + 2 * q], e[8 * g + 2 * q + 1], h[q], l[q]);
           st_a8(inbuf + C::OFF_ENC_HI, 1024, row, g, h[0], h[1], h[2], h[3]);
           if (kSplit) st_a8(inbuf + C::OFF_ENC_LO, 1024, row, g, l[0], l[1], l[2], l[3]);
-          if (SAVE && a.dump != nullptr)
-            *reinterpret_cast<uint4*>(a.dump + dump_off_ex(dumpP) + dump_blocked_off(tile, row, 64, g)) = make_uint4(h[0], h[1], h[2], h[3]);
+          if (SAVE && a.dump != nullptr) {
+            uint8_t* d = a.dump + dump_off_ex(dumpP) + dump_blocked_off(tile, row, 64, g);
+            *reinterpret_cast<uint4*>(d) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(d + dump_lo(dumpP)) = make_uint4(l[0], l[1], l[2], l[3]);
+          }
         }
       }
       fence_proxy_async_smem();
       mbar_arrive(&enc_ready[0]);
+      if (CLASSIFY) continue;                     // tier 1 stops at the alpha head: no view-dir encoding
       if (tl >= 1) w_free[1].wait(&enc_free[1]);  // step 9 of the previous tile has read the old view-dir encoding
 #pragma unroll 1
       for (int rr = 0; rr < 2; ++rr) {
@@ -544,8 +593,11 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
           for (int q = 0; q < 4; ++q) split2<kSplit>(v[8 * g + 2 * q], v[8 * g + 2 * q + 1], h[q], l[q]);
           st_a8(inbuf + C::OFF_DIR_HI, 512, row, g, h[0], h[1], h[2], h[3]);
           if (kSplit) st_a8(inbuf + C::OFF_DIR_LO, 512, row, g, l[0], l[1], l[2], l[3]);
-          if (SAVE && a.dump != nullptr)
-            *reinterpret_cast<uint4*>(a.dump + dump_off_ev(dumpP) + dump_blocked_off(tile, row, 32, g)) = make_uint4(h[0], h[1], h[2], h[3]);
+          if (SAVE && a.dump != nullptr) {
+            uint8_t* d = a.dump + dump_off_ev(dumpP) + dump_blocked_off(tile, row, 32, g);
+            *reinterpret_cast<uint4*>(d) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(d + dump_lo(dumpP)) = make_uint4(l[0], l[1], l[2], l[3]);
+          }
         }
       }
       fence_proxy_async_smem();
@@ -563,11 +615,12 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
     mbar_arrive(&a_ready[0]);
     mbar_arrive(&a_ready[1]);
     uint32_t tl = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++tl) {
-      const int64_t p = int64_t(tile) * 128 + row;
+    uint32_t vbits = 0u;   // tier 2: max |sigma~ - sigma| of this thread's points, as float bits
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+      const int64_t p = point_of(tile, row);
       float sigma = 0.f;
       uint32_t* mrow = (SAVE && a.relu_mask != nullptr) ? a.relu_mask + size_t(tile) * MASK_TILE_WORDS + (ch * 2) * 128 + row : nullptr;
-      for (int step = 0; step < 9; ++step) {
+      for (int step = 0; step < (CLASSIFY ? 8 : 9); ++step) {
         const float* bias = sTail + TAIL_BIAS + step * 256 + col0;
         const float* walpha = (step == 7) ? sTail + TAIL_WALPHA + col0 : nullptr;
         const bool relu = step != 8;  // feature_linear has no activation (RH:110)
@@ -621,11 +674,12 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
           mrow[(step * 8 + 0) * 128] = sign_bits(H);
           mrow[(step * 8 + 1) * 128] = sign_bits(H + 16);
         }
-        if (SAVE && a.dump != nullptr) dump64(a.dump + dump_off_h(dumpP, step), tile, row, 256, col0, H);       // step 8: F
+        if (SAVE && a.dump != nullptr) dump64_hl(a.dump + dump_off_h(dumpP, step), dump_lo(dumpP), tile, row, 256, col0, H, L);   // step 8: F
         // ---- the chunks that read A[K 0..127] were issued before accumulator 0's last ones (common.cuh issue_slot), so they
         // retired with it: the first half of the activations may be overwritten now, while half 1 is still in the tensor pipe
         if (tid == 0) NSR_TR(tl, step, 9);
-        store(0);
+        if (CLASSIFY && step == 7) tc_fence_before_sync();   // tier 1 ends here: nothing consumes these activations
+        else store(0);
         mbar_arrive(&a_ready[0]);
         if (tid == 0) NSR_TR(tl, step, 11);
         // ---- every MMA of this step has retired
@@ -644,10 +698,30 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
           mrow[(step * 8 + 4) * 128] = sign_bits(H);
           mrow[(step * 8 + 5) * 128] = sign_bits(H + 16);
         }
-        if (SAVE && a.dump != nullptr) dump64(a.dump + dump_off_h(dumpP, step), tile, row, 256, 128 + col0, H);
-        store(1);
+        if (SAVE && a.dump != nullptr) dump64_hl(a.dump + dump_off_h(dumpP, step), dump_lo(dumpP), tile, row, 256, 128 + col0, H, L);
+        if (CLASSIFY && step == 7) tc_fence_before_sync();
+        else store(1);
         mbar_arrive(&a_ready[1]);
         if (tid == 0) NSR_TR(tl, step, 12);
+      }
+      if constexpr (CLASSIFY) {
+        // ---- tier 1: sigma~ = alpha head of the fp32 post-ReLU activations (RH:109); certainly-empty points stop here, the others
+        // join the active list (order within the list is irrelevant: every row of a tier-2 tile is independent of the others)
+        if (ch == 1) sXch[row] = make_float4(0.f, 0.f, 0.f, sigma);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (ch == 0) {   // warps 0..3, warp-uniform
+          const float sg = (sigma + sXch[row].w) + sTail[TAIL_MISC];
+          const bool act = p >= 0 && !(sg <= -a.tau);       // NaN counts as active
+          if (p >= 0) reinterpret_cast<float4*>(a.raw)[p] = make_float4(0.f, 0.f, 0.f, sg);
+          const uint32_t m = __ballot_sync(0xffffffffu, act);
+          if (m != 0u) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(a.ctrl + AS_COUNT, uint32_t(__popc(m)));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (act) a.list[base + __popc(m & ((1u << lane) - 1u))] = int32_t(p);
+          }
+        }
+        continue;
       }
       // ---- step 9: views layer accumulates in ACC1; rgb head on CUDA cores (RH:113-117)
       w_acc[1].wait(&acc_ready[1]);
@@ -657,7 +731,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
       mbar_arrive(&a_ready[0]);
       float r0 = 0.f, r1 = 0.f, r2 = 0.f;
       uint32_t mv0 = 0u, mv1 = 0u;   // sign bits of this thread's 2 x 32 views-layer columns
-      uint32_t HV[32];               // the same columns as packed fp16 (only kept for the dump)
+      uint32_t HV[32], HVL[32];      // the same columns as packed fp16 hi / residual words (only kept for the dump)
       {
         const float* bias = sTail + TAIL_BIAS + 9 * 256 + col0;
         const float4* wr = reinterpret_cast<const float4*>(sTail + TAIL_WRGB) + col0;
@@ -695,14 +769,14 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
             r2 = fmaf(h1, w1.z, r2);
           }
           if (SAVE) {
-            HV[2 * j] = pack_f16x2(hq0[0], hq0[1]);
-            HV[2 * j + 1] = pack_f16x2(hq0[2], hq0[3]);
-            HV[16 + 2 * j] = pack_f16x2(hq1[0], hq1[1]);
-            HV[16 + 2 * j + 1] = pack_f16x2(hq1[2], hq1[3]);
+            split2<true>(hq0[0], hq0[1], HV[2 * j], HVL[2 * j]);
+            split2<true>(hq0[2], hq0[3], HV[2 * j + 1], HVL[2 * j + 1]);
+            split2<true>(hq1[0], hq1[1], HV[16 + 2 * j], HVL[16 + 2 * j]);
+            split2<true>(hq1[2], hq1[3], HV[16 + 2 * j + 1], HVL[16 + 2 * j + 1]);
           }
         }
       }
-      if (SAVE && a.dump != nullptr) dump64(a.dump + dump_off_hv(dumpP), tile, row, 128, col0, HV);
+      if (SAVE && a.dump != nullptr) dump64_hl(a.dump + dump_off_hv(dumpP), dump_lo(dumpP), tile, row, 128, col0, HV, HVL);
       if (SAVE && mrow != nullptr) {
         mrow[(64 + 0) * 128] = mv0;
         mrow[(64 + 1) * 128] = mv1;
@@ -710,28 +784,38 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
       // ---- the two column halves of a row meet in shared memory; the ch == 0 thread writes raw[p]
       if (ch == 1) sXch[row] = make_float4(r0, r1, r2, sigma);
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (ch == 0 && p < a.n_points) {
+      if (ch == 0 && p >= 0) {
         const float4 o = sXch[row];
         const float* misc = sTail + TAIL_MISC;
-        reinterpret_cast<float4*>(a.raw)[p] =
-            make_float4((r0 + o.x) + misc[1], (r1 + o.y) + misc[2], (r2 + o.z) + misc[3], (sigma + o.w) + misc[0]);  // RH:118
+        const float sg = (sigma + o.w) + misc[0];
+        if (use_list) {   // tier 2 verification: how far was tier 1's sigma~ (still in raw[p]) from this one?
+          const uint32_t d = __float_as_uint(fabsf(sg - a.raw[p * 4 + 3]));
+          vbits = d > vbits ? d : vbits;
+        }
+        reinterpret_cast<float4*>(a.raw)[p] = make_float4((r0 + o.x) + misc[1], (r1 + o.y) + misc[2], (r2 + o.z) + misc[3], sg);  // RH:118
       }
     }
+    if (use_list && ch == 0) {
+      const uint32_t v = __reduce_max_sync(0xffffffffu, vbits);
+      if (lane == 0 && v != 0u) atomicMax(a.ctrl + AS_VMAX, v);
+    }
   }
+  if (a.ctrl != nullptr && a.role == AS_ROLE_REDO && blockIdx.x == 0 && tid == 0) a.ctrl[AS_DENSE_FINAL] = 1u;
   tc_fence_before_sync();
   __syncthreads();
   if (warp == MMA_WARP) tmem_dealloc(0u, 512);
 }
 
-template <int SPLIT, bool SAVE>
+template <int SPLIT, bool SAVE, bool CLASSIFY = false>
 static int launch_variant(const MlpArgs& a, int grid, cudaStream_t st) {
-  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(&nerf_mlp_kernel<SPLIT, SAVE>), Cfg<SPLIT>::SM_TOTAL)) return rc;
-  nerf_mlp_kernel<SPLIT, SAVE><<<grid, MLP_THREADS, Cfg<SPLIT>::SM_TOTAL, st>>>(a);
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(&nerf_mlp_kernel<SPLIT, SAVE, CLASSIFY>), Cfg<SPLIT>::SM_TOTAL)) return rc;
+  nerf_mlp_kernel<SPLIT, SAVE, CLASSIFY><<<grid, MLP_THREADS, Cfg<SPLIT>::SM_TOTAL, st>>>(a);
   count_launch();
   return check_launch("nerf_mlp_kernel");
 }
 
 static int launch_by_flags(const MlpArgs& a, int grid, uint32_t flags, cudaStream_t st) {
+  if (a.role == AS_ROLE_TIER1) return launch_variant<1, false, true>(a, grid, st);
   if (a.relu_mask != nullptr || a.dump != nullptr) {
     if (flags & (NSR_FLAG_FAST_FP16 | NSR_FLAG_MIXED_F8)) {
       set_error("mlp_forward: sign bits / activations are saved for the backward pass, which is built for the default precision only");
@@ -745,7 +829,7 @@ static int launch_by_flags(const MlpArgs& a, int grid, uint32_t flags, cudaStrea
 }
 
 int launch_mlp_forward(const float* rays, const float* z_or_pts, int64_t n, int S, const void* packed, uint32_t flags,
-                       float* raw, cudaStream_t st, uint32_t* relu_mask, void* dump) {
+                       float* raw, cudaStream_t st, uint32_t* relu_mask, void* dump, int role, void* active_set) {
   const int64_t n_points = n * S;
   if (n_points == 0) return NSR_OK;
   if (n_points > (int64_t(1) << 31) * 64) {
@@ -766,11 +850,37 @@ int launch_mlp_forward(const float* rays, const float* z_or_pts, int64_t n, int 
   a.relu_mask = relu_mask;
   a.dump = static_cast<uint8_t*>(dump);
   a.trace = nullptr;
+  a.ctrl = nullptr;
+  a.list = nullptr;
+  a.role = AS_ROLE_PLAIN;
+  a.tau = 0.f;
+  a.verify_bits = 0u;
+  if (role != AS_ROLE_PLAIN) {
+    if (active_set == nullptr || n_points >= (int64_t(1) << 31)) {
+      set_error("mlp_forward: two-tier launch without an active set (or more than 2^31 points)");
+      return NSR_E_INVALID;
+    }
+    if ((flags & (NSR_FLAG_FAST_FP16 | NSR_FLAG_MIXED_F8 | NSR_FLAG_PTS_INPUT)) || (dump != nullptr)) {
+      set_error("mlp_forward: the two-tier evaluation runs the default precision on depth input, without the activation dump");
+      return NSR_E_INVALID;
+    }
+    const TwoTierParams& tt = two_tier_params();
+    a.ctrl = static_cast<uint32_t*>(active_set);
+    a.list = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(active_set) + AS_CTRL_BYTES);
+    a.role = role;
+    a.tau = tt.tau;
+    memcpy(&a.verify_bits, &tt.verify_max, 4);
+  }
+#ifdef NSR_DEBUG_HOOKS
   const char* experiment = getenv("NSR_EXPERIMENT");
   a.experiment = experiment != nullptr ? atoi(experiment) : 0;
+#else
+  a.experiment = 0;
+#endif
   const int grid = a.num_tiles < num_sms ? a.num_tiles : num_sms;
+#ifdef NSR_DEBUG_HOOKS   // compiled out of the production library: `python -m neural_sim_nerf_b200.build --debug-hooks`
   const char* trace_file = getenv("NSR_TRACE_FILE");  // debug only: synchronous, dumps CTA 0's timeline
-  if (trace_file != nullptr && a.num_tiles >= 4 * grid) {
+  if (trace_file != nullptr && a.num_tiles >= 4 * grid && role == AS_ROLE_PLAIN) {
     const size_t nb = 4 * 10 * 16 * sizeof(unsigned long long);
     cudaMalloc(&a.trace, nb);
     cudaMemset(a.trace, 0, nb);
@@ -790,6 +900,7 @@ int launch_mlp_forward(const float* rays, const float* z_or_pts, int64_t n, int 
     }
     return rc;
   }
+#endif
   return launch_by_flags(a, grid, flags, st);
 }
 

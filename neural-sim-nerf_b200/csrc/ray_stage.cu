@@ -350,9 +350,14 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
     resample_merge_kernel(const float* __restrict__ z, const float* __restrict__ weights, int64_t n, int S, int Ni,
                           const float* __restrict__ u, float* __restrict__ z_fine, float* __restrict__ z_samples,
-                          float* __restrict__ z_std) {
+                          float* __restrict__ z_std, const uint32_t* __restrict__ ctrl_coarse, uint32_t* __restrict__ ctrl_fine,
+                          uint32_t force_count) {
   extern __shared__ float sm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // two-tier evaluation (common.cuh "active set"): a coarse pass that found most of its points non-empty (or failed its
+  // verification) predicts a fine pass where tier 1 would certify next to nothing -- skip it there
+  if (ctrl_fine != nullptr && blockIdx.x == 0 && threadIdx.x == 0)
+    ctrl_fine[AS_FORCE_DENSE] = (ctrl_coarse[AS_FORCE_DENSE] | ctrl_coarse[AS_DENSE_FINAL] | uint32_t(ctrl_coarse[AS_COUNT] > force_count)) ? 1u : 0u;
   const int64_t ray = blockIdx.x * int64_t(WARPS_PER_BLOCK) + warp;
   if (ray >= n) return;
   const int B = S - 1, T = S + Ni;
@@ -403,12 +408,15 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
       z_fine[ray * T + i + lo] = e;
     }
   } else {
+    // NaNs order last (as torch.sort places them), ties by index: the ranks always form a permutation
     for (int i = lane; i < T; i += 32) {
       const float e = all[i];
+      const bool e_nan = e != e;
       int rank = 0;
       for (int j = 0; j < T; ++j) {
         const float o = all[j];
-        rank += (o < e) || (o == e && j < i);
+        const bool o_nan = o != o;
+        rank += e_nan ? (!o_nan || j < i) : (!o_nan && ((o < e) || (o == e && j < i)));
       }
       z_fine[ray * T + rank] = e;
     }
@@ -492,7 +500,8 @@ int launch_sample_pdf(const float* bins, const float* weights, int64_t n, int B,
 }
 
 int launch_resample_merge(const float* z, const float* w, int64_t n, int S, int Ni, const float* u, float* z_fine,
-                          float* z_samples, float* z_std, cudaStream_t st) {
+                          float* z_samples, float* z_std, cudaStream_t st, const uint32_t* ctrl_coarse, uint32_t* ctrl_fine,
+                          uint32_t force_count) {
   if (n == 0) return NSR_OK;
   const size_t smem = size_t(WARPS_PER_BLOCK) * (3 * S + S + Ni) * sizeof(float);
   if (smem > 48 * 1024) {
@@ -500,7 +509,7 @@ int launch_resample_merge(const float* z, const float* w, int64_t n, int S, int 
     return NSR_E_UNSUPPORTED;
   }
   const unsigned grid = unsigned((n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
-  resample_merge_kernel<<<grid, WARPS_PER_BLOCK * 32, smem, st>>>(z, w, n, S, Ni, u, z_fine, z_samples, z_std);
+  resample_merge_kernel<<<grid, WARPS_PER_BLOCK * 32, smem, st>>>(z, w, n, S, Ni, u, z_fine, z_samples, z_std, ctrl_coarse, ctrl_fine, force_count);
   count_launch();
   return check_launch("resample_merge_kernel");
 }

@@ -1,6 +1,7 @@
 // Weight gradients of one network pass (the loss.backward() of RN:691-707 as far as the MLP parameters go):
 //   dW_l = G_l^T H_{l-1}   ([out x points] . [points x in]),   db_l = column sums of G_l,
-// from the fp16 operands the backward kernel dumped (common.cuh "dump").  The dump is already in the UMMA MN-major
+// from the fp16 hi / residual operand pairs the backward kernel dumped (common.cuh "dump"), as the error-compensated product
+// G_hi H_hi + G_lo H_hi + G_hi H_lo (three MMAs into one fp32 accumulator, like the forward pass).  The dump is already in the UMMA MN-major
 // canonical layout, so 32-point slices of it go by cp.async.bulk straight into shared memory and serve as BOTH
 // operands of tcgen05.mma with the POINT index as K: D[out feature (lane), in feature (column)] accumulates in
 // TMEM over all the tiles a CTA owns (split-K over CTAs), and is added to the fp32 gradient with atomics at the end.
@@ -10,8 +11,8 @@
 
 namespace nsr {
 
-constexpr int WG_STAGES = 5;
-constexpr int WG_STAGE_BYTES = 32 * 1024;   // [G slice: 32 points x <=256 features][H slice: 32 points x <=256 features]
+constexpr int WG_STAGES = 3;
+constexpr int WG_STAGE_BYTES = 64 * 1024;   // [G hi | G lo | H hi | H lo], each a slice of 32 points x <=256 features (16 KB)
 constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 256;
 constexpr int WG_NUM_JOBS = 12;
 
@@ -25,7 +26,8 @@ struct WJobs {
   WJob j[WG_NUM_JOBS];
 };
 
-__global__ void __launch_bounds__(128, 1) wgrad_gemm_kernel(const uint8_t* __restrict__ dump, WJobs jobs, int n_tiles, const float* gscale) {
+__global__ void __launch_bounds__(128, 1) wgrad_gemm_kernel(const uint8_t* __restrict__ dump, size_t lo_off, WJobs jobs, int n_tiles,
+                                                            const float* gscale) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
   uint64_t* empty = full + WG_STAGES;
@@ -63,21 +65,28 @@ __global__ void __launch_bounds__(128, 1) wgrad_gemm_kernel(const uint8_t* __res
         if (it >= WG_STAGES) mbar_wait(&empty[s], ((it / WG_STAGES) - 1) & 1);
         const int tile = int(blockIdx.x) + (it >> 2) * int(gridDim.x), sl = it & 3;
         uint8_t* dst = smem + s * WG_STAGE_BYTES;
-        mbar_arrive_expect_tx(&full[s], g_bytes + h_bytes);
-        bulk_g2s(dst, gbase + size_t(tile) * 128 * job.g_w * 2 + size_t(sl) * g_bytes, g_bytes, &full[s]);
-        bulk_g2s(dst + 16384, hbase + size_t(tile) * 128 * job.h_w * 2 + size_t(sl) * h_bytes, h_bytes, &full[s]);
+        mbar_arrive_expect_tx(&full[s], 2 * (g_bytes + h_bytes));
+        const uint8_t* gsrc = gbase + size_t(tile) * 128 * job.g_w * 2 + size_t(sl) * g_bytes;
+        const uint8_t* hsrc = hbase + size_t(tile) * 128 * job.h_w * 2 + size_t(sl) * h_bytes;
+        bulk_g2s(dst, gsrc, g_bytes, &full[s]);
+        bulk_g2s(dst + 16384, gsrc + lo_off, g_bytes, &full[s]);
+        bulk_g2s(dst + 32768, hsrc, h_bytes, &full[s]);
+        bulk_g2s(dst + 49152, hsrc + lo_off, h_bytes, &full[s]);
       }
       const int jt = it - (WG_STAGES - 1);
       if (jt >= 0) {        // consumer side: slice `jt`
         const int s = jt % WG_STAGES;
         mbar_wait(&full[s], (jt / WG_STAGES) & 1);
-        const uint32_t sg = smem_u32(smem + s * WG_STAGE_BYTES), sh = sg + 16384;
+        const uint32_t sg = smem_u32(smem + s * WG_STAGE_BYTES), sgl = sg + 16384, sh = sg + 32768, shl = sg + 49152;
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {   // 16 points per MMA
           for (int mh = 0; mh < m_halves; ++mh) {
-            const uint64_t ad = make_sdesc(sg + mh * 16 * 128 + ks * 2 * lbo_g, lbo_g, 128, 0);
-            const uint64_t bd = make_sdesc(sh + ks * 2 * lbo_h, lbo_h, 128, 0);
-            umma_ss(tmem + mh * job.h_w, ad, bd, idesc, (jt | ks) != 0);
+            const uint32_t ao = mh * 16 * 128 + ks * 2 * lbo_g, bo = ks * 2 * lbo_h;
+            const uint64_t a_hi = make_sdesc(sg + ao, lbo_g, 128, 0), a_lo = make_sdesc(sgl + ao, lbo_g, 128, 0);
+            const uint64_t b_hi = make_sdesc(sh + bo, lbo_h, 128, 0), b_lo = make_sdesc(shl + bo, lbo_h, 128, 0);
+            umma_ss(tmem + mh * job.h_w, a_hi, b_hi, idesc, (jt | ks) != 0);
+            umma_ss(tmem + mh * job.h_w, a_lo, b_hi, idesc, 1u);
+            umma_ss(tmem + mh * job.h_w, a_hi, b_lo, idesc, 1u);
           }
         }
         umma_commit(&empty[s]);
@@ -127,7 +136,7 @@ struct SJobs {
 // warp reads 16 bytes next to its neighbours' (512 B per warp) and -- W being 128 or 256 -- always meets the same feature group
 // t % W / 8: its 8 x n_out partial sums stay in registers over all tiles, are folded over the 8 rows of a feature group with
 // shuffles, over the warps through shared memory, and leave the block as one atomicAdd per output element.
-__global__ void __launch_bounds__(256) wgrad_skinny_kernel(const uint8_t* __restrict__ dump, const float* __restrict__ d_raw,
+__global__ void __launch_bounds__(256) wgrad_skinny_kernel(const uint8_t* __restrict__ dump, size_t lo_off, const float* __restrict__ d_raw,
                                                            long long n_points, SJobs jobs, int n_tiles, const float* gscale) {
   const SJob job = jobs.j[blockIdx.y];
   const int t = threadIdx.x;
@@ -149,6 +158,7 @@ __global__ void __launch_bounds__(256) wgrad_skinny_kernel(const uint8_t* __rest
 #pragma unroll 4
     for (int rb = rb0; rb < 16; rb += rb_step) {
       const uint4 u = *reinterpret_cast<const uint4*>(base + (size_t(rb) * W + within) * 16);
+      const uint4 ul = *reinterpret_cast<const uint4*>(base + lo_off + (size_t(rb) * W + within) * 16);
       float co[3] = {1.f, 0.f, 0.f};
       if (has_coef) {
         const long long p = (long long)tile * 128 + rb * 8 + rlow;
@@ -166,10 +176,13 @@ __global__ void __launch_bounds__(256) wgrad_skinny_kernel(const uint8_t* __rest
           for (int j = 0; j < 3; ++j) csum[j] += co[j];
         }
       }
-      const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+      const uint32_t w4[4] = {u.x, u.y, u.z, u.w}, l4[4] = {ul.x, ul.y, ul.z, ul.w};
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w4[q]));
+        float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w4[q]));
+        const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&l4[q]));
+        f.x += fl.x;
+        f.y += fl.y;
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
           acc[j][2 * q] = fmaf(co[j], f.x, acc[j][2 * q]);
@@ -249,7 +262,7 @@ int launch_weight_grads(const void* dump_v, const float* d_raw, int64_t n_points
   add(dump_off_gv(P), 128, dump_off_ev(P), 32, dW[8], 283, 256, 27);
   add(dump_off_gf(P), 256, dump_off_h(P, 7), 256, dW[9], 256, 0, 256);                                 // feature_linear
   const int splits = 12;
-  wgrad_gemm_kernel<<<dim3(splits, WG_NUM_JOBS), 128, WG_SMEM, st>>>(dump, g, n_tiles, gscale);
+  wgrad_gemm_kernel<<<dim3(splits, WG_NUM_JOBS), 128, WG_SMEM, st>>>(dump, dump_lo(P), g, n_tiles, gscale);
   count_launch();
   int rc = check_launch("wgrad_gemm_kernel");
   if (rc) return rc;
@@ -261,7 +274,7 @@ int launch_weight_grads(const void* dump_v, const float* d_raw, int64_t n_points
   s.j[k++] = SJob{(unsigned long long)dump_off_gf(P), 256, -1, 1, dB[9], 256, nullptr};
   s.j[k++] = SJob{(unsigned long long)dump_off_h(P, 7), 256, 3, 1, dW[10], 256, dB[10]};                                   // alpha_linear: sigma column
   s.j[k++] = SJob{(unsigned long long)dump_off_hv(P), 128, 0, 3, dW[11], 128, dB[11]};                                     // rgb_linear: rgb columns
-  wgrad_skinny_kernel<<<dim3(n_tiles < 74 ? n_tiles : 74, SK_NUM_JOBS), 256, 0, st>>>(dump, d_raw, (long long)n_points, s, n_tiles, gscale);
+  wgrad_skinny_kernel<<<dim3(n_tiles < 74 ? n_tiles : 74, SK_NUM_JOBS), 256, 0, st>>>(dump, dump_lo(P), d_raw, (long long)n_points, s, n_tiles, gscale);
   count_launch();
   return check_launch("wgrad_skinny_kernel");
 }

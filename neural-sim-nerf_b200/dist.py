@@ -56,21 +56,34 @@ def render_rays_sharded(rays_flat, render_fn, gather=True):
     return out
 
 
-def reduce_psi_grad(chunk_grads):
+def _collective_device():
+    """Where tensors must live for the active backend's collectives: NCCL only moves CUDA tensors, gloo takes CPU ones."""
+    if dist.get_backend() == 'nccl':
+        return torch.device('cuda', torch.cuda.current_device())
+    return torch.device('cpu')
+
+
+def reduce_psi_grad(chunk_grads, n_psi=None):
     """chunk_grads: this rank's list of per-chunk dL/dpsi tensors (what render_path_grad returns as
-    `dLdpsis`, RN:190).  Returns the reference's estimator over ALL ranks: mean over every chunk of
-    every image (MAIN:191) -- one all_reduce(SUM) of [sum, count]."""
+    `dLdpsis`, RN:190 -- CPU tensors, `.cpu().detach()`; any device is accepted).  Returns the reference's estimator over ALL
+    ranks: mean over every chunk of every image (MAIN:191) -- one all_reduce(SUM) of [sum, count] on the device the backend
+    needs (CUDA under NCCL, CPU under gloo), result on that device.  A rank with no chunks contributes zeros; `n_psi` (length
+    of psi) is only needed when NO rank may have any chunk."""
     if len(chunk_grads):
-        s = torch.stack([g.reshape(-1).to(torch.float64) for g in chunk_grads], 0).sum(0)
+        s = torch.stack([g.detach().reshape(-1).to(torch.float64) for g in chunk_grads], 0).sum(0)
     else:
         s = None
     rank, ws = world()
     if ws == 1:
-        return (s / max(len(chunk_grads), 1)).to(torch.float32)
-    dev = chunk_grads[0].device if len(chunk_grads) else torch.device('cuda', torch.cuda.current_device()) if dist.get_backend() == 'nccl' else torch.device('cpu')
-    n_psi = torch.tensor([s.numel() if s is not None else 0], device=dev)
-    dist.all_reduce(n_psi, op=dist.ReduceOp.MAX)
-    buf = torch.zeros(int(n_psi.item()) + 1, dtype=torch.float64, device=dev)
+        if s is None:
+            if n_psi is None:
+                raise ValueError('reduce_psi_grad: no chunk gradients (render_path_grad returned an empty list) and n_psi not given')
+            return torch.zeros(n_psi, dtype=torch.float32)
+        return (s / len(chunk_grads)).to(torch.float32)
+    dev = _collective_device()
+    width = torch.tensor([s.numel() if s is not None else (n_psi or 0)], device=dev)
+    dist.all_reduce(width, op=dist.ReduceOp.MAX)
+    buf = torch.zeros(int(width.item()) + 1, dtype=torch.float64, device=dev)
     if s is not None:
         buf[:-1] = s.to(dev)
         buf[-1] = len(chunk_grads)
@@ -84,7 +97,7 @@ def all_reduce_grads_(tensors):
     rank, ws = world()
     if ws == 1 or not tensors:
         return tensors
-    flat = torch.cat([t.reshape(-1) for t in tensors])
+    flat = torch.cat([t.reshape(-1) for t in tensors]).to(_collective_device())
     dist.all_reduce(flat, op=dist.ReduceOp.SUM)
     off = 0
     for t in tensors:

@@ -22,7 +22,7 @@ import torch.nn as nn
 import torch.nn.functional as F  # noqa: F401  (RN:6 star-exports it: `from utils.run_nerf_noscale import *` users may rely on `F`)
 
 from . import _lib
-from ._lib import FLAG_FAST_FP16, FLAG_LINDISP, FLAG_MIXED_F8, FLAG_PTS_INPUT, FLAG_WHITE_BKGD, check, lib, ptr
+from ._lib import FLAG_DENSE, FLAG_FAST_FP16, FLAG_LINDISP, FLAG_MIXED_F8, FLAG_PTS_INPUT, FLAG_WHITE_BKGD, check, lib, ptr
 
 device = torch.device('cuda' if torch.cuda.is_available() else 'cpu')
 
@@ -32,13 +32,16 @@ device = torch.device('cuda' if torch.cuda.is_available() else 'cpu')
 MIN_RAYS_PER_LAUNCH = int(os.environ.get('NSR_MIN_CHUNK', 1 << 16))
 
 # MLP arithmetic of the forward pass (DESIGN.md "precision"):
-#   'fp16x3'  error-compensated fp16 hi/lo split everywhere (3 MMAs per product): ~1e-5 from the fp32 reference;
+#   'fp16x3'  error-compensated fp16 hi/lo split (3 MMAs per product): ~1e-5 from the fp32 reference.  The render entry points
+#             apply it to the ACTIVE sample points only -- a cheap first tier certifies the empty ones (sigma <= 0: weight exactly
+#             0), see include/nsr_b200.h "two-tier evaluation"; the maps are bit-identical to evaluating every point;
+#   'fp16x3-dense'  the same arithmetic on every point (NSR_FLAG_DENSE);
 #   'mixed'   the split for the first three layers, fp16 + e4m3 residual products (NSR_FLAG_MIXED_F8) for the rest:
 #             2.25 tensor passes per product, ~2e-4 from the reference -- inside the 1e-3 bar;
 #   'fp16'    single fp16 MMA per product (NSR_FLAG_FAST_FP16): misses the bar on silhouette rays, opt-in only.
 # Passes that carry gradient always run 'fp16x3' (the backward kernel recomputes activations in that arithmetic).
 PRECISION = os.environ.get('NSR_PRECISION', 'fp16x3')
-_PREC_FLAGS = {'fp16x3': 0, 'mixed': FLAG_MIXED_F8, 'fp16': FLAG_FAST_FP16}
+_PREC_FLAGS = {'fp16x3': 0, 'fp16x3-dense': FLAG_DENSE, 'mixed': FLAG_MIXED_F8, 'fp16': FLAG_FAST_FP16}
 
 
 def set_precision(mode):
@@ -318,8 +321,9 @@ def _mask_fits(n_bytes, dev):
 
 def _forward_impl(rays, cfg, keep_for_backward, save_mask=False, save_dump=False):
     """One call of nsr_render_rays_forward(_ex).  Returns (outputs tuple, saved) with saved = (z_vals [n,T], raw [n,T,4],
-    z0 [n,S], raw0 [n,S,4], relu_mask, dump) of the last and (when N_importance > 0) the coarse pass, or Nones.
-    save_dump (training batches): the last pass also writes its activations for the weight-gradient GEMMs (~5 KB per point)."""
+    z0 [n,S], raw0 [n,S,4], relu_mask, dump, active_set) of the last and (when N_importance > 0) the coarse pass, or Nones.
+    save_dump (training batches): the last pass also writes its activations for the weight-gradient GEMMs (~5 KB per point).
+    A caller-visible raw (retraw=True) forces the dense evaluation: the two-tier route leaves (0,0,0,sigma~) at empty points."""
     L = lib()
     n, dev = rays.shape[0], rays.device
     S, Ni = cfg['S'], cfg['Ni']
@@ -333,7 +337,11 @@ def _forward_impl(rays, cfg, keep_for_backward, save_mask=False, save_dump=False
     zv = new(n, T) if keep_for_backward else None
     ws_bytes = L.nsr_render_workspace_bytes(n, S, Ni)
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
-    mask = dump = None
+    mask = dump = aset = None
+    flags = cfg['flags'] | (FLAG_DENSE if cfg['retraw'] else 0)
+    if keep_for_backward and not save_dump and n > 0 and not (flags & (FLAG_FAST_FP16 | FLAG_MIXED_F8 | FLAG_DENSE)):
+        # pose path: the backward pass only visits the active points of the last pass (dL/draw == 0 exactly elsewhere)
+        aset = torch.empty(L.nsr_active_set_bytes(n, T), dtype=torch.uint8, device=dev)
     if (save_mask or save_dump) and keep_for_backward and SAVE_RELU_MASK and n > 0 and not (cfg['flags'] & (FLAG_FAST_FP16 | FLAG_MIXED_F8)):
         mb = L.nsr_relu_mask_bytes(n, T)
         db = L.nsr_mlp_dump_bytes(n, T) if save_dump else 0
@@ -344,18 +352,21 @@ def _forward_impl(rays, cfg, keep_for_backward, save_mask=False, save_dump=False
                     dump = torch.empty(db, dtype=torch.uint8, device=dev)
             except torch.cuda.OutOfMemoryError:
                 mask = dump = None               # the recompute route needs neither
-    check(L.nsr_render_rays_forward_ex(ptr(rays), n, ptr(cfg['pc']), ptr(cfg['pf']), S, Ni, cfg['flags'], ptr(cfg['t_rand']), ptr(cfg['u']),
+    check(L.nsr_render_rays_forward_ex(ptr(rays), n, ptr(cfg['pc']), ptr(cfg['pf']), S, Ni, flags, ptr(cfg['t_rand']), ptr(cfg['u']),
                                        ptr(rgb), ptr(disp), ptr(acc), ptr(rgb0), ptr(disp0), ptr(acc0), ptr(zstd),
-                                       ptr(raw), ptr(zv), None, ptr(mask), ptr(dump), ptr(ws), ws_bytes, _stream()), 'nsr_render_rays_forward')
+                                       ptr(raw), ptr(zv), None, ptr(mask), ptr(dump), ptr(aset), ptr(ws), ws_bytes, _stream()), 'nsr_render_rays_forward')
     z0 = raw0 = None
     if keep_for_backward and Ni > 0:
-        # the coarse pass's depths and raw outputs sit at the head of the workspace (include/nsr_b200.h layout: z0 | w0 | raw0 | ...)
-        a256 = lambda x: (x + 255) // 256 * 256
-        o_z0, o_raw0 = 0, 2 * a256(n * S * 4)
-        z0 = ws[o_z0:o_z0 + n * S * 4].view(torch.float32).view(n, S).clone()
-        raw0 = ws[o_raw0:o_raw0 + n * S * 16].view(torch.float32).view(n, S, 4).clone()
+        # the coarse pass's depths and raw outputs are left in the workspace (nsr_render_workspace_layout: z0 | w0 | raw0 | ...).
+        # (After a two-tier pass raw0 holds (0,0,0,sigma~) at the certified-empty points: alpha == 0 there either way, so a
+        # backward pass through rgb0 gets the same -- zero -- dL/draw for them.)
+        off = (ctypes.c_size_t * 8)()
+        if L.nsr_render_workspace_layout(n, S, Ni, off, 8) != 8:
+            check(-1, 'nsr_render_workspace_layout')
+        z0 = ws[off[0]:off[0] + n * S * 4].view(torch.float32).view(n, S).clone()
+        raw0 = ws[off[2]:off[2] + n * S * 16].view(torch.float32).view(n, S, 4).clone()
     outs = [rgb, disp, acc] + ([rgb0, disp0, acc0, zstd] if Ni > 0 else []) + ([raw] if cfg['retraw'] else [])
-    return tuple(outs), (zv, raw, z0, raw0, mask, dump)
+    return tuple(outs), (zv, raw, z0, raw0, mask, dump, aset)
 
 
 def _params_of(net):
@@ -374,8 +385,11 @@ class _RenderRaysFn(torch.autograd.Function):
         pose_only = not any(torch.is_tensor(p) and p.requires_grad for p in params)     # RN:168-181: no dL/dMLP wanted
         # pose path: keep the ReLU sign bits; training batches: the activations of the last pass too -- either way the backward
         # kernel of that pass recomputes nothing (whole images with parameter gradients do not fit: _mask_fits decides)
-        outs, saved = _forward_impl(rays, cfg, keep_for_backward=True, save_mask=True, save_dump=not pose_only)
-        ctx.relu_mask, ctx.dump = saved[4], saved[5]
+        # (rays that require grad = the pose path even if the modules' parameters carry the nn.Module default requires_grad=True, as
+        # in the unpatched render_path_grad loop, RN:168-181: no activation dump then; should the caller ask for parameter gradients
+        # after all, the backward pass recomputes what it needs)
+        outs, saved = _forward_impl(rays, cfg, keep_for_backward=True, save_mask=True, save_dump=not pose_only and not ray_batch.requires_grad)
+        ctx.relu_mask, ctx.dump, ctx.active_set = saved[4], saved[5], saved[6]
         ctx.save_for_backward(rays, *[t for t in saved[:4] if t is not None])
         ctx.have_coarse = saved[2] is not None
         ctx.cfg = cfg
@@ -386,7 +400,7 @@ class _RenderRaysFn(torch.autograd.Function):
         return outs
 
     @staticmethod
-    def _one_pass(rays, zv, raw, net_blob, flags, g, want_dump, relu_mask=None, fwd_dump=None):
+    def _one_pass(rays, zv, raw, net_blob, flags, g, want_dump, relu_mask=None, fwd_dump=None, active_set=None):
         L = lib()
         n, T = zv.shape
         d_rays = torch.empty(n, 11, dtype=torch.float32, device=rays.device)
@@ -394,16 +408,20 @@ class _RenderRaysFn(torch.autograd.Function):
         ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=rays.device)
         dump = grads = dWp = dBp = None
         if want_dump:   # parameter gradients: the kernels ADD this pass's dL/dW, dL/db into zero-initialised fp32 tensors
-            dump = fwd_dump if fwd_dump is not None else torch.empty(L.nsr_mlp_dump_bytes(n, T), dtype=torch.uint8, device=rays.device)
+            try:
+                dump = fwd_dump if fwd_dump is not None else torch.empty(L.nsr_mlp_dump_bytes(n, T), dtype=torch.uint8, device=rays.device)
+            except torch.cuda.OutOfMemoryError as e:
+                raise _lib.NsrError(f'parameter gradients of {n} rays x {T} samples need {L.nsr_mlp_dump_bytes(n, T) >> 20} MiB of scratch '
+                                    '(~10 KB per sample point): render in smaller chunks') from e
             shapes = _EXPECTED_SHAPES
             grads = [torch.zeros(s, dtype=torch.float32, device=rays.device) for s in shapes] + \
                     [torch.zeros(s[0], dtype=torch.float32, device=rays.device) for s in shapes]
             dWp = (ctypes.c_void_p * 12)(*[t.data_ptr() for t in grads[:12]])
             dBp = (ctypes.c_void_p * 12)(*[t.data_ptr() for t in grads[12:]])
         if want_dump and fwd_dump is None:
-            relu_mask = None                     # parameter gradients need the activations: recompute them unless the forward pass dumped them
+            relu_mask = active_set = None        # parameter gradients need every activation: recompute them (densely) unless the forward pass dumped them
         check(L.nsr_render_rays_backward_ex(ptr(rays), ptr(zv), ptr(raw), n, T, ptr(net_blob), flags, ptr(g), ptr(d_rays), ptr(dump),
-                                            dWp, dBp, ptr(relu_mask), ptr(ws), ws_bytes, _stream()), 'nsr_render_rays_backward')
+                                            dWp, dBp, ptr(relu_mask), ptr(active_set), ptr(ws), ws_bytes, _stream()), 'nsr_render_rays_backward')
         return d_rays, grads
 
     @staticmethod
@@ -426,7 +444,7 @@ class _RenderRaysFn(torch.autograd.Function):
             blob = cfg['pc'] if fine_is_coarse else cfg['pf']
             want = need_c if fine_is_coarse else need_f
             dr, gr = _RenderRaysFn._one_pass(rays, zv, raw, blob, wflag, d_rgb.detach().float().contiguous(), want, ctx.relu_mask,
-                                             ctx.dump if (want and ctx.relu_mask is not None) else None)
+                                             ctx.dump if (want and ctx.relu_mask is not None) else None, ctx.active_set)
             d_rays = dr
             if fine_is_coarse:
                 g_c = gr
@@ -705,7 +723,8 @@ def render_image_grad(H, W, K, c2w, g_rgb, **kw):
     cfg = dict(pc=pc, pf=pf, S=S, Ni=Ni, flags=flags, t_rand=None, u=None, retraw=False)
     with torch.no_grad():
         outs, saved = _forward_impl(rays, cfg, keep_for_backward=True, save_mask=False)
-        d_rays, _ = _RenderRaysFn._one_pass(rays, saved[0], saved[1], pf if pf is not None else pc, flags & FLAG_WHITE_BKGD, g, False, None)
+        d_rays, _ = _RenderRaysFn._one_pass(rays, saved[0], saved[1], pf if pf is not None else pc, flags & FLAG_WHITE_BKGD, g, False, None,
+                                            None, saved[6])
         d_c2w = rays_grad_to_c2w(H, W, K, rays, d_rays)
     return outs[0].view(H, W, 3), d_c2w
 
@@ -720,7 +739,7 @@ class _AsyncImageWriter:
     def _pinned(self, key, t, slot):
         k = (key, tuple(t.shape), t.dtype, slot)
         if k not in self.slots:
-            self.slots[k] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+            self.slots[k] = torch.empty(t.shape, dtype=t.dtype, device='cpu', pin_memory=True)
         return self.slots[k]
 
     def submit(self, index, tensors, on_ready):
@@ -890,7 +909,7 @@ _train_cache = weakref.WeakKeyDictionary()      # optimizer -> cached pointer ta
 def _adam_state(optimizer, p):
     st = optimizer.state[p]
     if len(st) == 0:                                        # as torch.optim.Adam initialises it lazily
-        st['step'] = torch.tensor(0.0, dtype=torch.float32)
+        st['step'] = torch.tensor(0.0, dtype=torch.float32, device='cpu')
         st['exp_avg'] = torch.zeros_like(p, memory_format=torch.preserve_format)
         st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
     return st

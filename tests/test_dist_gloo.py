@@ -41,6 +41,8 @@ def worker(rank, world, port, q):
     # fewer images than ranks: rank 1 renders nothing, the mean is still over the chunks that exist
     lone = D.reduce_psi_grad(chunks[:2] if rank == 0 else [])
     ok_psi = ok_psi and torch.allclose(lone, torch.stack(chunks[:2]).mean(0), atol=1e-6)
+    # device of the collective follows the backend, not the inputs (render_path_grad hands back CPU tensors, RN:190)
+    ok_psi = ok_psi and D._collective_device().type == 'cpu' and red.device.type == 'cpu'
     poses, (plo, phi) = D.shard_poses(list(range(50)))
     grads = [torch.full((3,), float(rank + 1)), torch.full((2, 2), float(10 * (rank + 1)))]
     D.all_reduce_grads_(grads)
@@ -75,3 +77,12 @@ def test_world_size_2_gloo():
     for r in res:
         assert all(r[1:5]), r
     assert sum(r[5] for r in res) == 50
+
+
+def test_reduce_psi_grad_single_process_edge_cases():
+    import neural_sim_nerf_b200.dist as D
+    g = [torch.arange(8.), torch.ones(8)]
+    assert torch.allclose(D.reduce_psi_grad(g), (g[0] + g[1]) / 2)
+    with pytest.raises(ValueError):
+        D.reduce_psi_grad([])
+    assert torch.equal(D.reduce_psi_grad([], n_psi=8), torch.zeros(8))

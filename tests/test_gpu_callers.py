@@ -150,7 +150,7 @@ def test_render_path_and_render_path_grad(nsr, nets, tmp_path):
     got_mean = torch.mean(torch.stack(dLdpsis), 0)
     assert rgbs.shape == (2, H, W, 3) and len(dLdpsis) == 2
     scale = ref_mean.abs().max().item()
-    assert (got_mean - ref_mean).abs().max().item() <= 2e-3 * scale, (got_mean, ref_mean)
+    assert (got_mean - ref_mean).abs().max().item() <= 1e-3 * scale, (got_mean, ref_mean)
     assert os.path.exists(tmp_path / '2' / 'withgrad' / '001.png')
     # --- render_path
     imgs, disps = nsr.render_path(prob, [p.detach() for p in poses], hwf, Kc, chunk, kw, savedir=str(tmp_path), object_id=2)
@@ -232,4 +232,43 @@ def test_bilevel_psi_gradient_end_to_end(nsr, wfit, nets):
     got_mean = torch.stack(dLdpsis).mean(0)
     scale = ref_mean.abs().max().item()
     assert scale > 0
-    assert (got_mean - ref_mean).abs().max().item() <= 2e-3 * scale, (got_mean, ref_mean)
+    assert (got_mean - ref_mean).abs().max().item() <= 1e-3 * scale, (got_mean, ref_mean)
+
+
+_STAND_IN = '''
+def render(*args, **kwargs):
+    raise RuntimeError("the stand-in module's own render() must have been replaced")
+
+
+def render_path(render_poses, hwf, K, chunk, render_kwargs):
+    """shaped like the reference's image loop: `render` is looked up in THIS module's globals at call time (RN:233)"""
+    H, W, focal = hwf
+    frames = []
+    for c2w in render_poses:
+        rgb, disp, acc, extras = render(H, W, K, chunk=chunk, c2w=c2w[:3, :4], **render_kwargs)
+        frames.append(rgb)
+    return frames
+'''
+
+
+def test_install_on_a_stand_in_module_runs_on_the_gpu(nsr, nets):
+    """install() (INTEGRATION.md's two-line binding) on a minimal module whose image loop resolves `render` through its own
+    globals like RN:233 does: after the patch the loop renders on the GPU, with the same pixels as calling nsr.render directly
+    (the CPU test tests/test_host_logic.py does the same on the unmodified reference module)."""
+    import types
+    mod = types.ModuleType('stand_in_run_nerf')
+    exec(_STAND_IN, mod.__dict__)
+    poses = torch.stack([O.pose_spherical(90., 22.5 - 180., 1.01), O.pose_spherical(90., 202.5 - 180., 1.01)]).cuda()
+    with pytest.raises(RuntimeError):
+        mod.render_path(poses, [24, 24, 80.], K24, 512, kwargs(nets))
+    assert nsr.install(mod) is mod
+    assert mod.render is nsr.render and mod.render_path.__globals__['render'] is nsr.render
+    before = nsr.lib().nsr_launch_count()
+    with torch.no_grad():
+        frames = mod.render_path(poses, [24, 24, 80.], K24, 512, kwargs(nets))
+        direct = [nsr.render(24, 24, K24, chunk=512, c2w=p[:3, :4], **kwargs(nets))[0] for p in poses]
+    assert nsr.lib().nsr_launch_count() > before
+    assert len(frames) == 2 and frames[0].shape == (24, 24, 3) and frames[0].is_cuda
+    for a, b in zip(frames, direct):
+        assert torch.equal(a, b)
+    assert float(frames[0].max()) > 0.05, 'the fitted object must be visible'

@@ -182,6 +182,8 @@ def test_train_step_vs_cpu_oracle(nsr, wfit):
                     g = opt.state[p]['exp_avg'] / 0.1
                     scale = float(g_ref[(k, n)].abs().max())
                     if scale > 0:
+                        # (the oracle resamples its own fine depths here: RH:239 bin flips add to the arithmetic error, so this end-to-end
+                        # bound is looser than the 1e-3 of tests/test_gpu_backward.py, which compares on identical sample positions)
                         assert float((g.cpu() - g_ref[(k, n)]).abs().max()) <= 3e-3 * scale, (k, n)
     # an Adam step moves every coordinate by at most ~lr: after two steps the two trajectories may differ by a fraction of that where
     # a tiny gradient changes sign between the two arithmetic routes; bound the bulk tightly and the worst case by the step size

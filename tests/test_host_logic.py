@@ -187,3 +187,47 @@ def test_philox_known_answers():
     assert u.dtype == np.float32 and u.shape == (10001,) and 0.0 <= u.min() and u.max() < 1.0
     assert abs(float(u.mean()) - 0.5) < 0.01
     assert np.array_equal(u[:37], O.philox_uniform(1234, 1, 37))            # addressable by index: a prefix is a prefix
+
+
+_PATCHED = ['render', 'batchify_rays', 'render_rays', 'run_network', 'raw2outputs', 'sample_pdf', 'get_rays']
+
+
+@pytest.mark.skipif(not ref_import.available(), reason='reference tree only exists in the build container')
+def test_install_rebinds_the_live_reference_module(wfit, tmp_path):
+    """The two-line binding of INTEGRATION.md on the UNMODIFIED reference module: after nsr.install(RN) the reference's own image
+    loops resolve `render` to this package (render_path RN:233 and render_path_grad RN:168 look it up in RN's globals), a
+    star-import of the module (MAIN:35) hands out the new functions, and a call through RN.render_path lands in our code -- which
+    refuses CPU tensors instead of emulating (no GPU in this container)."""
+    RN, RH = ref_import.load()
+    saved = {k: getattr(RN, k) for k in _PATCHED + ['render_path', 'render_path_grad']}
+    ref_render_path, ref_render_path_grad = RN.render_path, RN.render_path_grad
+    try:
+        assert nsr.install(RN) is RN
+        for k in _PATCHED:
+            assert getattr(RN, k) is getattr(nsr, k), k
+        assert RN.render_path is ref_render_path and RN.render_path_grad is ref_render_path_grad      # loops=False keeps the loops
+        assert ref_render_path.__globals__['render'] is nsr.render                                    # RN:233
+        assert ref_render_path_grad.__globals__['render'] is nsr.render                               # RN:168
+        assert ref_render_path_grad.__globals__['get_rays'] is nsr.get_rays                           # RN:148
+        ns = {}
+        exec('from utils.run_nerf_noscale import *', ns)                                              # MAIN:35
+        assert ns['render'] is nsr.render and ns['render_path'] is ref_render_path and ns['render_rays'] is nsr.render_rays
+        # drive the reference's own loop: it must reach this package's render(), which fails loudly without a GPU
+        nets = []
+        for sd in wfit:
+            m = nsr.NeRF()
+            m.load_state_dict(sd)
+            nets.append(m)
+        kw = dict(network_fn=nets[0], network_query_fn=None, N_samples=8, N_importance=8, network_fine=nets[1], use_viewdirs=True,
+                  ndc=False, near=0.3, far=1.9, white_bkgd=False, raw_noise_std=0., perturb=False)
+        poses = O.pose_spherical(90., 22.5 - 180., 1.01)[None]
+        if not torch.cuda.is_available():
+            with pytest.raises(RuntimeError) as ei:            # NsrError or torch's "no NVIDIA driver": either way raised from OUR render()
+                ref_render_path(None, poses, [4, 4, 100.], [[100., 0, 2.], [0, 100., 2.], [0, 0, 1]], 512, kw, savedir=str(tmp_path))   # RN:227 needs a savedir
+            frames = [f.path for f in ei.traceback]
+            assert any(str(f).endswith('run_nerf_noscale.py') for f in frames) and any(str(f).endswith('neural-sim-nerf_b200/run_nerf.py') for f in frames), frames
+        assert nsr.install(RN, loops=True) is RN
+        assert RN.render_path is nsr.render_path and RN.render_path_grad is nsr.render_path_grad
+    finally:
+        for k, v in saved.items():
+            setattr(RN, k, v)

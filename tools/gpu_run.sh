@@ -7,6 +7,10 @@ tests)
   timeout 1200 python -m pytest tests -m gpu -q -rA -s > gpurun_out/pytest_gpu.txt 2>&1
   echo "pytest exit $?" >> gpurun_out/pytest_gpu.txt
   grep -E "passed|failed|PASSED|FAILED|max err|err:" gpurun_out/pytest_gpu.txt | tail -40 ;;
+tt)
+  timeout 900 python -m pytest tests/test_gpu_two_tier.py -m gpu -q -rA -s -x > gpurun_out/pytest_tt.txt 2>&1
+  echo "pytest exit $?" >> gpurun_out/pytest_tt.txt
+  grep -E "passed|failed|PASSED|FAILED|active|Error|error|assert" gpurun_out/pytest_tt.txt | tail -40 ;;
 smoke)
   timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.txt 2>&1
   echo "smoke exit $?" >> gpurun_out/smoke.txt; tail -3 gpurun_out/smoke.txt ;;

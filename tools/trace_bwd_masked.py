@@ -18,9 +18,9 @@ rgb, raw, zv = new(n, 3), new(n, T, 4), new(n, T)
 ws = torch.empty(L.nsr_render_workspace_bytes(n, S, Ni), dtype=torch.uint8, device='cuda')
 mask = torch.empty(L.nsr_relu_mask_bytes(n, T), dtype=torch.uint8, device='cuda')
 assert L.nsr_render_rays_forward_ex(P(rays), n, P(pc), P(pf), S, Ni, 0, None, None, P(rgb), None, None, None, None, None, None, P(raw), P(zv), None,
-                                    P(mask), None, P(ws), ws.numel(), None) == 0
+                                    P(mask), None, None, P(ws), ws.numel(), None) == 0
 g = torch.randn(n, 3, device='cuda'); d_rays = new(n, 11)
 bws = torch.empty(L.nsr_render_backward_workspace_bytes(n, T), dtype=torch.uint8, device='cuda')
 for _ in range(2):
-    assert L.nsr_render_rays_backward_ex(P(rays), P(zv), P(raw), n, T, P(pf), 0, P(g), P(d_rays), None, None, None, P(mask), P(bws), bws.numel(), None) == 0
+    assert L.nsr_render_rays_backward_ex(P(rays), P(zv), P(raw), n, T, P(pf), 0, P(g), P(d_rays), None, None, None, P(mask), None, P(bws), bws.numel(), None) == 0
 torch.cuda.synchronize()
