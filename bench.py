@@ -10,8 +10,11 @@ has no early termination).  A step = one forward render of all rays of one image
 
 One JSON line on stdout (rank 0).  `value` = whole-job rays/s with the rays resident in HBM;
 `e2e` = the same through the public render(rays=...) call with pinned-host rays copied in and
-rgb/disp/acc copied out every step; `roofline` = the fine-pass MLP kernel against the measured
-bf16 tensor peak; `cpu_baseline` = the oracle port on the host cores on a bounded ray sample.
+rgb/disp/acc copied out every step; `roofline` = the dominant MLP kernel against the measured
+bf16 tensor peak (`roofline_kernels`: every MLP kernel of the forward and backward passes, `roofline_step`:
+the whole step in reference-algorithm FLOPs); `cpu_baseline` = the oracle port on the host cores on a bounded
+ray sample; `parity` = the timed image's pixels against those CPU-rendered rays (the run FAILS above 1e-3);
+`baselines` = the other BASELINE configs on the host cores and the eager-PyTorch path on this GPU.
 """
 import argparse
 import json
@@ -30,6 +33,8 @@ H = W = 400
 N_SAMPLES, N_IMPORTANCE = 64, 128
 RAYS_PER_IMAGE = H * W
 FLOP_PER_POINT = 2 * 593408                      # SURVEY.md §8(d) / BASELINE.md §3
+FLOP_PER_POINT_TIER1 = 2 * (63 * 256 + 4 * 256 * 256 + 319 * 256 + 2 * 256 * 256 + 256)   # pts_linears.0-7 + alpha head (RH:99-109)
+K_200 = [[666.6666870117188, 0.0, 97.715], [0.0, 667.11, 100.315], [0.0, 0.0, 1.0]]          # BASELINE config 1: the 400x400 camera / 2
 FLOP_PER_RAY = (N_SAMPLES + N_SAMPLES + N_IMPORTANCE) * FLOP_PER_POINT
 METRIC = 'rays/sec (64c+128f samples, 400x400)'
 
@@ -95,11 +100,11 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU legs (oracle port)
-def _cpu_setup(n_rays):
+def _cpu_setup(n_rays, pose_index=0, rank=0):
     import torch
     import nerf_oracle as O
     sdc, sdf = load_weights()
-    ro, rd = O.get_rays(H, W, O.YCBV_K_400, pose_for(0, 0))
+    ro, rd = O.get_rays(H, W, O.YCBV_K_400, pose_for(pose_index, rank))
     sel = torch.linspace(0, RAYS_PER_IMAGE - 1, n_rays).long()
     rays = torch.stack([ro.reshape(-1, 3)[sel], rd.reshape(-1, 3)[sel]], 0)
     kw = dict(near=O.YCBV_NEAR, far=O.YCBV_FAR, N_samples=N_SAMPLES, N_importance=N_IMPORTANCE)
@@ -128,19 +133,105 @@ def pick_cpu_threads(run, rays):
     return best
 
 
-def cpu_render_rate(n_rays, repeats):
+def cpu_render_rate(n_rays, repeats, pose_index=0, rank=0):
     """The reference algorithm (oracle restatement, same chunk=512 / netchunk=65536 structure as
-    RN:43-55 / RN:14-23) on the host cores; returns rays/s over `repeats` passes of `n_rays` rays."""
+    RN:43-55 / RN:14-23) on the host cores; returns rays/s over `repeats` passes of `n_rays` rays, the thread count, the
+    pass times and the rendered maps of the last pass (what `parity` compares the GPU image with)."""
     import torch
-    rays, run = _cpu_setup(n_rays)
+    rays, run = _cpu_setup(n_rays, pose_index, rank)
     threads = pick_cpu_threads(run, rays)
     times = []
+    out = None
     with torch.no_grad():
         for _ in range(repeats):
             t0 = time.perf_counter()
-            run(rays)
+            out = run(rays)
             times.append(time.perf_counter() - t0)
-    return n_rays / (sum(times) / len(times)), threads, times
+    return n_rays / (sum(times) / len(times)), threads, times, out
+
+
+def cpu_config1_rate(n_rays):
+    """BASELINE config 1 on the host cores: 200x200 camera, 64 coarse samples only (RN:58 with N_importance = 0), chunk 512."""
+    import torch
+    import nerf_oracle as O
+    sdc, _ = load_weights()
+    ro, rd = O.get_rays(200, 200, K_200, pose_for(0, 0))
+    sel = torch.linspace(0, 200 * 200 - 1, n_rays).long()
+    rays = torch.stack([ro.reshape(-1, 3)[sel], rd.reshape(-1, 3)[sel]], 0)
+    run = lambda: O.render(200, 200, K_200, sdc, None, chunk=512, rays=rays, near=O.YCBV_NEAR, far=O.YCBV_FAR, N_samples=64, N_importance=0)
+    with torch.no_grad():
+        run()
+        t0 = time.perf_counter()
+        run()
+        dt = time.perf_counter() - t0
+    return n_rays / dt, dt
+
+
+def cpu_config3_rate(n_rays):
+    """BASELINE config 3 on the host cores, the pattern of RN:168-181: per 512-ray chunk render (retraw) with autograd, then
+    autograd.grad(rgb, batch_rays, grad_outputs=grad_E chunk)."""
+    import torch
+    import nerf_oracle as O
+    sdc, sdf = load_weights()
+    ro, rd = O.get_rays(H, W, O.YCBV_K_400, pose_for(0, 0))
+    sel = torch.linspace(0, RAYS_PER_IMAGE - 1, n_rays).long()
+    o, d = ro.reshape(-1, 3)[sel], rd.reshape(-1, 3)[sel]
+    g = torch.randn(n_rays, 3, generator=torch.Generator().manual_seed(0))
+
+    def run():
+        for i in range(0, n_rays, 512):
+            batch = torch.stack([o[i:i + 512], d[i:i + 512]], 0).requires_grad_(True)
+            rgb = O.render(H, W, O.YCBV_K_400, sdc, sdf, chunk=512, rays=batch, near=O.YCBV_NEAR, far=O.YCBV_FAR, N_samples=N_SAMPLES,
+                           N_importance=N_IMPORTANCE, retraw=True)[0]
+            torch.autograd.grad(rgb, batch, grad_outputs=g[i:i + 512])
+    t0 = time.perf_counter()
+    run()
+    dt = time.perf_counter() - t0
+    return n_rays / dt, dt
+
+
+def eager_gpu_rates(dev):
+    """The reference algorithm as eager PyTorch on THIS GPU (the oracle restatement with every tensor on cuda: the kernels
+    nn.Linear / sin / cumprod / searchsorted / sort dispatch to, fp32) -- the baseline SURVEY.md 2.1 names ("beat eager PyTorch").
+    TF32 off (true fp32, what the reference gets by default) and on; the reference's chunk = 512 (CFG:25) on a 16 384-ray
+    sample, and chunk = 32768 (nerf-pytorch's default) on the whole image."""
+    import torch
+    import nerf_oracle as O
+    sdc, sdf = load_weights()
+    sdc = {k: v.to(dev) for k, v in sdc.items()}
+    sdf = {k: v.to(dev) for k, v in sdf.items()}
+    out = {}
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    try:
+        with torch.device(dev), torch.no_grad():
+            ro, rd = O.get_rays(H, W, O.YCBV_K_400, pose_for(0, 0).to(dev))
+            for tf32 in (False, True):
+                torch.backends.cuda.matmul.allow_tf32 = tf32
+                torch.backends.cudnn.allow_tf32 = tf32
+                for chunk, n_rays in ((512, 16384), (32768, RAYS_PER_IMAGE)):
+                    sel = torch.linspace(0, RAYS_PER_IMAGE - 1, n_rays).long()
+                    rays = torch.stack([ro.reshape(-1, 3)[sel], rd.reshape(-1, 3)[sel]], 0)
+                    run = lambda: O.render(H, W, O.YCBV_K_400, sdc, sdf, chunk=chunk, rays=rays, near=O.YCBV_NEAR, far=O.YCBV_FAR,
+                                           N_samples=N_SAMPLES, N_importance=N_IMPORTANCE)
+                    run()
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    run()
+                    torch.cuda.synchronize()
+                    dt = time.perf_counter() - t0
+                    out[f'fp32_tf32_{"on" if tf32 else "off"}_chunk{chunk}'] = {'rays_per_s': n_rays / dt, 'rays': n_rays, 'seconds': dt}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    return out
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of each MLP kernel, from the committed ncu --set full captures
+    (profiles/ncu_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep files).  bench.py refuses to run without it:
+    a traffic regression must show up as a changed file, not as a stale literal."""
+    path = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    with open(path) as f:
+        return json.load(f), os.path.relpath(path, ROOT)
 
 
 def run_reference(args):

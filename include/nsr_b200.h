@@ -172,6 +172,13 @@ int nsr_render_rays_forward_ex(const float* rays, int64_t n_rays, const void* pa
                                float* z_std, float* raw, float* z_vals_out, float* weights_out, void* relu_mask,
                                void* dump_out, void* active_set, void* workspace, size_t workspace_bytes, void* stream);
 
+/* One network pass of the two-tier evaluation by itself (what nsr_render_rays_forward runs per pass), on depth input:
+ * stages is a bit mask -- 1: tier 1 (zeroes the control words, writes (0,0,0,sigma~) to raw_out for every point and fills the active
+ * list), 2: tier 2 (default arithmetic on the active points, raw_out and optionally relu_mask in active-list tile order),
+ * 4: the conditional dense re-evaluation.  7 = the whole pass.  For profiling and tests; raw_out [n,S,4], active_set as above. */
+int nsr_mlp_two_tier(const float* rays, const float* z_vals, int64_t n_rays, int n_samples, const void* packed_net, float* raw_out,
+                     void* active_set, void* relu_mask, int stages, void* stream);
+
 /* Knobs of the two-tier evaluation (process-wide; change them only while no work is being enqueued).  enabled = 0 makes every
  * pass dense.  Requires tau > verify_max >= 0.  nsr_get_two_tier: any pointer may be NULL. */
 int nsr_set_two_tier(int enabled, float tau, float verify_max, float force_fraction);
@@ -209,6 +216,12 @@ int nsr_render_rays_backward_ex(const float* rays, const float* z_vals, const fl
                                 const void* packed_net, uint32_t flags, const float* d_rgb_map, float* d_rays, void* dump,
                                 float* const* dW, float* const* dB, const void* relu_mask, const void* active_set, void* workspace,
                                 size_t workspace_bytes, void* stream);
+
+/* The MLP stage of the backward pass by itself (what nsr_render_rays_backward_ex runs between the compositing backward and the per-ray
+ * reduction): dL/draw [n,T,4] -> d_pts [n,T,8] = (dL/dpoint[3], 0, dL/dviewdir[3], 0) per sample.  relu_mask / active_set as above
+ * (with an active set the other points' rows are zeroed).  For profiling and tests. */
+int nsr_mlp_backward(const float* rays, const float* z_vals, int64_t n_rays, int n_total_samples, const void* packed_net, const float* d_raw,
+                     float* d_pts, const void* relu_mask, const void* active_set, void* stream);
 
 /*
  * Ray generation + packing.  Replaces RH:156-165 get_rays and RN:91-112 (use_viewdirs, ndc=False):

@@ -43,6 +43,8 @@ _SIGNATURES = {
                                             c_vp, c_size, c_vp]),
     'nsr_active_set_bytes': (c_size, [c_i64, c_int]),
     'nsr_render_workspace_layout': (c_int, [c_i64, c_int, c_int, c_vp, c_int]),
+    'nsr_mlp_two_tier': (c_int, [c_f32p, c_f32p, c_i64, c_int, c_vp, c_f32p, c_vp, c_vp, c_int, c_vp]),
+    'nsr_mlp_backward': (c_int, [c_f32p, c_f32p, c_i64, c_int, c_vp, c_f32p, c_f32p, c_vp, c_vp, c_vp]),
     'nsr_set_two_tier': (c_int, [c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float]),
     'nsr_get_two_tier': (c_int, [c_vp, c_vp, c_vp, c_vp]),
     'nsr_render_backward_workspace_bytes': (c_size, [c_i64, c_int]),

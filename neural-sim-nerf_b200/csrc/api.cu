@@ -146,6 +146,26 @@ int nsr_mlp_forward(const float* rays, const float* z_or_pts, int64_t n_rays, in
   return launch_mlp_forward(rays, z_or_pts, n_rays, n_samples, packed_net, flags, raw_out, static_cast<cudaStream_t>(stream));
 }
 
+int nsr_mlp_two_tier(const float* rays, const float* z_vals, int64_t n_rays, int n_samples, const void* packed_net, float* raw_out,
+                     void* active_set, void* relu_mask, int stages, void* stream) {
+  NSR_REQUIRE(n_rays >= 0 && n_samples > 0 && stages > 0 && stages < 8, "nsr_mlp_two_tier: bad sizes / stages");
+  if (n_rays == 0) return NSR_OK;
+  NSR_REQUIRE(rays && z_vals && packed_net && raw_out && active_set, "nsr_mlp_two_tier: null argument");
+  NSR_REQUIRE((reinterpret_cast<uintptr_t>(raw_out) & 15) == 0 && (reinterpret_cast<uintptr_t>(active_set) & 255) == 0 &&
+                  (reinterpret_cast<uintptr_t>(packed_net) & 127) == 0 && (reinterpret_cast<uintptr_t>(relu_mask) & 15) == 0,
+              "nsr_mlp_two_tier: raw_out must be 16-byte, active_set 256-byte, packed_net 128-byte, relu_mask 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint32_t* mask = static_cast<uint32_t*>(relu_mask);
+  int rc;
+  if (stages & 1) {
+    if (cudaMemsetAsync(active_set, 0, AS_CTRL_BYTES, st) != cudaSuccess) return check_launch("active_set init");
+    if ((rc = launch_mlp_forward(rays, z_vals, n_rays, n_samples, packed_net, 0, raw_out, st, nullptr, nullptr, AS_ROLE_TIER1, active_set))) return rc;
+  }
+  if ((stages & 2) && (rc = launch_mlp_forward(rays, z_vals, n_rays, n_samples, packed_net, 0, raw_out, st, mask, nullptr, AS_ROLE_TIER2, active_set))) return rc;
+  if ((stages & 4) && (rc = launch_mlp_forward(rays, z_vals, n_rays, n_samples, packed_net, 0, raw_out, st, mask, nullptr, AS_ROLE_REDO, active_set))) return rc;
+  return NSR_OK;
+}
+
 int nsr_raw2outputs(const float* raw, const float* z_vals, const float* rays_d, int ld_rays_d, int64_t n_rays,
                     int n_samples, uint32_t flags, float* rgb_map, float* disp_map, float* acc_map, float* weights,
                     float* depth_map, void* stream) {
@@ -223,7 +243,7 @@ static int mlp_pass(const float* rays, const float* z, int64_t n, int S, const v
   int rc;
   if ((rc = launch_mlp_forward(rays, z, n, S, packed, 0, raw, st, nullptr, nullptr, AS_ROLE_TIER1, as))) return rc;
   if ((rc = launch_mlp_forward(rays, z, n, S, packed, 0, raw, st, mask, nullptr, AS_ROLE_TIER2, as))) return rc;
-  return launch_mlp_forward(rays, z, n, S, packed, 0, raw, st, mask, nullptr, AS_ROLE_REDO, as);
+  return launch_mlp_forward(rays, z, n, S, packed, 0, raw, st, mask, nullptr, AS_ROLE_REDO, as);   // exits at once unless verification failed
 }
 
 int nsr_render_rays_forward_ex(const float* rays, int64_t n, const void* packed_coarse, const void* packed_fine, int S,
@@ -345,6 +365,20 @@ int nsr_render_rays_backward_ex(const float* rays, const float* z_vals, const fl
   if ((rc = launch_ray_grad_reduce(rays, z_vals, d_pts, d_dnorm, n, T, d_rays, st))) return rc;
   if (dW) return launch_weight_grads(dump, d_raw, n * int64_t(T), gmax, dW, dB, st);
   return NSR_OK;
+}
+
+int nsr_mlp_backward(const float* rays, const float* z_vals, int64_t n_rays, int n_total_samples, const void* packed_net, const float* d_raw,
+                     float* d_pts, const void* relu_mask, const void* active_set, void* stream) {
+  NSR_REQUIRE(n_rays >= 0 && n_total_samples > 0, "nsr_mlp_backward: bad sizes");
+  if (n_rays == 0) return NSR_OK;
+  NSR_REQUIRE(rays && z_vals && packed_net && d_raw && d_pts, "nsr_mlp_backward: null argument");
+  NSR_REQUIRE((reinterpret_cast<uintptr_t>(d_raw) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_pts) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(relu_mask) & 15) == 0 && (reinterpret_cast<uintptr_t>(active_set) & 255) == 0,
+              "nsr_mlp_backward: d_raw / d_pts / relu_mask must be 16-byte, active_set 256-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (active_set != nullptr && cudaMemsetAsync(d_pts, 0, size_t(n_rays) * n_total_samples * 32, st) != cudaSuccess) return check_launch("d_pts memset");
+  return launch_mlp_backward(rays, z_vals, n_rays, n_total_samples, packed_net, d_raw, d_pts, nullptr, nullptr, st,
+                             static_cast<const uint32_t*>(relu_mask), active_set);
 }
 
 int nsr_make_rays(int H, int W, const float* K_host, const float* c2w_host, float near_, float far_, float* rays_out, void* stream) {
