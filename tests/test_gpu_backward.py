@@ -1,8 +1,8 @@
 """GPU parity of the backward pass: dL/d(rays) from dL/d(rgb_map), against PyTorch autograd
 through the CPU oracle (the reference's own tape, RN:168-181, is autograd over the same ops).
 
-Tolerance: |d| <= 2e-3 * max|grad| per tensor (gradients of a sharp scene span many decades; the bound is relative
-to the largest component of the same gradient tensor) and a cosine similarity > 0.99999.
+Tolerance (check_grad): every element within 1e-3 * (max|grad| + |grad|) of the reference gradient, the largest deviation within
+1e-3 * max|grad| of the same tensor (gradients of a sharp scene span many decades), cosine similarity > 0.99999.
 """
 import numpy as np
 import pytest
@@ -108,43 +108,118 @@ def test_coarse_only_backward_and_unsupported_grads(nsr, wfit, nets):
     assert not out['acc_map'].requires_grad and not out['disp_map'].requires_grad   # not built -> not differentiable, loudly
 
 
+def decode_relu_bits(mask_u8, n_points):
+    """The forward pass's saved ReLU states (common.cuh MASK_*: per 128-point tile 68 words x 128 rows; word l*8+w = columns
+    [32w, 32w+32) of pts_linears.l, word 64+w of views_linears.0; bit j = column 2j, bit 16+j = column 2j+1)
+    -> (layers [P,8,256], views [P,128]) as float64 0/1."""
+    w = mask_u8.view(torch.int32).view(-1, 68, 128)
+    j = torch.arange(16, device=w.device)
+    even = (w[..., None] >> j) & 1
+    odd = (w[..., None] >> (16 + j)) & 1
+    bits = torch.stack([even, odd], -1).reshape(w.shape[0], 68, 128, 32).permute(0, 2, 1, 3).reshape(w.shape[0] * 128, 68 * 32)[:n_points]
+    return bits[:, :2048].reshape(n_points, 8, 256).double(), bits[:, 2048:2176].double()
+
+
+def conditioned_render(rays, z, sd, relu_layers, relu_views, sigma_on, white=False):
+    """RN:26-40 + RH:99-122 + RN:343-387 in float64 with every ReLU's on/off state GIVEN (h = a * state) instead of decided by the
+    sign of a: the function the backward kernels differentiate.  Returns rgb_map, the pre-activations and their noise scales
+    (sum |w||h| + |b|, what an fp32 rounding error of the dot product is proportional to)."""
+    lin = torch.nn.functional.linear
+    n, T = z.shape
+    r = rays.double()
+    pts = (r[:, None, 0:3] + r[:, None, 3:6] * z.double()[:, :, None]).reshape(-1, 3)
+    ex = O.embed(pts, O.N_FREQ_XYZ)
+    ev = O.embed(r[:, None, 8:11].expand(n, T, 3).reshape(-1, 3), O.N_FREQ_DIR)
+    pre, scale = [], []
+    h = ex
+    for i in range(8):
+        W, b = sd[f'pts_linears.{i}.weight'], sd[f'pts_linears.{i}.bias']
+        a = lin(h, W, b)
+        pre.append(a)
+        scale.append(lin(h.detach().abs(), W.detach().abs(), b.detach().abs()))
+        h = a * relu_layers[:, i]
+        if i == O.SKIP_AFTER:
+            h = torch.cat([ex, h], -1)
+    sigma = lin(h, sd['alpha_linear.weight'], sd['alpha_linear.bias'])
+    feat = lin(h, sd['feature_linear.weight'], sd['feature_linear.bias'])
+    hin = torch.cat([feat, ev], -1)
+    W, b = sd['views_linears.0.weight'], sd['views_linears.0.bias']
+    av = lin(hin, W, b)
+    pre.append(av)
+    scale.append(lin(hin.detach().abs(), W.detach().abs(), b.detach().abs()))
+    rgb = lin(av * relu_views, sd['rgb_linear.weight'], sd['rgb_linear.bias'])
+    raw = torch.cat([rgb, sigma * sigma_on.reshape(-1, 1)], -1).reshape(n, T, 4)      # RN:356's relu with its state given, too
+    out = O.raw2outputs(raw, z.double(), r[:, 3:6], None, white)
+    return out[0], pre, scale, sigma.reshape(n, T)
+
+
 def test_parameter_gradients_match_autograd(nsr, wfit):
-    """loss = mse(rgb, target) + mse(rgb0, target) (RN:691-696), loss.backward() -> dL/dMLP for BOTH networks."""
+    """loss = mse(rgb, target) + mse(rgb0, target) (RN:691-696), loss.backward() -> dL/dMLP for BOTH networks,
+    every element within 1e-3 * max|grad| of the float64 gradient.
+
+    What "the gradient" is needs care.  dL/dW is discontinuous in the last bits of the forward pass: a ReLU whose pre-activation
+    is within fp32 rounding noise of zero is ON in one correct fp32 evaluation and OFF in another, and one such unit at a point that
+    carries a large dL/draw moves dL/dW by ~2e-3 of its maximum on this very batch -- torch's own fp32 autograd on the CPU (MKL) and
+    on the GPU (cuBLAS) differ from each other by that amount (tools/dump_check.py prints it).  So the test pins exactly what is
+    well defined: (1) our gradient equals the float64 gradient of the network WITH THE RELU STATES OUR FORWARD PASS SAW (its saved
+    sign bits) to 1e-3 everywhere; (2) those states differ from the float64 signs only on units whose |pre-activation| is below
+    1e-5 of its rounding-noise scale sum|w||h|+|b| (measured: 9e-7), and on fewer than 1 unit in 10^5 (measured: 17 of 60 M); (3) the loss itself agrees to 1e-4."""
+    import ctypes
     rays = camera_rays(12, 22.5)
     n = rays.shape[0]
     target = torch.rand(n, 3, generator=torch.Generator().manual_seed(5))
-    # reference: autograd through the oracle with the state-dict tensors as leaves
     nets = []
     for sd in wfit:
         m = nsr.NeRF()
         m.load_state_dict(sd)
         nets.append(m.cuda())
-    # The fine depths come out of sample_pdf, whose `denom < 1e-5` branch (RH:239) flips on last-bit differences of
-    # the coarse weights; gradients are compared on identical sample positions, so take ours (C ABI, z_vals_out).
-    import ctypes
     L = nsr.lib()
     rg = rays.cuda()
-    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    P = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
     new = lambda *s: torch.empty(*s, device='cuda')
-    zf = new(n, 192)
-    o = [new(n, 3), new(n), new(n), new(n, 3), new(n), new(n), new(n)]
-    wsb = L.nsr_render_workspace_bytes(n, 64, 128)
-    ws = torch.empty(wsb, dtype=torch.uint8, device='cuda')
-    rc = L.nsr_render_rays_forward(P(rg), n, P(nsr.packed_weights(nets[0])), P(nsr.packed_weights(nets[1])), 64, 128, 0, None, None,
-                                   *[P(t) for t in o], None, P(zf), None, P(ws), wsb, None)
-    assert rc == 0, L.nsr_last_error()
-    torch.cuda.synchronize()
-    # reference: autograd through the oracle with the state-dict tensors as leaves
-    sdc = {k: v.clone().requires_grad_(True) for k, v in wfit[0].items()}
-    sdf = {k: v.clone().requires_grad_(True) for k, v in wfit[1].items()}
-    ref = O.render_rays(rays, sdc, sdf, 64, 128, z_fine=zf.cpu())
-    loss_ref = ((ref['rgb_map'] - target) ** 2).mean() + ((ref['rgb0'] - target) ** 2).mean()
-    loss_ref.backward()
+    pc, pf = nsr.packed_weights(nets[0]), nsr.packed_weights(nets[1])
+
+    def forward_states(S, Ni):
+        T = S + Ni
+        rgb, raw, zv = new(n, 3), new(n, T, 4), new(n, T)
+        ws = torch.empty(L.nsr_render_workspace_bytes(n, S, Ni), dtype=torch.uint8, device='cuda')
+        mask = torch.empty(L.nsr_relu_mask_bytes(n, T), dtype=torch.uint8, device='cuda')
+        rc = L.nsr_render_rays_forward_ex(P(rg), n, P(pc), P(pf), S, Ni, 0, None, None, P(rgb), None, None, None, None, None, None, P(raw), P(zv),
+                                          None, P(mask), None, None, P(ws), ws.numel(), None)
+        assert rc == 0, L.nsr_last_error()
+        torch.cuda.synchronize()
+        return zv, raw, decode_relu_bits(mask, n * T)
+    z0, raw0, st0 = forward_states(64, 0)          # the coarse pass (carries gradient through rgb0)
+    zf, rawf, stf = forward_states(64, 128)        # the last pass: the fine network on the merged depths
     # ours, through the public render_rays + loss.backward()
-    out = nsr.render_rays(rays.cuda(), nets[0], None, 64, N_importance=128, network_fine=nets[1])
+    out = nsr.render_rays(rg, nets[0], None, 64, N_importance=128, network_fine=nets[1])
     loss = ((out['rgb_map'] - target.cuda()) ** 2).mean() + ((out['rgb0'] - target.cuda()) ** 2).mean()
     loss.backward()
+    # float64 with the given ReLU states
+    sdc = {k: v.cuda().double().requires_grad_(True) for k, v in wfit[0].items()}
+    sdf = {k: v.cuda().double().requires_grad_(True) for k, v in wfit[1].items()}
+    rgb0_r, pre0, sc0, sig0 = conditioned_render(rg, z0, sdc, st0[0], st0[1], (raw0[..., 3] > 0).double())
+    rgb_r, pref, scf, sigf = conditioned_render(rg, zf, sdf, stf[0], stf[1], (rawf[..., 3] > 0).double())
+    loss_ref = ((rgb_r - target.cuda().double()) ** 2).mean() + ((rgb0_r - target.cuda().double()) ** 2).mean()
+    loss_ref.backward()
     assert abs(loss.item() - loss_ref.item()) <= 1e-4 * max(1.0, abs(loss_ref.item()))
+    # (2) the states are the float64 signs except at rounding level
+    for tag, pre, sc, st, sig, raw in (('coarse', pre0, sc0, st0, sig0, raw0), ('fine', pref, scf, stf, sigf, rawf)):
+        flips, units, worst = 0, 0, 0.0
+        for l in range(9):
+            a, s = pre[l].detach(), sc[l]
+            state = st[0][:, l] if l < 8 else st[1]
+            bad = (a > 0).double() != state
+            flips += int(bad.sum())
+            units += a.numel()
+            if bool(bad.any()):
+                worst = max(worst, float((a.abs() / s)[bad].max()))
+        bad = (sig.detach() > 0) != (raw[..., 3] > 0)
+        if bool(bad.any()):
+            worst = max(worst, float((sig.detach().abs()[bad]).max() / 60.0))
+        print(f'{tag}: {flips + int(bad.sum())} ReLU states of {units} differ from the float64 signs; largest |pre-activation| / noise scale among them {worst:.2e}')
+        assert worst <= 1e-5 and flips <= 1e-5 * units
+    # (1) gradients
     failures = []
     for net, sd, tag in ((nets[0], sdc, 'coarse'), (nets[1], sdf, 'fine')):
         for name, prm in net.named_parameters():
@@ -154,6 +229,13 @@ def test_parameter_gradients_match_autograd(nsr, wfit):
             except AssertionError as e:
                 failures.append(str(e))
     assert not failures, failures
+    # for the record: plain fp32 autograd (the reference's arithmetic, CPU) against the same float64 gradient
+    s32 = [{k: v.clone().requires_grad_(True) for k, v in sd.items()} for sd in wfit]
+    ref = O.render_rays(rays, s32[0], s32[1], 64, 128, z_fine=zf.cpu())
+    (((ref['rgb_map'] - target) ** 2).mean() + ((ref['rgb0'] - target) ** 2).mean()).backward()
+    worst32 = max(float((s32[1][k].grad.double() - sdf[k].grad.cpu()).abs().max() / sdf[k].grad.abs().max()) for k in sdf)
+    worst_us = max(float((p_.grad.double() - sdf[k].grad).abs().max() / sdf[k].grad.abs().max()) for k, p_ in nets[1].named_parameters())
+    print(f'fine network, worst tensor: torch fp32 CPU autograd vs state-conditioned float64 {worst32:.2e}; ours {worst_us:.2e}')
 
 
 def test_parameter_gradients_many_samples_no_resampling(nsr, wfit):
