@@ -281,6 +281,15 @@ struct MlpArgs {
   uint32_t verify_bits;       // re-evaluation launch: runs iff ctrl[AS_VMAX] > verify_bits
 };
 
+// debug experiments (NSR_EXPERIMENT, debug-hook builds only; results are garbage, timings isolate one cost each):
+//   1 no weight streaming after the first lap   2 epilogue skips its TMEM stores   3 epilogue skips the conversion arithmetic
+//   4 encoders skip sincosf   5 no MMA is issued (commits only)   100+g: grid limited to g CTAs
+#ifdef NSR_DEBUG_HOOKS
+#define NSR_EXP(n) (a.experiment == (n))
+#else
+#define NSR_EXP(n) false
+#endif
+
 #define NSR_TR(tl, step, slot)                                                                         \
   do {                                                                                                 \
     if (a.trace != nullptr && blockIdx.x == 0 && (tl) < 4) a.trace[((tl) * 10 + (step)) * 16 + (slot)] = clock64(); \
@@ -290,12 +299,30 @@ struct MlpArgs {
 // SAVE: also write the ReLU sign bits (a.relu_mask) and, when a.dump != NULL, the activation half of the weight-gradient dump
 // for the backward pass.  A separate instantiation, so the plain render kernel carries none of that code.
 // CLASSIFY: tier 1 of the two-tier evaluation (SPLIT = 1 only): GEMM steps 0..7 + alpha head, sigma~ and the active list out.
+// Warp roles: mlp_common.cuh (12 warps).  The tier-1 kernel (CLASSIFY) issues one MMA per product, so its step is bounded by the
+// latency of the epilogue, not by the tensor pipe (with no MMA issued at all it still took 82 % of its time): it runs 16 epilogue
+// warps, 8 per accumulator half, so that the two halves drain concurrently and each scheduler has four warps to hide latency behind.
+template <bool CLASSIFY>
+struct Roles {
+  static constexpr int EPI_WARPS = CLASSIFY ? 16 : 8;
+  static constexpr int ENC0 = EPI_WARPS, MMA = EPI_WARPS + 2, PROD = EPI_WARPS + 3;
+  static constexpr int THREADS = (EPI_WARPS + 4) * 32;
+};
+static_assert(Roles<false>::THREADS == MLP_THREADS && Roles<false>::ENC0 == ENC_WARP0 && Roles<false>::MMA == MMA_WARP &&
+              Roles<false>::PROD == PROD_WARP, "mlp_common.cuh warp roles");
+
 template <int SPLIT, bool SAVE, bool CLASSIFY>
-__global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
+__global__ void __launch_bounds__(Roles<CLASSIFY>::THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
   using C = Cfg<SPLIT>;
+  using R = Roles<CLASSIFY>;
   constexpr bool kSplit = C::kSplit;
   constexpr bool kMixed = C::kMixed;
   constexpr int kSteps = CLASSIFY ? 8 : NUM_STEPS;   // GEMM steps per tile
+#ifndef NSR_ACCFREE_SPLIT
+#define NSR_ACCFREE_SPLIT 0
+#endif
+  // hand ACC1 back to the MMA warp as soon as it is in registers (separate barrier) instead of with the activations it turns into
+  constexpr bool kAccFree = (SPLIT == 1) || NSR_ACCFREE_SPLIT;
   static_assert(!CLASSIFY || (SPLIT == 1 && !SAVE), "tier 1 is the single-pass fp16 arithmetic, nothing saved");
   // ---- role with respect to the active set: every thread of every CTA takes the same decision from the control block, which no
   // kernel of this launch's role modifies in the words read here
@@ -333,7 +360,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
   uint64_t* a_ready = acc_ready + 2;                               // [2]        epilogue (256) -> MMA
   uint64_t* enc_ready = a_ready + 2;                               // [0] xyz encoding, [1] view-dir encoding: encoders -> MMA
   uint64_t* enc_free = enc_ready + 2;                              // [0] after step 5, [1] after step 9: MMA commit -> encoders
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(enc_free + 2);
+  uint64_t* acc_free1 = enc_free + 2;                              // [1]        epilogue (256): ACC1 is in registers -> MMA (kAccFree)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free1 + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const size_t dumpP = size_t(a.num_tiles) * 128;   // (dump: dense launches only)   // rows of the optional dump
@@ -345,21 +373,29 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
     }
     for (int h = 0; h < 2; ++h) {
       mbar_init(&acc_ready[h], 1);
-      mbar_init(&a_ready[h], EPI_THREADS);
+      mbar_init(&a_ready[h], CLASSIFY ? R::EPI_WARPS * 32 : EPI_THREADS);
       mbar_init(&enc_ready[h], ENC_THREADS);
       mbar_init(&enc_free[h], 1);
     }
+    mbar_init(acc_free1, CLASSIFY ? R::EPI_WARPS * 32 : EPI_THREADS);
     fence_mbar_init();
   }
-  if (warp == MMA_WARP) tmem_alloc(tmem_slot, 512);
-  for (int i = tid; i < TAIL_FLOATS; i += MLP_THREADS)
+  if (warp == R::MMA) tmem_alloc(tmem_slot, 512);
+  for (int i = tid; i < TAIL_FLOATS; i += R::THREADS)
     reinterpret_cast<float*>(smem + C::SM_TAIL)[i] = reinterpret_cast<const float*>(a.packed + WEIGHT_BYTES)[i];
+  if constexpr (CLASSIFY) {   // tier 1 adds its biases in packed fp16: the table lives where the (unused) view-dir encoding would
+    static_assert(C::DIR_BYTES >= 8 * 256 * 2, "fp16 bias table");
+    for (int i = tid; i < 8 * 128; i += R::THREADS) {
+      const float2 b = reinterpret_cast<const float2*>(a.packed + WEIGHT_BYTES)[i];   // TAIL_BIAS == 0
+      reinterpret_cast<uint32_t*>(smem + C::SM_INBUF + C::OFF_DIR_HI)[i] = pack_f16x2(b.x, b.y);
+    }
+  }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   if (*tmem_slot != 0u) __trap();  // the whole TMEM of the SM is ours: the allocation must start at 0
 
-  if (warp == PROD_WARP) {
+  if (warp == R::PROD) {
     // ===================================================================== weight producer (TMA engine)
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
@@ -372,7 +408,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
             int nh, kc;
             issue_slot(nk, step_k_early(step), nhs, i, nh, kc);
             if (!first_lap) mbar_wait(&empty[stage], phase ^ 1);
-            if (a.experiment == 1 && !first_lap) {
+            if (NSR_EXP(1) && !first_lap) {
               mbar_arrive(&full[stage]);
             } else {
               mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
@@ -388,7 +424,75 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
         }
       }
     }
-  } else if (warp == MMA_WARP) {
+  } else if (warp == R::MMA && CLASSIFY) {
+    // ===================================================================== MMA issuer of the tier-1 kernel: a static schedule
+    // With one MMA per product a chunk is 4 instructions = 256 tensor-pipe cycles, and the generic issue loop below (slot
+    // arithmetic, ring bookkeeping, ~90 SASS instructions and three barrier probes per chunk) takes longer than that: measured
+    // 98 cycles per MMA for the bare loop (tools/mma_rate_probe1.cu) against 64 for the same instructions issued back to back
+    // (tools/operand_reuse_probe.cu).  Tier 1 consumes 60 chunks per tile through a 10-stage ring and runs 8 steps, so every ring
+    // stage, barrier parity and descriptor offset of a tile is a compile-time constant: the whole tile is unrolled.
+    static_assert(!CLASSIFY || (C::STAGES == 10 && kSteps == 8 && !kSplit), "static tier-1 schedule");
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc_f16(128, 128);
+    constexpr uint32_t HI_B = sdesc_hi(1024);
+    const uint32_t ring_lo = sdesc_lo(smem_u32(sRing), 128);
+    const uint32_t enc_hi = sdesc_lo(smem_u32(smem + C::SM_INBUF) + C::OFF_ENC_HI, 128);
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+      mbar_wait(&enc_ready[0], tl & 1);
+      int cbase = 0;   // chunks of the tile consumed so far (compile-time after unrolling)
+#pragma unroll
+      for (int step = 0; step < 8; ++step) {
+        const int nk = step_k_chunks(step), k_early = step_k_early(step);
+        const uint32_t par = step & 1;   // 8 steps per tile: the n-th wait of a per-step barrier has parity step & 1
+        if (lane == 0) NSR_TR(tl, step, 0);
+        mbar_wait(&a_ready[0], par);     // A[K 0..127] of this step written, ACC0 drained
+        if (lane == 0) NSR_TR(tl, step, 1);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int slot = 0; slot < 2 * nk; ++slot) {
+          int nh, kc;
+          issue_slot(nk, k_early, 2, slot, nh, kc);
+          const int c = cbase + slot, stage = c % 10;
+          if (slot == k_early) {         // first chunk of half 1: ACC1 must be back (in the epilogue's registers)
+            if (lane == 0) NSR_TR(tl, step, 5);
+            mbar_wait(acc_free1, par);
+            if (lane == 0) NSR_TR(tl, step, 6);
+            tc_fence_after_sync();
+          }
+          if (slot == 2 * k_early) {     // first late-K chunk: A[K 128..255] written
+            if (lane == 0) NSR_TR(tl, step, 2);
+            mbar_wait(&a_ready[1], par);
+            if (lane == 0) NSR_TR(tl, step, 3);
+            tc_fence_after_sync();
+          }
+          mbar_wait(&full[stage], (c / 10) & 1);   // 6 uses of every stage per tile: the parity pattern repeats tile after tile
+          if (leader && !NSR_EXP(5)) {
+            const uint32_t acc = nh ? TM_ACC1 : TM_ACC0;
+            const uint32_t b = ring_lo + stage * (CHUNK_BYTES >> 4);
+            if ((step == 0 || step == 5) && kc == 0) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) umma_ss2(acc, enc_hi + j * 16, HI_B, b + j * 16, HI_B, idesc, j ? 1u : 0u);
+            } else {
+              const uint32_t at = TM_AHI + (step == 5 ? kc - 1 : kc) * 32;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) umma_ts2(acc, at + j * 8, b + j * 16, HI_B, idesc, (j || kc) ? 1u : 0u);
+            }
+          }
+          if (leader) umma_commit(&empty[stage]);
+          if (slot == last_slot_half0(nk, k_early)) {
+            if (lane == 0) NSR_TR(tl, step, 7);
+            if (leader) umma_commit(&acc_ready[0]);
+          }
+          if (slot == 2 * nk - 1 && leader) umma_commit(&acc_ready[1]);
+        }
+        if (nk == k_early) mbar_wait(&a_ready[1], par);   // step 0 has no late-K chunk: consume the phase all the same
+        if (lane == 0) NSR_TR(tl, step, 4);
+        if (step == 5 && leader) umma_commit(&enc_free[0]);  // last reader of the xyz encoding
+        cbase += 2 * nk;
+      }
+    }
+  } else if (warp == R::MMA) {
     // ===================================================================== MMA issuer
     // The whole warp runs the (uniform) control flow and waits; one elected lane issues the tcgen05
     // instructions, so descriptors and addresses live in uniform registers.
@@ -400,7 +504,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
     const uint32_t enc_hi = sdesc_lo(inbuf + C::OFF_ENC_HI, 128), enc_lo = sdesc_lo(inbuf + C::OFF_ENC_LO, 128);
     const uint32_t dir_hi = sdesc_lo(inbuf + C::OFF_DIR_HI, 128), dir_lo = sdesc_lo(inbuf + C::OFF_DIR_LO, 128);
     uint32_t stage = 0, phase = 0, tl = 0;
-    Waiter w_a[2], w_enc[2];
+    Waiter w_a[2], w_enc[2], w_f1;
     bool ready = false;  // result of an early try_wait on full[stage]
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
       w_enc[0].wait(&enc_ready[0]);
@@ -408,13 +512,15 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
         if (step == 9) w_enc[1].wait(&enc_ready[1]);
         const int nk = step_k_chunks(step);
         const int nhs = step_n_halves(step);
-        bool waited1 = false;
+        bool waited1 = false, waitedf = !kAccFree;
         if (lane == 0) NSR_TR(tl, step, 0);
         w_a[0].wait(&a_ready[0]);  // A[K 0..127] of this step written, ACC0 drained
         if (lane == 0) NSR_TR(tl, step, 1);
         if (step == 9) {           // the single 128-wide half of step 9 accumulates in ACC1
           w_a[1].wait(&a_ready[1]);
           waited1 = true;
+          if (kAccFree) w_f1.wait(acc_free1);
+          waitedf = true;
         }
         tc_fence_after_sync();
         const int k_early = step_k_early(step), slot_h0 = nhs == 2 ? last_slot_half0(nk, k_early) : -1;
@@ -428,7 +534,16 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
             if ((step == 0 || step == 5) && kc == 0) src = 0;
             else if (step == 9 && kc == 4) src = 2;
             else if (step == 5) ak = kc - 1;
-            if (!waited1 && (nh == 1 || (src == 1 && ak >= 2))) {
+            // kAccFree: the early-K chunks of half 1 only need ACC1 back (its previous contents are in the epilogue's registers),
+            // not the second half of the activations -- they run under the previous step's second drain
+            if (!waitedf && nh == 1) {
+              if (lane == 0) NSR_TR(tl, step, 5);
+              w_f1.wait(acc_free1);
+              if (lane == 0) NSR_TR(tl, step, 6);
+              tc_fence_after_sync();
+              waitedf = true;
+            }
+            if (!waited1 && ((!kAccFree && nh == 1) || (src == 1 && ak >= 2))) {
               if (lane == 0) NSR_TR(tl, step, 2);
               w_a[1].wait(&a_ready[1]);  // A[K 128..255] written, ACC1 drained
               if (lane == 0) NSR_TR(tl, step, 3);
@@ -439,7 +554,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
             // descriptors: only the start-address field moves (16-byte units): +16 per k-step of 16 elements
             const uint32_t bh = ring_lo + stage * (C::STAGE_BYTES >> 4), bl = bh + (CHUNK_BYTES >> 4);
             const uint32_t acc0 = kc != 0;  // first MMA of a half overwrites the accumulator
-            if (leader) {
+            if (leader && !NSR_EXP(5)) {
               if (kMixed && src == 1 && step >= MIX_X3_STEPS) {
                 // fp16 main term + the two residual products as e4m3 MMAs (K = 32 each) into the same accumulator
                 const uint32_t ah = TM_AHI + ak * 32, a8l = TM_A8L + ak * 16, a8h = TM_A8H + ak * 16;
@@ -480,8 +595,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
                   }
                 }
               }
-              umma_commit(&empty[stage]);
             }
+            if (leader) umma_commit(&empty[stage]);
             if (++stage == C::STAGES) {
               stage = 0;
               phase ^= 1;
@@ -491,19 +606,21 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
           }
           // accumulator 0 is complete after its late-K chunks (every MMA that read A[K 0..127] has been issued before them: the
           // commit covers those too); accumulator 1 (and the single half of step 9) with the step's last chunk
+          if (slot == slot_h0 && lane == 0) NSR_TR(tl, step, 7);
           if (slot == slot_h0 && leader) umma_commit(&acc_ready[0]);
           if (slot == nk * nhs - 1 && leader) umma_commit(&acc_ready[1]);
         }
-        if (!waited1) w_a[1].wait(&a_ready[1]);  // keep the parity in step (cannot happen with this network)
+        if (!waited1) w_a[1].wait(&a_ready[1]);  // keep the parity in step (step 0: no late-K chunk)
+        if (!waitedf) w_f1.wait(acc_free1);
         if (lane == 0) NSR_TR(tl, step, 4);
         if (step == 5 && leader) umma_commit(&enc_free[0]);  // last reader of the xyz encoding
       }
       if (!CLASSIFY && leader) umma_commit(&enc_free[1]);
     }
-  } else if (warp >= ENC_WARP0) {
+  } else if (warp >= R::ENC0) {
     // ===================================================================== encoders (2 warps, 2 rows per thread):
     // tile i+1's encodings while tile i is in the tensor pipe
-    const int er = tid - ENC_WARP0 * 32;
+    const int er = tid - R::ENC0 * 32;
     uint32_t tl = 0;
     Waiter w_free[2];
     uint8_t* inbuf = smem + C::SM_INBUF;
@@ -538,14 +655,33 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
         e[0] = x[rr][0];
         e[1] = x[rr][1];
         e[2] = x[rr][2];
-#pragma unroll
-        for (int k = 0; k < 10; ++k) {
+        if constexpr (CLASSIFY) {
+          // tier 1 only certifies (its operands are rounded to 11 bits anyway): one accurate sincosf per coordinate, the octaves by
+          // angle doubling -- the error doubles per octave, 3e-5 at 2^9 x, a sixteenth of an fp16 ulp of the encoding
 #pragma unroll
           for (int d = 0; d < 3; ++d) {
             float sn, cs;
-            sincosf(x[rr][d] * float(1 << k), &sn, &cs);
-            e[3 + 6 * k + d] = sn;
-            e[3 + 6 * k + 3 + d] = cs;
+            sincosf(x[rr][d], &sn, &cs);
+#pragma unroll
+            for (int k = 0; k < 10; ++k) {
+              e[3 + 6 * k + d] = sn;
+              e[3 + 6 * k + 3 + d] = cs;
+              const float s2 = 2.f * sn * cs, c2 = fmaf(-2.f * sn, sn, 1.f);
+              sn = s2;
+              cs = c2;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 10; ++k) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              float sn, cs;
+              if (NSR_EXP(4)) sn = cs = x[rr][d];
+              else sincosf(x[rr][d] * float(1 << k), &sn, &cs);
+              e[3 + 6 * k + d] = sn;
+              e[3 + 6 * k + 3 + d] = cs;
+            }
           }
         }
         e[63] = 0.f;
@@ -603,6 +739,96 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
       fence_proxy_async_smem();
       mbar_arrive(&enc_ready[1]);
     }
+  } else if constexpr (CLASSIFY) {
+    // ===================================================================== tier-1 epilogue: 16 warps, 32 columns per thread
+    // thread = (row, 32-column quarter cq): all 512 threads turn ACC0 into A[K 0..127], then ACC1 into A[K 128..255].  The step is a
+    // dependency chain (accumulator complete -> converted -> next step's MMAs), so what counts is the latency of one conversion:
+    // a quarter of a half per thread, four warps per scheduler to hide the TMEM and shared-memory latencies behind.
+    const int quad = warp & 3, cq = warp >> 2;
+    const int row = quad * 32 + lane;
+    const int col0 = cq * 32;
+    const uint32_t tlane = uint32_t(quad * 32) << 16;
+    Waiter w_acc[2];
+    mbar_arrive(&a_ready[0]);                     // initial credits
+    mbar_arrive(&a_ready[1]);
+    if (kAccFree) mbar_arrive(acc_free1);
+    const bool tracer = tid == 0;                 // debug timeline
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+      const int64_t p = point_of(tile, row);
+      float sigma = 0.f;
+      for (int step = 0; step < 8; ++step) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t H[16];
+          w_acc[half].wait(&acc_ready[half]);
+          if (tracer) NSR_TR(tl, step, 8 + 4 * half);
+          tc_fence_after_sync();
+          {
+            uint32_t u[32];
+            tmem_ld32(tlane + (half ? TM_ACC1 : TM_ACC0) + col0, u);
+            tmem_ld_wait();
+            if (tracer) NSR_TR(tl, step, 9 + 4 * half);
+            if (half == 1 && kAccFree) {   // ACC1 lives in registers now: the next step's (half 1, K early) chunks may overwrite it
+              tc_fence_before_sync();
+              mbar_arrive(acc_free1);
+            }
+            if (step < 7) {
+              // fp16(acc) + fp16(bias) with the ReLU fused, two columns per instruction: 2.5x fewer issue slots than the fp32 form,
+              // and the conversion's latency is what the step waits for.  (One more rounding than the tier-2 arithmetic: tier 1
+              // only certifies, and its distance to tier 2 is verified at run time.)
+              const uint4* b16 = reinterpret_cast<const uint4*>(smem + C::SM_INBUF + C::OFF_DIR_HI + (step * 256 + 128 * half + col0) * 2);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 bb = b16[j];
+                H[4 * j] = hfma2_relu_one(pack_f16x2(__uint_as_float(u[8 * j]), __uint_as_float(u[8 * j + 1])), bb.x);
+                H[4 * j + 1] = hfma2_relu_one(pack_f16x2(__uint_as_float(u[8 * j + 2]), __uint_as_float(u[8 * j + 3])), bb.y);
+                H[4 * j + 2] = hfma2_relu_one(pack_f16x2(__uint_as_float(u[8 * j + 4]), __uint_as_float(u[8 * j + 5])), bb.z);
+                H[4 * j + 3] = hfma2_relu_one(pack_f16x2(__uint_as_float(u[8 * j + 6]), __uint_as_float(u[8 * j + 7])), bb.w);
+              }
+            } else {
+              // step 7 feeds the alpha head only (RH:109): fp32 throughout, nothing is stored
+              const float* bias = sTail + TAIL_BIAS + 7 * 256 + 128 * half + col0;
+              const float* walpha = sTail + TAIL_WALPHA + 128 * half + col0;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 bb = *reinterpret_cast<const float4*>(bias + 4 * j), wa = *reinterpret_cast<const float4*>(walpha + 4 * j);
+                sigma = fmaf(fmaxf(__uint_as_float(u[4 * j]) + bb.x, 0.f), wa.x, sigma);
+                sigma = fmaf(fmaxf(__uint_as_float(u[4 * j + 1]) + bb.y, 0.f), wa.y, sigma);
+                sigma = fmaf(fmaxf(__uint_as_float(u[4 * j + 2]) + bb.z, 0.f), wa.z, sigma);
+                sigma = fmaf(fmaxf(__uint_as_float(u[4 * j + 3]) + bb.w, 0.f), wa.w, sigma);
+              }
+            }
+          }
+          if (tracer) NSR_TR(tl, step, 10 + 4 * half);
+          if (step < 7 && !NSR_EXP(2)) {              // (nothing consumes the activations of step 7: tier 1 ends at the alpha head)
+            tmem_st16(tlane + TM_AHI + 64 * half + col0 / 2, *reinterpret_cast<const uint32_t(*)[16]>(&H[0]));
+            tmem_st_wait();
+          }
+          tc_fence_before_sync();
+          mbar_arrive(&a_ready[half]);
+          if (tracer) NSR_TR(tl, step, 11 + 4 * half);
+        }
+      }
+      // ---- sigma~ = alpha head of the fp32 post-ReLU activations (RH:109), four partial sums per row; certainly-empty points stop
+      // here, the others join the active list (order within the list is irrelevant: every row of a tier-2 tile is independent).
+      // The partials are safe in shared memory until the next tile's step 7: that needs a_ready arrivals of every thread of this tile.
+      if (cq != 0) reinterpret_cast<float*>(sXch)[row * 4 + cq] = sigma;
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      if (cq == 0) {   // warps 0..3, warp-uniform
+        const float4 o = sXch[row];
+        const float sg = ((sigma + o.y) + (o.z + o.w)) + sTail[TAIL_MISC];
+        const bool act = p >= 0 && !(sg <= -a.tau);       // NaN counts as active
+        if (p >= 0) reinterpret_cast<float4*>(a.raw)[p] = make_float4(0.f, 0.f, 0.f, sg);
+        const uint32_t m = __ballot_sync(0xffffffffu, act);
+        if (m != 0u) {
+          uint32_t base = 0;
+          if (lane == 0) base = atomicAdd(a.ctrl + AS_COUNT, uint32_t(__popc(m)));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (act) a.list[base + __popc(m & ((1u << lane) - 1u))] = int32_t(p);
+        }
+      }
+    }
   } else {
     // ===================================================================== epilogue warps
     // thread = (row, column half): row = 32 (warp & 3) + lane == TMEM lane; columns [col0, col0 + 64) of ACC0 / ACC1
@@ -614,13 +840,14 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
     // initial credits: nothing to wait for before the very first step
     mbar_arrive(&a_ready[0]);
     mbar_arrive(&a_ready[1]);
+    if (kAccFree) mbar_arrive(acc_free1);
     uint32_t tl = 0;
     uint32_t vbits = 0u;   // tier 2: max |sigma~ - sigma| of this thread's points, as float bits
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
       const int64_t p = point_of(tile, row);
       float sigma = 0.f;
       uint32_t* mrow = (SAVE && a.relu_mask != nullptr) ? a.relu_mask + size_t(tile) * MASK_TILE_WORDS + (ch * 2) * 128 + row : nullptr;
-      for (int step = 0; step < (CLASSIFY ? 8 : 9); ++step) {
+      for (int step = 0; step < 9; ++step) {
         const float* bias = sTail + TAIL_BIAS + step * 256 + col0;
         const float* walpha = (step == 7) ? sTail + TAIL_WALPHA + col0 : nullptr;
         const bool relu = step != 8;  // feature_linear has no activation (RH:110)
@@ -630,6 +857,11 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
         uint32_t H[32], L[kSplit ? 32 : 1];
         // bias (+ReLU, + alpha head) and operand split of this thread's 64 columns of accumulator half `half`
         auto convert = [&](const uint32_t(&u0)[32], const uint32_t(&u1)[32], int half) {
+          if (NSR_EXP(3)) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) H[j] = u0[j] ^ u1[j];
+            return;
+          }
           const float* bh = bias + 128 * half;
           const float* wa = walpha ? walpha + 128 * half : nullptr;
           if constexpr (kMixed) {
@@ -647,6 +879,10 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
         };
         // accumulator column c is K index c of the next step: fp16 pairs -> packed column c / 2, e4m3 quads -> c / 4
         auto store = [&](int half) {
+          if (NSR_EXP(2)) {
+            tc_fence_before_sync();
+            return;
+          }
           tmem_st16(tlane + TM_AHI + 64 * half + col0 / 2, *reinterpret_cast<const uint32_t(*)[16]>(&H[0]));
           tmem_st16(tlane + TM_AHI + 64 * half + col0 / 2 + 16, *reinterpret_cast<const uint32_t(*)[16]>(&H[16]));
           if (kMixed && f8next) {
@@ -678,8 +914,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
         // ---- the chunks that read A[K 0..127] were issued before accumulator 0's last ones (common.cuh issue_slot), so they
         // retired with it: the first half of the activations may be overwritten now, while half 1 is still in the tensor pipe
         if (tid == 0) NSR_TR(tl, step, 9);
-        if (CLASSIFY && step == 7) tc_fence_before_sync();   // tier 1 ends here: nothing consumes these activations
-        else store(0);
+        store(0);
         mbar_arrive(&a_ready[0]);
         if (tid == 0) NSR_TR(tl, step, 11);
         // ---- every MMA of this step has retired
@@ -692,6 +927,10 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
           tmem_ld32(tlane + TM_ACC1 + col0, u0);
           tmem_ld32(tlane + TM_ACC1 + col0 + 32, u1);
           tmem_ld_wait();
+          if (kAccFree) {   // ACC1 lives in registers now: the next step's (half 1, K early) chunks may overwrite it
+            tc_fence_before_sync();
+            mbar_arrive(acc_free1);
+          }
           convert(u0, u1, 1);
         }
         if (SAVE && mrow != nullptr && step < 8) {
@@ -699,29 +938,9 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
           mrow[(step * 8 + 5) * 128] = sign_bits(H + 16);
         }
         if (SAVE && a.dump != nullptr) dump64_hl(a.dump + dump_off_h(dumpP, step), dump_lo(dumpP), tile, row, 256, 128 + col0, H, L);
-        if (CLASSIFY && step == 7) tc_fence_before_sync();
-        else store(1);
+        store(1);
         mbar_arrive(&a_ready[1]);
         if (tid == 0) NSR_TR(tl, step, 12);
-      }
-      if constexpr (CLASSIFY) {
-        // ---- tier 1: sigma~ = alpha head of the fp32 post-ReLU activations (RH:109); certainly-empty points stop here, the others
-        // join the active list (order within the list is irrelevant: every row of a tier-2 tile is independent of the others)
-        if (ch == 1) sXch[row] = make_float4(0.f, 0.f, 0.f, sigma);
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (ch == 0) {   // warps 0..3, warp-uniform
-          const float sg = (sigma + sXch[row].w) + sTail[TAIL_MISC];
-          const bool act = p >= 0 && !(sg <= -a.tau);       // NaN counts as active
-          if (p >= 0) reinterpret_cast<float4*>(a.raw)[p] = make_float4(0.f, 0.f, 0.f, sg);
-          const uint32_t m = __ballot_sync(0xffffffffu, act);
-          if (m != 0u) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(a.ctrl + AS_COUNT, uint32_t(__popc(m)));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (act) a.list[base + __popc(m & ((1u << lane) - 1u))] = int32_t(p);
-          }
-        }
-        continue;
       }
       // ---- step 9: views layer accumulates in ACC1; rgb head on CUDA cores (RH:113-117)
       w_acc[1].wait(&acc_ready[1]);
@@ -743,6 +962,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
         // ACC1 now lives in registers: hand it back before the head arithmetic, so the next tile's step 0 is not held up
         tc_fence_before_sync();
         mbar_arrive(&a_ready[1]);
+        if (kAccFree) mbar_arrive(acc_free1);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 b0 = *reinterpret_cast<const float4*>(bias + 4 * j), b1 = *reinterpret_cast<const float4*>(bias + 32 + 4 * j);
@@ -803,13 +1023,13 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
   if (a.ctrl != nullptr && a.role == AS_ROLE_REDO && blockIdx.x == 0 && tid == 0) a.ctrl[AS_DENSE_FINAL] = 1u;
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == MMA_WARP) tmem_dealloc(0u, 512);
+  if (warp == R::MMA) tmem_dealloc(0u, 512);
 }
 
 template <int SPLIT, bool SAVE, bool CLASSIFY = false>
 static int launch_variant(const MlpArgs& a, int grid, cudaStream_t st) {
   if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(&nerf_mlp_kernel<SPLIT, SAVE, CLASSIFY>), Cfg<SPLIT>::SM_TOTAL)) return rc;
-  nerf_mlp_kernel<SPLIT, SAVE, CLASSIFY><<<grid, MLP_THREADS, Cfg<SPLIT>::SM_TOTAL, st>>>(a);
+  nerf_mlp_kernel<SPLIT, SAVE, CLASSIFY><<<grid, Roles<CLASSIFY>::THREADS, Cfg<SPLIT>::SM_TOTAL, st>>>(a);
   count_launch();
   return check_launch("nerf_mlp_kernel");
 }
@@ -877,10 +1097,11 @@ int launch_mlp_forward(const float* rays, const float* z_or_pts, int64_t n, int 
 #else
   a.experiment = 0;
 #endif
-  const int grid = a.num_tiles < num_sms ? a.num_tiles : num_sms;
+  int grid = a.num_tiles < num_sms ? a.num_tiles : num_sms;
+  if (a.experiment >= 100 && a.experiment - 100 < grid) grid = a.experiment - 100;
 #ifdef NSR_DEBUG_HOOKS   // compiled out of the production library: `python -m neural_sim_nerf_b200.build --debug-hooks`
   const char* trace_file = getenv("NSR_TRACE_FILE");  // debug only: synchronous, dumps CTA 0's timeline
-  if (trace_file != nullptr && a.num_tiles >= 4 * grid && role == AS_ROLE_PLAIN) {
+  if (trace_file != nullptr && a.num_tiles >= 4 * grid && (role == AS_ROLE_PLAIN || role == AS_ROLE_TIER1)) {
     const size_t nb = 4 * 10 * 16 * sizeof(unsigned long long);
     cudaMalloc(&a.trace, nb);
     cudaMemset(a.trace, 0, nb);
@@ -890,7 +1111,8 @@ int launch_mlp_forward(const float* rays, const float* z_or_pts, int64_t n, int 
     cudaMemcpy(host, a.trace, nb, cudaMemcpyDeviceToHost);
     cudaFree(a.trace);
     if (FILE* f = fopen(trace_file, "a")) {
-      fprintf(f, "# launch split=%d tiles=%d\n", (flags & NSR_FLAG_FAST_FP16) ? 1 : ((flags & NSR_FLAG_MIXED_F8) ? 2 : 3), a.num_tiles);
+      fprintf(f, "# launch split=%d tiles=%d%s\n", (flags & NSR_FLAG_FAST_FP16) ? 1 : ((flags & NSR_FLAG_MIXED_F8) ? 2 : 3), a.num_tiles,
+              role == AS_ROLE_TIER1 ? " tier1" : "");
       for (int i = 0; i < 40; ++i) {
         fprintf(f, "%d %d", i / 10, i % 10);
         for (int k = 0; k < 16; ++k) fprintf(f, " %llu", host[i * 16 + k]);

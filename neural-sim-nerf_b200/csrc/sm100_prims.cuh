@@ -228,6 +228,12 @@ __device__ __forceinline__ uint32_t pack_f16x2_relu(float a, float b) {
   asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
   return r;
 }
+// max(x + b, 0) on two packed fp16 lanes in one instruction (fma.rn.relu: x * 1 + b)
+__device__ __forceinline__ uint32_t hfma2_relu_one(uint32_t x, uint32_t b) {
+  uint32_t r;
+  asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(0x3c003c00u), "r"(b));
+  return r;
+}
 // four fp32 -> packed e4m3 bytes (byte i = value i), round-to-nearest, saturating to +-448
 __device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float d) {
   uint32_t r;
