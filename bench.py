@@ -99,17 +99,39 @@ class ClockSampler:
                 'samples': len(self.samples)}
 
 
-# ----------------------------------------------------------------------------- CPU legs (oracle port)
-def _cpu_setup(n_rays, pose_index=0, rank=0):
-    import torch
+# ----------------------------------------------------------------------------- CPU legs
+def cpu_kind():
+    """'reference': the UNMODIFIED reference modules (RN.render and its own NeRF nn.Modules), live from /root/reference or from their
+    bytecode build in oracle/_ref (oracle/build_ref.py -- what the GPU box has); 'port': the oracle restatement, when neither exists."""
+    import ref_import
+    return 'reference' if ref_import.usable() else 'port'
+
+
+def _cpu_renderer(N_importance=N_IMPORTANCE):
+    """run(rays [2,n,3], **extra) -> [rgb, disp, acc, extras] on the host cores through the reference's own render() (RN:58-123) with
+    chunk = 512 (CFG:25) and netchunk = 65536, or through the oracle port of it."""
     import nerf_oracle as O
     sdc, sdf = load_weights()
-    ro, rd = O.get_rays(H, W, O.YCBV_K_400, pose_for(pose_index, rank))
-    sel = torch.linspace(0, RAYS_PER_IMAGE - 1, n_rays).long()
-    rays = torch.stack([ro.reshape(-1, 3)[sel], rd.reshape(-1, 3)[sel]], 0)
-    kw = dict(near=O.YCBV_NEAR, far=O.YCBV_FAR, N_samples=N_SAMPLES, N_importance=N_IMPORTANCE)
-    run = lambda r: O.render(H, W, O.YCBV_K_400, sdc, sdf, chunk=512, rays=r, **kw)
-    return rays, run
+    if cpu_kind() == 'reference':
+        import ref_import
+        RN, _ = ref_import.load()
+        kw = ref_import.render_kwargs(sdc, sdf, O.YCBV_NEAR, O.YCBV_FAR, N_samples=N_SAMPLES, N_importance=N_importance)
+        return lambda r, **extra: RN.render(H, W, O.YCBV_K_400, chunk=512, rays=r, **dict(kw, **extra))
+    kw = dict(near=O.YCBV_NEAR, far=O.YCBV_FAR, N_samples=N_SAMPLES, N_importance=N_importance)
+    return lambda r, **extra: O.render(H, W, O.YCBV_K_400, sdc, sdf if N_importance > 0 else None, chunk=512, rays=r, **dict(kw, **extra))
+
+
+def _cpu_rays(n_rays, pose_index=0, rank=0, HW=(H, W), K=None):
+    import torch
+    import nerf_oracle as O
+    ro, rd = O.get_rays(HW[0], HW[1], K if K is not None else O.YCBV_K_400, pose_for(pose_index, rank))
+    sel = torch.linspace(0, HW[0] * HW[1] - 1, n_rays).long()
+    return torch.stack([ro.reshape(-1, 3)[sel], rd.reshape(-1, 3)[sel]], 0), sel
+
+
+def _cpu_setup(n_rays, pose_index=0, rank=0):
+    rays, _ = _cpu_rays(n_rays, pose_index, rank)
+    return rays, _cpu_renderer()
 
 
 def pick_cpu_threads(run, rays):
@@ -138,31 +160,29 @@ def cpu_render_rate(n_rays, repeats, pose_index=0, rank=0):
     RN:43-55 / RN:14-23) on the host cores; returns rays/s over `repeats` passes of `n_rays` rays, the thread count, the
     pass times and the rendered maps of the last pass (what `parity` compares the GPU image with)."""
     import torch
-    rays, run = _cpu_setup(n_rays, pose_index, rank)
-    threads = pick_cpu_threads(run, rays)
-    times = []
-    out = None
-    with torch.no_grad():
-        for _ in range(repeats):
-            t0 = time.perf_counter()
-            out = run(rays)
-            times.append(time.perf_counter() - t0)
+    import ref_import
+    with ref_import.cpu_shim():
+        rays, run = _cpu_setup(n_rays, pose_index, rank)
+        threads = pick_cpu_threads(run, rays)
+        times = []
+        out = None
+        with torch.no_grad():
+            for _ in range(repeats):
+                t0 = time.perf_counter()
+                out = run(rays)
+                times.append(time.perf_counter() - t0)
     return n_rays / (sum(times) / len(times)), threads, times, out
 
 
 def cpu_config1_rate(n_rays):
     """BASELINE config 1 on the host cores: 200x200 camera, 64 coarse samples only (RN:58 with N_importance = 0), chunk 512."""
     import torch
-    import nerf_oracle as O
-    sdc, _ = load_weights()
-    ro, rd = O.get_rays(200, 200, K_200, pose_for(0, 0))
-    sel = torch.linspace(0, 200 * 200 - 1, n_rays).long()
-    rays = torch.stack([ro.reshape(-1, 3)[sel], rd.reshape(-1, 3)[sel]], 0)
-    run = lambda: O.render(200, 200, K_200, sdc, None, chunk=512, rays=rays, near=O.YCBV_NEAR, far=O.YCBV_FAR, N_samples=64, N_importance=0)
+    rays, _ = _cpu_rays(n_rays, HW=(200, 200), K=K_200)
+    run = _cpu_renderer(N_importance=0)
     with torch.no_grad():
-        run()
+        run(rays[:, :512])
         t0 = time.perf_counter()
-        run()
+        run(rays)
         dt = time.perf_counter() - t0
     return n_rays / dt, dt
 
@@ -171,52 +191,54 @@ def cpu_config3_rate(n_rays):
     """BASELINE config 3 on the host cores, the pattern of RN:168-181: per 512-ray chunk render (retraw) with autograd, then
     autograd.grad(rgb, batch_rays, grad_outputs=grad_E chunk)."""
     import torch
-    import nerf_oracle as O
-    sdc, sdf = load_weights()
-    ro, rd = O.get_rays(H, W, O.YCBV_K_400, pose_for(0, 0))
-    sel = torch.linspace(0, RAYS_PER_IMAGE - 1, n_rays).long()
-    o, d = ro.reshape(-1, 3)[sel], rd.reshape(-1, 3)[sel]
+    rays, _ = _cpu_rays(n_rays)
+    run = _cpu_renderer()
     g = torch.randn(n_rays, 3, generator=torch.Generator().manual_seed(0))
-
-    def run():
-        for i in range(0, n_rays, 512):
-            batch = torch.stack([o[i:i + 512], d[i:i + 512]], 0).requires_grad_(True)
-            rgb = O.render(H, W, O.YCBV_K_400, sdc, sdf, chunk=512, rays=batch, near=O.YCBV_NEAR, far=O.YCBV_FAR, N_samples=N_SAMPLES,
-                           N_importance=N_IMPORTANCE, retraw=True)[0]
-            torch.autograd.grad(rgb, batch, grad_outputs=g[i:i + 512])
     t0 = time.perf_counter()
-    run()
+    for i in range(0, n_rays, 512):
+        batch = rays[:, i:i + 512].clone().requires_grad_(True)
+        rgb = run(batch, retraw=True)[0]
+        torch.autograd.grad(rgb, batch, grad_outputs=g[i:i + 512])
     dt = time.perf_counter() - t0
     return n_rays / dt, dt
 
 
 def eager_gpu_rates(dev):
-    """The reference algorithm as eager PyTorch on THIS GPU (the oracle restatement with every tensor on cuda: the kernels
-    nn.Linear / sin / cumprod / searchsorted / sort dispatch to, fp32) -- the baseline SURVEY.md 2.1 names ("beat eager PyTorch").
-    TF32 off (true fp32, what the reference gets by default) and on; the reference's chunk = 512 (CFG:25) on a 16 384-ray
-    sample, and chunk = 32768 (nerf-pytorch's default) on the whole image."""
+    """The reference's own eager PyTorch path on THIS GPU -- the baseline SURVEY.md 2.1 names ("beat eager PyTorch"): RN.render with
+    its NeRF modules on cuda (the kernels nn.Linear / sin / cumprod / searchsorted / sort dispatch to, fp32), or the oracle port
+    with every tensor on cuda when the reference modules are not there.  TF32 off (what the reference gets by default) and on; the
+    reference's chunk = 512 (CFG:25) on a 16 384-ray sample, and chunk = 32768 (nerf-pytorch's default) on the whole image."""
     import torch
     import nerf_oracle as O
     sdc, sdf = load_weights()
-    sdc = {k: v.to(dev) for k, v in sdc.items()}
-    sdf = {k: v.to(dev) for k, v in sdf.items()}
-    out = {}
+    kind = cpu_kind()
+    out = {'kind': kind}
     old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
     try:
         with torch.device(dev), torch.no_grad():
             ro, rd = O.get_rays(H, W, O.YCBV_K_400, pose_for(0, 0).to(dev))
+            if kind == 'reference':
+                import ref_import
+                RN, _ = ref_import.load()
+                kw = ref_import.render_kwargs(sdc, sdf, O.YCBV_NEAR, O.YCBV_FAR, N_samples=N_SAMPLES, N_importance=N_IMPORTANCE)
+                kw['network_fn'].to(dev)
+                kw['network_fine'].to(dev)
+                render = lambda rays, chunk: RN.render(H, W, O.YCBV_K_400, chunk=chunk, rays=rays, **kw)
+            else:
+                sdc = {k: v.to(dev) for k, v in sdc.items()}
+                sdf = {k: v.to(dev) for k, v in sdf.items()}
+                render = lambda rays, chunk: O.render(H, W, O.YCBV_K_400, sdc, sdf, chunk=chunk, rays=rays, near=O.YCBV_NEAR, far=O.YCBV_FAR,
+                                                      N_samples=N_SAMPLES, N_importance=N_IMPORTANCE)
             for tf32 in (False, True):
                 torch.backends.cuda.matmul.allow_tf32 = tf32
                 torch.backends.cudnn.allow_tf32 = tf32
                 for chunk, n_rays in ((512, 16384), (32768, RAYS_PER_IMAGE)):
                     sel = torch.linspace(0, RAYS_PER_IMAGE - 1, n_rays).long()
                     rays = torch.stack([ro.reshape(-1, 3)[sel], rd.reshape(-1, 3)[sel]], 0)
-                    run = lambda: O.render(H, W, O.YCBV_K_400, sdc, sdf, chunk=chunk, rays=rays, near=O.YCBV_NEAR, far=O.YCBV_FAR,
-                                           N_samples=N_SAMPLES, N_importance=N_IMPORTANCE)
-                    run()
+                    render(rays, chunk)
                     torch.cuda.synchronize()
                     t0 = time.perf_counter()
-                    run()
+                    render(rays, chunk)
                     torch.cuda.synchronize()
                     dt = time.perf_counter() - t0
                     out[f'fp32_tf32_{"on" if tf32 else "off"}_chunk{chunk}'] = {'rays_per_s': n_rays / dt, 'rays': n_rays, 'seconds': dt}
@@ -240,27 +262,31 @@ def run_reference(args):
         return
     n = 2048
     import torch
-    rays, run = _cpu_setup(n)
-    threads = pick_cpu_threads(run, rays)
-    with torch.no_grad():
-        for _ in range(args.warmup):
-            run(rays)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            run(rays)
-        dt = time.perf_counter() - t0
+    import ref_import
+    kind = cpu_kind()
+    with ref_import.cpu_shim():
+        rays, run = _cpu_setup(n)
+        threads = pick_cpu_threads(run, rays)
+        with torch.no_grad():
+            for _ in range(args.warmup):
+                run(rays)
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                run(rays)
+            dt = time.perf_counter() - t0
     value = n * args.steps / dt
-    sample = (f'{n} rays (uniform subsample of one 400x400 image) per step, chunk=512, netchunk=65536, fp32, torch CPU, '
+    what = 'the unmodified reference render() (RN:58-123, oracle/_ref bytecode build)' if kind == 'reference' else 'the oracle port of RN:58-123'
+    sample = (f'{what}: {n} rays (uniform subsample of one 400x400 image) per step, chunk=512, netchunk=65536, fp32, torch CPU, '
               f'{threads} of {os.cpu_count()} threads (fastest of the candidates tried)')
     print(json.dumps({
-        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'rays/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'impl': 'reference', 'device': 'cpu', 'metric': METRIC, 'value': value, 'unit': 'rays/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': 'BASELINE config 2: 400x400 rays, 64 coarse + 128 fine, forward render (bounded sample per step)',
                    'rays_per_step': n, 'N_samples': N_SAMPLES, 'N_importance': N_IMPORTANCE},
-        'cpu_baseline': {'value': value, 'unit': 'rays/s', 'cores': threads, 'kind': 'port', 'sample': sample},
+        'cpu_baseline': {'value': value, 'unit': 'rays/s', 'cores': threads, 'kind': kind, 'sample': sample},
         'e2e': {'value': value, 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-        'gpu_launches': 0,
+        'gpu_launches': 0, 'gpus_used': 0,
     }))
 
 
@@ -396,7 +422,8 @@ def run_ours(args):
     d_rays = new(n, 11)
     zsave, rawsave = new(n, T), new(n, T, 4)
     d_c2w = new(12)
-    relu_mask = torch.empty(L.nsr_relu_mask_bytes(n, T), dtype=torch.uint8, device=dev)    # 272 B per sample point: 8.4 GB per image
+    relu_mask = torch.empty(L.nsr_relu_mask_bytes(n, T), dtype=torch.uint8, device=dev)    # 272 B per ACTIVE sample point (room for all: 8.4 GB)
+    aset = torch.empty(L.nsr_active_set_bytes(n, T), dtype=torch.uint8, device=dev)         # the last pass's active list: forward -> backward
     cws = torch.empty(L.nsr_c2w_grad_workspace_bytes(), dtype=torch.uint8, device=dev)
     Kf = (ctypes.c_float * 9)(*[float(v) for row in O.YCBV_K_400 for v in row])
 
@@ -404,9 +431,9 @@ def run_ours(args):
         r = rays_dev[s % len(rays_dev)]
         rc = L.nsr_render_rays_forward_ex(P(r), n, P(pc), P(pf), N_SAMPLES, N_IMPORTANCE, 0, None, None, P(outs['rgb']), P(outs['disp']),
                                           P(outs['acc']), P(outs['rgb0']), P(outs['disp0']), P(outs['acc0']), P(outs['zstd']), P(rawsave),
-                                          P(zsave), None, P(relu_mask), None, None, P(ws), ws_bytes, stream)
+                                          P(zsave), None, P(relu_mask), None, P(aset), P(ws), ws_bytes, stream)
         rc = rc or L.nsr_render_rays_backward_ex(P(r), P(zsave), P(rawsave), n, T, P(pf), 0, P(g_rgb), P(d_rays), None, None, None,
-                                                 P(relu_mask), None, P(bws), bws_bytes, stream)
+                                                 P(relu_mask), P(aset), P(bws), bws_bytes, stream)
         rc = rc or L.nsr_rays_grad_to_c2w(H, W, Kf, P(r), P(d_rays), None, n, P(d_c2w), 0, P(cws), stream)
         if rc != 0:
             raise RuntimeError(L.nsr_last_error().decode())
@@ -422,42 +449,92 @@ def run_ours(args):
     e1.record()
     barrier()
     ms_pg = max_over_ranks(e0.elapsed_time(e1))
-    pose_grad = {'workload': 'BASELINE config 3/4: per rank and step one 400x400 image forward (saving one bit per ReLU, 272 B/point) + backward '
-                             'dL/d(rays) without recompute -> dL/dc2w (closed form) + all-reduce of the 12 pose-gradient floats over the ranks',
+    pose_grad = {'workload': 'BASELINE config 3/4: per rank and step one 400x400 image forward (two-tier; one bit per ReLU of the active points saved, '
+                             '272 B/point) + backward dL/d(rays) over the active set without recompute -> dL/dc2w (closed form) + all-reduce of the 12 '
+                             'pose-gradient floats over the ranks',
                  'rays_per_s': world * n * args.steps / (ms_pg * 1e-3), 'ms_per_step': ms_pg / args.steps,
                  'collective': 'ncclAllReduce(SUM) of 48 bytes per step' if world > 1 else 'none (1 rank)',
                  'algorithmic_tflops': world * n * args.steps * (64 + 192 + 192) * FLOP_PER_POINT / (ms_pg * 1e-3) / 1e12}
-    del bws, zsave, rawsave, d_rays, relu_mask
+    mlp_bwd_ms = None
+    if rank == 0:       # the MLP stage of that backward pass by itself (for roofline_kernels): d_raw is in the backward workspace
+        d_raw_view = bws[:n * T * 16].view(torch.float32)
+        d_pts_tmp = new(n, T, 8)
+        for _ in range(2):
+            L.nsr_mlp_backward(P(rays_dev[(args.warmup + args.steps - 1) % len(rays_dev)]), P(zsave), n, T, P(pf), P(d_raw_view), P(d_pts_tmp), P(relu_mask), P(aset), stream)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            L.nsr_mlp_backward(P(rays_dev[(args.warmup + args.steps - 1) % len(rays_dev)]), P(zsave), n, T, P(pf), P(d_raw_view), P(d_pts_tmp), P(relu_mask), P(aset), stream)
+        e1.record()
+        torch.cuda.synchronize()
+        mlp_bwd_ms = e0.elapsed_time(e1) / 3
+        bwd_active = int(aset[:4].view(torch.int32).item())
+        del d_pts_tmp
+    del bws, zsave, rawsave, d_rays, relu_mask, aset
 
-    # ------------------------------------------------------------- roofline of the dominant kernel (fine-pass MLP)
-    roofline = cpu_base = fast = mixed = fwd_bwd = stages = train = None
+    # ------------------------------------------------------------- rooflines of the MLP kernels, each timed back to back
+    roofline = cpu_base = fast = mixed = fwd_bwd = stages = train = parity = baselines = None
+    roofline_kernels = roofline_step = None
     if rank == 0:
         zf = new(n, T)
         rawf = new(n, T, 4)
-        step_device(0)  # leaves valid fine depths in the workspace; regenerate them explicitly for the kernel-only loop
+        # the fine pass's real depths (z_vals_out) of pose 0 and its real active list
+        rc = L.nsr_render_rays_forward(P(rays_dev[0]), n, P(pc), P(pf), N_SAMPLES, N_IMPORTANCE, 0, None, None, P(outs['rgb']), P(outs['disp']),
+                                       P(outs['acc']), P(outs['rgb0']), P(outs['disp0']), P(outs['acc0']), P(outs['zstd']), None, P(zf), None,
+                                       P(ws), ws_bytes, stream)
+        assert rc == 0, L.nsr_last_error()
+        as1 = torch.zeros(L.nsr_active_set_bytes(n, T), dtype=torch.uint8, device=dev)
         z0, w0 = new(n, N_SAMPLES), new(n, N_SAMPLES)
         t = torch.linspace(0, 1, N_SAMPLES, device=dev)
         z0.copy_(O.YCBV_NEAR * (1 - t) + O.YCBV_FAR * t)
         w0.uniform_(0, 1)
-        L.nsr_resample_merge(P(z0), P(w0), n, N_SAMPLES, N_IMPORTANCE, None, P(zf), None, None, stream)
         reps = max(3, args.steps)
-        for _ in range(2):
-            L.nsr_mlp_forward(P(rays_dev[0]), P(zf), n, T, P(pf), 0, P(rawf), stream)
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(reps):
-            L.nsr_mlp_forward(P(rays_dev[0]), P(zf), n, T, P(pf), 0, P(rawf), stream)
-        e1.record()
-        torch.cuda.synchronize()
-        k_ms = e0.elapsed_time(e1) / reps
+
+        def time_kernel(fn):
+            for _ in range(2):
+                assert fn() == 0, L.nsr_last_error()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+
         peaks, how = measured_peaks()
-        flops = n * T * FLOP_PER_POINT
-        achieved = flops / (k_ms * 1e-3) / 1e12
         peak = peaks.get('bf16_tflops_sustained', peaks['bf16_tflops'])
-        roofline = {'bound': 'tensor', 'kernel': 'nerf_mlp_kernel (fine pass, 192 samples/ray)', 'achieved': achieved, 'peak': peak,
-                    'unit': 'TFLOP/s', 'frac': achieved / peak,
-                    'traffic': 583430656, 'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this launch (profiles/r01_v10_ncu_fine_mlp_summary.csv); the launch writes raw [n,192,4] = 491.5 MB and reads depths + rays + weights = 132 MB', 'peak_source': f'{how} bf16_tflops_sustained (kernel timed back to back)',
-                    'ms_per_launch': k_ms, 'algorithmic_flop_per_launch': flops}
+        traffic, traffic_file = ncu_traffic()
+        t1_ms = time_kernel(lambda: L.nsr_mlp_two_tier(P(rays_dev[0]), P(zf), n, T, P(pf), P(rawf), P(as1), None, 1, stream))
+        n_act = int(as1[:4].view(torch.int32).item())
+        t2_ms = time_kernel(lambda: L.nsr_mlp_two_tier(P(rays_dev[0]), P(zf), n, T, P(pf), P(rawf), P(as1), None, 2, stream))
+        k_ms = time_kernel(lambda: L.nsr_mlp_forward(P(rays_dev[0]), P(zf), n, T, P(pf), 0, P(rawf), stream))
+        flops = n * T * FLOP_PER_POINT
+
+        def entry(key, kernel, ms, alg_flop, mma_per_product, note):
+            ach = alg_flop / (ms * 1e-3) / 1e12
+            t_ = traffic.get(key)
+            return {'bound': 'tensor', 'kernel': kernel, 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
+                    'traffic': None if t_ is None else t_['dram_bytes'], 'traffic_source': None if t_ is None else f"{traffic_file}: {t_['source']}",
+                    'peak_source': f'{how} bf16_tflops_sustained (kernel timed back to back)', 'ms_per_launch': ms,
+                    'algorithmic_flop_per_launch': alg_flop, 'tensor_flop_issued_per_algorithmic_flop': mma_per_product, 'note': note}
+
+        roofline_kernels = [
+            entry('fine_tier1', 'nerf_mlp_kernel<1,false,true> (fine pass, tier 1: pts_linears.0-7 + alpha head of all 160000 x 192 points, fp16)',
+                  t1_ms, n * T * FLOP_PER_POINT_TIER1, 1, 'algorithmic = the FLOPs of the layers this kernel evaluates (RH:99-109), every point'),
+            entry('fine_tier2', f'nerf_mlp_kernel<3,false,false> (fine pass, tier 2: the whole network on the {n_act} active points, fp16x3)',
+                  t2_ms, n_act * FLOP_PER_POINT, 3, 'algorithmic = 1 186 816 FLOP x the active points only'),
+            entry('fine_dense', 'nerf_mlp_kernel<3,false,false> (fine pass evaluated densely, fp16x3: NSR_FLAG_DENSE / round 1)', k_ms, flops, 3,
+                  'every point through the error-compensated arithmetic'),
+        ]
+        if mlp_bwd_ms is not None:
+            roofline_kernels.append(entry('bwd_masked_active', f'nerf_mlp_bwd_kernel<true> (data gradient from saved ReLU bits, {bwd_active} active points, fp16x3)',
+                                          mlp_bwd_ms, bwd_active * FLOP_PER_POINT, 3, 'algorithmic = the transposed network, 1 186 816 FLOP per active point'))
+        roofline = dict(max(roofline_kernels[:2], key=lambda r: r['ms_per_launch']))      # the longer of the two launches that make the fine pass
+        step_ach = n * FLOP_PER_RAY / (ms_total / args.steps * 1e-3) / 1e12
+        roofline_step = {'what': 'the whole forward step in FLOPs of the reference algorithm (64 + 64 + 128... = 256 point evaluations per ray x 1 186 816), '
+                                 'including the views branch the empty points never run here', 'achieved': step_ach, 'peak': peak, 'unit': 'TFLOP/s',
+                         'frac': step_ach / peak}
+        achieved = roofline['achieved']
         if world == 1:          # side legs only at N=1 (the scaling runs stay short; cpu_baseline is an N=1 figure)
             # every point through fp16x3 (NSR_FLAG_DENSE): what round 1 measured as the default
             DENSE = 32
@@ -633,11 +710,53 @@ def run_ours(args):
                 ms = time_stage(fn)
                 stages.append({'kernel': name, 'ms': ms, 'algorithmic_bytes': nbytes, 'gb_per_s': nbytes / (ms * 1e-3) / 1e9,
                                'frac_of_hbm_peak': nbytes / (ms * 1e-3) / 1e9 / hbm})
-            stages.append({'kernel': 'nerf_mlp_kernel fine (192 samples/ray)', 'ms': k_ms, 'algorithmic_tflops': achieved, 'frac_of_tensor_peak': achieved / peak})
+            stages.append({'kernel': 'nerf_mlp_kernel fine, dense fp16x3 (192 samples/ray)', 'ms': k_ms, 'algorithmic_tflops': flops / (k_ms * 1e-3) / 1e12,
+                           'frac_of_tensor_peak': flops / (k_ms * 1e-3) / 1e12 / peak})
             # CPU baseline: the oracle port on this box's host cores, bounded sample
-            rate, cores, times = cpu_render_rate(4096, 2)
-            cpu_base = {'value': rate, 'unit': 'rays/s', 'cores': cores, 'kind': 'port',
-                        'sample': f'2 passes over 4096 rays of the same image (chunk=512, netchunk=65536, fp32 torch CPU, {cores} of {os.cpu_count()} threads = fastest tried, {sum(times):.1f} s)'}
+            kind = cpu_kind()
+            rate, cores, times, cpu_out = cpu_render_rate(4096, 2)
+            what = 'the unmodified reference render() (RN:58-123; oracle/_ref bytecode build of /root/reference)' if kind == 'reference' else 'the oracle port of RN:58-123'
+            cpu_base = {'value': rate, 'unit': 'rays/s', 'cores': cores, 'kind': kind,
+                        'sample': f'{what}: 2 passes over 4096 rays of the same image (chunk=512, netchunk=65536, fp32 torch CPU, {cores} of {os.cpu_count()} threads = fastest tried, {sum(times):.1f} s)'}
+            # parity of the timed workload: the image of pose 0 as the GPU path renders it against those CPU-rendered rays
+            step_device(0)
+            torch.cuda.synchronize()
+            sel = torch.linspace(0, RAYS_PER_IMAGE - 1, 4096).long()
+            errs = {}
+            for key, ref_t in (('rgb', cpu_out[0]), ('acc', cpu_out[2]), ('rgb0', cpu_out[3]['rgb0']), ('acc0', cpu_out[3]['acc0'])):
+                got = outs[key][sel.to(dev)].cpu()
+                errs[key] = float(((got - ref_t).abs() / ref_t.abs().clamp(min=1.0)).max())
+            gd, rd_ = outs['disp'][sel.to(dev)].cpu(), cpu_out[1]
+            nan_equal = bool((torch.isnan(gd) == torch.isnan(rd_)).all())
+            ok_ = ~torch.isnan(rd_) & (cpu_out[2] > 1e-2)          # disparity = 1 / (depth / acc): ill-conditioned as acc -> 0
+            errs['disp(acc>0.01)'] = float(((gd[ok_] - rd_[ok_]).abs() / rd_[ok_].abs().clamp(min=1.0)).max()) if bool(ok_.any()) else 0.0
+            parity = {'max_rel_err': max(errs.values()), 'per_output': errs, 'n_rays': 4096, 'nan_equal': nan_equal, 'tolerance': 1e-3,
+                      'against': kind, 'rel_err': '|a - b| / max(1, |b|)', 'ok': bool(max(errs.values()) <= 1e-3 and nan_equal)}
+            # the other BASELINE configs on the host cores, and the reference's eager PyTorch path on this GPU
+            import ref_import
+            with ref_import.cpu_shim():
+                torch.set_num_threads(cores)
+                c1_rate, c1_s = cpu_config1_rate(4096)
+                c3_rate, c3_s = cpu_config3_rate(1024)
+            # config 1 on the GPU path: 200x200, 64 coarse samples only, through render(c2w=...)
+            kw1 = dict(kw, N_importance=0, network_fine=None)
+            c2w1 = pose_for(0, 0).to(dev)
+
+            def gpu_config1():
+                with torch.no_grad():
+                    return nsr.render(200, 200, K_200, chunk=1 << 20, c2w=c2w1, **kw1)
+
+            c1_gpu_ms = time_stage(gpu_config1, reps=10)
+            baselines = {
+                'kind': kind, 'cores': cores,
+                'config1_cpu': {'workload': 'BASELINE config 1: 200x200 camera, 64 coarse samples only (N_importance = 0), forward, chunk 512; 4096-ray sample',
+                                'rays_per_s': c1_rate, 'seconds': c1_s},
+                'config1_gpu': {'workload': 'the same config through render(c2w=...) on this GPU, whole 200x200 image', 'rays_per_s': 40000 / (c1_gpu_ms * 1e-3),
+                                'ms_per_image': c1_gpu_ms},
+                'config3_cpu': {'workload': 'BASELINE config 3, the pattern of RN:168-181: per 512-ray chunk render + autograd.grad(rgb, batch_rays); 1024-ray sample',
+                                'rays_per_s': c3_rate, 'seconds': c3_s, 'gpu_counterpart': 'pose_grad / fwd_bwd'},
+                'eager_pytorch_on_this_gpu': eager_gpu_rates(dev),
+            }
 
     if world > 1:
         dist.barrier()
@@ -646,7 +765,8 @@ def run_ours(args):
         print(json.dumps({
             'metric': METRIC, 'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f16x3: fp16 hi/lo-split operands (x_hi.W_hi + x_lo.W_hi + x_hi.W_lo), f32 accumulate, tcgen05 kind::f16; f32 everywhere else',
+            'dtype': 'f16 / f16x3: tier 1 (every point, density only) one fp16 tcgen05 MMA per product; tier 2 (active points) fp16 hi/lo-split operands '
+                     '(x_hi.W_hi + x_lo.W_hi + x_hi.W_lo); f32 accumulate; f32 everywhere else',
             'data': 'synthetic',
             'config': {'workload': 'BASELINE config 2: one 400x400 image (160000 rays) per GPU per step, 64 coarse + 128 fine, forward render',
                        'rays_per_step_per_gpu': n, 'N_samples': N_SAMPLES, 'N_importance': N_IMPORTANCE, 'parallelism': f'dp{world} (rays sharded by image, no forward collective)',
@@ -654,10 +774,14 @@ def run_ours(args):
                        'l2': 'per-step intermediates 0.86 GB >> 126 MB L2; rays rotate over 8 poses'},
             'e2e': {'value': e2e_value, 'unit': 'rays/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e / args.steps,
                     'api': 'render(H, W, K, chunk, rays=<pinned host [2,N,3] -> cuda>, **render_kwargs_test) + D2H of rgb/disp/acc'},
-            'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_base,
+            'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'roofline_kernels': roofline_kernels, 'roofline_step': roofline_step,
+            'cpu_baseline': cpu_base, 'parity': parity, 'baselines': baselines,
             'flop_per_ray': FLOP_PER_RAY, 'tflops_device_resident': value * FLOP_PER_RAY / 1e12,
-            'tensor_flop_issued_per_algorithmic_flop': 3, 'two_tier': two_tier, 'fast_fp16_mode': fast, 'mixed_f8_mode': mixed, 'fwd_bwd': fwd_bwd, 'pose_grad': pose_grad, 'train_step': train, 'stages': stages,
+            'two_tier': two_tier, 'fast_fp16_mode': fast, 'mixed_f8_mode': mixed, 'fwd_bwd': fwd_bwd, 'pose_grad': pose_grad, 'train_step': train, 'stages': stages,
         }))
+        if parity is not None and not parity['ok']:
+            sys.stderr.write(f'bench.py: PARITY FAILED on the timed image: {parity}\n')
+            sys.exit(3)
 
 
 def main():

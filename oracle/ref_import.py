@@ -1,8 +1,8 @@
-"""Import the UNMODIFIED reference renderer modules from /root/reference (build container only).
+"""Import the UNMODIFIED reference renderer modules: from /root/reference in the build container, else from the bytecode
+build of the same files in oracle/_ref/ (oracle/build_ref.py; it travels to the GPU box, /root/reference does not).
 
-TEST INFRASTRUCTURE.  /root/reference does not exist on the GPU box, so nothing
-that runs there may call this; it is used by oracle/make_golden.py and
-tests/test_oracle_pinned.py (skipped when the tree is absent).
+TEST INFRASTRUCTURE: used by oracle/make_golden.py, tests/test_oracle_pinned.py (live tree only) and bench.py's CPU baseline legs
+(`cpu_baseline.kind: "reference"`).  The product package never imports it.
 
 Recipe:
   * sys.path gets /root/reference/optimization so `utils.run_nerf_noscale` resolves;
@@ -17,18 +17,30 @@ import sys
 import types
 
 REF_ROOT = '/root/reference/optimization'
+BUILT_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref')
 
 
 def available():
+    """The live reference tree (build container)."""
     return os.path.isdir(REF_ROOT)
+
+
+def built():
+    """The bytecode build of the reference modules (oracle/build_ref.py), importable sourceless."""
+    return os.path.isfile(os.path.join(BUILT_ROOT, 'utils', 'run_nerf_noscale.pyc'))
+
+
+def usable():
+    return available() or built()
 
 
 def load():
     """Returns (RN, RH): the reference's run_nerf_noscale and run_nerf_helpers modules."""
     import torch
-    if not available():
-        raise RuntimeError('reference tree not present (expected in the build container only)')
-    for name in ('imageio', 'matplotlib', 'matplotlib.pyplot', 'cv2'):
+    if not usable():
+        raise RuntimeError('neither /root/reference nor oracle/_ref (python oracle/build_ref.py) is present')
+    root = REF_ROOT if available() else BUILT_ROOT
+    for name in ('imageio', 'matplotlib', 'matplotlib.pyplot', 'cv2', 'tqdm'):
         if name not in sys.modules:
             try:
                 __import__(name)
@@ -36,12 +48,29 @@ def load():
                 sys.modules[name] = types.ModuleType(name)
     if not torch.cuda.is_available():
         torch.Tensor.cuda = lambda self, *a, **k: self
-    if REF_ROOT not in sys.path:
-        sys.path.insert(0, REF_ROOT)
+    # (with a GPU present, CPU runs of the reference go inside `with cpu_shim():`)
+    if root not in sys.path:
+        sys.path.insert(0, root)
     import utils.run_nerf_noscale as RN
     import utils.run_nerf_helpers as RH
     # RH:2 switches autograd anomaly mode on globally at import; leave the choice to the caller.
     return RN, RH
+
+
+class cpu_shim:
+    """Context manager: the reference's hard-coded `.cuda()` calls (RH:158,159,208; RN:359,363,366,376,439) become no-ops, so that
+    its CPU path can be timed on a box that has a GPU.  Restores torch.Tensor.cuda on exit."""
+
+    def __enter__(self):
+        import torch
+        self.saved = torch.Tensor.cuda
+        torch.Tensor.cuda = lambda t, *a, **k: t
+        return self
+
+    def __exit__(self, *exc):
+        import torch
+        torch.Tensor.cuda = self.saved
+        return False
 
 
 def build_models(sd_coarse, sd_fine):
