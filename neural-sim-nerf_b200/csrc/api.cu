@@ -69,7 +69,7 @@ int ensure_dynamic_smem(const void* func, int bytes) {
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // two-tier evaluation knobs (process-wide; set them before launching work, not concurrently with it)
-static TwoTierParams g_two_tier = {4.0f, 1.0f, 0.30f};
+static TwoTierParams g_two_tier = {4.0f, 1.5f, 0.30f};   // tau, verify_max (measured max |sigma~ - sigma|: 0.74), force_fraction
 static bool g_two_tier_enabled = true;
 const TwoTierParams& two_tier_params() { return g_two_tier; }
 
