@@ -33,6 +33,31 @@ def shard_poses(render_poses, rank=None, world_size=None):
     return render_poses[lo:hi], (lo, hi)
 
 
+def plan_images(n_images, rank=None, world_size=None):
+    """K images of one epoch over the ranks without a ragged tail: the first (K // ws) * ws images go out whole, contiguous and
+    balanced ([lo, hi) for this rank); each of the K % ws remainder images is cut into row bands over a group of ws // (K % ws)
+    ranks, so that 50 images on 8 GPUs cost 6.25 image-times per rank instead of 7.  Returns ((lo, hi), shared) with
+    shared = [(image_index, part, n_parts, owner_rank), ...] for this rank (at most one entry); owner_rank holds part 0."""
+    r, w = world()
+    rank = r if rank is None else rank
+    world_size = w if world_size is None else world_size
+    whole = (n_images // world_size) * world_size
+    lo, hi = shard_bounds(whole, rank, world_size)
+    rem = n_images - whole
+    shared = []
+    if rem:
+        group = world_size // rem            # ranks per remainder image (ranks beyond rem * group stay idle for it)
+        j, part = divmod(rank, group)
+        if j < rem:
+            shared.append((whole + j, part, group, j * group))
+    return (lo, hi), shared
+
+
+def row_band(H, part, n_parts):
+    """Rows [r0, r1) of an H-row image for band `part` of `n_parts` (balanced, contiguous)."""
+    return shard_bounds(H, part, n_parts)
+
+
 def render_rays_sharded(rays_flat, render_fn, gather=True):
     """Render a [N,11] ray batch with every rank taking a contiguous slice.  `render_fn(rays) -> dict`
     (e.g. functools.partial(render_rays, **render_kwargs)).  With gather=True every rank returns the
@@ -63,12 +88,17 @@ def _collective_device():
     return torch.device('cpu')
 
 
-def reduce_psi_grad(chunk_grads, n_psi=None):
+def reduce_psi_grad(chunk_grads, n_psi=None, counts=None):
     """chunk_grads: this rank's list of per-chunk dL/dpsi tensors (what render_path_grad returns as
     `dLdpsis`, RN:190 -- CPU tensors, `.cpu().detach()`; any device is accepted).  Returns the reference's estimator over ALL
     ranks: mean over every chunk of every image (MAIN:191) -- one all_reduce(SUM) of [sum, count] on the device the backend
     needs (CUDA under NCCL, CPU under gloo), result on that device.  A rank with no chunks contributes zeros; `n_psi` (length
-    of psi) is only needed when NO rank may have any chunk."""
+    of psi) is only needed when NO rank may have any chunk.  `counts` (one number per entry, default 1): how many entries of the
+    mean an entry stands for -- a row band of an image shared by g ranks (plan_images) carries that band's share of the image's
+    gradient and counts 1/g, so that the g bands together weigh like one image."""
+    if counts is not None and len(counts) != len(chunk_grads):
+        raise ValueError('reduce_psi_grad: counts must match chunk_grads')
+    total = float(sum(counts)) if counts is not None else float(len(chunk_grads))
     if len(chunk_grads):
         s = torch.stack([g.detach().reshape(-1).to(torch.float64) for g in chunk_grads], 0).sum(0)
     else:
@@ -79,14 +109,14 @@ def reduce_psi_grad(chunk_grads, n_psi=None):
             if n_psi is None:
                 raise ValueError('reduce_psi_grad: no chunk gradients (render_path_grad returned an empty list) and n_psi not given')
             return torch.zeros(n_psi, dtype=torch.float32)
-        return (s / len(chunk_grads)).to(torch.float32)
+        return (s / total).to(torch.float32)
     dev = _collective_device()
     width = torch.tensor([s.numel() if s is not None else (n_psi or 0)], device=dev)
     dist.all_reduce(width, op=dist.ReduceOp.MAX)
     buf = torch.zeros(int(width.item()) + 1, dtype=torch.float64, device=dev)
     if s is not None:
         buf[:-1] = s.to(dev)
-        buf[-1] = len(chunk_grads)
+        buf[-1] = total
     dist.all_reduce(buf, op=dist.ReduceOp.SUM)
     return (buf[:-1] / buf[-1].clamp(min=1)).to(torch.float32)
 

@@ -682,10 +682,13 @@ def rays_grad_to_c2w(H, W, K, rays, d_rays, pixel_idx=None):
     return out
 
 
-def render_image_grad(H, W, K, c2w, g_rgb, **kw):
+def render_image_grad(H, W, K, c2w, g_rgb, rows=None, **kw):
     """One image forward + backward for the pose path (RN:148-181 for all H*W rays at once): returns (rgb_map [H,W,3],
     dL/dc2w [3,4]) given g_rgb = dL/drgb_map [H*W,3].  No autograd graph is built: rays come from the device-resident c2w,
-    the fine pass is back-propagated by nsr_render_rays_backward and dL/d(ray_batch) is folded to the pose in closed form."""
+    the fine pass is back-propagated by nsr_render_rays_backward and dL/d(ray_batch) is folded to the pose in closed form.
+    rows = (r0, r1): only image rows [r0, r1) are rendered and back-propagated (g_rgb still covers the whole image); returns
+    (rgb_map [r1-r0,W,3], this slice's contribution to dL/dc2w) -- contributions of disjoint slices add up to the image's
+    gradient, which is how dist.py shards one image over several GPUs."""
     if not _image_path_ok(kw):
         raise NotImplementedError('render_image_grad covers use_viewdirs=True, ndc=False, perturb=0, raw_noise_std=0, scalar near/far')
     if PRECISION == 'fp16':
@@ -702,6 +705,21 @@ def render_image_grad(H, W, K, c2w, g_rgb, **kw):
     g = g_rgb.detach().to(device=dev, dtype=torch.float32).reshape(-1, 3).contiguous()
     if g.shape[0] != H * W:
         raise ValueError(f'g_rgb {tuple(g_rgb.shape)} does not match a {H}x{W} image')
+    if rows is not None:
+        r0, r1 = int(rows[0]), int(rows[1])
+        if not (0 <= r0 < r1 <= H):
+            raise ValueError(f'render_image_grad: rows {rows} outside a {H}-row image')
+        rays = torch.empty(H * W, 11, dtype=torch.float32, device=dev)
+        check(L.nsr_make_rays_dev(H, W, Kh.ctypes.data_as(ctypes.c_void_p), ptr(c), 4, float(kw['near']), float(kw['far']), ptr(rays), _stream()),
+              'nsr_make_rays_dev')
+        part = rays[r0 * W:r1 * W]
+        cfg = dict(pc=pc, pf=pf, S=S, Ni=Ni, flags=flags, t_rand=None, u=None, retraw=False)
+        with torch.no_grad():
+            outs, saved = _forward_impl(part, cfg, keep_for_backward=True, save_mask=True)
+            d_rays, _ = _RenderRaysFn._one_pass(part, saved[0], saved[1], pf if pf is not None else pc, flags & FLAG_WHITE_BKGD,
+                                                g[r0 * W:r1 * W].contiguous(), False, saved[4], None, saved[6])
+            d_c2w = rays_grad_to_c2w(H, W, K, part, d_rays, pixel_idx=torch.arange(r0 * W, r1 * W, device=dev, dtype=torch.int32))
+        return outs[0].view(r1 - r0, W, 3), d_c2w
     ws_bytes = L.nsr_render_image_grad_workspace_bytes(H, W, S, Ni)
     ws = None
     if SAVE_RELU_MASK and _mask_fits(ws_bytes, dev):

@@ -41,6 +41,12 @@ def worker(rank, world, port, q):
     # fewer images than ranks: rank 1 renders nothing, the mean is still over the chunks that exist
     lone = D.reduce_psi_grad(chunks[:2] if rank == 0 else [])
     ok_psi = ok_psi and torch.allclose(lone, torch.stack(chunks[:2]).mean(0), atol=1e-6)
+    # an image shared by both ranks as row bands (dist.plan_images): each band carries its share of the gradient and counts 1/2
+    whole = [torch.randn(8, generator=g) for _ in range(2)]           # two whole-image entries, one per rank
+    img = torch.randn(8, generator=g)                                 # the shared image's entry, split 30 / 70 between the bands
+    band = img * (0.3 if rank == 0 else 0.7)
+    mix = D.reduce_psi_grad([whole[rank], band], counts=[1.0, 0.5])
+    ok_psi = ok_psi and torch.allclose(mix, (whole[0] + whole[1] + img) / 3.0, atol=1e-6)
     # device of the collective follows the backend, not the inputs (render_path_grad hands back CPU tensors, RN:190)
     ok_psi = ok_psi and D._collective_device().type == 'cpu' and red.device.type == 'cpu'
     poses, (plo, phi) = D.shard_poses(list(range(50)))
@@ -61,6 +67,31 @@ def test_shard_bounds_cover_everything():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_plan_images_covers_every_image_once():
+    import neural_sim_nerf_b200.dist as D
+    for K in (1, 7, 8, 9, 50, 64):
+        for w in (1, 2, 4, 8):
+            plans = [D.plan_images(K, r, w) for r in range(w)]
+            whole = (K // w) * w
+            spans = [p[0] for p in plans]
+            assert spans[0][0] == 0 and spans[-1][1] == whole and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert len({b - a for a, b in spans}) == 1                                   # no ragged tail among the whole images
+            shared = [e for p in plans for e in p[1]]
+            for img in range(whole, K):
+                parts = sorted(e[1] for e in shared if e[0] == img)
+                n_parts = {e[2] for e in shared if e[0] == img}
+                assert len(n_parts) == 1 and parts == list(range(n_parts.pop()))          # every band exactly once
+                assert {e[3] for e in shared if e[0] == img} == {min(r for r in range(w) if plans[r][1] and plans[r][1][0][0] == img)}
+            assert all(whole <= e[0] < K for e in shared)
+            for H in (400, 7):
+                for n_parts in (1, 3, 4):
+                    bands = [D.row_band(H, q, n_parts) for q in range(n_parts)]
+                    assert bands[0][0] == 0 and bands[-1][1] == H and all(a[1] == b[0] for a, b in zip(bands, bands[1:]))
+    # 50 images on 8 GPUs: 6 whole images per rank + a quarter of one of the two remainder images
+    (lo, hi), shared = D.plan_images(50, 5, 8)
+    assert (lo, hi) == (30, 36) and shared == [(49, 1, 4, 4)]
 
 
 def test_world_size_2_gloo():

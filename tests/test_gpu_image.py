@@ -203,3 +203,24 @@ def test_render_image_grad_routes_agree(nsr, nets):
     assert scale > 0 and float((out[True][1] - out[False][1]).abs().max()) <= 1e-5 * scale
     with pytest.raises(ValueError):
         nsr.render_image_grad(H, W, K, pose, g[:-1], **kw)
+
+
+def test_row_bands_of_an_image_add_up(nsr, nets):
+    """render_image_grad(rows=...): what dist.plan_images hands to each rank of a group -- the bands' pixels are the image's rows,
+    their dL/dc2w contributions add up to the whole image's gradient."""
+    H = W = 48
+    K = [[160.0, 0, 23.4], [0, 160.1, 24.1], [0, 0, 1]]
+    kw = dict(network_fn=nets[0], network_query_fn=None, N_samples=64, N_importance=128, network_fine=nets[1], use_viewdirs=True, ndc=False,
+              near=O.YCBV_NEAR, far=O.YCBV_FAR, white_bkgd=False, raw_noise_std=0., perturb=False, lindisp=False)
+    pose = O.pose_spherical(90., 112.5 - 180., 1.01)[:3, :4].cuda()
+    g = torch.randn(H * W, 3, device='cuda', generator=torch.Generator(device='cuda').manual_seed(11))
+    rgb_all, d_all = nsr.run_nerf.render_image_grad(H, W, K, pose, g, **kw)
+    total = torch.zeros_like(d_all)
+    for r0, r1 in ((0, 13), (13, 14), (14, 48)):
+        rgb_b, d_b = nsr.run_nerf.render_image_grad(H, W, K, pose, g, rows=(r0, r1), **kw)
+        assert torch.equal(rgb_b, rgb_all[r0:r1])
+        total += d_b
+    assert float(d_all.abs().max()) > 0
+    assert float((total - d_all).abs().max()) <= 1e-5 * float(d_all.abs().max())
+    with pytest.raises(ValueError):
+        nsr.run_nerf.render_image_grad(H, W, K, pose, g, rows=(10, 49), **kw)

@@ -13,7 +13,9 @@ detectron2 is not in this image, so the detector side -- create_dataset / train 
           Momentum update of psi, learning-rate schedule                 MAIN:1203-1212
 
   python tools/bilevel_stub.py [--epochs 2] [--K 8] [--hw 400]
-  torchrun --nproc-per-node N tools/bilevel_stub.py ...      poses sharded over the ranks, one all-reduce of dL/dpsi per epoch
+  torchrun --nproc-per-node N tools/bilevel_stub.py ...      poses sharded over the ranks, one all-reduce of dL/dpsi per epoch;
+      the K % N remainder images are cut into row bands over groups of ranks (dist.plan_images), so K = 50 on 8 GPUs costs 6.25
+      image-times per rank instead of 7
 
 Prints one JSON line with the wall-clock split per epoch (rank 0).
 """
@@ -110,27 +112,78 @@ def main():
         # ---- 1. D_train: K images from the current psi (MAIN:1179-1180), every rank renders its share of the poses
         prob = torch.softmax(psi / 0.25, 0)
         poses, log = nsr.sample_pose_nograd(prob, args.K, args.gumble_T, seed=epoch, device=dev)
-        lo, hi = nd.shard_bounds(args.K, rank, world)
+        (lo, hi), shared = nd.plan_images(args.K, rank, world)
+        n_rem = args.K - (args.K // world) * world
+        group = world // n_rem if n_rem else 1
+        cap = -(-H // group)                                                                     # rows of the largest band
         savedir = os.path.join(workdir, 'epoch{:02d}_rank{}'.format(epoch, rank))
+        os.makedirs(os.path.join(savedir, str(object_id)), exist_ok=True)
         if hi > lo:
             nsr.render_path(None, poses[lo:hi], hwf, K, chunk, kw, savedir=savedir, object_id=object_id)
+        n_local = hi - lo                                                                        # PNGs this rank's detector reads
+        if n_rem and world > 1:
+            # remainder images: every rank of a group renders one row band; the bands meet on the owner rank, which writes the PNG
+            band = torch.zeros(cap, W, 3, dtype=torch.uint8, device=dev)
+            if shared:
+                img, part, g_, owner = shared[0]
+                r0, r1 = nd.row_band(H, part, g_)
+                rr = nsr.make_rays(H, W, K, poses[img][:3, :4], YCBV_NEAR, YCBV_FAR)[r0 * W:r1 * W]
+                with torch.no_grad():
+                    rgb_b = nsr.render(H, W, K, chunk=1 << 20, rays=torch.stack([rr[:, 0:3], rr[:, 3:6]], 0), **kw)[0]
+                band[:r1 - r0] = nsr.run_nerf.to8b_device(rgb_b).view(r1 - r0, W, 3)
+            bands = [torch.empty_like(band) for _ in range(world)]
+            dist.all_gather(bands, band)
+            if shared and shared[0][1] == 0:
+                img, _, g_, owner = shared[0]
+                rows_ = [bands[owner + q][:nd.row_band(H, q, g_)[1] - nd.row_band(H, q, g_)[0]] for q in range(g_)]
+                nsr.run_nerf._imwrite(os.path.join(savedir, str(object_id), '{:03d}.png'.format(n_local)), torch.cat(rows_, 0).cpu().numpy())
+                n_local += 1
+        elif n_rem:                                                                              # one rank: the tail images go out whole
+            nsr.render_path(None, poses[hi:], hwf, K, chunk, kw, savedir=os.path.join(savedir, 'tail'), object_id=object_id)
+            for q in range(args.K - hi):
+                os.replace(os.path.join(savedir, 'tail', str(object_id), '{:03d}.png'.format(q)),
+                           os.path.join(savedir, str(object_id), '{:03d}.png'.format(n_local + q)))
+            n_local += args.K - hi
         torch.cuda.synchronize()
         t['render_images_s'] = time.perf_counter() - t0
         # ---- 2. detector (stub)
         t1 = time.perf_counter()
-        grad_E = stub_detector(savedir, object_id, range(hi - lo), H, W, epoch * world + rank) if hi > lo else []
+        grad_E = stub_detector(savedir, object_id, range(n_local), H, W, epoch * world + rank) if n_local else []
+        shared_g = None
+        if n_rem and world > 1:
+            # the owner's detector saw the shared image: its grad_E goes to the ranks that hold the other bands
+            for j in range(n_rem):
+                buf = torch.zeros(3, H, W, device=dev)
+                if rank == j * group:
+                    buf.copy_(grad_E[-1]['grad_E'][0])
+                dist.broadcast(buf, src=j * group)
+                if shared and shared[0][0] == (args.K // world) * world + j:
+                    shared_g = buf
         t['stub_detector_s'] = time.perf_counter() - t1
         # ---- 3. dL_val/dpsi = dI/dpsi . grad_E (MAIN:1199-1200), poses replayed with gradient
         t2 = time.perf_counter()
         prob_g = torch.softmax(psi.to(dev) / 0.25, 0).requires_grad_()
         poses_g = nsr.sample_pose(prob_g, args.K, args.gumble_T, log)
-        dLdpsis = []
+        dLdpsis, counts = [], []
         if hi > lo:
-            _, dLdpsis = nsr.render_path_grad(prob_g, poses_g[lo:hi], hwf, K, chunk, grad_E, kw)
+            _, dLdpsis = nsr.render_path_grad(prob_g, poses_g[lo:hi], hwf, K, chunk, grad_E[:hi - lo], kw)
+            counts = [1.0] * len(dLdpsis)
+        if n_rem and world > 1:
+            if shared:
+                img, part, g_, owner = shared[0]
+                pose = poses_g[img][:3, :4]
+                _, d_c2w = nsr.run_nerf.render_image_grad(H, W, K, pose, shared_g.permute(1, 2, 0).reshape(-1, 3), rows=nd.row_band(H, part, g_), **kw)
+                d = torch.autograd.grad(pose, prob_g, grad_outputs=d_c2w.to(pose.dtype), retain_graph=True)[0]
+                dLdpsis.append((d / max(1, -(-H * W // chunk))).cpu().detach())
+                counts.append(1.0 / g_)
+        elif n_rem:
+            _, tail = nsr.render_path_grad(prob_g, poses_g[hi:], hwf, K, chunk, grad_E[hi - lo:], kw)
+            dLdpsis += tail
+            counts += [1.0] * len(tail)
         torch.cuda.synchronize()
         t['render_images_grad_s'] = time.perf_counter() - t2
         t3 = time.perf_counter()
-        grad_psi = nd.reduce_psi_grad([g.to(dev) for g in dLdpsis]).cpu()                        # MAIN:191 over all ranks
+        grad_psi = nd.reduce_psi_grad([g.to(dev) for g in dLdpsis], n_psi=8, counts=counts).cpu()   # MAIN:191 over all ranks
         t['reduce_s'] = time.perf_counter() - t3
         # ---- 4. update psi (MAIN:1203, 1212)
         psi = opt.update(psi, grad_psi)
@@ -145,7 +198,7 @@ def main():
         rays = args.K * H * W
         last = split[-1]
         print(json.dumps({'workload': f'bilevel outer loop with a stub detector: {args.epochs} epochs x K={args.K} images of {H}x{W}, 64+128 samples, '
-                                      f'{world} GPU(s), poses sharded by rank',
+                                      f'{world} GPU(s), poses sharded by rank, remainder images in row bands over rank groups',
                           'epochs': split,
                           'render_images_rays_per_s': rays / last['render_images_s'],
                           'render_images_grad_rays_per_s': rays / last['render_images_grad_s'],
