@@ -298,18 +298,26 @@ __device__ void sample_pdf_warp(const float* bins, float* w, float* cdf, int B, 
   // The `denom < 1e-5` test below (RH:239) sits right on top of the value empty bins produce
   // (1e-5 / ~1.0006), and u = 1.0 sits on top of cdf[-1]; one ulp in the normaliser or in a prefix moves whole
   // samples by a bin width.  So normaliser and cdf are rounded exactly as ATen's CPU kernels round them:
-  // torch.sum in its vector order (aten_row_sum), cumsum sequentially in fp64 with every prefix rounded to fp32
-  // (one lane, <= 255 adds; negligible next to the MLP).
+  // torch.sum in its vector order (aten_row_sum), cumsum in fp64 with every prefix rounded to fp32.
   const float s = aten_row_sum(w, nw, lane);
   for (int i = lane; i < nw; i += 32) w[i] = __fdiv_rn(w[i], s);
   __syncwarp();
-  if (lane == 0) {
-    double run = 0.0;
-    cdf[0] = 0.f;
-    for (int i = 0; i < nw; ++i) {
-      run += double(w[i]);
-      cdf[i + 1] = float(run);
+  // ATen's CPU cumsum accumulates sequentially in fp64 and rounds every prefix to fp32.  The pdf values are fp32 numbers in
+  // [2^-23, 1] and a prefix stays below 2, so every fp64 partial sum is EXACT (24 + 23 + 1 significant bits at most): the sum is
+  // associative here and a warp scan gives the sequential loop's prefixes bit for bit (stage test: tests/test_gpu_parity.py).
+  if (lane == 0) cdf[0] = 0.f;
+  double carry = 0.0;
+  for (int i0 = 0; i0 < nw; i0 += 32) {
+    const int i = i0 + lane;
+    double v = i < nw ? double(w[i]) : 0.0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const double o = __shfl_up_sync(FULL, v, d);
+      if (lane >= d) v += o;
     }
+    v += carry;
+    if (i < nw) cdf[i + 1] = float(v);
+    carry = __shfl_sync(FULL, v, 31);
   }
   __syncwarp();
   for (int k = lane; k < N; k += 32) {
