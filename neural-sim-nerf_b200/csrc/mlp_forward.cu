@@ -311,10 +311,20 @@ struct Roles {
 static_assert(Roles<false>::THREADS == MLP_THREADS && Roles<false>::ENC0 == ENC_WARP0 && Roles<false>::MMA == MMA_WARP &&
               Roles<false>::PROD == PROD_WARP, "mlp_common.cuh warp roles");
 
-template <int SPLIT, bool SAVE, bool CLASSIFY>
+// PAIR (tier 1 only): the kernel runs as clusters of two CTAs on the two SMs of a TPC and issues tcgen05.mma.cta_group::2 -- one
+// instruction stream (the leader's, cluster rank 0) drives both tensor cores with M = 256: each CTA keeps its own tile (its TMEM, its
+// encodings, its epilogue) but only HALF of every weight chunk (64 of the 128 output rows, 8 KB), so both the TMA writes into shared
+// memory and the tensor core's B reads out of it halve.  That is what bounded the single-CTA kernel: 64 B/cycle written + 64 B/cycle
+// read is all the shared memory has.  Barriers: weights / accumulators / encodings are released by multicast
+// commits (both CTAs); the epilogue and encoder warps of BOTH CTAs arrive, one lane per warp, on the LEADER's barriers; the
+// follower's otherwise idle MMA warp relays "my half of the chunk has landed" to the leader's full barrier.
+template <int SPLIT, bool SAVE, bool CLASSIFY, bool PAIR = false>
 __global__ void __launch_bounds__(Roles<CLASSIFY>::THREADS, 1) nerf_mlp_kernel(MlpArgs a) {
   using C = Cfg<SPLIT>;
   using R = Roles<CLASSIFY>;
+  static_assert(!PAIR || CLASSIFY, "the CTA-pair variant is built for the tier-1 kernel");
+  constexpr int kStageBytes = PAIR ? C::STAGE_BYTES / 2 : C::STAGE_BYTES;
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;   // == blockIdx.x & 1
   constexpr bool kSplit = C::kSplit;
   constexpr bool kMixed = C::kMixed;
   constexpr int kSteps = CLASSIFY ? 8 : NUM_STEPS;   // GEMM steps per tile
@@ -365,22 +375,28 @@ __global__ void __launch_bounds__(Roles<CLASSIFY>::THREADS, 1) nerf_mlp_kernel(M
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const size_t dumpP = size_t(a.num_tiles) * 128;   // (dump: dense launches only)   // rows of the optional dump
+  // PAIR: the two CTAs of a pair take tiles (2i, 2i+1) together, so the tile range is rounded up to even (a tile beyond the last
+  // one has no valid row: point_of returns -1 everywhere)
+  const int tile_end = PAIR ? ((num_tiles + 1) & ~1) : num_tiles;
 
   if (tid == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(&full[s], 1);
+      mbar_init(&full[s], (PAIR && crank == 0) ? 2 : 1);   // PAIR leader: own producer (+ bytes) and the follower's relay
       mbar_init(&empty[s], 1);
     }
     for (int h = 0; h < 2; ++h) {
       mbar_init(&acc_ready[h], 1);
-      mbar_init(&a_ready[h], CLASSIFY ? R::EPI_WARPS * 32 : EPI_THREADS);
-      mbar_init(&enc_ready[h], ENC_THREADS);
+      mbar_init(&a_ready[h], PAIR ? 2 * R::EPI_WARPS : (CLASSIFY ? R::EPI_WARPS * 32 : EPI_THREADS));   // PAIR: one arrival per warp, both CTAs
+      mbar_init(&enc_ready[h], PAIR ? 4 : ENC_THREADS);
       mbar_init(&enc_free[h], 1);
     }
-    mbar_init(acc_free1, CLASSIFY ? R::EPI_WARPS * 32 : EPI_THREADS);
+    mbar_init(acc_free1, PAIR ? 2 * R::EPI_WARPS : (CLASSIFY ? R::EPI_WARPS * 32 : EPI_THREADS));
     fence_mbar_init();
   }
-  if (warp == R::MMA) tmem_alloc(tmem_slot, 512);
+  if (warp == R::MMA) {
+    if constexpr (PAIR) tmem_alloc_pair(tmem_slot, 512);
+    else tmem_alloc(tmem_slot, 512);
+  }
   for (int i = tid; i < TAIL_FLOATS; i += R::THREADS)
     reinterpret_cast<float*>(smem + C::SM_TAIL)[i] = reinterpret_cast<const float*>(a.packed + WEIGHT_BYTES)[i];
   if constexpr (CLASSIFY) {   // tier 1 adds its biases in packed fp16: the table lives where the (unused) view-dir encoding would
@@ -392,15 +408,24 @@ __global__ void __launch_bounds__(Roles<CLASSIFY>::THREADS, 1) nerf_mlp_kernel(M
   }
   tc_fence_before_sync();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // the peer's barriers are initialised before any remote arrive / multicast commit
   tc_fence_after_sync();
   if (*tmem_slot != 0u) __trap();  // the whole TMEM of the SM is ours: the allocation must start at 0
+  // PAIR: addresses of the LEADER's barriers in the cluster window (the leader maps onto itself)
+  [[maybe_unused]] uint32_t lead_a_ready[2] = {0u, 0u}, lead_acc_free1 = 0u, lead_enc_ready0 = 0u;
+  if constexpr (PAIR) {
+    lead_a_ready[0] = mapa_u32(smem_u32(&a_ready[0]), 0);
+    lead_a_ready[1] = mapa_u32(smem_u32(&a_ready[1]), 0);
+    lead_acc_free1 = mapa_u32(smem_u32(acc_free1), 0);
+    lead_enc_ready0 = mapa_u32(smem_u32(&enc_ready[0]), 0);
+  }
 
   if (warp == R::PROD) {
     // ===================================================================== weight producer (TMA engine)
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       bool first_lap = true;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
         int base = kMixed ? MIX_CHUNK0 : 0;          // first packed chunk of the step
         for (int step = 0; step < kSteps; ++step) {
           const int nk = step_k_chunks(step), nhs = step_n_halves(step);
@@ -411,8 +436,11 @@ __global__ void __launch_bounds__(Roles<CLASSIFY>::THREADS, 1) nerf_mlp_kernel(M
             if (NSR_EXP(1) && !first_lap) {
               mbar_arrive(&full[stage]);
             } else {
-              mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
-              bulk_g2s(sRing + stage * C::STAGE_BYTES, a.packed + size_t(base + nh * nk + kc) * CHUNK_PAIR_BYTES, C::STAGE_BYTES, &full[stage]);
+              // (PAIR: this CTA's half of the chunk's output rows -- the packed chunk keeps 8-row groups 1024 B apart, so rows
+              // [64 r, 64 r + 64) are its bytes [8192 r, 8192 r + 8192))
+              mbar_arrive_expect_tx(&full[stage], kStageBytes);
+              bulk_g2s(sRing + stage * kStageBytes, a.packed + size_t(base + nh * nk + kc) * CHUNK_PAIR_BYTES + (PAIR ? crank * kStageBytes : 0u),
+                       kStageBytes, &full[stage]);
             }
             if (++stage == C::STAGES) {
               stage = 0;
@@ -433,20 +461,40 @@ __global__ void __launch_bounds__(Roles<CLASSIFY>::THREADS, 1) nerf_mlp_kernel(M
     // stage, barrier parity and descriptor offset of a tile is a compile-time constant: the whole tile is unrolled.
     static_assert(!CLASSIFY || (C::STAGES == 10 && kSteps == 8 && !kSplit), "static tier-1 schedule");
     const bool leader = elect_one();
-    const uint32_t idesc = make_idesc_f16(128, 128);
+    const uint32_t idesc = make_idesc_f16(PAIR ? 256 : 128, 128);
     constexpr uint32_t HI_B = sdesc_hi(1024);
     const uint32_t ring_lo = sdesc_lo(smem_u32(sRing), 128);
     const uint32_t enc_hi = sdesc_lo(smem_u32(smem + C::SM_INBUF) + C::OFF_ENC_HI, 128);
+    // PAIR: barriers the peer arrives on are awaited with cluster-scope acquire; commits reach both CTAs
+    auto wait_b = [&](uint64_t* bar, uint32_t par) {
+      if constexpr (PAIR) mbar_wait_cluster(bar, par);
+      else mbar_wait(bar, par);
+    };
+    auto commit_b = [&](uint64_t* bar) {
+      if constexpr (PAIR) umma_commit_pair(bar);
+      else umma_commit(bar);
+    };
     uint32_t tl = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
-      mbar_wait(&enc_ready[0], tl & 1);
+    if (PAIR && crank != 0) {
+      // follower: the leader issues for the pair.  This warp only relays the arrival of this CTA's half of every chunk.
+      const uint32_t lead_full = mapa_u32(smem_u32(&full[0]), 0);
+      for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
+#pragma unroll 1
+        for (int c = 0; c < 60; ++c) {
+          mbar_wait(&full[c % 10], (c / 10) & 1);
+          if (lane == 0) mbar_arrive_cluster(lead_full + (c % 10) * 8);
+        }
+      }
+    } else
+    for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++tl) {
+      wait_b(&enc_ready[0], tl & 1);
       int cbase = 0;   // chunks of the tile consumed so far (compile-time after unrolling)
 #pragma unroll
       for (int step = 0; step < 8; ++step) {
         const int nk = step_k_chunks(step), k_early = step_k_early(step);
         const uint32_t par = step & 1;   // 8 steps per tile: the n-th wait of a per-step barrier has parity step & 1
         if (lane == 0) NSR_TR(tl, step, 0);
-        mbar_wait(&a_ready[0], par);     // A[K 0..127] of this step written, ACC0 drained
+        wait_b(&a_ready[0], par);        // A[K 0..127] of this step written, ACC0 drained
         if (lane == 0) NSR_TR(tl, step, 1);
         tc_fence_after_sync();
 #pragma unroll
@@ -456,39 +504,45 @@ __global__ void __launch_bounds__(Roles<CLASSIFY>::THREADS, 1) nerf_mlp_kernel(M
           const int c = cbase + slot, stage = c % 10;
           if (slot == k_early) {         // first chunk of half 1: ACC1 must be back (in the epilogue's registers)
             if (lane == 0) NSR_TR(tl, step, 5);
-            mbar_wait(acc_free1, par);
+            wait_b(acc_free1, par);
             if (lane == 0) NSR_TR(tl, step, 6);
             tc_fence_after_sync();
           }
           if (slot == 2 * k_early) {     // first late-K chunk: A[K 128..255] written
             if (lane == 0) NSR_TR(tl, step, 2);
-            mbar_wait(&a_ready[1], par);
+            wait_b(&a_ready[1], par);
             if (lane == 0) NSR_TR(tl, step, 3);
             tc_fence_after_sync();
           }
-          mbar_wait(&full[stage], (c / 10) & 1);   // 6 uses of every stage per tile: the parity pattern repeats tile after tile
+          wait_b(&full[stage], (c / 10) & 1);   // 6 uses of every stage per tile: the parity pattern repeats tile after tile
           if (leader && !NSR_EXP(5)) {
             const uint32_t acc = nh ? TM_ACC1 : TM_ACC0;
-            const uint32_t b = ring_lo + stage * (CHUNK_BYTES >> 4);
+            const uint32_t b = ring_lo + stage * (kStageBytes >> 4);
             if ((step == 0 || step == 5) && kc == 0) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) umma_ss2(acc, enc_hi + j * 16, HI_B, b + j * 16, HI_B, idesc, j ? 1u : 0u);
+              for (int j = 0; j < 4; ++j) {
+                if constexpr (PAIR) umma_ss2_pair(acc, enc_hi + j * 16, HI_B, b + j * 16, HI_B, idesc, j ? 1u : 0u);
+                else umma_ss2(acc, enc_hi + j * 16, HI_B, b + j * 16, HI_B, idesc, j ? 1u : 0u);
+              }
             } else {
               const uint32_t at = TM_AHI + (step == 5 ? kc - 1 : kc) * 32;
 #pragma unroll
-              for (int j = 0; j < 4; ++j) umma_ts2(acc, at + j * 8, b + j * 16, HI_B, idesc, (j || kc) ? 1u : 0u);
+              for (int j = 0; j < 4; ++j) {
+                if constexpr (PAIR) umma_ts2_pair(acc, at + j * 8, b + j * 16, HI_B, idesc, (j || kc) ? 1u : 0u);
+                else umma_ts2(acc, at + j * 8, b + j * 16, HI_B, idesc, (j || kc) ? 1u : 0u);
+              }
             }
           }
-          if (leader) umma_commit(&empty[stage]);
+          if (leader) commit_b(&empty[stage]);
           if (slot == last_slot_half0(nk, k_early)) {
             if (lane == 0) NSR_TR(tl, step, 7);
-            if (leader) umma_commit(&acc_ready[0]);
+            if (leader) commit_b(&acc_ready[0]);
           }
-          if (slot == 2 * nk - 1 && leader) umma_commit(&acc_ready[1]);
+          if (slot == 2 * nk - 1 && leader) commit_b(&acc_ready[1]);
         }
-        if (nk == k_early) mbar_wait(&a_ready[1], par);   // step 0 has no late-K chunk: consume the phase all the same
+        if (nk == k_early) wait_b(&a_ready[1], par);   // step 0 has no late-K chunk: consume the phase all the same
         if (lane == 0) NSR_TR(tl, step, 4);
-        if (step == 5 && leader) umma_commit(&enc_free[0]);  // last reader of the xyz encoding
+        if (step == 5 && leader) commit_b(&enc_free[0]);  // last reader of the xyz encoding
         cbase += 2 * nk;
       }
     }
@@ -624,7 +678,7 @@ __global__ void __launch_bounds__(Roles<CLASSIFY>::THREADS, 1) nerf_mlp_kernel(M
     uint32_t tl = 0;
     Waiter w_free[2];
     uint8_t* inbuf = smem + C::SM_INBUF;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+    for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++tl) {
       float x[2][3], vd[2][3];
 #pragma unroll
       for (int rr = 0; rr < 2; ++rr) {
@@ -700,7 +754,12 @@ __global__ void __launch_bounds__(Roles<CLASSIFY>::THREADS, 1) nerf_mlp_kernel(M
         }
       }
       fence_proxy_async_smem();
-      mbar_arrive(&enc_ready[0]);
+      if constexpr (PAIR) {                       // one arrival per warp on the LEADER's barrier (it issues for both CTAs)
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(lead_enc_ready0);
+      } else {
+        mbar_arrive(&enc_ready[0]);
+      }
       if (CLASSIFY) continue;                     // tier 1 stops at the alpha head: no view-dir encoding
       if (tl >= 1) w_free[1].wait(&enc_free[1]);  // step 9 of the previous tile has read the old view-dir encoding
 #pragma unroll 1
@@ -749,12 +808,29 @@ __global__ void __launch_bounds__(Roles<CLASSIFY>::THREADS, 1) nerf_mlp_kernel(M
     const int col0 = cq * 32;
     const uint32_t tlane = uint32_t(quad * 32) << 16;
     Waiter w_acc[2];
-    mbar_arrive(&a_ready[0]);                     // initial credits
-    mbar_arrive(&a_ready[1]);
-    if (kAccFree) mbar_arrive(acc_free1);
+    // arrivals towards the MMA warp: every thread on the CTA's own barrier, or (PAIR) one lane per warp on the leader's
+    auto arrive_a = [&](int half) {
+      if constexpr (PAIR) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(lead_a_ready[half]);
+      } else {
+        mbar_arrive(&a_ready[half]);
+      }
+    };
+    auto arrive_f1 = [&]() {
+      if constexpr (PAIR) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(lead_acc_free1);
+      } else {
+        mbar_arrive(acc_free1);
+      }
+    };
+    arrive_a(0);                                  // initial credits
+    arrive_a(1);
+    if (kAccFree) arrive_f1();
     const bool tracer = tid == 0;                 // debug timeline
     uint32_t tl = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+    for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++tl) {
       const int64_t p = point_of(tile, row);
       float sigma = 0.f;
       for (int step = 0; step < 8; ++step) {
@@ -771,7 +847,7 @@ __global__ void __launch_bounds__(Roles<CLASSIFY>::THREADS, 1) nerf_mlp_kernel(M
             if (tracer) NSR_TR(tl, step, 9 + 4 * half);
             if (half == 1 && kAccFree) {   // ACC1 lives in registers now: the next step's (half 1, K early) chunks may overwrite it
               tc_fence_before_sync();
-              mbar_arrive(acc_free1);
+              arrive_f1();
             }
             if (step < 7) {
               // fp16(acc) + fp16(bias) with the ReLU fused, two columns per instruction: 2.5x fewer issue slots than the fp32 form,
@@ -806,7 +882,7 @@ __global__ void __launch_bounds__(Roles<CLASSIFY>::THREADS, 1) nerf_mlp_kernel(M
             tmem_st_wait();
           }
           tc_fence_before_sync();
-          mbar_arrive(&a_ready[half]);
+          arrive_a(half);
           if (tracer) NSR_TR(tl, step, 11 + 4 * half);
         }
       }
@@ -1023,7 +1099,12 @@ __global__ void __launch_bounds__(Roles<CLASSIFY>::THREADS, 1) nerf_mlp_kernel(M
   if (a.ctrl != nullptr && a.role == AS_ROLE_REDO && blockIdx.x == 0 && tid == 0) a.ctrl[AS_DENSE_FINAL] = 1u;
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == R::MMA) tmem_dealloc(0u, 512);
+  if constexpr (PAIR) {
+    cluster_sync_all();   // the peer may still arrive on this CTA's barriers / read its shared memory until it is done too
+    if (warp == R::MMA) tmem_dealloc_pair(0u, 512);
+  } else {
+    if (warp == R::MMA) tmem_dealloc(0u, 512);
+  }
 }
 
 template <int SPLIT, bool SAVE, bool CLASSIFY = false>
@@ -1034,8 +1115,39 @@ static int launch_variant(const MlpArgs& a, int grid, cudaStream_t st) {
   return check_launch("nerf_mlp_kernel");
 }
 
+// tier 1 as clusters of two CTAs (tcgen05 ... cta_group::2): an even grid, launched with the cluster attribute
+static int launch_tier1_pair(const MlpArgs& a, int grid, cudaStream_t st) {
+  auto kernel = &nerf_mlp_kernel<1, false, true, true>;
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), Cfg<1>::SM_TOTAL)) return rc;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(unsigned(grid), 1, 1);
+  cfg.blockDim = dim3(Roles<true>::THREADS, 1, 1);
+  cfg.dynamicSmemBytes = Cfg<1>::SM_TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, kernel, a) != cudaSuccess) return check_launch("nerf_mlp_kernel (CTA pairs)");
+  count_launch();
+  return check_launch("nerf_mlp_kernel (CTA pairs)");
+}
+
 static int launch_by_flags(const MlpArgs& a, int grid, uint32_t flags, cudaStream_t st) {
-  if (a.role == AS_ROLE_TIER1) return launch_variant<1, false, true>(a, grid, st);
+  if (a.role == AS_ROLE_TIER1) {
+    // CTA pairs by default (NSR_TIER1_PAIR=0: one CTA per SM, for A/B runs); the pair kernel wants an even grid of at least 2
+    static const bool pair = [] {
+      const char* e = getenv("NSR_TIER1_PAIR");
+      return e == nullptr || atoi(e) != 0;
+    }();
+    const int tiles_even = (a.num_tiles + 1) & ~1;
+    const int pgrid = (grid & ~1) < tiles_even ? (grid & ~1) : tiles_even;
+    if (pair && pgrid >= 2 && a.experiment < 100) return launch_tier1_pair(a, pgrid, st);
+    return launch_variant<1, false, true>(a, grid, st);
+  }
   if (a.relu_mask != nullptr || a.dump != nullptr) {
     if (flags & (NSR_FLAG_FAST_FP16 | NSR_FLAG_MIXED_F8)) {
       set_error("mlp_forward: sign bits / activations are saved for the backward pass, which is built for the default precision only");
