@@ -183,6 +183,10 @@ int nsr_mlp_two_tier(const float* rays, const float* z_vals, int64_t n_rays, int
  * pass dense.  Requires tau > verify_max >= 0.  nsr_get_two_tier: any pointer may be NULL. */
 int nsr_set_two_tier(int enabled, float tau, float verify_max, float force_fraction);
 int nsr_get_two_tier(int* enabled, float* tau, float* verify_max, float* force_fraction);
+/* Tier 1 as clusters of two CTAs (tcgen05 ... cta_group::2: one instruction stream drives the tensor cores of both SMs of a TPC, each
+ * CTA holding half of every weight chunk).  Process-wide, default off (environment NSR_TIER1_PAIR=1 turns it on at load); returns the
+ * previous setting.  Results are bit-identical either way; DESIGN.md 3.1a has the measurements. */
+int nsr_set_tier1_pair(int enabled);
 
 /* Bytes of scratch nsr_render_rays_backward needs for n rays of T = n_samples + n_importance depths. */
 size_t nsr_render_backward_workspace_bytes(int64_t n_rays, int n_total_samples);

@@ -218,6 +218,8 @@ int nsr_set_two_tier(int enabled, float tau, float verify_max, float force_fract
   return NSR_OK;
 }
 
+int nsr_set_tier1_pair(int enabled) { return set_tier1_pair(enabled); }
+
 int nsr_get_two_tier(int* enabled, float* tau, float* verify_max, float* force_fraction) {
   if (enabled) *enabled = g_two_tier_enabled ? 1 : 0;
   if (tau) *tau = g_two_tier.tau;

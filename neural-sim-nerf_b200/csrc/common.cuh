@@ -211,6 +211,7 @@ int launch_pack_net(const float* const* weights, const float* const* biases, voi
 int launch_mlp_forward(const float* rays, const float* z_or_pts, int64_t n, int S, const void* packed, uint32_t flags,
                        float* raw, cudaStream_t st, uint32_t* relu_mask = nullptr, void* dump = nullptr, int role = AS_ROLE_PLAIN,
                        void* active_set = nullptr);
+int set_tier1_pair(int enabled);   // tier 1 as CTA pairs (cta_group::2); returns the previous setting
 // mlp_backward.cu: d_raw [n,S,4] -> d_pts [n,S,8] = (dL/dpoint[3], 0, dL/dviewdir[3], 0) per sample
 int launch_mlp_backward(const float* rays, const float* z, int64_t n, int S, const void* packed, const float* d_raw,
                         float* d_pts, void* dump, const float* gscale, cudaStream_t st, const uint32_t* relu_mask = nullptr,

@@ -250,12 +250,13 @@ struct Cfg {
   static constexpr int SM_RING = INBUF_BYTES;
   static constexpr int SM_BUDGET = 227 * 1024;
   static constexpr int SM_XCH_BYTES = 128 * 16;    // per-row partial (r, g, b, sigma) handed between the two column halves
-  static constexpr int STAGES_FIT = (SM_BUDGET - SM_RING - TAIL_BYTES - SM_XCH_BYTES - 256) / STAGE_BYTES;
+  static constexpr int SM_BAR_BYTES = 512;         // up to 2 x 20 ring barriers (CTA-pair tier 1) + 9 others + the TMEM slot
+  static constexpr int STAGES_FIT = (SM_BUDGET - SM_RING - TAIL_BYTES - SM_XCH_BYTES - SM_BAR_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 10 ? 10 : STAGES_FIT;
   static constexpr int SM_TAIL = SM_RING + STAGES * STAGE_BYTES;
   static constexpr int SM_XCH = SM_TAIL + TAIL_BYTES;
   static constexpr int SM_BAR = SM_XCH + SM_XCH_BYTES;
-  static constexpr int SM_TOTAL = SM_BAR + 256;
+  static constexpr int SM_TOTAL = SM_BAR + SM_BAR_BYTES;
   static_assert(STAGES >= 3, "weight ring too shallow");
 };
 
@@ -324,6 +325,7 @@ __global__ void __launch_bounds__(Roles<CLASSIFY>::THREADS, 1) nerf_mlp_kernel(M
   using R = Roles<CLASSIFY>;
   static_assert(!PAIR || CLASSIFY, "the CTA-pair variant is built for the tier-1 kernel");
   constexpr int kStageBytes = PAIR ? C::STAGE_BYTES / 2 : C::STAGE_BYTES;
+  constexpr int kStages = PAIR ? 2 * C::STAGES : C::STAGES;   // half-size stages: the same ring memory holds twice as many chunks
   const uint32_t crank = PAIR ? cluster_ctarank() : 0u;   // == blockIdx.x & 1
   constexpr bool kSplit = C::kSplit;
   constexpr bool kMixed = C::kMixed;
@@ -365,8 +367,8 @@ __global__ void __launch_bounds__(Roles<CLASSIFY>::THREADS, 1) nerf_mlp_kernel(M
   const float* sTail = reinterpret_cast<const float*>(smem + C::SM_TAIL);
   float4* sXch = reinterpret_cast<float4*>(smem + C::SM_XCH);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::SM_BAR);  // [STAGES]   producer -> MMA (tx bytes)
-  uint64_t* empty = full + C::STAGES;                              // [STAGES]   MMA commit -> producer
-  uint64_t* acc_ready = empty + C::STAGES;                         // [2]        MMA commit -> epilogue
+  uint64_t* empty = full + kStages;                                // [STAGES]   MMA commit -> producer
+  uint64_t* acc_ready = empty + kStages;                           // [2]        MMA commit -> epilogue
   uint64_t* a_ready = acc_ready + 2;                               // [2]        epilogue (256) -> MMA
   uint64_t* enc_ready = a_ready + 2;                               // [0] xyz encoding, [1] view-dir encoding: encoders -> MMA
   uint64_t* enc_free = enc_ready + 2;                              // [0] after step 5, [1] after step 9: MMA commit -> encoders
@@ -380,7 +382,7 @@ __global__ void __launch_bounds__(Roles<CLASSIFY>::THREADS, 1) nerf_mlp_kernel(M
   const int tile_end = PAIR ? ((num_tiles + 1) & ~1) : num_tiles;
 
   if (tid == 0) {
-    for (int s = 0; s < C::STAGES; ++s) {
+    for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], (PAIR && crank == 0) ? 2 : 1);   // PAIR leader: own producer (+ bytes) and the follower's relay
       mbar_init(&empty[s], 1);
     }
@@ -442,7 +444,7 @@ __global__ void __launch_bounds__(Roles<CLASSIFY>::THREADS, 1) nerf_mlp_kernel(M
               bulk_g2s(sRing + stage * kStageBytes, a.packed + size_t(base + nh * nk + kc) * CHUNK_PAIR_BYTES + (PAIR ? crank * kStageBytes : 0u),
                        kStageBytes, &full[stage]);
             }
-            if (++stage == C::STAGES) {
+            if (++stage == kStages) {
               stage = 0;
               phase ^= 1;
               first_lap = false;
@@ -478,12 +480,14 @@ __global__ void __launch_bounds__(Roles<CLASSIFY>::THREADS, 1) nerf_mlp_kernel(M
     if (PAIR && crank != 0) {
       // follower: the leader issues for the pair.  This warp only relays the arrival of this CTA's half of every chunk.
       const uint32_t lead_full = mapa_u32(smem_u32(&full[0]), 0);
+      uint32_t rl = 0;
       for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x) {
 #pragma unroll 1
         for (int c = 0; c < 60; ++c) {
-          mbar_wait(&full[c % 10], (c / 10) & 1);
-          if (lane == 0) mbar_arrive_cluster(lead_full + (c % 10) * 8);
+          mbar_wait(&full[c % kStages], ((c / kStages) + rl * (60 / kStages)) & 1);
+          if (lane == 0) mbar_arrive_cluster(lead_full + (c % kStages) * 8);
         }
+        ++rl;
       }
     } else
     for (int tile = blockIdx.x; tile < tile_end; tile += gridDim.x, ++tl) {
@@ -501,7 +505,7 @@ __global__ void __launch_bounds__(Roles<CLASSIFY>::THREADS, 1) nerf_mlp_kernel(M
         for (int slot = 0; slot < 2 * nk; ++slot) {
           int nh, kc;
           issue_slot(nk, k_early, 2, slot, nh, kc);
-          const int c = cbase + slot, stage = c % 10;
+          const int c = cbase + slot, stage = c % kStages;
           if (slot == k_early) {         // first chunk of half 1: ACC1 must be back (in the epilogue's registers)
             if (lane == 0) NSR_TR(tl, step, 5);
             wait_b(acc_free1, par);
@@ -514,7 +518,9 @@ __global__ void __launch_bounds__(Roles<CLASSIFY>::THREADS, 1) nerf_mlp_kernel(M
             if (lane == 0) NSR_TR(tl, step, 3);
             tc_fence_after_sync();
           }
-          wait_b(&full[stage], (c / 10) & 1);   // 6 uses of every stage per tile: the parity pattern repeats tile after tile
+          // 60 chunks per tile through 10 (20) stages: 6 (3) uses of every stage per tile -- the parity pattern repeats (alternates)
+          // from one tile to the next
+          wait_b(&full[stage], ((c / kStages) + tl * (60 / kStages)) & 1);
           if (leader && !NSR_EXP(5)) {
             const uint32_t acc = nh ? TM_ACC1 : TM_ACC0;
             const uint32_t b = ring_lo + stage * (kStageBytes >> 4);
@@ -1107,6 +1113,19 @@ __global__ void __launch_bounds__(Roles<CLASSIFY>::THREADS, 1) nerf_mlp_kernel(M
   }
 }
 
+static int& tier1_pair_flag() {
+  static int flag = [] {
+    const char* e = getenv("NSR_TIER1_PAIR");
+    return (e != nullptr && atoi(e) != 0) ? 1 : 0;
+  }();
+  return flag;
+}
+int set_tier1_pair(int enabled) {
+  const int old = tier1_pair_flag();
+  tier1_pair_flag() = enabled ? 1 : 0;
+  return old;
+}
+
 template <int SPLIT, bool SAVE, bool CLASSIFY = false>
 static int launch_variant(const MlpArgs& a, int grid, cudaStream_t st) {
   if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(&nerf_mlp_kernel<SPLIT, SAVE, CLASSIFY>), Cfg<SPLIT>::SM_TOTAL)) return rc;
@@ -1138,14 +1157,11 @@ static int launch_tier1_pair(const MlpArgs& a, int grid, cudaStream_t st) {
 
 static int launch_by_flags(const MlpArgs& a, int grid, uint32_t flags, cudaStream_t st) {
   if (a.role == AS_ROLE_TIER1) {
-    // CTA pairs by default (NSR_TIER1_PAIR=0: one CTA per SM, for A/B runs); the pair kernel wants an even grid of at least 2
-    static const bool pair = [] {
-      const char* e = getenv("NSR_TIER1_PAIR");
-      return e == nullptr || atoi(e) != 0;
-    }();
+    // one CTA per SM by default; as CTA pairs on request (nsr_set_tier1_pair / NSR_TIER1_PAIR=1: same results bit for bit, and on a
+    // power-capped B200 the same speed -- DESIGN.md 3.1a).  The pair kernel wants an even grid of at least 2.
     const int tiles_even = (a.num_tiles + 1) & ~1;
     const int pgrid = (grid & ~1) < tiles_even ? (grid & ~1) : tiles_even;
-    if (pair && pgrid >= 2 && a.experiment < 100) return launch_tier1_pair(a, pgrid, st);
+    if (tier1_pair_flag() && pgrid >= 2 && a.experiment < 100) return launch_tier1_pair(a, pgrid, st);
     return launch_variant<1, false, true>(a, grid, st);
   }
   if (a.relu_mask != nullptr || a.dump != nullptr) {

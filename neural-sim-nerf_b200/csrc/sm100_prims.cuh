@@ -189,20 +189,14 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
   return r;
 }
+// Arrive on a barrier of a peer CTA (default semantics, as CUTLASS' ClusterBarrier::arrive does).  NOT .release.cluster: that form
+// costs a cluster-scope fence per arrival (~800 cycles, measured: it made the relayed weight ring three times slower), and nothing
+// here needs it -- what the arrivals order is TMEM traffic (tcgen05 fences) and shared memory that each SM's own tensor core reads.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {   // a local barrier that peers arrive on
-  uint32_t ok = 0;
-  while (!ok) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  }
+  mbar_wait(bar, parity);
 }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols) : "memory");

@@ -316,3 +316,39 @@ def test_full_size_image_bit_identical(nsr, nets, knobs):
     c0, c1 = two['ctrl_ws']
     print(f'400x400: active fraction coarse {c0[0] / (n * S):.4f} fine {c1[0] / (n * T):.4f}; verification {bits_to_float(c0[1]):.3e} / {bits_to_float(c1[1]):.3e}')
     assert c1[2] == 0 and c1[3] == 0
+
+
+@pytest.mark.parametrize('n_side', [23, 40])
+def test_tier1_as_cta_pairs_gives_the_same_bits(nsr, nets, n_side):
+    """nsr_set_tier1_pair(1): tier 1 runs as clusters of two CTAs (tcgen05 cta_group::2, half of every weight chunk per SM, the
+    leader CTA issuing for both).  Same arithmetic, so the same sigma~, the same active set (as a set) and the same maps, bit for bit;
+    an odd number of tiles exercises the padded last pair."""
+    L = nsr.lib()
+    rays = camera_rays(n_side, 22.5)
+    n = rays.shape[0]
+    pc, pf = nsr.packed_weights(nets[0]), nsr.packed_weights(nets[1])
+    P = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+    res = {}
+    old = L.nsr_set_tier1_pair(0)
+    try:
+        for pair in (0, 1):
+            L.nsr_set_tier1_pair(pair)
+            outs = [torch.empty(n, 3, device='cuda'), torch.empty(n, device='cuda'), torch.empty(n, device='cuda'), torch.empty(n, device='cuda')]
+            raw, zv = torch.empty(n, T, 4, device='cuda'), torch.empty(n, T, device='cuda')
+            aset = torch.zeros(L.nsr_active_set_bytes(n, T), dtype=torch.uint8, device='cuda')
+            ws = torch.empty(L.nsr_render_workspace_bytes(n, S, NI), dtype=torch.uint8, device='cuda')
+            rc = L.nsr_render_rays_forward_ex(P(rays), n, P(pc), P(pf), S, NI, 0, None, None, P(outs[0]), P(outs[1]), P(outs[2]), None, None, None,
+                                              P(outs[3]), P(raw), P(zv), None, None, None, P(aset), P(ws), ws.numel(), None)
+            assert rc == 0, L.nsr_last_error()
+            torch.cuda.synchronize()
+            cnt = int(aset[:4].view(torch.int32).item())
+            lst = torch.sort(aset[256:256 + 4 * cnt].view(torch.int32)).values
+            res[pair] = (outs, raw, zv, cnt, lst)
+    finally:
+        L.nsr_set_tier1_pair(old)
+    a, b = res[0], res[1]
+    assert a[3] == b[3] and a[3] > 0 and torch.equal(a[4], b[4])
+    assert ((n * S + 127) // 128) % 2 == (1 if n_side == 23 else 0)          # 23 x 23 rays: the coarse pass has an odd tile count
+    for x, y in zip(a[0], b[0]):
+        assert bool(((x == y) | (torch.isnan(x) & torch.isnan(y))).all())
+    assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
