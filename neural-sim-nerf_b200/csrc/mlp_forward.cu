@@ -284,7 +284,7 @@ struct MlpArgs {
 
 // debug experiments (NSR_EXPERIMENT, debug-hook builds only; results are garbage, timings isolate one cost each):
 //   1 no weight streaming after the first lap   2 epilogue skips its TMEM stores   3 epilogue skips the conversion arithmetic
-//   4 encoders skip sincosf   5 no MMA is issued (commits only)   100+g: grid limited to g CTAs
+//   4 encoders skip sincosf   5 no MMA is issued (commits only)   6 only every second weight chunk is streamed   100+g: grid limited to g CTAs
 #ifdef NSR_DEBUG_HOOKS
 #define NSR_EXP(n) (a.experiment == (n))
 #else
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(Roles<CLASSIFY>::THREADS, 1) nerf_mlp_kernel(M
             int nh, kc;
             issue_slot(nk, step_k_early(step), nhs, i, nh, kc);
             if (!first_lap) mbar_wait(&empty[stage], phase ^ 1);
-            if (NSR_EXP(1) && !first_lap) {
+            if ((NSR_EXP(1) || (NSR_EXP(6) && (i & 1))) && !first_lap) {   // 6: every second chunk only
               mbar_arrive(&full[stage]);
             } else {
               // (PAIR: this CTA's half of the chunk's output rows -- the packed chunk keeps 8-row groups 1024 B apart, so rows
