@@ -766,10 +766,17 @@ def run_ours(args):
                  lambda: L.nsr_to8b(P(outs['rgb']), n * 3, P(rgb8), stream)),
             ]
             stages = []
+            ncu_key = {'raw2outputs_kernel S=64': 'composite_coarse', 'resample_merge_kernel': 'resample_merge', 'raw2outputs_kernel S=192': 'composite_fine'}
             for name, nbytes, fn in stage_defs:
                 ms = time_stage(fn)
-                stages.append({'kernel': name, 'ms': ms, 'algorithmic_bytes': nbytes, 'gb_per_s': nbytes / (ms * 1e-3) / 1e9,
-                               'frac_of_hbm_peak': nbytes / (ms * 1e-3) / 1e9 / hbm})
+                st_ = {'kernel': name, 'ms': ms, 'algorithmic_bytes': nbytes, 'gb_per_s': nbytes / (ms * 1e-3) / 1e9,
+                       'frac_of_hbm_peak': nbytes / (ms * 1e-3) / 1e9 / hbm}
+                for prefix, key in ncu_key.items():          # ncu-reported DRAM bytes of the same kernel in a real render (profiles/ncu_traffic.json)
+                    if name.startswith(prefix) and key in traffic:
+                        t_ = traffic[key]
+                        st_.update({'dram_bytes_ncu': t_['dram_bytes'], 'ncu_duration': t_['duration_under_ncu'],
+                                    'gb_per_s_ncu_bytes': t_['dram_bytes'] / (ms * 1e-3) / 1e9, 'frac_of_hbm_peak_ncu_bytes': t_['dram_bytes'] / (ms * 1e-3) / 1e9 / hbm})
+                stages.append(st_)
             stages.append({'kernel': 'nerf_mlp_kernel fine, dense fp16x3 (192 samples/ray)', 'ms': k_ms, 'algorithmic_tflops': flops / (k_ms * 1e-3) / 1e12,
                            'frac_of_tensor_peak': flops / (k_ms * 1e-3) / 1e12 / peak})
             # CPU baseline: the oracle port on this box's host cores, bounded sample

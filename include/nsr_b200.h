@@ -236,6 +236,9 @@ int nsr_make_rays(int H, int W, const float* K_host, const float* c2w_host, floa
 
 /* The same from a c2w that lives on the DEVICE (rows ld_c2w >= 4 floats apart: a [3,4] or the top of a [4,4] matrix), e.g. the
  * pose sampler's output (LL:63-72): the pose never visits the host. */
+/* RN:91-112 for rays generated by the caller (render(rays=...), RN:163-170): rays_o, rays_d [n,3] device -> rays_out [n,11] =
+ * (o, d, near, far, d / |d|), the layout every other entry point takes. */
+int nsr_pack_rays(const float* rays_o, const float* rays_d, int64_t n_rays, float near_, float far_, float* rays_out, void* stream);
 int nsr_make_rays_dev(int H, int W, const float* K_host, const float* c2w_dev, int ld_c2w, float near_, float far_,
                       float* rays_out, void* stream);
 

@@ -52,6 +52,7 @@ _SIGNATURES = {
     'nsr_mlp_dump_bytes': (c_size, [c_i64, c_int]),
     'nsr_render_rays_backward': (c_int, [c_f32p, c_f32p, c_f32p, c_i64, c_int, c_vp, c_u32, c_f32p, c_f32p, c_vp, c_vp, c_vp, c_vp, c_size, c_vp]),
     'nsr_make_rays': (c_int, [c_int, c_int, c_vp, c_vp, ctypes.c_float, ctypes.c_float, c_f32p, c_vp]),
+    'nsr_pack_rays': (c_int, [c_f32p, c_f32p, c_i64, ctypes.c_float, ctypes.c_float, c_f32p, c_vp]),
     'nsr_make_rays_dev': (c_int, [c_int, c_int, c_vp, c_f32p, c_int, ctypes.c_float, ctypes.c_float, c_f32p, c_vp]),
     'nsr_to8b': (c_int, [c_f32p, c_i64, c_vp, c_vp]),
     'nsr_c2w_grad_workspace_bytes': (c_size, []),

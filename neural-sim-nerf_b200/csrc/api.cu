@@ -388,6 +388,13 @@ int nsr_make_rays(int H, int W, const float* K_host, const float* c2w_host, floa
   return launch_make_rays(H, W, K_host, c2w_host, near_, far_, rays_out, static_cast<cudaStream_t>(stream));
 }
 
+int nsr_pack_rays(const float* rays_o, const float* rays_d, int64_t n_rays, float near_, float far_, float* rays_out, void* stream) {
+  NSR_REQUIRE(n_rays >= 0, "nsr_pack_rays: bad size");
+  if (n_rays == 0) return NSR_OK;
+  NSR_REQUIRE(rays_o && rays_d && rays_out, "nsr_pack_rays: null argument");
+  return launch_pack_rays(rays_o, rays_d, n_rays, near_, far_, rays_out, static_cast<cudaStream_t>(stream));
+}
+
 int nsr_make_rays_dev(int H, int W, const float* K_host, const float* c2w_dev, int ld_c2w, float near_, float far_, float* rays_out,
                       void* stream) {
   NSR_REQUIRE(H > 0 && W > 0 && K_host && c2w_dev && rays_out && ld_c2w >= 4, "nsr_make_rays_dev: bad argument");

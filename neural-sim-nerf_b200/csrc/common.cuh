@@ -183,6 +183,7 @@ int launch_resample_merge(const float* z, const float* w, int64_t n, int S, int 
                           uint32_t* ctrl_fine = nullptr, uint32_t force_count = 0);
 int launch_make_rays(int H, int W, const float* K9, const float* c2w12, float near_, float far_, float* rays,
                      cudaStream_t st);
+int launch_pack_rays(const float* o, const float* d, int64_t n, float near_, float far_, float* rays, cudaStream_t st);
 // image_stage.cu
 int launch_to8b(const float* x, int64_t n, uint8_t* out, cudaStream_t st);
 int launch_make_rays_dev(int H, int W, const float* K9, const float* c2w_dev, int ld_c2w, float near_, float far_, float* rays,

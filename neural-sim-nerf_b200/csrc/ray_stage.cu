@@ -463,6 +463,35 @@ __global__ void make_rays_kernel(int H, int W, Cam cam, float near_, float far_,
   o[10] = __fdiv_rn(rd[2], nrm);
 }
 
+// RN:91-112 for rays that were generated elsewhere (render(rays=...), the route of RN:163-170): (rays_o, rays_d) [n,3] each ->
+// [n,11] = o, d, near, far, d / |d|.  Same arithmetic as make_rays_kernel's tail.
+__global__ void pack_rays_kernel(const float* __restrict__ o, const float* __restrict__ d, int64_t n, float near_, float far_,
+                                 float* __restrict__ rays) {
+  const int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (idx >= n) return;
+  const float d0 = d[idx * 3], d1 = d[idx * 3 + 1], d2 = d[idx * 3 + 2];
+  const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)));
+  float* r = rays + idx * 11;
+  r[0] = o[idx * 3];
+  r[1] = o[idx * 3 + 1];
+  r[2] = o[idx * 3 + 2];
+  r[3] = d0;
+  r[4] = d1;
+  r[5] = d2;
+  r[6] = near_;
+  r[7] = far_;
+  r[8] = __fdiv_rn(d0, nrm);  // RN:97
+  r[9] = __fdiv_rn(d1, nrm);
+  r[10] = __fdiv_rn(d2, nrm);
+}
+
+int launch_pack_rays(const float* o, const float* d, int64_t n, float near_, float far_, float* rays, cudaStream_t st) {
+  if (n == 0) return NSR_OK;
+  pack_rays_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(o, d, n, near_, far_, rays);
+  count_launch();
+  return check_launch("pack_rays_kernel");
+}
+
 // ----------------------------------------------------------------------------- launchers
 int launch_coarse_z(const float* rays, int64_t n, int S, uint32_t flags, const float* t_rand, float* z, cudaStream_t st) {
   if (n == 0) return NSR_OK;

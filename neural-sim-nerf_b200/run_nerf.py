@@ -560,6 +560,14 @@ def render(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far
     if c2w is not None and not ndc and c2w_staticcam is None and scalar_bounds and not (torch.is_tensor(c2w) and c2w.requires_grad and torch.is_grad_enabled()):
         packed = make_rays(H, W, K, c2w, near, far)          # fused ray generation
         sh = (H, W, 3)
+    elif (c2w is None and not ndc and c2w_staticcam is None and scalar_bounds and torch.is_tensor(rays[1]) and rays[1].is_cuda and
+          not (torch.is_grad_enabled() and (rays[0].requires_grad or rays[1].requires_grad))):
+        # caller-made rays, nothing to differentiate: RN:97 + RN:106-112 in one kernel instead of five tensor ops
+        rays_o, rays_d = rays
+        sh = rays_d.shape
+        o, d = _f32c(rays_o.reshape(-1, 3), 'rays_o'), _f32c(rays_d.reshape(-1, 3), 'rays_d')
+        packed = torch.empty(o.shape[0], 11, dtype=torch.float32, device=d.device)
+        check(lib().nsr_pack_rays(ptr(o), ptr(d), o.shape[0], float(near), float(far), ptr(packed), _stream()), 'nsr_pack_rays')
     else:
         if c2w is not None:
             rays_o, rays_d = get_rays(H, W, K, c2w)

@@ -224,3 +224,18 @@ def test_row_bands_of_an_image_add_up(nsr, nets):
     assert float((total - d_all).abs().max()) <= 1e-5 * float(d_all.abs().max())
     with pytest.raises(ValueError):
         nsr.run_nerf.render_image_grad(H, W, K, pose, g, rows=(10, 49), **kw)
+
+
+def test_pack_rays_kernel_matches_the_reference_ops(nsr):
+    """nsr_pack_rays = RN:97 + RN:106-112 (viewdirs = d / |d|, cat[o, d, near, far, viewdirs]) for caller-made rays; render(rays=...) uses it."""
+    import ctypes
+    g = torch.Generator(device='cuda').manual_seed(7)
+    o = torch.randn(1003, 3, device='cuda', generator=g)
+    d = torch.randn(1003, 3, device='cuda', generator=g) * 3.0
+    out = torch.empty(1003, 11, device='cuda')
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    assert nsr.lib().nsr_pack_rays(P(o), P(d), 1003, 0.25, 2.5, P(out), None) == 0
+    torch.cuda.synchronize()
+    ref = torch.cat([o, d, torch.full((1003, 1), 0.25, device='cuda'), torch.full((1003, 1), 2.5, device='cuda'), d / torch.norm(d, dim=-1, keepdim=True)], -1)
+    assert torch.equal(out[:, :8], ref[:, :8])
+    assert float((out[:, 8:] - ref[:, 8:]).abs().max()) <= 2e-7
