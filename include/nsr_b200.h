@@ -46,6 +46,8 @@ extern "C" {
                                   every network (2.6e-3 on 3x-scaled random ones): opt-in ("precision").
                                   Forward only; NSR_FLAG_FAST_FP16 wins if both are set. */
 
+#define NSR_FLAG_EMBEDDED_INPUT 64u /* nsr_mlp_forward: `z_or_pts` holds already-embedded inputs [n*S, 90] = 63 xyz + 27 view-dir channels
+                                      (what NeRF.forward takes, RH:99-122); `rays` is not read and may be NULL */
 #define NSR_FLAG_DENSE 32u     /* evaluate EVERY sample point with the default fp16 hi/lo arithmetic.  Without it the render entry points
                                   use the two-tier evaluation ("active set", below) wherever its outputs are bit-identical. */
 

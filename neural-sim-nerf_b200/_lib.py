@@ -82,6 +82,7 @@ EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 FLAG_LINDISP = 1
 FLAG_WHITE_BKGD = 2
 FLAG_PTS_INPUT = 4
+FLAG_EMBEDDED_INPUT = 64
 FLAG_FAST_FP16 = 8
 FLAG_MIXED_F8 = 16
 FLAG_DENSE = 32

@@ -140,7 +140,8 @@ int nsr_mlp_forward(const float* rays, const float* z_or_pts, int64_t n_rays, in
                     uint32_t flags, float* raw_out, void* stream) {
   NSR_REQUIRE(n_rays >= 0 && n_samples > 0, "nsr_mlp_forward: bad sizes n_rays=%lld n_samples=%d", (long long)n_rays, n_samples);
   if (n_rays == 0) return NSR_OK;
-  NSR_REQUIRE(rays && z_or_pts && packed_net && raw_out, "nsr_mlp_forward: null argument");
+  NSR_REQUIRE((rays || (flags & NSR_FLAG_EMBEDDED_INPUT)) && z_or_pts && packed_net && raw_out, "nsr_mlp_forward: null argument");
+  NSR_REQUIRE(!((flags & NSR_FLAG_EMBEDDED_INPUT) && (flags & NSR_FLAG_PTS_INPUT)), "nsr_mlp_forward: PTS_INPUT and EMBEDDED_INPUT exclude each other");
   NSR_REQUIRE((reinterpret_cast<uintptr_t>(raw_out) & 15) == 0, "nsr_mlp_forward: raw_out must be 16-byte aligned");
   NSR_REQUIRE((reinterpret_cast<uintptr_t>(packed_net) & 127) == 0, "nsr_mlp_forward: packed_net must be 128-byte aligned");
   return launch_mlp_forward(rays, z_or_pts, n_rays, n_samples, packed_net, flags, raw_out, static_cast<cudaStream_t>(stream));

@@ -691,7 +691,14 @@ __global__ void __launch_bounds__(Roles<CLASSIFY>::THREADS, 1) nerf_mlp_kernel(M
         const int64_t p = point_of(tile, er + rr * 64);
 #pragma unroll
         for (int d = 0; d < 3; ++d) x[rr][d] = vd[rr][d] = 0.f;
-        if (p >= 0) {
+        if (p >= 0 && (a.flags & NSR_FLAG_EMBEDDED_INPUT)) {
+          // NeRF.forward(x) on pre-embedded input (RH:99-122): x[p] = [63 xyz channels | 27 view-dir channels], copied below
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            x[rr][d] = a.z_or_pts[p * 90 + d];
+            vd[rr][d] = a.z_or_pts[p * 90 + 63 + d];
+          }
+        } else if (p >= 0) {
           const int64_t ray = p / a.S;
           const float* rp = a.rays + ray * 11;
           if (a.flags & NSR_FLAG_PTS_INPUT) {
@@ -731,6 +738,10 @@ __global__ void __launch_bounds__(Roles<CLASSIFY>::THREADS, 1) nerf_mlp_kernel(M
               cs = c2;
             }
           }
+        } else if (a.flags & NSR_FLAG_EMBEDDED_INPUT) {
+          const int64_t p = point_of(tile, row);
+#pragma unroll
+          for (int c = 3; c < 63; ++c) e[c] = p >= 0 ? a.z_or_pts[p * 90 + c] : 0.f;
         } else {
 #pragma unroll
           for (int k = 0; k < 10; ++k) {
@@ -775,14 +786,20 @@ __global__ void __launch_bounds__(Roles<CLASSIFY>::THREADS, 1) nerf_mlp_kernel(M
         v[0] = vd[rr][0];
         v[1] = vd[rr][1];
         v[2] = vd[rr][2];
+        if (a.flags & NSR_FLAG_EMBEDDED_INPUT) {
+          const int64_t p = point_of(tile, row);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+          for (int c = 3; c < 27; ++c) v[c] = p >= 0 ? a.z_or_pts[p * 90 + 63 + c] : 0.f;
+        } else {
 #pragma unroll
-          for (int d = 0; d < 3; ++d) {
-            float sn, cs;
-            sincosf(vd[rr][d] * float(1 << k), &sn, &cs);
-            v[3 + 6 * k + d] = sn;
-            v[3 + 6 * k + 3 + d] = cs;
+          for (int k = 0; k < 4; ++k) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              float sn, cs;
+              sincosf(vd[rr][d] * float(1 << k), &sn, &cs);
+              v[3 + 6 * k + d] = sn;
+              v[3 + 6 * k + 3 + d] = cs;
+            }
           }
         }
 #pragma unroll
@@ -1208,7 +1225,7 @@ int launch_mlp_forward(const float* rays, const float* z_or_pts, int64_t n, int 
       set_error("mlp_forward: two-tier launch without an active set (or more than 2^31 points)");
       return NSR_E_INVALID;
     }
-    if ((flags & (NSR_FLAG_FAST_FP16 | NSR_FLAG_MIXED_F8 | NSR_FLAG_PTS_INPUT)) || (dump != nullptr)) {
+    if ((flags & (NSR_FLAG_FAST_FP16 | NSR_FLAG_MIXED_F8 | NSR_FLAG_PTS_INPUT | NSR_FLAG_EMBEDDED_INPUT)) || (dump != nullptr)) {
       set_error("mlp_forward: the two-tier evaluation runs the default precision on depth input, without the activation dump");
       return NSR_E_INVALID;
     }

@@ -22,7 +22,7 @@ import torch.nn as nn
 import torch.nn.functional as F  # noqa: F401  (RN:6 star-exports it: `from utils.run_nerf_noscale import *` users may rely on `F`)
 
 from . import _lib
-from ._lib import FLAG_DENSE, FLAG_FAST_FP16, FLAG_LINDISP, FLAG_MIXED_F8, FLAG_PTS_INPUT, FLAG_WHITE_BKGD, check, lib, ptr
+from ._lib import FLAG_DENSE, FLAG_EMBEDDED_INPUT, FLAG_FAST_FP16, FLAG_LINDISP, FLAG_MIXED_F8, FLAG_PTS_INPUT, FLAG_WHITE_BKGD, check, lib, ptr
 
 device = torch.device('cuda' if torch.cuda.is_available() else 'cpu')
 
@@ -112,8 +112,20 @@ class NeRF(nn.Module):
             self.output_linear = nn.Linear(W, output_ch)
 
     def forward(self, x):
-        """x [..., 90] already embedded (RH:99-122) -> [..., 4], on the tensor-core kernel."""
-        raise NotImplementedError('call run_network()/render_rays(); the fused kernel embeds and evaluates in one pass')
+        """RH:99-122: x [..., input_ch + input_ch_views] already embedded -> [..., 4] = (rgb, sigma) raw, on the tensor-core kernel
+        (nsr_mlp_forward with NSR_FLAG_EMBEDDED_INPUT: the encoder warps copy the 90 channels instead of computing them).
+        Forward only: the differentiable routes are render() / render_rays() / train_step(), whose backward kernels start from
+        points, not from embeddings -- asking this call for a graph raises instead of silently returning a constant."""
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError('NeRF.forward(x) is forward-only here (wrap it in torch.no_grad()); gradients flow through '
+                                      'render() / render_rays() / train_step()')
+        if x.shape[-1] != 90:
+            raise NotImplementedError(f'embedded input must have 63 + 27 = 90 channels, got {x.shape[-1]}')
+        xf = _f32c(x.reshape(-1, 90), 'x')
+        raw = torch.empty(xf.shape[0], 4, dtype=torch.float32, device=xf.device)
+        check(lib().nsr_mlp_forward(None, ptr(xf), xf.shape[0], 1, ptr(packed_weights(self)), FLAG_EMBEDDED_INPUT | _prec_flag(), ptr(raw), _stream()),
+              'nsr_mlp_forward')
+        return raw.reshape(*x.shape[:-1], 4)
 
 
 # ----------------------------------------------------------------------------- packed-weight cache

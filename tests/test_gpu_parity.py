@@ -121,6 +121,28 @@ def test_mlp_matches_reference(nsr, golden, nets):
         print(f'{key}: max err {mx:.3e}')
 
 
+def test_nerf_forward_on_embedded_input(nsr, golden, nets, wfit):
+    """NeRF.forward(x) (RH:99-122) on pre-embedded input [.., 63 + 27]: the kernel copies the channels instead of computing them;
+    same raw as run_network on the points, within the MLP tolerance of the oracle; forward-only (asking for a graph raises)."""
+    rays = C(golden['rays'])
+    z = C(golden['z1'])
+    pts = (rays[:, None, 0:3] + rays[:, None, 3:6] * z[:, :, None])[:64]
+    dirs = rays[:64, None, 8:11].expand(pts.shape)
+    x = torch.cat([O.embed(pts.cpu(), O.N_FREQ_XYZ), O.embed(dirs.cpu(), O.N_FREQ_DIR)], -1)        # [64, 192, 90]
+    with torch.no_grad():
+        got = nets[1](x.cuda())
+        via_points = nsr.run_network(pts.contiguous(), rays[:64, 8:11].contiguous(), nets[1])
+    ref = O.mlp_forward(x.reshape(-1, 90), wfit[1]).reshape(64, 192, 4)
+    assert got.shape == (64, 192, 4)
+    mx = assert_close(got, ref.numpy(), TOL_RAW, 'NeRF.forward(embedded)')
+    assert_close(got, via_points.cpu().numpy(), TOL_RAW, 'embedded vs points')
+    print(f'NeRF.forward(embedded): max err {mx:.3e}')
+    with pytest.raises(NotImplementedError):
+        nets[1](x.cuda())                       # parameters require grad and grad mode is on: no silent constant
+    with pytest.raises(NotImplementedError), torch.no_grad():
+        nets[1](x.cuda()[..., :63])
+
+
 @pytest.mark.parametrize('retraw', [True, False])
 def test_render_rays_matches_reference(nsr, golden, nets, retraw):
     """retraw=True takes the dense evaluation (a caller-visible raw), retraw=False the two-tier one (include/nsr_b200.h)."""
