@@ -1008,9 +1008,8 @@ def train_step(batch_rays, target_s, optimizer, near=0., far=1., seed=None, **kw
         rays_d = _f32c(rays_d, 'batch_rays').reshape(-1, 3)
         rays_o = _f32c(rays_o, 'batch_rays').reshape(-1, 3)
         n = rays_d.shape[0]
-        vd = rays_d / torch.norm(rays_d, dim=-1, keepdim=True)                                   # RN:97
-        bounds = torch.tensor([float(near), float(far)], dtype=torch.float32, device=rays_d.device).expand(n, 2)
-        rays = torch.cat([rays_o, rays_d, bounds, vd], -1).contiguous()                          # RN:106-112
+        rays = torch.empty(n, 11, dtype=torch.float32, device=rays_d.device)                     # RN:97 + RN:106-112, one kernel
+        check(L.nsr_pack_rays(ptr(rays_o), ptr(rays_d), n, float(near), float(far), ptr(rays), _stream()), 'nsr_pack_rays')
         target = _f32c(target_s, 'target_s').reshape(-1, 3)
     if target.shape[0] != n:
         raise ValueError(f'target_s {tuple(target_s.shape)} does not match batch_rays {tuple(batch_rays.shape)}')
