@@ -473,25 +473,27 @@ def run_ours(args):
             pair.append(nsr.packed_weights(mo).clone())
         obj_blobs.append(pair)
     assert len({b[1].data_ptr() for b in obj_blobs}) == n_obj and not torch.equal(obj_blobs[0][1], obj_blobs[1][1])
-    import neural_sim_nerf_b200.dist as nsr_dist
-    slo, shi = nsr_dist.shard_bounds(n, rank, world)
-    ns = shi - slo
+    # rays are dealt out round-robin (ray i -> rank i % world): a contiguous band through the object would carry twice the active
+    # points of a band through the background, and the step ends with the slowest rank
+    o_pix = torch.arange(rank, n, world, device=dev, dtype=torch.int32)
+    ns = int(o_pix.numel())
+    o_rays = [r_[o_pix.long()].contiguous() for r_ in rays_dev]
+    o_grgb = g_rgb[o_pix.long()].contiguous()
     o_ws = torch.empty(L.nsr_render_workspace_bytes(ns, N_SAMPLES, N_IMPORTANCE), dtype=torch.uint8, device=dev)
     o_bws = torch.empty(L.nsr_render_backward_workspace_bytes(ns, T), dtype=torch.uint8, device=dev)
     o_mask = torch.empty(L.nsr_relu_mask_bytes(ns, T), dtype=torch.uint8, device=dev)
     o_aset = torch.empty(L.nsr_active_set_bytes(ns, T), dtype=torch.uint8, device=dev)
     o_z, o_raw, o_drays = new(ns, T), new(ns, T, 4), new(ns, 11)
     o_rgb = new(ns, 3)
-    o_pix = torch.arange(slo, shi, device=dev, dtype=torch.int32)
     o_dc2w = torch.zeros(n_obj, 12, device=dev)
 
     def step_objects(s):
         for o in range(n_obj):
-            r = rays_dev[(s + o) % len(rays_dev)][slo:shi]
+            r = o_rays[(s + o) % len(o_rays)]
             bc, bf = obj_blobs[o]
             rc = L.nsr_render_rays_forward_ex(P(r), ns, P(bc), P(bf), N_SAMPLES, N_IMPORTANCE, 0, None, None, P(o_rgb), None, None, None, None, None,
                                               None, P(o_raw), P(o_z), None, P(o_mask), None, P(o_aset), P(o_ws), o_ws.numel(), stream)
-            rc = rc or L.nsr_render_rays_backward_ex(P(r), P(o_z), P(o_raw), ns, T, P(bf), 0, P(g_rgb[slo:shi]), P(o_drays), None, None, None,
+            rc = rc or L.nsr_render_rays_backward_ex(P(r), P(o_z), P(o_raw), ns, T, P(bf), 0, P(o_grgb), P(o_drays), None, None, None,
                                                      P(o_mask), P(o_aset), P(o_bws), o_bws.numel(), stream)
             rc = rc or L.nsr_rays_grad_to_c2w(H, W, Kf, P(r), P(o_drays), P(o_pix), ns, P(o_dc2w[o]), 0, P(cws), stream)
             if rc != 0:
@@ -509,12 +511,12 @@ def run_ours(args):
     barrier()
     ms_obj = max_over_ranks(e0.elapsed_time(e1))
     objects8 = {'workload': f'BASELINE config 4: {n_obj} objects with their own coarse + fine networks ({2 * n_obj} packed blobs resident per GPU), one 400x400 image '
-                            f'each per step, every image\'s rays sharded over the {world} rank(s); forward (two-tier, sign bits saved) + backward over the '
+                            f'each per step, every image\'s rays dealt round-robin over the {world} rank(s); forward (two-tier, sign bits saved) + backward over the '
                             'active set -> dL/dc2w per object; one all-reduce of the [8,12] pose gradients per step',
                 'rays_per_s': n_obj * n * o_steps / (ms_obj * 1e-3), 'ms_per_step': ms_obj / o_steps, 'rays_per_rank_per_step': n_obj * ns,
                 'collective': 'ncclAllReduce(SUM) of 384 bytes per step' if world > 1 else 'none (1 rank)',
                 'finite': bool(torch.isfinite(o_dc2w).all()), 'distinct_gradients': bool(len({round(float(v), 9) for v in o_dc2w[:, 0]}) == n_obj)}
-    del o_ws, o_bws, o_mask, o_aset, o_z, o_raw, o_drays, obj_blobs
+    del o_ws, o_bws, o_mask, o_aset, o_z, o_raw, o_drays, obj_blobs, o_rays
     mlp_bwd_ms = None
     if rank == 0:       # the MLP stage of that backward pass by itself (for roofline_kernels): d_raw is in the backward workspace
         d_raw_view = bws[:n * T * 16].view(torch.float32)

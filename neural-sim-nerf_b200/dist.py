@@ -58,12 +58,30 @@ def row_band(H, part, n_parts):
     return shard_bounds(H, part, n_parts)
 
 
-def render_rays_sharded(rays_flat, render_fn, gather=True):
+def render_rays_sharded(rays_flat, render_fn, gather=True, interleave=False):
     """Render a [N,11] ray batch with every rank taking a contiguous slice.  `render_fn(rays) -> dict`
     (e.g. functools.partial(render_rays, **render_kwargs)).  With gather=True every rank returns the
-    full-size maps (all_gather of the per-rank slices); otherwise only its own slice."""
+    full-size maps (all_gather of the per-rank slices); otherwise only its own slice.
+    interleave=True deals the rays out round-robin instead (ray i -> rank i % world_size): the renderer's work per ray depends on
+    what the ray hits (two-tier evaluation), so contiguous slices of an image are unevenly loaded and a strided deal is not."""
     rank, ws = world()
     n = rays_flat.shape[0]
+    if interleave:
+        local = render_fn(rays_flat[rank::ws].contiguous())
+        if ws == 1 or not gather:
+            return local
+        out = {}
+        cap = (n + ws - 1) // ws
+        for k, v in local.items():
+            padded = torch.zeros((cap,) + tuple(v.shape[1:]), dtype=v.dtype, device=v.device)
+            padded[:v.shape[0]] = v
+            parts = [torch.empty_like(padded) for _ in range(ws)]
+            dist.all_gather(parts, padded)
+            full = torch.empty((n,) + tuple(v.shape[1:]), dtype=v.dtype, device=v.device)
+            for r, p in enumerate(parts):
+                full[r::ws] = p[:len(range(r, n, ws))]
+            out[k] = full
+        return out
     lo, hi = shard_bounds(n, rank, ws)
     local = render_fn(rays_flat[lo:hi])
     if ws == 1 or not gather:

@@ -43,6 +43,10 @@ def main():
         got = D.render_rays_sharded(rays, lambda r: {k: v for k, v in fn(r).items() if k in ('rgb_map', 'acc_map', 'rgb0')}, gather=True)
     for k, v in got.items():
         assert v.shape == full[k].shape and torch.equal(v, full[k]), k
+    with torch.no_grad():
+        dealt = D.render_rays_sharded(rays, lambda r: {k: v for k, v in fn(r).items() if k in ('rgb_map', 'acc_map')}, gather=True, interleave=True)
+    for k, v in dealt.items():
+        assert torch.equal(v, full[k]), k
     # 2. dL/dMLP: sharded batch + one all-reduce == whole batch
     n = 1024
     batch = rays[:n]

@@ -29,6 +29,8 @@ def worker(rank, world, port, q):
     rays = torch.randn(1001, 11)
     full = D.render_rays_sharded(rays, fake_render, gather=True)
     ok_render = all(torch.equal(full[k], fake_render(rays)[k]) for k in full)
+    dealt = D.render_rays_sharded(rays, fake_render, gather=True, interleave=True)
+    ok_render = ok_render and all(torch.equal(dealt[k], fake_render(rays)[k]) for k in dealt)
     mine = D.render_rays_sharded(rays, fake_render, gather=False)
     lo, hi = D.shard_bounds(1001, rank, world)
     ok_local = torch.equal(mine['acc_map'], rays[lo:hi, 3])

@@ -2,8 +2,10 @@
   ncu --set full --clock-control none --import-source on -k regex:'nerf_mlp|raw2outputs|resample_merge|ray_grad' -f -o gpurun_out/r02_kernels \\
       python tools/ncu_kernels.py
 Launch order (the keys tools/ncu_traffic.py gives them):
-  forward (two-tier, saving sign bits + active list): coarse_tier1, coarse_tier2, coarse_redo (exits), composite_coarse, resample_merge,
+  forward render (two-tier): coarse_tier1, coarse_tier2, coarse_redo (exits), composite_coarse, resample_merge,
       fine_tier1, fine_tier2, fine_redo (exits), composite_fine
+  the same forward keeping raw, the sign bits of the active points and the active list for the backward pass: the same nine with the
+      prefix "pg_" (pg_fine_tier2 writes 272 B of sign bits per active point)
   backward over the active set: composite_bwd, bwd_masked_active, ray_grad_reduce
   fine_dense: the fine pass evaluated densely (fp16x3, every point)
 """
@@ -29,6 +31,8 @@ aset = torch.empty(L.nsr_active_set_bytes(n, T), dtype=torch.uint8, device='cuda
 g = torch.randn(n, 3, device='cuda'); d_rays = new(n, 11)
 bws = torch.empty(L.nsr_render_backward_workspace_bytes(n, T), dtype=torch.uint8, device='cuda')
 torch.cuda.synchronize()
+assert L.nsr_render_rays_forward(P(rays), n, P(pc), P(pf), S, Ni, 0, None, None, P(rgb), None, None, None, None, None, None, None, None, None,
+                                 P(ws), ws.numel(), None) == 0, L.nsr_last_error()
 assert L.nsr_render_rays_forward_ex(P(rays), n, P(pc), P(pf), S, Ni, 0, None, None, P(rgb), None, None, None, None, None, None, P(raw), P(zv), None,
                                     P(mask), None, P(aset), P(ws), ws.numel(), None) == 0, L.nsr_last_error()
 assert L.nsr_render_rays_backward_ex(P(rays), P(zv), P(raw), n, T, P(pf), 0, P(g), P(d_rays), None, None, None, P(mask), P(aset), P(bws), bws.numel(), None) == 0

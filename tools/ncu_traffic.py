@@ -2,8 +2,8 @@
   python tools/ncu_traffic.py gpurun_out/r02_kernels.ncu-rep profiles/r02_ncu_kernels.csv > profiles/ncu_traffic.json
 Per launch: dram__bytes_read.sum + dram__bytes_write.sum (what bench.py reports as roofline.traffic), duration, tensor-pipe activity."""
 import csv, io, json, subprocess, sys
-ORDER = ['coarse_tier1', 'coarse_tier2', 'coarse_redo', 'composite_coarse', 'resample_merge', 'fine_tier1', 'fine_tier2', 'fine_redo', 'composite_fine',
-         'composite_bwd', 'bwd_masked_active', 'ray_grad_reduce', 'fine_dense']
+FWD = ['coarse_tier1', 'coarse_tier2', 'coarse_redo', 'composite_coarse', 'resample_merge', 'fine_tier1', 'fine_tier2', 'fine_redo', 'composite_fine']
+ORDER = FWD + ['pg_' + k for k in FWD] + ['composite_bwd', 'bwd_masked_active', 'ray_grad_reduce', 'fine_dense']
 KEEP = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
         'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed',
         'sm__cycles_elapsed.avg', 'sm__cycles_elapsed.avg.per_second', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
