@@ -652,14 +652,15 @@ def run_ours(args):
             g_rgb = torch.randn(n, 3, device=dev)
             d_rays = new(n, 11)
             zsave, rawsave = new(n, T), new(n, T, 4)
+            aset_fb = torch.empty(L.nsr_active_set_bytes(n, T), dtype=torch.uint8, device=dev)
 
             def step_fwd_bwd(s):
                 r = rays_dev[s % len(rays_dev)]
-                rc = L.nsr_render_rays_forward(P(r), n, P(pc), P(pf), N_SAMPLES, N_IMPORTANCE, 0, None, None, P(outs['rgb']), P(outs['disp']),
-                                               P(outs['acc']), P(outs['rgb0']), P(outs['disp0']), P(outs['acc0']), P(outs['zstd']), P(rawsave),
-                                               P(zsave), None, P(ws), ws_bytes, stream)
-                rc = rc or L.nsr_render_rays_backward(P(r), P(zsave), P(rawsave), n, T, P(pf), 0, P(g_rgb), P(d_rays), None, None, None,
-                                                      P(bws), bws_bytes, stream)
+                rc = L.nsr_render_rays_forward_ex(P(r), n, P(pc), P(pf), N_SAMPLES, N_IMPORTANCE, 0, None, None, P(outs['rgb']), P(outs['disp']),
+                                                  P(outs['acc']), P(outs['rgb0']), P(outs['disp0']), P(outs['acc0']), P(outs['zstd']), P(rawsave),
+                                                  P(zsave), None, None, None, P(aset_fb), P(ws), ws_bytes, stream)
+                rc = rc or L.nsr_render_rays_backward_ex(P(r), P(zsave), P(rawsave), n, T, P(pf), 0, P(g_rgb), P(d_rays), None, None, None,
+                                                         None, P(aset_fb), P(bws), bws_bytes, stream)
                 if rc != 0:
                     raise RuntimeError(L.nsr_last_error().decode())
 
@@ -672,10 +673,10 @@ def run_ours(args):
             e1.record()
             torch.cuda.synchronize()
             fb_ms = e0.elapsed_time(e1) / args.steps
-            fwd_bwd = {'workload': 'BASELINE config 3 on the recompute route (no extra memory): forward + backward dL/d(rays) from dL/d(rgb_map), 160000 rays, 64+128 samples (fine pass recomputed in the backward kernel)',
+            fwd_bwd = {'workload': 'BASELINE config 3 on the recompute route (4 B per sample point of extra memory, the active list): forward (two-tier) + backward dL/d(rays) from dL/d(rgb_map), 160000 rays, 64+128 samples; the backward kernel recomputes the fine pass on the active points',
                        'rays_per_s': n / (fb_ms * 1e-3), 'ms_per_step': fb_ms, 'algorithmic_flop_per_ray': (64 + 192 + 192) * FLOP_PER_POINT,
                        'algorithmic_tflops': n * (64 + 192 + 192) * FLOP_PER_POINT / (fb_ms * 1e-3) / 1e12}
-            del bws, zsave, rawsave
+            del bws, zsave, rawsave, aset_fb
             # secondary (SURVEY a-12 / RN:643-716): one optimisation step of both networks on N_rand = 1024 random rays through the
             # public API: render(rays=...) -> img2mse(rgb) + img2mse(rgb0) -> backward (dL/dMLP of both nets) -> Adam -> re-pack
             import copy

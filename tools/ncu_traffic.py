@@ -1,5 +1,6 @@
 """profiles/ncu_traffic.json from an ncu --set full capture of tools/ncu_kernels.py (run here, the .ncu-rep comes back in gpurun_out/):
   python tools/ncu_traffic.py gpurun_out/r02_kernels.ncu-rep profiles/r02_ncu_kernels.csv > profiles/ncu_traffic.json
+(or give it the `ncu -i ... --page raw --csv` dump made on the GPU box, when the report itself is too big to bring back)
 Per launch: dram__bytes_read.sum + dram__bytes_write.sum (what bench.py reports as roofline.traffic), duration, tensor-pipe activity."""
 import csv, io, json, subprocess, sys
 FWD = ['coarse_tier1', 'coarse_tier2', 'coarse_redo', 'composite_coarse', 'resample_merge', 'fine_tier1', 'fine_tier2', 'fine_redo', 'composite_fine']
@@ -10,7 +11,7 @@ KEEP = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__
         'l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
         'launch__registers_per_thread', 'launch__block_size', 'launch__grid_size', 'launch__shared_mem_per_block_dynamic', 'smsp__inst_executed.sum']
 rep = sys.argv[1]
-out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+out = open(rep).read() if rep.endswith('.csv') else subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 header, units, data = rows[0], rows[1], rows[2:]
 col = {h: i for i, h in enumerate(header)}
