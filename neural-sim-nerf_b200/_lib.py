@@ -48,6 +48,9 @@ _SIGNATURES = {
     'nsr_set_two_tier': (c_int, [c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float]),
     'nsr_get_two_tier': (c_int, [c_vp, c_vp, c_vp, c_vp]),
     'nsr_set_tier1_pair': (c_int, [c_int]),
+    'nsr_set_coarse_refine': (c_int, [c_int]),
+    'nsr_coarse_refine_workspace_bytes': (c_size, [c_i64]),
+    'nsr_coarse_refine': (c_int, [c_f32p, c_f32p, c_i64, c_int, c_vp, c_f32p, c_vp, c_size, c_vp]),
     'nsr_render_backward_workspace_bytes': (c_size, [c_i64, c_int]),
     'nsr_mlp_dump_bytes': (c_size, [c_i64, c_int]),
     'nsr_render_rays_backward': (c_int, [c_f32p, c_f32p, c_f32p, c_i64, c_int, c_vp, c_u32, c_f32p, c_f32p, c_vp, c_vp, c_vp, c_vp, c_size, c_vp]),

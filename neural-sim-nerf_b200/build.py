@@ -5,7 +5,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ['csrc/api.cu', 'csrc/ray_stage.cu', 'csrc/image_stage.cu', 'csrc/train_stage.cu', 'csrc/mlp_forward.cu', 'csrc/mlp_backward.cu', 'csrc/wgrad.cu']
+SOURCES = ['csrc/api.cu', 'csrc/ray_stage.cu', 'csrc/image_stage.cu', 'csrc/train_stage.cu', 'csrc/mlp_forward.cu', 'csrc/mlp_backward.cu', 'csrc/wgrad.cu', 'csrc/refine.cu']
 OUT = os.path.join(HERE, 'libnsr_b200.so')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
          '-shared', '-Xcompiler', '-fPIC']

@@ -71,11 +71,12 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 // two-tier evaluation knobs (process-wide; set them before launching work, not concurrently with it)
 static TwoTierParams g_two_tier = {4.0f, 1.5f, 0.30f};   // tau, verify_max (measured max |sigma~ - sigma|: 0.74), force_fraction
 static bool g_two_tier_enabled = true;
+static bool g_coarse_refine = true;
 const TwoTierParams& two_tier_params() { return g_two_tier; }
 
 // byte offsets of the blocks inside nsr_render_rays_forward's workspace
 struct FwdLayout {
-  size_t z0, w0, raw0, z1, raw1, as0, as1, total;
+  size_t z0, w0, raw0, z1, raw1, as0, as1, rf, total;
 };
 static FwdLayout fwd_layout(int64_t n, int S, int Ni) {
   const size_t T = size_t(S) + size_t(Ni);
@@ -95,6 +96,8 @@ static FwdLayout fwd_layout(int64_t n, int S, int Ni) {
   b += n > 0 ? align_up(active_set_bytes(n * int64_t(S)), 256) : 0;
   L.as1 = b;
   b += n > 0 ? align_up(active_set_bytes(n * int64_t(T)), 256) : 0;
+  L.rf = b;                                        // coarse-pass refinement list (refine.cu); after the blocks the layout call reports
+  b += (n > 0 && Ni > 0) ? align_up(refine_workspace_bytes(n), 256) : 0;
   L.total = b;
   return L;
 }
@@ -221,6 +224,24 @@ int nsr_set_two_tier(int enabled, float tau, float verify_max, float force_fract
 
 int nsr_set_tier1_pair(int enabled) { return set_tier1_pair(enabled); }
 
+int nsr_set_coarse_refine(int enabled) {
+  const int old = g_coarse_refine ? 1 : 0;
+  g_coarse_refine = enabled != 0;
+  return old;
+}
+
+int nsr_coarse_refine(const float* rays, const float* z_vals, int64_t n_rays, int n_samples, const void* packed_net, float* raw, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  NSR_REQUIRE(n_rays >= 0 && n_samples >= 2, "nsr_coarse_refine: bad sizes");
+  if (n_rays == 0) return NSR_OK;
+  NSR_REQUIRE(rays && z_vals && packed_net && raw && workspace, "nsr_coarse_refine: null argument");
+  NSR_REQUIRE(workspace_bytes >= refine_workspace_bytes(n_rays) && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+              "nsr_coarse_refine: workspace too small or not 256-byte aligned");
+  return launch_coarse_refine(rays, z_vals, n_rays, n_samples, packed_net, raw, workspace, static_cast<cudaStream_t>(stream));
+}
+
+size_t nsr_coarse_refine_workspace_bytes(int64_t n_rays) { return refine_workspace_bytes(n_rays); }
+
 int nsr_get_two_tier(int* enabled, float* tau, float* verify_max, float* force_fraction) {
   if (enabled) *enabled = g_two_tier_enabled ? 1 : 0;
   if (tau) *tau = g_two_tier.tau;
@@ -304,6 +325,8 @@ int nsr_render_rays_forward_ex(const float* rays, int64_t n, const void* packed_
     if (z_vals_out) cudaMemcpyAsync(z_vals_out, z0, size_t(n) * S * 4, cudaMemcpyDeviceToDevice, st);
     return check_launch("render_rays_forward(coarse only)");
   }
+  // hierarchical sampling is ill-conditioned in the density of barely-hit rays: those few points again, in fp32 (refine.cu)
+  if (g_coarse_refine && !mflags && (rc = launch_coarse_refine(rays, z0, n, S, packed_coarse, raw0, ws + lay.rf, st))) return rc;
   if ((rc = launch_raw2outputs(raw0, z0, rays + 3, 11, n, S, cflags, rgb0, disp0, acc0, w0, nullptr, st))) return rc;  // RN:467
   float* zf = z_vals_out ? z_vals_out : z1;
   const uint32_t force_count = uint32_t(double(g_two_tier.force_frac) * double(n) * double(S));

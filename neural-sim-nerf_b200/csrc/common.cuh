@@ -63,7 +63,18 @@ constexpr int TAIL_MISC = 3328;         // b_alpha, b_rgb[0..2]
 constexpr int TAIL_MIXSCALE = 3336;     // [10] 2^-b of each step's mixed-precision chunks
 constexpr int TAIL_FLOATS = 3360;
 constexpr int TAIL_BYTES = TAIL_FLOATS * 4;  // 13440
-constexpr int PACKED_BYTES = WEIGHT_BYTES + TAIL_BYTES;
+// fp32 copy of the density branch (pts_linears.0-7 + alpha head) after the tail, for the coarse-pass refinement (refine.cu): layer l
+// TRANSPOSED, [K_l][256] floats (thread j of a block reads W[k][j]: coalesced), then w_alpha [256].  K = 63, 256 x4, 319 (cat[xyz
+// encoding, h], RH:105-106), 256, 256.
+constexpr int REF_OFF = WEIGHT_BYTES + TAIL_BYTES;            // 7,353,472 (16-byte aligned)
+__host__ __device__ constexpr int ref_layer_k(int l) { return l == 0 ? 63 : (l == 5 ? 319 : 256); }
+__host__ __device__ constexpr int ref_layer_off(int l) {      // in floats; l = 8 -> w_alpha
+  int o = 0;
+  for (int i = 0; i < l; ++i) o += ref_layer_k(i) * 256;
+  return o;
+}
+constexpr int REF_FLOATS = ref_layer_off(8) + 256;            // 491,264
+constexpr int PACKED_BYTES = REF_OFF + REF_FLOATS * 4;
 
 __host__ __device__ constexpr int step_n_halves(int s) { return s == 9 ? 1 : 2; }
 __host__ __device__ constexpr int step_k_chunks(int s) { return s == 0 ? 1 : ((s == 5 || s == 9) ? 5 : 4); }
@@ -184,6 +195,9 @@ int launch_resample_merge(const float* z, const float* w, int64_t n, int S, int 
 int launch_make_rays(int H, int W, const float* K9, const float* c2w12, float near_, float far_, float* rays,
                      cudaStream_t st);
 int launch_pack_rays(const float* o, const float* d, int64_t n, float near_, float far_, float* rays, cudaStream_t st);
+// refine.cu: fp32 re-evaluation of the coarse density where hierarchical sampling is ill-conditioned (DESIGN.md "coarse refinement")
+size_t refine_workspace_bytes(int64_t n_rays);
+int launch_coarse_refine(const float* rays, const float* z, int64_t n, int S, const void* packed, float* raw, void* workspace, cudaStream_t st);
 // image_stage.cu
 int launch_to8b(const float* x, int64_t n, uint8_t* out, cudaStream_t st);
 int launch_make_rays_dev(int H, int W, const float* K9, const float* c2w_dev, int ld_c2w, float near_, float far_, float* rays,

@@ -192,6 +192,18 @@ __global__ void pack_net_kernel(NetPtrs p, uint8_t* __restrict__ out) {
         lo[chunk_off(nl, kl) >> 1] = __float2half_rn(v - __half2float(h));
       }
     }
+  } else if (c >= MIX_CHUNK0 + NUM_CHUNKS + 1 + NUM_STEPS) {  // fp32 transposed copy of the density branch (common.cuh REF_*)
+    const int l = c - (MIX_CHUNK0 + NUM_CHUNKS + 1 + NUM_STEPS);
+    float* dst = reinterpret_cast<float*>(out + REF_OFF) + ref_layer_off(l);
+    if (l == 8) {
+      for (int j = threadIdx.x; j < 256; j += blockDim.x) dst[j] = p.w[10][j];
+    } else {
+      const int K = ref_layer_k(l);
+      for (int e = threadIdx.x; e < K * 256; e += blockDim.x) {
+        const int k = e / 256, j = e % 256;
+        dst[e] = p.w[l][j * K + k];
+      }
+    }
   } else if (c == MIX_CHUNK0 + NUM_CHUNKS) {  // fp32 tail
     float* t = reinterpret_cast<float*>(out + WEIGHT_BYTES);
     for (int i = threadIdx.x; i < TAIL_FLOATS; i += blockDim.x) {
@@ -227,7 +239,7 @@ int launch_pack_net(const float* const* weights, const float* const* biases, voi
     p.w[i] = weights[i];
     p.b[i] = biases[i];
   }
-  pack_net_kernel<<<2 * NUM_CHUNKS + NUM_BWD_CHUNKS + 1 + NUM_STEPS, 256, 0, st>>>(p, static_cast<uint8_t*>(packed));
+  pack_net_kernel<<<2 * NUM_CHUNKS + NUM_BWD_CHUNKS + 1 + NUM_STEPS + 9, 256, 0, st>>>(p, static_cast<uint8_t*>(packed));
   count_launch();
   return check_launch("pack_net_kernel");
 }

@@ -1,0 +1,156 @@
+// Coarse-pass refinement: the density of the few coarse sample points that hierarchical sampling is ill-conditioned in, re-evaluated
+// in fp32 on the CUDA cores.
+//
+// Why.  sample_pdf (RH:199-243) places the fine samples by the coarse weights normalised over the ray: pdf_i = (w_i + 1e-5) / sum.
+// On a ray that only grazes the object the sum is tiny (acc0 ~ 1e-3) and carried by one or two samples whose density is barely
+// positive (sigma ~ 0.02): the tensor-core arithmetic's ABSOLUTE error on sigma (~1e-4..3e-4: fp16 hi/lo operands, tensor-core
+// accumulation) is then a per-cent error of that weight, the pdf shifts, most of the 128 fine samples move by a fraction of a bin, and
+// at a silhouette the pixel moves by up to 4e-2 -- 4 of the 160 000 rays of the test image were outside the 1e-3 bar that way
+// (tools/parity_full_image.py, tools/parity_outliers.py), while the reference on the CPU and the reference on CUDA agree with each
+// other to 3e-4 on the same rays.  Opaque rays are immune (the sum is ~1), and so are empty ones (all weights 0).
+//
+// What.  After the coarse network pass: (1) select_refine_kernel, one warp per ray, sums the ray's optical depth from raw0; on rays
+// that are not opaque (optical depth < REFINE_TAU_LIMIT, i.e. acc0 < 0.75) every sample whose sigma is not clearly negative goes on a
+// list; (2) refine_sigma_kernel evaluates pts_linears.0-7 + the alpha head for the listed points in fp32 (FMA chains over K, accurate
+// sincosf encoding, the fp32 weights kept TRANSPOSED behind the packed tail: common.cuh REF_*), eight points per 256-thread block
+// pass, one output unit per thread, and overwrites raw0[p].sigma.  A few thousand points per image: ~0.1 ms next to 54 ms.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace nsr {
+
+constexpr float REFINE_TAU_LIMIT = 1.3863f;   // optical depth of acc0 = 0.75
+constexpr float REFINE_SIGMA_MIN = -0.01f;    // samples with sigma above this on such a ray are re-evaluated
+constexpr int REFINE_POINTS = 8;              // points per block pass (one warp each in the head reduction)
+constexpr unsigned FULLMASK = 0xffffffffu;
+
+// workspace: [count u32, padded to 256 B][list: int32 x cap]
+static inline int64_t refine_cap(int64_t n_rays) { return 2 * n_rays + 1024; }
+size_t refine_workspace_bytes(int64_t n_rays) { return 256 + size_t(refine_cap(n_rays)) * 4; }
+
+__global__ void __launch_bounds__(256) select_refine_kernel(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays,
+                                                            int64_t n, int S, uint32_t* __restrict__ count, int32_t* __restrict__ list, uint32_t cap) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+  if (ray >= n) return;
+  const float* rp = rays + ray * 11;
+  const float nrm = sqrtf(rp[3] * rp[3] + rp[4] * rp[4] + rp[5] * rp[5]);
+  float tau = 0.f;
+  for (int i = lane; i < S; i += 32) {
+    const float sg = raw[(ray * S + i) * 4 + 3];
+    const float dist = (i + 1 < S ? z[ray * S + i + 1] - z[ray * S + i] : 1e10f) * nrm;   // RN:358-361
+    tau += fmaxf(sg, 0.f) * dist;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) tau += __shfl_xor_sync(FULLMASK, tau, d);
+  if (!(tau < REFINE_TAU_LIMIT)) return;   // opaque (or NaN): the normaliser is ~1, a 1e-4 error of one sigma does not move the pdf
+  for (int i0 = 0; i0 < S; i0 += 32) {
+    const int i = i0 + lane;
+    const bool pick = i < S && raw[(ray * S + i) * 4 + 3] > REFINE_SIGMA_MIN;
+    const uint32_t m = __ballot_sync(FULLMASK, pick);
+    if (m == 0u) continue;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(count, uint32_t(__popc(m)));
+    base = __shfl_sync(FULLMASK, base, 0);
+    const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
+    if (pick && pos < cap) list[pos] = int32_t(ray * S + i);
+  }
+}
+
+__global__ void __launch_bounds__(256) refine_sigma_kernel(const int32_t* __restrict__ list, const uint32_t* __restrict__ count, uint32_t cap,
+                                                           const float* __restrict__ rays, const float* __restrict__ z, int S,
+                                                           const uint8_t* __restrict__ packed, float* __restrict__ raw) {
+  constexpr int R = REFINE_POINTS;
+  __shared__ float enc[R][64];
+  __shared__ float hbuf[2][R][256];
+  const float* W32 = reinterpret_cast<const float*>(packed + REF_OFF);
+  const float* tail = reinterpret_cast<const float*>(packed + WEIGHT_BYTES);
+  const int j = threadIdx.x, warp = j >> 5, lane = j & 31;
+  const uint32_t n = min(*count, cap);
+  for (uint32_t base = blockIdx.x * R; base < n; base += gridDim.x * R) {
+    __syncthreads();   // the previous pass is done with the shared buffers
+    // ---- gamma(x) (RH:47-48) of the R points: 64 channels each (63 + a zero), two passes of 256 threads
+    for (int t = j; t < R * 64; t += 256) {
+      const int r = t >> 6, c = t & 63;
+      float v = 0.f;
+      if (base + r < n && c < 63) {
+        const int64_t p = list[base + r];
+        const float* rp = rays + (p / S) * 11;
+        const int d = c < 3 ? c : (c - 3) % 3;
+        const float x = __fadd_rn(rp[d], __fmul_rn(rp[3 + d], z[p]));   // RN:463
+        if (c < 3) {
+          v = x;
+        } else {
+          const int k = (c - 3) / 6;
+          const float a = x * float(1 << k);
+          v = ((c - 3) % 6) < 3 ? sinf(a) : cosf(a);
+        }
+      }
+      enc[r][c] = v;
+    }
+    __syncthreads();
+    // ---- pts_linears.0-7: thread j = output unit j of all R points, fp32 FMA chain over K
+    int cur = 0;
+#pragma unroll 1
+    for (int l = 0; l < 8; ++l) {
+      const float* W = W32 + ref_layer_off(l);
+      float acc[R];
+      const float b = tail[TAIL_BIAS + l * 256 + j];
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = b;
+      if (l == 0 || l == 5) {
+#pragma unroll 1
+        for (int k = 0; k < 63; ++k) {
+          const float w = W[k * 256 + j];
+#pragma unroll
+          for (int r = 0; r < R; ++r) acc[r] = fmaf(enc[r][k], w, acc[r]);
+        }
+        W += 63 * 256;
+      }
+      if (l != 0) {
+        const float(*h)[256] = hbuf[cur];
+#pragma unroll 4
+        for (int k = 0; k < 256; ++k) {
+          const float w = W[k * 256 + j];
+#pragma unroll
+          for (int r = 0; r < R; ++r) acc[r] = fmaf(h[r][k], w, acc[r]);
+        }
+      }
+      const int nxt = l == 0 ? cur : cur ^ 1;
+#pragma unroll
+      for (int r = 0; r < R; ++r) hbuf[nxt][r][j] = fmaxf(acc[r], 0.f);
+      cur = nxt;
+      __syncthreads();
+    }
+    // ---- alpha head (RH:109): warp r reduces point r
+    {
+      const int r = warp;
+      const float* wa = W32 + ref_layer_off(8);
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s = fmaf(hbuf[cur][r][lane + 32 * q], wa[lane + 32 * q], s);
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(FULLMASK, s, d);
+      if (lane == 0 && base + r < n) raw[int64_t(list[base + r]) * 4 + 3] = s + tail[TAIL_MISC];
+    }
+  }
+}
+
+int launch_coarse_refine(const float* rays, const float* z, int64_t n, int S, const void* packed, float* raw, void* workspace, cudaStream_t st) {
+  if (n == 0) return NSR_OK;
+  uint32_t* count = static_cast<uint32_t*>(workspace);
+  int32_t* list = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(workspace) + 256);
+  const uint32_t cap = uint32_t(refine_cap(n));
+  if (cudaMemsetAsync(count, 0, 4, st) != cudaSuccess) return check_launch("refine count init");
+  select_refine_kernel<<<unsigned((n * 32 + 255) / 256), 256, 0, st>>>(raw, z, rays, n, S, count, list, cap);
+  count_launch();
+  if (int rc = check_launch("select_refine_kernel")) return rc;
+  int sms = 0;
+  if (int rc = current_device_sms(&sms)) return rc;
+  refine_sigma_kernel<<<4 * sms, 256, 0, st>>>(list, count, cap, rays, z, S, static_cast<const uint8_t*>(packed), raw);
+  count_launch();
+  return check_launch("refine_sigma_kernel");
+}
+
+}  // namespace nsr

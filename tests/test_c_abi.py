@@ -40,7 +40,8 @@ def test_python_binding_covers_header(built_lib):
     L = nsr.lib()
     assert L.nsr_version() >= 100
     # 73 forward + 78 backward (transposed) + 73 mixed-precision forward operand chunk pairs (32 KiB each) + fp32 tail
-    assert L.nsr_packed_net_bytes() == (73 + 78 + 73) * 32768 + 3360 * 4
+    # 73 forward + 78 backward + 73 mixed-precision chunk pairs, the fp32 tail, the fp32 transposed density branch (refinement)
+    assert L.nsr_packed_net_bytes() == (73 + 78 + 73) * 32768 + 3360 * 4 + (256 * (63 + 256 * 4 + 319 + 256 * 2) + 256) * 4
     assert L.nsr_render_backward_workspace_bytes(512, 192) >= 512 * 192 * (16 + 32)
     assert L.nsr_render_workspace_bytes(0, 64, 128) == 0
     assert L.nsr_render_workspace_bytes(512, 64, 128) >= 512 * (64 * 4 * 2 + 64 * 16 + 192 * 4 + 192 * 16)
