@@ -193,8 +193,8 @@ int nsr_set_tier1_pair(int enabled);
 /* Coarse-pass refinement.  sample_pdf (RH:199-243) normalises the coarse weights over the ray, so on a ray that barely touches the
  * object (acc0 ~ 1e-3, one sample with sigma ~ 0.02) the tensor-core arithmetic's absolute error on sigma (~1e-4) is a per-cent
  * error of the pdf, the fine samples move, and at a silhouette the pixel leaves the 1e-3 bar (4 of 160 000 rays of the test image).
- * nsr_render_rays_forward therefore re-evaluates the density of those few coarse points in fp32 on the CUDA cores before the coarse
- * compositing: on every ray whose coarse optical depth is below 1.386 (acc0 < 0.75), every sample with sigma > -0.01; raw[p].sigma
+ * nsr_render_rays_forward therefore re-evaluates the density of those few coarse points with fp64 accumulation on the CUDA cores before the coarse
+ * compositing: on every ray whose coarse optical depth is below 4.605 (acc0 < 0.99), every sample with sigma > -0.01; raw[p].sigma
  * is overwritten in place.  On by default whenever N_importance > 0 and the precision is the default one; nsr_set_coarse_refine
  * returns the previous setting.  nsr_coarse_refine is the stage by itself on raw [n,S,4] / z_vals [n,S] (workspace:
  * nsr_coarse_refine_workspace_bytes(n_rays) bytes, 256-byte aligned; its first u32 holds the number of points found, at most

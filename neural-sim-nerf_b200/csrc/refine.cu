@@ -1,5 +1,5 @@
 // Coarse-pass refinement: the density of the few coarse sample points that hierarchical sampling is ill-conditioned in, re-evaluated
-// in fp32 on the CUDA cores.
+// with fp64 accumulation on the CUDA cores.
 //
 // Why.  sample_pdf (RH:199-243) places the fine samples by the coarse weights normalised over the ray: pdf_i = (w_i + 1e-5) / sum.
 // On a ray that only grazes the object the sum is tiny (acc0 ~ 1e-3) and carried by one or two samples whose density is barely
@@ -7,11 +7,12 @@
 // accumulation) is then a per-cent error of that weight, the pdf shifts, most of the 128 fine samples move by a fraction of a bin, and
 // at a silhouette the pixel moves by up to 4e-2 -- 4 of the 160 000 rays of the test image were outside the 1e-3 bar that way
 // (tools/parity_full_image.py, tools/parity_outliers.py), while the reference on the CPU and the reference on CUDA agree with each
-// other to 3e-4 on the same rays.  Opaque rays are immune (the sum is ~1), and so are empty ones (all weights 0).
+// other to 3e-4 on the same rays.  Empty rays are immune (all weights 0); opaque ones nearly so (the sum is ~1: what is left there is a
+// fine sample in the low-density bin in front of the surface moving by ~1e-5, 1.1e-3 on one ray of the test image).
 //
 // What.  After the coarse network pass: (1) select_refine_kernel, one warp per ray, sums the ray's optical depth from raw0; on rays
-// that are not opaque (optical depth < REFINE_TAU_LIMIT, i.e. acc0 < 0.75) every sample whose sigma is not clearly negative goes on a
-// list; (2) refine_sigma_kernel evaluates pts_linears.0-7 + the alpha head for the listed points in fp32 (FMA chains over K, accurate
+// that are not opaque (optical depth < REFINE_TAU_LIMIT, i.e. acc0 < 0.99) every sample whose sigma is not clearly negative goes on a
+// list; (2) refine_sigma_kernel evaluates pts_linears.0-7 + the alpha head for the listed points (fp64 FMA chains over K, fp32 layer outputs, accurate
 // sincosf encoding, the fp32 weights kept TRANSPOSED behind the packed tail: common.cuh REF_*), eight points per 256-thread block
 // pass, one output unit per thread, and overwrites raw0[p].sigma.  A few thousand points per image: ~0.1 ms next to 54 ms.
 #include <math.h>
@@ -20,7 +21,7 @@
 
 namespace nsr {
 
-constexpr float REFINE_TAU_LIMIT = 1.3863f;   // optical depth of acc0 = 0.75
+constexpr float REFINE_TAU_LIMIT = 4.6052f;   // optical depth of acc0 = 0.99
 constexpr float REFINE_SIGMA_MIN = -0.01f;    // samples with sigma above this on such a ray are re-evaluated
 constexpr int REFINE_POINTS = 8;              // points per block pass (one warp each in the head reduction)
 constexpr unsigned FULLMASK = 0xffffffffu;
@@ -95,16 +96,18 @@ __global__ void __launch_bounds__(256) refine_sigma_kernel(const int32_t* __rest
 #pragma unroll 1
     for (int l = 0; l < 8; ++l) {
       const float* W = W32 + ref_layer_off(l);
-      float acc[R];
-      const float b = tail[TAIL_BIAS + l * 256 + j];
+      // products of fp32 numbers accumulated in fp64, one rounding to fp32 per unit: each layer's output is the correctly rounded
+      // value of the exact dot product, so what separates this evaluation from the reference's is the reference's own fp32 rounding
+      double acc[R];
+      const double b = double(tail[TAIL_BIAS + l * 256 + j]);
 #pragma unroll
       for (int r = 0; r < R; ++r) acc[r] = b;
       if (l == 0 || l == 5) {
 #pragma unroll 1
         for (int k = 0; k < 63; ++k) {
-          const float w = W[k * 256 + j];
+          const double w = double(W[k * 256 + j]);
 #pragma unroll
-          for (int r = 0; r < R; ++r) acc[r] = fmaf(enc[r][k], w, acc[r]);
+          for (int r = 0; r < R; ++r) acc[r] = fma(double(enc[r][k]), w, acc[r]);
         }
         W += 63 * 256;
       }
@@ -112,14 +115,14 @@ __global__ void __launch_bounds__(256) refine_sigma_kernel(const int32_t* __rest
         const float(*h)[256] = hbuf[cur];
 #pragma unroll 4
         for (int k = 0; k < 256; ++k) {
-          const float w = W[k * 256 + j];
+          const double w = double(W[k * 256 + j]);
 #pragma unroll
-          for (int r = 0; r < R; ++r) acc[r] = fmaf(h[r][k], w, acc[r]);
+          for (int r = 0; r < R; ++r) acc[r] = fma(double(h[r][k]), w, acc[r]);
         }
       }
       const int nxt = l == 0 ? cur : cur ^ 1;
 #pragma unroll
-      for (int r = 0; r < R; ++r) hbuf[nxt][r][j] = fmaxf(acc[r], 0.f);
+      for (int r = 0; r < R; ++r) hbuf[nxt][r][j] = fmaxf(float(acc[r]), 0.f);
       cur = nxt;
       __syncthreads();
     }
@@ -127,12 +130,12 @@ __global__ void __launch_bounds__(256) refine_sigma_kernel(const int32_t* __rest
     {
       const int r = warp;
       const float* wa = W32 + ref_layer_off(8);
-      float s = 0.f;
+      double s = 0.0;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) s = fmaf(hbuf[cur][r][lane + 32 * q], wa[lane + 32 * q], s);
+      for (int q = 0; q < 8; ++q) s = fma(double(hbuf[cur][r][lane + 32 * q]), double(wa[lane + 32 * q]), s);
 #pragma unroll
       for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(FULLMASK, s, d);
-      if (lane == 0 && base + r < n) raw[int64_t(list[base + r]) * 4 + 3] = s + tail[TAIL_MISC];
+      if (lane == 0 && base + r < n) raw[int64_t(list[base + r]) * 4 + 3] = float(s + double(tail[TAIL_MISC]));
     }
   }
 }
