@@ -200,6 +200,7 @@ int nsr_set_tier1_pair(int enabled);
  * nsr_coarse_refine_workspace_bytes(n_rays) bytes, 256-byte aligned; its first u32 holds the number of points found, at most
  * 2 n_rays + 1024 are re-evaluated). */
 int nsr_set_coarse_refine(int enabled);
+int nsr_set_coarse_refine_limit(float acc_limit);   /* rays with coarse acc0 below this (default 0.99) are refined */
 size_t nsr_coarse_refine_workspace_bytes(int64_t n_rays);
 int nsr_coarse_refine(const float* rays, const float* z_vals, int64_t n_rays, int n_samples, const void* packed_net, float* raw, void* workspace,
                       size_t workspace_bytes, void* stream);

@@ -242,6 +242,12 @@ int nsr_coarse_refine(const float* rays, const float* z_vals, int64_t n_rays, in
 
 size_t nsr_coarse_refine_workspace_bytes(int64_t n_rays) { return refine_workspace_bytes(n_rays); }
 
+int nsr_set_coarse_refine_limit(float acc_limit) {
+  NSR_REQUIRE(acc_limit > 0.f && acc_limit < 1.f, "nsr_set_coarse_refine_limit: acc_limit must be in (0, 1)");
+  set_refine_tau_limit(-logf(1.f - acc_limit));
+  return NSR_OK;
+}
+
 int nsr_get_two_tier(int* enabled, float* tau, float* verify_max, float* force_fraction) {
   if (enabled) *enabled = g_two_tier_enabled ? 1 : 0;
   if (tau) *tau = g_two_tier.tau;
@@ -631,6 +637,7 @@ int nsr_train_step(const float* rays, const float* target, int64_t n, const nsr_
   }
   if ((rc = launch_coarse_z(rays, n, S, zflags, perturb ? t_rand : nullptr, z0, st))) return rc;
   if ((rc = launch_mlp_forward(rays, z0, n, S, pc, 0, raw0, st, Ni > 0 ? bits0 : bits, Ni > 0 ? dump0 : dump))) return rc;
+  if (Ni > 0 && g_coarse_refine && (rc = launch_coarse_refine(rays, z0, n, S, pc, raw0, fwd + fwd_layout(n, S, Ni).rf, st))) return rc;   // as render() does
   if (raw_noise_std > 0.f && (rc = launch_sigma_noise(seed, 2u, raw0, n * int64_t(S), raw_noise_std, st))) return rc;  // RN:365-366
   if ((rc = launch_raw2outputs(raw0, z0, rays + 3, 11, n, S, cflags, Ni > 0 ? rgb0 : rgb, nullptr, nullptr, w0, nullptr, st))) return rc;
   if (Ni > 0) {

@@ -11,7 +11,7 @@
 // fine sample in the low-density bin in front of the surface moving by ~1e-5, 1.1e-3 on one ray of the test image).
 //
 // What.  After the coarse network pass: (1) select_refine_kernel, one warp per ray, sums the ray's optical depth from raw0; on rays
-// that are not opaque (optical depth < REFINE_TAU_LIMIT, i.e. acc0 < 0.99) every sample whose sigma is not clearly negative goes on a
+// that are not opaque (optical depth below the limit, default 4.6 i.e. acc0 < 0.99) every sample whose sigma is not clearly negative goes on a
 // list; (2) refine_sigma_kernel evaluates pts_linears.0-7 + the alpha head for the listed points (fp64 FMA chains over K, fp32 layer outputs, accurate
 // sincosf encoding, the fp32 weights kept TRANSPOSED behind the packed tail: common.cuh REF_*), eight points per 256-thread block
 // pass, one output unit per thread, and overwrites raw0[p].sigma.  A few thousand points per image: ~0.1 ms next to 54 ms.
@@ -21,9 +21,10 @@
 
 namespace nsr {
 
-constexpr float REFINE_TAU_LIMIT = 4.6052f;   // optical depth of acc0 = 0.99
+static float g_refine_tau_limit = 4.6052f;     // optical depth of acc0 = 0.99 (nsr_set_coarse_refine_limit)
+void set_refine_tau_limit(float tau) { g_refine_tau_limit = tau; }
 constexpr float REFINE_SIGMA_MIN = -0.01f;    // samples with sigma above this on such a ray are re-evaluated
-constexpr int REFINE_POINTS = 8;              // points per block pass (one warp each in the head reduction)
+constexpr int REFINE_POINTS = 16;             // points per block pass: the 1.97 MB of fp32 weights are re-read from L2 once per pass
 constexpr unsigned FULLMASK = 0xffffffffu;
 
 // workspace: [count u32, padded to 256 B][list: int32 x cap]
@@ -31,7 +32,8 @@ static inline int64_t refine_cap(int64_t n_rays) { return 2 * n_rays + 1024; }
 size_t refine_workspace_bytes(int64_t n_rays) { return 256 + size_t(refine_cap(n_rays)) * 4; }
 
 __global__ void __launch_bounds__(256) select_refine_kernel(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays,
-                                                            int64_t n, int S, uint32_t* __restrict__ count, int32_t* __restrict__ list, uint32_t cap) {
+                                                            int64_t n, int S, float tau_limit, uint32_t* __restrict__ count, int32_t* __restrict__ list,
+                                                            uint32_t cap) {
   const int lane = threadIdx.x & 31;
   const int64_t ray = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
   if (ray >= n) return;
@@ -45,7 +47,7 @@ __global__ void __launch_bounds__(256) select_refine_kernel(const float* __restr
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) tau += __shfl_xor_sync(FULLMASK, tau, d);
-  if (!(tau < REFINE_TAU_LIMIT)) return;   // opaque (or NaN): the normaliser is ~1, a 1e-4 error of one sigma does not move the pdf
+  if (!(tau < tau_limit)) return;   // opaque (or NaN): the normaliser is ~1, a 1e-4 error of one sigma does not move the pdf
   for (int i0 = 0; i0 < S; i0 += 32) {
     const int i = i0 + lane;
     const bool pick = i < S && raw[(ray * S + i) * 4 + 3] > REFINE_SIGMA_MIN;
@@ -68,7 +70,10 @@ __global__ void __launch_bounds__(256) refine_sigma_kernel(const int32_t* __rest
   const float* W32 = reinterpret_cast<const float*>(packed + REF_OFF);
   const float* tail = reinterpret_cast<const float*>(packed + WEIGHT_BYTES);
   const int j = threadIdx.x, warp = j >> 5, lane = j & 31;
-  const uint32_t n = min(*count, cap);
+  // more candidates than the list holds (a fog-like scene: every ray translucent): WHICH of them made it onto the list depends on the
+  // order of the atomics, so refining a subset would make the render irreproducible -- refine none
+  if (*count > cap) return;
+  const uint32_t n = *count;
   for (uint32_t base = blockIdx.x * R; base < n; base += gridDim.x * R) {
     __syncthreads();   // the previous pass is done with the shared buffers
     // ---- gamma(x) (RH:47-48) of the R points: 64 channels each (63 + a zero), two passes of 256 threads
@@ -126,9 +131,8 @@ __global__ void __launch_bounds__(256) refine_sigma_kernel(const int32_t* __rest
       cur = nxt;
       __syncthreads();
     }
-    // ---- alpha head (RH:109): warp r reduces point r
-    {
-      const int r = warp;
+    // ---- alpha head (RH:109): warp w reduces points w, w + 8
+    for (int r = warp; r < R; r += 8) {
       const float* wa = W32 + ref_layer_off(8);
       double s = 0.0;
 #pragma unroll
@@ -146,7 +150,7 @@ int launch_coarse_refine(const float* rays, const float* z, int64_t n, int S, co
   int32_t* list = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(workspace) + 256);
   const uint32_t cap = uint32_t(refine_cap(n));
   if (cudaMemsetAsync(count, 0, 4, st) != cudaSuccess) return check_launch("refine count init");
-  select_refine_kernel<<<unsigned((n * 32 + 255) / 256), 256, 0, st>>>(raw, z, rays, n, S, count, list, cap);
+  select_refine_kernel<<<unsigned((n * 32 + 255) / 256), 256, 0, st>>>(raw, z, rays, n, S, g_refine_tau_limit, count, list, cap);
   count_launch();
   if (int rc = check_launch("select_refine_kernel")) return rc;
   int sms = 0;
