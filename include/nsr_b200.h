@@ -194,13 +194,13 @@ int nsr_set_tier1_pair(int enabled);
  * object (acc0 ~ 1e-3, one sample with sigma ~ 0.02) the tensor-core arithmetic's absolute error on sigma (~1e-4) is a per-cent
  * error of the pdf, the fine samples move, and at a silhouette the pixel leaves the 1e-3 bar (4 of 160 000 rays of the test image).
  * nsr_render_rays_forward therefore re-evaluates the density of those few coarse points with fp64 accumulation on the CUDA cores before the coarse
- * compositing: on every ray whose coarse optical depth is below 4.605 (acc0 < 0.99), every sample with sigma > -0.01; raw[p].sigma
+ * compositing: on every ray whose coarse optical depth is below 2.303 (acc0 < 0.9), every sample with sigma > -0.01; raw[p].sigma
  * is overwritten in place.  On by default whenever N_importance > 0 and the precision is the default one; nsr_set_coarse_refine
  * returns the previous setting.  nsr_coarse_refine is the stage by itself on raw [n,S,4] / z_vals [n,S] (workspace:
  * nsr_coarse_refine_workspace_bytes(n_rays) bytes, 256-byte aligned; its first u32 holds the number of points found, at most
  * 2 n_rays + 1024 are re-evaluated). */
 int nsr_set_coarse_refine(int enabled);
-int nsr_set_coarse_refine_limit(float acc_limit);   /* rays with coarse acc0 below this (default 0.99) are refined */
+int nsr_set_coarse_refine_limit(float acc_limit);   /* rays with coarse acc0 below this (default 0.9) are refined */
 size_t nsr_coarse_refine_workspace_bytes(int64_t n_rays);
 int nsr_coarse_refine(const float* rays, const float* z_vals, int64_t n_rays, int n_samples, const void* packed_net, float* raw, void* workspace,
                       size_t workspace_bytes, void* stream);

@@ -11,7 +11,7 @@
 // fine sample in the low-density bin in front of the surface moving by ~1e-5, 1.1e-3 on one ray of the test image).
 //
 // What.  After the coarse network pass: (1) select_refine_kernel, one warp per ray, sums the ray's optical depth from raw0; on rays
-// that are not opaque (optical depth below the limit, default 4.6 i.e. acc0 < 0.99) every sample whose sigma is not clearly negative goes on a
+// that are not opaque (optical depth below the limit, default 2.3 i.e. acc0 < 0.9) every sample whose sigma is not clearly negative goes on a
 // list; (2) refine_sigma_kernel evaluates pts_linears.0-7 + the alpha head for the listed points (fp64 FMA chains over K, fp32 layer outputs, accurate
 // sincosf encoding, the fp32 weights kept TRANSPOSED behind the packed tail: common.cuh REF_*), eight points per 256-thread block
 // pass, one output unit per thread, and overwrites raw0[p].sigma.  A few thousand points per image: ~0.1 ms next to 54 ms.
@@ -21,7 +21,7 @@
 
 namespace nsr {
 
-static float g_refine_tau_limit = 4.6052f;     // optical depth of acc0 = 0.99 (nsr_set_coarse_refine_limit)
+static float g_refine_tau_limit = 2.3026f;     // optical depth of acc0 = 0.9 (nsr_set_coarse_refine_limit)
 void set_refine_tau_limit(float tau) { g_refine_tau_limit = tau; }
 constexpr float REFINE_SIGMA_MIN = -0.01f;    // samples with sigma above this on such a ray are re-evaluated
 constexpr int REFINE_POINTS = 16;             // points per block pass: the 1.97 MB of fp32 weights are re-read from L2 once per pass
@@ -65,8 +65,10 @@ __global__ void __launch_bounds__(256) refine_sigma_kernel(const int32_t* __rest
                                                            const float* __restrict__ rays, const float* __restrict__ z, int S,
                                                            const uint8_t* __restrict__ packed, float* __restrict__ raw) {
   constexpr int R = REFINE_POINTS;
-  __shared__ float enc[R][64];
-  __shared__ float hbuf[2][R][256];
+  // activations are kept [k][point]: a thread needs h[k] of all R points for every k, i.e. R consecutive floats = four broadcast
+  // LDS.128 instead of sixteen LDS.32 (the scalar version was bound by shared-memory load instructions, not by the fp64 pipe)
+  __shared__ __align__(16) float enc[64][R];
+  __shared__ __align__(16) float hbuf[2][256][R];
   const float* W32 = reinterpret_cast<const float*>(packed + REF_OFF);
   const float* tail = reinterpret_cast<const float*>(packed + WEIGHT_BYTES);
   const int j = threadIdx.x, warp = j >> 5, lane = j & 31;
@@ -76,7 +78,7 @@ __global__ void __launch_bounds__(256) refine_sigma_kernel(const int32_t* __rest
   const uint32_t n = *count;
   for (uint32_t base = blockIdx.x * R; base < n; base += gridDim.x * R) {
     __syncthreads();   // the previous pass is done with the shared buffers
-    // ---- gamma(x) (RH:47-48) of the R points: 64 channels each (63 + a zero), two passes of 256 threads
+    // ---- gamma(x) (RH:47-48) of the R points: 64 channels each (63 + a zero)
     for (int t = j; t < R * 64; t += 256) {
       const int r = t >> 6, c = t & 63;
       float v = 0.f;
@@ -93,41 +95,45 @@ __global__ void __launch_bounds__(256) refine_sigma_kernel(const int32_t* __rest
           v = ((c - 3) % 6) < 3 ? sinf(a) : cosf(a);
         }
       }
-      enc[r][c] = v;
+      enc[c][r] = v;
     }
     __syncthreads();
-    // ---- pts_linears.0-7: thread j = output unit j of all R points, fp32 FMA chain over K
+    // ---- pts_linears.0-7: thread j = output unit j of all R points.  Products of fp32 numbers accumulated in fp64, one rounding to
+    // fp32 per unit: each layer's output is the correctly rounded value of the exact dot product, so what separates this evaluation
+    // from the reference's is the reference's own fp32 rounding
     int cur = 0;
 #pragma unroll 1
     for (int l = 0; l < 8; ++l) {
       const float* W = W32 + ref_layer_off(l);
-      // products of fp32 numbers accumulated in fp64, one rounding to fp32 per unit: each layer's output is the correctly rounded
-      // value of the exact dot product, so what separates this evaluation from the reference's is the reference's own fp32 rounding
       double acc[R];
       const double b = double(tail[TAIL_BIAS + l * 256 + j]);
 #pragma unroll
       for (int r = 0; r < R; ++r) acc[r] = b;
+      auto step = [&](const float* hk, float wf) {   // hk: the R values of input k
+        const double w = double(wf);
+#pragma unroll
+        for (int q = 0; q < R / 4; ++q) {
+          const float4 h4 = *reinterpret_cast<const float4*>(hk + 4 * q);
+          acc[4 * q] = fma(double(h4.x), w, acc[4 * q]);
+          acc[4 * q + 1] = fma(double(h4.y), w, acc[4 * q + 1]);
+          acc[4 * q + 2] = fma(double(h4.z), w, acc[4 * q + 2]);
+          acc[4 * q + 3] = fma(double(h4.w), w, acc[4 * q + 3]);
+        }
+      };
       if (l == 0 || l == 5) {
 #pragma unroll 1
-        for (int k = 0; k < 63; ++k) {
-          const double w = double(W[k * 256 + j]);
-#pragma unroll
-          for (int r = 0; r < R; ++r) acc[r] = fma(double(enc[r][k]), w, acc[r]);
-        }
+        for (int k = 0; k < 63; ++k) step(enc[k], W[k * 256 + j]);
         W += 63 * 256;
       }
       if (l != 0) {
-        const float(*h)[256] = hbuf[cur];
-#pragma unroll 4
-        for (int k = 0; k < 256; ++k) {
-          const double w = double(W[k * 256 + j]);
-#pragma unroll
-          for (int r = 0; r < R; ++r) acc[r] = fma(double(h[r][k]), w, acc[r]);
-        }
+#pragma unroll 2
+        for (int k = 0; k < 256; ++k) step(hbuf[cur][k], W[k * 256 + j]);
       }
       const int nxt = l == 0 ? cur : cur ^ 1;
 #pragma unroll
-      for (int r = 0; r < R; ++r) hbuf[nxt][r][j] = fmaxf(float(acc[r]), 0.f);
+      for (int q = 0; q < R / 4; ++q)
+        *reinterpret_cast<float4*>(&hbuf[nxt][j][4 * q]) = make_float4(fmaxf(float(acc[4 * q]), 0.f), fmaxf(float(acc[4 * q + 1]), 0.f),
+                                                                       fmaxf(float(acc[4 * q + 2]), 0.f), fmaxf(float(acc[4 * q + 3]), 0.f));
       cur = nxt;
       __syncthreads();
     }
@@ -136,7 +142,7 @@ __global__ void __launch_bounds__(256) refine_sigma_kernel(const int32_t* __rest
       const float* wa = W32 + ref_layer_off(8);
       double s = 0.0;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) s = fma(double(hbuf[cur][r][lane + 32 * q]), double(wa[lane + 32 * q]), s);
+      for (int q = 0; q < 8; ++q) s = fma(double(hbuf[cur][lane + 32 * q][r]), double(wa[lane + 32 * q]), s);
 #pragma unroll
       for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(FULLMASK, s, d);
       if (lane == 0 && base + r < n) raw[int64_t(list[base + r]) * 4 + 3] = float(s + double(tail[TAIL_MISC]));
