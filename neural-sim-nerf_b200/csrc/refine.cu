@@ -12,7 +12,7 @@
 //
 // What.  After the coarse network pass: (1) select_refine_kernel, one warp per ray, sums the ray's optical depth from raw0; on rays
 // that are not opaque (optical depth below the limit, default 2.3 i.e. acc0 < 0.9) every sample whose sigma is not clearly negative goes on a
-// list; (2) refine_sigma_kernel evaluates pts_linears.0-7 + the alpha head for the listed points (fp64 FMA chains over K, fp32 layer outputs, accurate
+// list; (2) refine_sigma_kernel evaluates pts_linears.0-7 + the alpha head for the listed points (fp64-accumulated sums over K, fp32 layer outputs, accurate
 // sincosf encoding, the fp32 weights kept TRANSPOSED behind the packed tail: common.cuh REF_*), eight points per 256-thread block
 // pass, one output unit per thread, and overwrites raw0[p].sigma.  A few thousand points per image: ~0.1 ms next to 54 ms.
 #include <math.h>
@@ -24,7 +24,7 @@ namespace nsr {
 static float g_refine_tau_limit = 2.3026f;     // optical depth of acc0 = 0.9 (nsr_set_coarse_refine_limit)
 void set_refine_tau_limit(float tau) { g_refine_tau_limit = tau; }
 constexpr float REFINE_SIGMA_MIN = -0.01f;    // samples with sigma above this on such a ray are re-evaluated
-constexpr int REFINE_POINTS = 16;             // points per block pass: the 1.97 MB of fp32 weights are re-read from L2 once per pass
+constexpr int REFINE_POINTS = 8;              // points per block pass: the 1.97 MB of fp32 weights are re-read from L2 once per pass
 constexpr unsigned FULLMASK = 0xffffffffu;
 
 // workspace: [count u32, padded to 256 B][list: int32 x cap]
@@ -98,36 +98,57 @@ __global__ void __launch_bounds__(256) refine_sigma_kernel(const int32_t* __rest
       enc[c][r] = v;
     }
     __syncthreads();
-    // ---- pts_linears.0-7: thread j = output unit j of all R points.  Products of fp32 numbers accumulated in fp64, one rounding to
-    // fp32 per unit: each layer's output is the correctly rounded value of the exact dot product, so what separates this evaluation
-    // from the reference's is the reference's own fp32 rounding
+    // ---- pts_linears.0-7: thread j = output unit j of all R points, sums accumulated in fp64 (see below), one rounding to fp32 per
+    // unit as in the reference: what separates this evaluation from the reference's is mostly the reference's own fp32 rounding
     int cur = 0;
 #pragma unroll 1
     for (int l = 0; l < 8; ++l) {
       const float* W = W32 + ref_layer_off(l);
+      // (vector fp64 runs at ~1/10 of the fp32 rate on this part -- measured: an all-fp64 version of this loop took 1.5 ms for 9 000
+      // points -- so the products of 8 consecutive k are summed by fp32 FMAs and only the block sums are accumulated in fp64: a block
+      // of 8 carries ~1e-7 of its own size, and the long-range accumulation, where an fp32 chain loses its bits, is exact)
       double acc[R];
+      float part[R];
       const double b = double(tail[TAIL_BIAS + l * 256 + j]);
 #pragma unroll
-      for (int r = 0; r < R; ++r) acc[r] = b;
-      auto step = [&](const float* hk, float wf) {   // hk: the R values of input k
-        const double w = double(wf);
+      for (int r = 0; r < R; ++r) {
+        acc[r] = b;
+        part[r] = 0.f;
+      }
+      auto step = [&](const float* hk, float w) {   // hk: the R values of input k
 #pragma unroll
         for (int q = 0; q < R / 4; ++q) {
           const float4 h4 = *reinterpret_cast<const float4*>(hk + 4 * q);
-          acc[4 * q] = fma(double(h4.x), w, acc[4 * q]);
-          acc[4 * q + 1] = fma(double(h4.y), w, acc[4 * q + 1]);
-          acc[4 * q + 2] = fma(double(h4.z), w, acc[4 * q + 2]);
-          acc[4 * q + 3] = fma(double(h4.w), w, acc[4 * q + 3]);
+          part[4 * q] = fmaf(h4.x, w, part[4 * q]);
+          part[4 * q + 1] = fmaf(h4.y, w, part[4 * q + 1]);
+          part[4 * q + 2] = fmaf(h4.z, w, part[4 * q + 2]);
+          part[4 * q + 3] = fmaf(h4.w, w, part[4 * q + 3]);
+        }
+      };
+      auto flush = [&]() {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          acc[r] += double(part[r]);
+          part[r] = 0.f;
         }
       };
       if (l == 0 || l == 5) {
 #pragma unroll 1
-        for (int k = 0; k < 63; ++k) step(enc[k], W[k * 256 + j]);
+        for (int k0 = 0; k0 < 64; k0 += 8) {
+#pragma unroll
+          for (int k = k0; k < k0 + 8; ++k)
+            if (k < 63) step(enc[k], W[k * 256 + j]);
+          flush();
+        }
         W += 63 * 256;
       }
       if (l != 0) {
-#pragma unroll 2
-        for (int k = 0; k < 256; ++k) step(hbuf[cur][k], W[k * 256 + j]);
+#pragma unroll 1
+        for (int k0 = 0; k0 < 256; k0 += 8) {
+#pragma unroll
+          for (int k = k0; k < k0 + 8; ++k) step(hbuf[cur][k], W[k * 256 + j]);
+          flush();
+        }
       }
       const int nxt = l == 0 ? cur : cur ^ 1;
 #pragma unroll
