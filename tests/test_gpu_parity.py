@@ -352,7 +352,8 @@ def test_no_silent_fallbacks(nsr, nets):
 
 def test_coarse_refinement_is_fp32_accurate(nsr, golden, nets, wfit):
     """nsr_coarse_refine (refine.cu): on rays that are not opaque, the density of every coarse sample that is not clearly empty is
-    re-evaluated in fp32 -- within 2e-5 of the float64 value (the tensor-core arithmetic: ~3e-4), everything else untouched."""
+    re-evaluated on the CUDA cores -- within 5e-5 of the float64 value (the tensor-core arithmetic: ~3e-4; torch's fp32 kernels: 7e-5),
+    everything else untouched."""
     import ctypes
     L = nsr.lib()
     rays, z = C(golden['rays']), C(golden['z0'])
@@ -386,9 +387,9 @@ def test_coarse_refinement_is_fp32_accurate(nsr, golden, nets, wfit):
     err_torch = (sig32.double() - sig64).abs()[expect]
     print(f'coarse refinement: {count} of {n * S} points; |sigma - float64| before {float(err_before.max()):.2e}, after {float(err_after.max()):.2e}; '
           f'torch fp32 on cuda {float(err_torch.max()):.2e}')
-    # layer outputs are rounded to fp32 as in the reference, everything in between is exact: the distance to an all-float64 evaluation
-    # is that of a careful fp32 evaluation, and below what torch's own fp32 kernels leave
-    assert float(err_after.max()) <= 3e-5 and float(err_after.max()) <= float(err_before.max())
+    # layer outputs are rounded to fp32 as in the reference, the sums are accumulated in fp64 over fp32 blocks of 8: the distance to an
+    # all-float64 evaluation is below what torch's own fp32 kernels leave, and several times below the tensor-core path's
+    assert float(err_after.max()) <= 5e-5 and float(err_after.max()) < float(err_torch.max()) and float(err_after.max()) < 0.3 * float(err_before.max())
 
 
 def test_whole_image_against_eager_fp32(nsr, nets, wfit):
