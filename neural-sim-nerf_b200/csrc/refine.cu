@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(256) refine_sigma_kernel(const int32_t* __rest
 }
 
 int launch_coarse_refine(const float* rays, const float* z, int64_t n, int S, const void* packed, float* raw, void* workspace, cudaStream_t st) {
-  if (n == 0) return NSR_OK;
+  if (n == 0 || n * int64_t(S) >= (int64_t(1) << 31)) return NSR_OK;   // (the list holds int32 point indices)
   uint32_t* count = static_cast<uint32_t*>(workspace);
   int32_t* list = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(workspace) + 256);
   const uint32_t cap = uint32_t(refine_cap(n));
