@@ -201,6 +201,7 @@ int nsr_set_tier1_pair(int enabled);
  * 2 n_rays + 1024 are re-evaluated). */
 int nsr_set_coarse_refine(int enabled);
 int nsr_set_coarse_refine_limit(float acc_limit);   /* rays with coarse acc0 below this (default 0.9) are refined */
+int nsr_set_coarse_refine_sigma(float sigma_hi);    /* on every other ray too: the samples with -0.01 < sigma < sigma_hi */
 size_t nsr_coarse_refine_workspace_bytes(int64_t n_rays);
 int nsr_coarse_refine(const float* rays, const float* z_vals, int64_t n_rays, int n_samples, const void* packed_net, float* raw, void* workspace,
                       size_t workspace_bytes, void* stream);

@@ -50,6 +50,7 @@ _SIGNATURES = {
     'nsr_set_tier1_pair': (c_int, [c_int]),
     'nsr_set_coarse_refine': (c_int, [c_int]),
     'nsr_set_coarse_refine_limit': (c_int, [ctypes.c_float]),
+    'nsr_set_coarse_refine_sigma': (c_int, [ctypes.c_float]),
     'nsr_coarse_refine_workspace_bytes': (c_size, [c_i64]),
     'nsr_coarse_refine': (c_int, [c_f32p, c_f32p, c_i64, c_int, c_vp, c_f32p, c_vp, c_size, c_vp]),
     'nsr_render_backward_workspace_bytes': (c_size, [c_i64, c_int]),

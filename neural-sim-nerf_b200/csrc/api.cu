@@ -248,6 +248,11 @@ int nsr_set_coarse_refine_limit(float acc_limit) {
   return NSR_OK;
 }
 
+int nsr_set_coarse_refine_sigma(float sigma_hi) {
+  set_refine_sigma_hi(sigma_hi);
+  return NSR_OK;
+}
+
 int nsr_get_two_tier(int* enabled, float* tau, float* verify_max, float* force_fraction) {
   if (enabled) *enabled = g_two_tier_enabled ? 1 : 0;
   if (tau) *tau = g_two_tier.tau;

@@ -198,6 +198,7 @@ int launch_pack_rays(const float* o, const float* d, int64_t n, float near_, flo
 // refine.cu: fp32 re-evaluation of the coarse density where hierarchical sampling is ill-conditioned (DESIGN.md "coarse refinement")
 size_t refine_workspace_bytes(int64_t n_rays);
 void set_refine_tau_limit(float tau);
+void set_refine_sigma_hi(float sigma_hi);
 int launch_coarse_refine(const float* rays, const float* z, int64_t n, int S, const void* packed, float* raw, void* workspace, cudaStream_t st);
 // image_stage.cu
 int launch_to8b(const float* x, int64_t n, uint8_t* out, cudaStream_t st);

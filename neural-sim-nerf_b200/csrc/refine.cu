@@ -24,6 +24,8 @@ namespace nsr {
 static float g_refine_tau_limit = 2.3026f;     // optical depth of acc0 = 0.9 (nsr_set_coarse_refine_limit)
 void set_refine_tau_limit(float tau) { g_refine_tau_limit = tau; }
 constexpr float REFINE_SIGMA_MIN = -0.01f;    // samples with sigma above this on such a ray are re-evaluated
+static float g_refine_sigma_hi = 0.f;         // and, on EVERY ray, samples with sigma in (SIGMA_MIN, this): the surface-entry samples (0: none)
+void set_refine_sigma_hi(float s) { g_refine_sigma_hi = s; }
 constexpr int REFINE_POINTS = 8;              // points per block pass: the 1.97 MB of fp32 weights are re-read from L2 once per pass
 constexpr unsigned FULLMASK = 0xffffffffu;
 
@@ -32,7 +34,7 @@ static inline int64_t refine_cap(int64_t n_rays) { return 2 * n_rays + 1024; }
 size_t refine_workspace_bytes(int64_t n_rays) { return 256 + size_t(refine_cap(n_rays)) * 4; }
 
 __global__ void __launch_bounds__(256) select_refine_kernel(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays,
-                                                            int64_t n, int S, float tau_limit, uint32_t* __restrict__ count, int32_t* __restrict__ list,
+                                                            int64_t n, int S, float tau_limit, float sigma_hi, uint32_t* __restrict__ count, int32_t* __restrict__ list,
                                                             uint32_t cap) {
   const int lane = threadIdx.x & 31;
   const int64_t ray = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
@@ -47,10 +49,14 @@ __global__ void __launch_bounds__(256) select_refine_kernel(const float* __restr
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) tau += __shfl_xor_sync(FULLMASK, tau, d);
-  if (!(tau < tau_limit)) return;   // opaque (or NaN): the normaliser is ~1, a 1e-4 error of one sigma does not move the pdf
+  // opaque (or NaN) rays: the normaliser is ~1 and a 1e-4 error of a saturated sample's sigma moves nothing; only their
+  // low-density samples (the surface entry: alpha far from 1, so the absolute error of sigma passes into the weight undamped) count
+  const bool translucent = tau < tau_limit;
+  if (!translucent && !(sigma_hi > REFINE_SIGMA_MIN)) return;
   for (int i0 = 0; i0 < S; i0 += 32) {
     const int i = i0 + lane;
-    const bool pick = i < S && raw[(ray * S + i) * 4 + 3] > REFINE_SIGMA_MIN;
+    const float sg = i < S ? raw[(ray * S + i) * 4 + 3] : -1.f;
+    const bool pick = i < S && sg > REFINE_SIGMA_MIN && (translucent || sg < sigma_hi);
     const uint32_t m = __ballot_sync(FULLMASK, pick);
     if (m == 0u) continue;
     uint32_t base = 0;
@@ -177,7 +183,7 @@ int launch_coarse_refine(const float* rays, const float* z, int64_t n, int S, co
   int32_t* list = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(workspace) + 256);
   const uint32_t cap = uint32_t(refine_cap(n));
   if (cudaMemsetAsync(count, 0, 4, st) != cudaSuccess) return check_launch("refine count init");
-  select_refine_kernel<<<unsigned((n * 32 + 255) / 256), 256, 0, st>>>(raw, z, rays, n, S, g_refine_tau_limit, count, list, cap);
+  select_refine_kernel<<<unsigned((n * 32 + 255) / 256), 256, 0, st>>>(raw, z, rays, n, S, g_refine_tau_limit, g_refine_sigma_hi, count, list, cap);
   count_launch();
   if (int rc = check_launch("select_refine_kernel")) return rc;
   int sms = 0;

@@ -26,7 +26,8 @@ for phi in (22.5, 67.5, 112.5):
     raw0 = torch.empty(n, S, 4, device='cuda')
     assert L.nsr_mlp_forward(P(packed), P(z0), n, S, P(pc), 0, P(raw0), None) == 0
     ws = torch.zeros(L.nsr_coarse_refine_workspace_bytes(n), dtype=torch.uint8, device='cuda')
-    for lim in (None, 0.75, 0.9, 0.99):
+    for lim, shi in ((None, 0.), (0.9, 0.), (0.9, 2.), (0.9, 10.), (0.9, 30.)):
+        L.nsr_set_coarse_refine_sigma(shi)
         if lim is None:
             L.nsr_set_coarse_refine(0)
             cnt, ms = 0, 0.0
@@ -46,5 +47,5 @@ for phi in (22.5, 67.5, 112.5):
         with torch.no_grad():
             got = nsr.render_rays(packed, nets[0], None, 64, N_importance=128, network_fine=nets[1])['rgb_map']
         d = (got - ref).abs().max(-1).values
-        print(f'phi {phi:6.1f}  acc0 limit {str(lim):5s}: {cnt:7d} points, stage {ms:6.3f} ms (incl. a 41 MB copy); rays beyond 1e-3: {int((d > 1e-3).sum())}, max {float(d.max()):.2e}', flush=True)
-L.nsr_set_coarse_refine(1); L.nsr_set_coarse_refine_limit(0.9)
+        print(f'phi {phi:6.1f}  acc0 limit {str(lim):5s} sigma_hi {shi:4.0f}: {cnt:7d} points, stage {ms:6.3f} ms (incl. a 41 MB copy); rays beyond 1e-3: {int((d > 1e-3).sum())}, max {float(d.max()):.2e}', flush=True)
+L.nsr_set_coarse_refine(1); L.nsr_set_coarse_refine_limit(0.9); L.nsr_set_coarse_refine_sigma(0.)
