@@ -24,7 +24,7 @@ namespace nsr {
 static float g_refine_tau_limit = 2.3026f;     // optical depth of acc0 = 0.9 (nsr_set_coarse_refine_limit)
 void set_refine_tau_limit(float tau) { g_refine_tau_limit = tau; }
 constexpr float REFINE_SIGMA_MIN = -0.01f;    // samples with sigma above this on such a ray are re-evaluated
-static float g_refine_sigma_hi = 0.f;         // and, on EVERY ray, samples with sigma in (SIGMA_MIN, this): the surface-entry samples (0: none)
+static float g_refine_sigma_hi = 10.f;        // and, on EVERY ray, samples with sigma in (SIGMA_MIN, this): the surface-entry samples (0: none)
 void set_refine_sigma_hi(float s) { g_refine_sigma_hi = s; }
 constexpr int REFINE_POINTS = 8;              // points per block pass: the 1.97 MB of fp32 weights are re-read from L2 once per pass
 constexpr unsigned FULLMASK = 0xffffffffu;

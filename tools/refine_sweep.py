@@ -48,4 +48,4 @@ for phi in (22.5, 67.5, 112.5):
             got = nsr.render_rays(packed, nets[0], None, 64, N_importance=128, network_fine=nets[1])['rgb_map']
         d = (got - ref).abs().max(-1).values
         print(f'phi {phi:6.1f}  acc0 limit {str(lim):5s} sigma_hi {shi:4.0f}: {cnt:7d} points, stage {ms:6.3f} ms (incl. a 41 MB copy); rays beyond 1e-3: {int((d > 1e-3).sum())}, max {float(d.max()):.2e}', flush=True)
-L.nsr_set_coarse_refine(1); L.nsr_set_coarse_refine_limit(0.9); L.nsr_set_coarse_refine_sigma(0.)
+L.nsr_set_coarse_refine(1); L.nsr_set_coarse_refine_limit(0.9); L.nsr_set_coarse_refine_sigma(10.)
