@@ -14,7 +14,7 @@
 // that are not opaque (optical depth below the limit, default 2.3 i.e. acc0 < 0.9) every sample whose sigma is not clearly negative goes on a
 // list; (2) refine_sigma_kernel evaluates pts_linears.0-7 + the alpha head for the listed points (fp64-accumulated sums over K, fp32 layer outputs, accurate
 // sincosf encoding, the fp32 weights kept TRANSPOSED behind the packed tail: common.cuh REF_*), eight points per 256-thread block
-// pass, one output unit per thread, and overwrites raw0[p].sigma.  ~9 000 points per 400x400 image: 0.6 ms next to 54 ms.
+// pass, one output unit per thread, and overwrites raw0[p].sigma.  ~12 000 points per 400x400 image: 0.75 ms next to 54 ms.
 #include <math.h>
 
 #include "common.cuh"

@@ -373,10 +373,11 @@ def test_coarse_refinement_is_fp32_accurate(nsr, golden, nets, wfit):
     x = torch.cat([O.embed(pts.reshape(-1, 3), O.N_FREQ_XYZ), O.embed(rays[:, None, 8:11].expand(n, S, 3).reshape(-1, 3).cpu().double(), O.N_FREQ_DIR)], -1)
     sig64 = O.mlp_forward(x, sd)[:, 3].reshape(n, S)
     changed = (raw[..., 3] != before[..., 3]).cpu()
-    # which points should have been picked: rays with optical depth < 2.303 (acc0 < 0.9), samples with sigma > -0.01
+    # which points should have been picked: samples with sigma > -0.01 on rays with optical depth < 2.303 (acc0 < 0.9), and the
+    # low-density samples (sigma < 10: the surface entry) of every other ray
     dist = torch.cat([z[:, 1:] - z[:, :-1], torch.full_like(z[:, :1], 1e10)], -1) * rays[:, 3:6].norm(dim=-1, keepdim=True)
     tau = (before[..., 3].clamp(min=0) * dist).sum(-1)
-    expect = ((tau < 2.3026)[:, None] & (before[..., 3] > -0.01)).cpu()
+    expect = ((before[..., 3] > -0.01) & ((tau < 2.3026)[:, None] | (before[..., 3] < 10.0))).cpu()
     assert count == int(expect.sum()) and count > 0
     assert bool((changed <= expect).all())                              # nothing outside the selection was touched
     assert torch.equal(raw[..., :3], before[..., :3])
