@@ -10,11 +10,11 @@ def load(f):
     return [json.loads(l) for l in open(P(f)) if l.startswith('{')][0]
 
 
-b1, b2, b8 = load('r02_v3_bench.json'), load('r02_v1_bench_n2.json'), load('r02_v3_bench_n8.json')
+b1, b2, b8 = load('r02_v4_bench.json'), load('r02_v1_bench_n2.json'), load('r02_v3_bench_n8.json')
 ref, bl = load('r02_v1_bench_reference_arm.json'), load('r02_v1_bilevel_stub_n8_k50.json')
 tr = json.load(open(P('ncu_traffic.json')))
 L = ['# Round 2: scaling, stages, baselines (B200, sm_100a)\n',
-     'Sources: `r02_v3_bench.json` (N=1, final build), `r02_v1_bench_n2.json` (predates the coarse refinement and the round-robin ray dealing of the\n'
+     'Sources: `r02_v4_bench.json` (N=1, final build), `r02_v1_bench_n2.json` (predates the coarse refinement and the round-robin ray dealing of the\n'
      '`objects8` leg), `r02_v3_bench_n8.json` (final build; one box each), `r02_v1_bench_reference_arm.json`, `r02_v1_bilevel_stub_n8_k50.json`, `ncu_traffic.json` /\n'
      '`r02_ncu_kernels.csv` (ncu --set full of `tools/ncu_kernels.py`).  The driver\'s SCALE_r02.json is the authoritative N = 1, 2, 4, 8 series.\n',
      '## Throughput (whole job, rays/s; one 400x400 image per GPU per step, 64 + 128 samples)\n',
