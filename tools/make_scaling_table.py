@@ -10,21 +10,21 @@ def load(f):
     return [json.loads(l) for l in open(P(f)) if l.startswith('{')][0]
 
 
-b1, b2, b8 = load('r02_v4_bench.json'), load('r02_v1_bench_n2.json'), load('r02_v3_bench_n8.json')
+b1, b2, b4, b8 = load('r02_v4_bench.json'), load('r02_v4_bench_n2.json'), load('r02_v4_bench_n4.json'), load('r02_v3_bench_n8.json')
 ref, bl = load('r02_v1_bench_reference_arm.json'), load('r02_v1_bilevel_stub_n8_k50.json')
 tr = json.load(open(P('ncu_traffic.json')))
 L = ['# Round 2: scaling, stages, baselines (B200, sm_100a)\n',
-     'Sources: `r02_v4_bench.json` (N=1, final build), `r02_v1_bench_n2.json` (predates the coarse refinement and the round-robin ray dealing of the\n'
-     '`objects8` leg), `r02_v3_bench_n8.json` (final build; one box each), `r02_v1_bench_reference_arm.json`, `r02_v1_bilevel_stub_n8_k50.json`, `ncu_traffic.json` /\n'
-     '`r02_ncu_kernels.csv` (ncu --set full of `tools/ncu_kernels.py`).  The driver\'s SCALE_r02.json is the authoritative N = 1, 2, 4, 8 series.\n',
+     'Sources: `r02_v4_bench.json` (N=1), `r02_v4_bench_n2.json`, `r02_v4_bench_n4.json`, `r02_v3_bench_n8.json` (final build; one box each),\n'
+     '`r02_v1_bench_reference_arm.json`, `r02_v1_bilevel_stub_n8_k50.json`, `ncu_traffic.json` / `r02_ncu_kernels.csv` (ncu --set full of\n'
+     '`tools/ncu_kernels.py`).  The driver\'s SCALE_r02.json is the authoritative N = 1, 2, 4, 8 series.\n',
      '## Throughput (whole job, rays/s; one 400x400 image per GPU per step, 64 + 128 samples)\n',
      '| N GPUs | forward, rays in HBM | forward e2e (host rays in, maps out) | ms / step | pose_grad (fwd + bwd + NCCL all-reduce) | objects8 (config 4) |',
      '|---|---|---|---|---|---|']
-for n, b in ((1, b1), (2, b2), (8, b8)):
+for n, b in ((1, b1), (2, b2), (4, b4), (8, b8)):
     o = b['objects8']
     L.append(f"| {n} | {b['value']/1e6:.3f} M | {b['e2e']['value']/1e6:.3f} M | {b['ms_per_step']:.1f} | {b['pose_grad']['rays_per_s']/1e6:.3f} M ({b['pose_grad']['ms_per_step']:.1f} ms) | "
              f"{o['rays_per_s']/1e6:.3f} M ({o['ms_per_step']:.0f} ms per 8 images) |")
-L.append(f"\nScaling of the forward path: {b2['value']/b1['value']:.2f}x at 2 GPUs, {b8['value']/b1['value']:.2f}x at 8 (no forward collective; every GPU at its own 1 kW cap, SM clock ~1.63 of 1.97 GHz).\n")
+L.append(f"\nScaling of the forward path: {b2['value']/b1['value']:.2f}x at 2 GPUs, {b4['value']/b1['value']:.2f}x at 4, {b8['value']/b1['value']:.2f}x at 8 (no forward collective; every GPU at its own 1 kW cap, SM clock ~1.63 of 1.97 GHz).\n")
 L.append('## Baselines on the same box\n')
 c, bs = b1['cpu_baseline'], b1['baselines']
 e = bs['eager_pytorch_on_this_gpu']
