@@ -119,6 +119,16 @@ class NeRF(nn.Module):
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
             raise NotImplementedError('NeRF.forward(x) is forward-only here (wrap it in torch.no_grad()); gradients flow through '
                                       'render() / render_rays() / train_step()')
+        if _is_viewless(self):
+            # RH:119-120; the kernel returns the four columns the compositor reads (RN:361-364)
+            if self.output_linear.out_features != 4:
+                raise NotImplementedError('NeRF.forward(x) with use_viewdirs=False returns four columns; output_ch = '
+                                          f'{self.output_linear.out_features} (RN:267) has a fifth that no caller reads and the kernel does not compute')
+            if x.shape[-1] != 63:
+                raise NotImplementedError(f'embedded input must have 63 channels (input_ch_views = 0, RN:263), got {x.shape[-1]}')
+            x90 = torch.zeros(*x.shape[:-1], 90, dtype=torch.float32, device=x.device)
+            x90[..., :63] = x
+            x = x90
         if x.shape[-1] != 90:
             raise NotImplementedError(f'embedded input must have 63 + 27 = 90 channels, got {x.shape[-1]}')
         xf = _f32c(x.reshape(-1, 90), 'x')
@@ -131,6 +141,44 @@ class NeRF(nn.Module):
 # ----------------------------------------------------------------------------- packed-weight cache
 _EXPECTED_SHAPES = [(256, 63)] + [(256, 256)] * 4 + [(256, 319)] + [(256, 256)] * 2 + [(128, 283), (256, 256), (1, 256), (3, 128)]
 _pack_cache = weakref.WeakKeyDictionary()
+
+
+def _is_viewless(net):
+    """A NeRF(use_viewdirs=False) module: `output_linear` instead of the feature / alpha / rgb heads (RH:95-96)."""
+    return not getattr(net, 'use_viewdirs', True) and hasattr(net, 'output_linear')
+
+
+def _viewless_operands(net):
+    """use_viewdirs=False (RH:119-120: outputs = output_linear(h); columns 0..2 colour, 3 sigma, RN:361-364) on the kernel built for the
+    view-dependent head.  With A, a = rows 0..2 of output_linear, the twelve operand tensors are
+        feature_linear = I, 0          views_linears.0 = [A; -A; 0] on the 256 feature columns (0 on the 27 view columns), [a; -a; 0]
+        rgb_linear = [I3, -I3, 0], 0   alpha_linear = row 3 of output_linear
+    so that rgb = relu(A h + a) - relu(-(A h + a)) = A h + a.  (I and the +-1 are exact in fp16; the feature vector is h to 2^-22.)
+    Returns (parameters the blob depends on, weights, biases)."""
+    pts = list(net.pts_linears)
+    out = net.output_linear
+    if len(pts) != 8:
+        raise NotImplementedError(f'netdepth {len(pts)} != 8 is not supported by the sm_100a kernel')
+    for l, shp in zip(pts, _EXPECTED_SHAPES[:8]):
+        if tuple(l.weight.shape) != shp:
+            raise NotImplementedError(f'layer shape {tuple(l.weight.shape)} != {shp}: only D=8, W=256, multires=10 is built')
+    if out.weight.shape[1] != 256 or out.weight.shape[0] < 4:
+        raise NotImplementedError(f'output_linear {tuple(out.weight.shape)}: expected [4 or 5, 256] (RN:267)')
+    params = [l.weight for l in pts] + [out.weight] + [l.bias for l in pts] + [out.bias]
+    dev = out.weight.device
+    A, a = out.weight.detach()[:3], out.bias.detach()[:3]
+    wv = torch.zeros(128, 283, dtype=torch.float32, device=dev)
+    bv = torch.zeros(128, dtype=torch.float32, device=dev)
+    wv[0:3, :256], wv[3:6, :256] = A, -A
+    bv[0:3], bv[3:6] = a, -a
+    wr = torch.zeros(3, 128, dtype=torch.float32, device=dev)
+    for c in range(3):
+        wr[c, c], wr[c, 3 + c] = 1.0, -1.0
+    ws = [l.weight.detach().contiguous() for l in pts] + [wv, torch.eye(256, dtype=torch.float32, device=dev),
+                                                          out.weight.detach()[3:4].contiguous(), wr]
+    bs = [l.bias.detach().contiguous() for l in pts] + [bv, torch.zeros(256, dtype=torch.float32, device=dev),
+                                                        out.bias.detach()[3:4].contiguous(), torch.zeros(3, dtype=torch.float32, device=dev)]
+    return params, ws, bs
 
 
 def _net_tensors(net):
@@ -149,7 +197,11 @@ def _net_tensors(net):
 def packed_weights(net):
     """Device blob of `net` in the kernel's operand layout; re-packed (on the GPU) whenever a
     parameter's storage or version counter changes."""
-    layers = _net_tensors(net)
+    viewless = _is_viewless(net)
+    if viewless:
+        layers = list(net.pts_linears) + [net.output_linear]
+    else:
+        layers = _net_tensors(net)
     params = [l.weight for l in layers] + [l.bias for l in layers]
     key = tuple((p.data_ptr(), p._version, p.device.index) for p in params)
     hit = _pack_cache.get(net)
@@ -158,8 +210,11 @@ def packed_weights(net):
     for p in params:
         if not p.is_cuda or p.dtype != torch.float32:
             raise _lib.NsrError('network parameters must be fp32 CUDA tensors (no CPU fallback)')
-    ws = [l.weight.detach().contiguous() for l in layers]
-    bs = [l.bias.detach().contiguous() for l in layers]
+    if viewless:
+        _, ws, bs = _viewless_operands(net)
+    else:
+        ws = [l.weight.detach().contiguous() for l in layers]
+        bs = [l.bias.detach().contiguous() for l in layers]
     L = lib()
     blob = torch.empty(L.nsr_packed_net_bytes(), dtype=torch.uint8, device=params[0].device)
     wp = (ctypes.c_void_p * 12)(*[w.data_ptr() for w in ws])
@@ -199,17 +254,18 @@ def run_network(inputs, viewdirs, fn, embed_fn=None, embeddirs_fn=None, netchunk
     """RN:26-40: inputs [n,S,3], viewdirs [n,3], fn = NeRF module -> raw [n,S,4].
     embed_fn / embeddirs_fn / netchunk are accepted and ignored: encoding (multires 10 / 4) and
     chunking live inside the kernel."""
-    if viewdirs is None:
-        raise NotImplementedError('use_viewdirs=False networks are not built (CFG:8 sets use_viewdirs=True)')
-    _no_grad_inputs(inputs, viewdirs)
+    if viewdirs is None and not _is_viewless(fn):
+        raise ValueError('viewdirs=None needs a NeRF(use_viewdirs=False) network (RN:32, RH:119-120)')
+    _no_grad_inputs(inputs, *([] if viewdirs is None else [viewdirs]))
     sh = inputs.shape
     pts = _f32c(inputs, 'inputs').reshape(-1, sh[-2], 3) if inputs.dim() >= 3 else _f32c(inputs, 'inputs').reshape(-1, 1, 3)
     n, S = pts.shape[0], pts.shape[1]
-    vd = _f32c(viewdirs, 'viewdirs').reshape(-1, 3)
-    if vd.shape[0] != n:
-        raise ValueError(f'viewdirs {tuple(viewdirs.shape)} does not match inputs {tuple(inputs.shape)}')
     rays = torch.zeros(n, 11, dtype=torch.float32, device=pts.device)
-    rays[:, 8:11] = vd
+    if viewdirs is not None:
+        vd = _f32c(viewdirs, 'viewdirs').reshape(-1, 3)
+        if vd.shape[0] != n:
+            raise ValueError(f'viewdirs {tuple(viewdirs.shape)} does not match inputs {tuple(inputs.shape)}')
+        rays[:, 8:11] = vd
     raw = torch.empty(n, S, 4, dtype=torch.float32, device=pts.device)
     check(lib().nsr_mlp_forward(ptr(rays), ptr(pts), n, S, ptr(packed_weights(fn)), FLAG_PTS_INPUT | _prec_flag(), ptr(raw), _stream()),
           'nsr_mlp_forward')
@@ -266,8 +322,17 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
     """Volumetric rendering of a ray batch, RN:390-501.  ray_batch [n,11] = o d near far viewdir.
     `network_query_fn` is accepted for signature compatibility; the embedders it closes over
     (RN:281-284) are the fixed multires=10 / 4 ones compiled into the kernel."""
+    nets_used = [network_fn] + ([network_fine] if (network_fine is not None and int(N_importance) > 0) else [])
     if ray_batch.shape[-1] <= 8:
-        raise NotImplementedError('use_viewdirs=False ray batches are not built (CFG:8 sets use_viewdirs=True)')
+        # use_viewdirs=False (RN:111, RN:437): eight columns.  The kernels take eleven; the view columns meet zero weights.
+        if not all(_is_viewless(m) for m in nets_used):
+            raise ValueError('an 8-column ray batch (use_viewdirs=False, RN:111) needs NeRF(use_viewdirs=False) networks')
+        ray_batch = torch.cat([ray_batch, torch.zeros_like(ray_batch[:, :3])], -1)
+    if len({_is_viewless(m) for m in nets_used}) > 1:
+        raise ValueError('network_fn and network_fine must both be use_viewdirs=True or both use_viewdirs=False (RN:268-278 builds them alike)')
+    if torch.is_grad_enabled() and any(_is_viewless(m) and any(p.requires_grad for p in m.parameters()) for m in nets_used):
+        raise NotImplementedError('parameter gradients of use_viewdirs=False networks are not built: freeze them '
+                                  '(requires_grad_(False)) for the pose path, or train with use_viewdirs=True (CFG:8)')
     params = _params_of(network_fn) + (_params_of(network_fine) if (network_fine is not None and int(N_importance) > 0) else [])
     needs_grad = torch.is_grad_enabled() and (ray_batch.requires_grad or any(p.requires_grad for p in params))
     rays = _f32c(ray_batch, 'ray_batch')
@@ -382,6 +447,8 @@ def _forward_impl(rays, cfg, keep_for_backward, save_mask=False, save_dump=False
 
 
 def _params_of(net):
+    if _is_viewless(net):
+        return []                 # forward and dL/drays only (render_rays refuses trainable use_viewdirs=False networks)
     layers = _net_tensors(net)
     return [l.weight for l in layers] + [l.bias for l in layers]
 
@@ -471,7 +538,7 @@ class _RenderRaysFn(torch.autograd.Function):
         out += g_c if g_c is not None else [None] * n_par
         if len(ctx.needs_input_grad) > 2 + n_par:
             out += g_f if g_f is not None else [None] * n_par
-        return tuple(out)
+        return tuple(out[:len(ctx.needs_input_grad)])     # use_viewdirs=False networks pass no parameters (_params_of)
 
 
 def _render_rays_staged(rays, pc, pf, S, Ni, flags, t_rand, u, retraw, raw_noise_std, white_bkgd, ret):
@@ -567,7 +634,10 @@ def render(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far
            c2w_staticcam=None, **kwargs):
     """RN:58-123 -> [rgb_map, disp_map, acc_map, extras].  Same arguments as the reference."""
     if not use_viewdirs:
-        raise NotImplementedError('use_viewdirs=False is not built (CFG:8 sets use_viewdirs=True)')
+        # RN:91/111: no view directions in the ray batch; the networks must be the RH:95-96 kind (the reference fails in RH:100 otherwise)
+        nets_used = [kwargs.get('network_fn')] + ([kwargs['network_fine']] if kwargs.get('network_fine') is not None and kwargs.get('N_importance', 0) > 0 else [])
+        if not all(m is not None and _is_viewless(m) for m in nets_used):
+            raise ValueError('use_viewdirs=False needs NeRF(use_viewdirs=False) networks (RH:95-96)')
     scalar_bounds = not torch.is_tensor(near) and not torch.is_tensor(far)
     if c2w is not None and not ndc and c2w_staticcam is None and scalar_bounds and not (torch.is_tensor(c2w) and c2w.requires_grad and torch.is_grad_enabled()):
         packed = make_rays(H, W, K, c2w, near, far)          # fused ray generation
@@ -585,18 +655,19 @@ def render(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far
             rays_o, rays_d = get_rays(H, W, K, c2w)
         else:
             rays_o, rays_d = rays
-        viewdirs = rays_d
-        if c2w_staticcam is not None:
-            rays_o, rays_d = get_rays(H, W, K, c2w_staticcam)                   # RN:94-96
-        viewdirs = viewdirs / torch.norm(viewdirs, dim=-1, keepdim=True)        # RN:97
-        viewdirs = torch.reshape(viewdirs, [-1, 3]).float()
+        if use_viewdirs:                                                        # RN:91
+            viewdirs = rays_d
+            if c2w_staticcam is not None:
+                rays_o, rays_d = get_rays(H, W, K, c2w_staticcam)               # RN:94-96
+            viewdirs = viewdirs / torch.norm(viewdirs, dim=-1, keepdim=True)    # RN:97
+            viewdirs = torch.reshape(viewdirs, [-1, 3]).float()
         sh = rays_d.shape
         if ndc:
             rays_o, rays_d = ndc_rays(H, W, K[0][0], 1., rays_o, rays_d)        # RN:101-103
         rays_o = torch.reshape(rays_o, [-1, 3]).float()
         rays_d = torch.reshape(rays_d, [-1, 3]).float()
         nr, fr = near * torch.ones_like(rays_d[..., :1]), far * torch.ones_like(rays_d[..., :1])
-        packed = torch.cat([rays_o, rays_d, nr, fr, viewdirs], -1)              # RN:109-112
+        packed = torch.cat([rays_o, rays_d, nr, fr] + ([viewdirs] if use_viewdirs else []), -1)   # RN:109-112
         if not packed.is_cuda:
             raise _lib.NsrError('rays must live on the GPU (no CPU fallback)')
     all_ret = batchify_rays(packed, max(int(chunk), MIN_RAYS_PER_LAUNCH), **kwargs)
@@ -632,7 +703,8 @@ def _K9(K):
 def _image_path_ok(kw):
     """Can render(H, W, K, c2w=..., **kw) go through the one-call image entry?  (what MAIN:109-114 + create_nerf's
     render_kwargs_test amount to: use_viewdirs, no NDC, deterministic sampling, scalar bounds)"""
-    return (kw.get('use_viewdirs', False) and not kw.get('ndc', True) and kw.get('c2w_staticcam') is None
+    viewless = kw.get('network_fn') is not None and _is_viewless(kw['network_fn']) and (kw.get('network_fine') is None or _is_viewless(kw['network_fine']))
+    return (bool(kw.get('use_viewdirs', False)) != viewless and not kw.get('ndc', True) and kw.get('c2w_staticcam') is None
             and not kw.get('perturb', 0.) and not kw.get('raw_noise_std', 0.) and not kw.get('retraw', False)
             and not torch.is_tensor(kw.get('near', 0.)) and not torch.is_tensor(kw.get('far', 1.))
             and kw.get('network_fn') is not None)
@@ -644,7 +716,7 @@ def render_image(H, W, K, c2w, want=('rgb8', 'rgb_map', 'disp_map'), **kw):
     ('rgb8' [H,W,3] uint8, 'rgb_map' [H,W,3], 'disp_map', 'acc_map', 'rgb0', 'disp0', 'acc0', 'z_std' [H,W]) plus
     'rays' [H*W,11] (a view into the call's workspace).  `kw` = the reference's render_kwargs (RN:318-338 + near/far)."""
     if not _image_path_ok(kw):
-        raise NotImplementedError('render_image covers use_viewdirs=True, ndc=False, perturb=0, raw_noise_std=0, scalar near/far')
+        raise NotImplementedError('render_image covers ndc=False, perturb=0, raw_noise_std=0, scalar near/far (use_viewdirs matching the networks)')
     L = lib()
     net_c, net_f = kw['network_fn'], kw.get('network_fine')
     S, Ni = int(kw['N_samples']), int(kw.get('N_importance', 0))
@@ -710,7 +782,7 @@ def render_image_grad(H, W, K, c2w, g_rgb, rows=None, **kw):
     (rgb_map [r1-r0,W,3], this slice's contribution to dL/dc2w) -- contributions of disjoint slices add up to the image's
     gradient, which is how dist.py shards one image over several GPUs."""
     if not _image_path_ok(kw):
-        raise NotImplementedError('render_image_grad covers use_viewdirs=True, ndc=False, perturb=0, raw_noise_std=0, scalar near/far')
+        raise NotImplementedError('render_image_grad covers ndc=False, perturb=0, raw_noise_std=0, scalar near/far (use_viewdirs matching the networks)')
     if PRECISION == 'fp16':
         raise NotImplementedError("backward is not built for NSR_PRECISION='fp16'")
     L = lib()
@@ -899,17 +971,17 @@ def create_nerf(args):
     network_fine_state_dict, optimizer_state_dict.  Returns (render_kwargs_train, render_kwargs_test, start, grad_vars,
     optimizer).  Host-side plumbing only; geometries other than the one the kernels are built for are refused here."""
     _, input_ch = get_embedder(args.multires, args.i_embed)
-    if not args.use_viewdirs:
-        raise NotImplementedError('use_viewdirs=False is not built (CFG:8 sets use_viewdirs=True)')
-    _, input_ch_views = get_embedder(args.multires_views, args.i_embed)
-    geometry = dict(input_ch=input_ch, input_ch_views=input_ch_views, skips=[4], use_viewdirs=True,
+    input_ch_views = 0                                                                            # RN:263
+    if args.use_viewdirs:
+        _, input_ch_views = get_embedder(args.multires_views, args.i_embed)
+    geometry = dict(input_ch=input_ch, input_ch_views=input_ch_views, skips=[4], use_viewdirs=bool(args.use_viewdirs),
                     output_ch=5 if args.N_importance > 0 else 4)
     nets = [NeRF(D=args.netdepth, W=args.netwidth, **geometry).to(device)]
     if args.N_importance > 0:
         nets.append(NeRF(D=args.netdepth_fine, W=args.netwidth_fine, **geometry).to(device))
     if torch.cuda.is_available():
-        for m in nets:
-            _net_tensors(m)                       # refuse unsupported depths / widths / multires up front
+        for m in nets:                            # refuse unsupported depths / widths / multires up front
+            _viewless_operands(m) if _is_viewless(m) else _net_tensors(m)
     grad_vars = [p for m in nets for p in m.parameters()]
     optimizer = torch.optim.Adam(params=grad_vars, lr=args.lrate, betas=(0.9, 0.999))
     start = 0

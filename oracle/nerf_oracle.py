@@ -51,10 +51,12 @@ def embed(x, n_freq):
 
 
 # --------------------------------------------------------------------------
-# the MLP, RH:99-122  (D=8, W=256, skips=[4], use_viewdirs=True)
+# the MLP, RH:99-122  (D=8, W=256, skips=[4]; use_viewdirs=True, or False when the state-dict holds `output_linear`)
 # --------------------------------------------------------------------------
 def mlp_forward(x, sd):
-    """x: [P, 63+27] -> [P, 4] = (rgb_raw[3], sigma_raw[1]).  RH:99-122."""
+    """x: [P, 63+27] -> [P, 4] = (rgb_raw[3], sigma_raw[1]).  RH:99-122.
+    use_viewdirs=False (a state-dict with `output_linear.*`, RH:95-96): x [P, 63] -> [P, output_ch], RH:119-120; the
+    compositor reads columns 0..3 only (RN:361-364), a fifth column (output_ch = 5 when N_importance > 0, RN:267) is carried."""
     lin = torch.nn.functional.linear
     enc_xyz = x[..., :63]
     enc_dir = x[..., 63:]
@@ -63,6 +65,8 @@ def mlp_forward(x, sd):
         h = torch.relu(lin(h, sd[f'pts_linears.{i}.weight'], sd[f'pts_linears.{i}.bias']))
         if i == SKIP_AFTER:
             h = torch.cat([enc_xyz, h], dim=-1)          # RH:105-106 (input first)
+    if 'output_linear.weight' in sd:
+        return lin(h, sd['output_linear.weight'], sd['output_linear.bias'])     # RH:119-120
     sigma = lin(h, sd['alpha_linear.weight'], sd['alpha_linear.bias'])          # RH:109
     feat = lin(h, sd['feature_linear.weight'], sd['feature_linear.bias'])       # RH:110 (no activation)
     h = torch.cat([feat, enc_dir], dim=-1)                                      # RH:111
@@ -72,13 +76,15 @@ def mlp_forward(x, sd):
 
 
 def run_network(pts, viewdirs, sd, netchunk=1024 * 64):
-    """RN:26-40.  pts [n,S,3], viewdirs [n,3] -> raw [n,S,4]."""
+    """RN:26-40.  pts [n,S,3], viewdirs [n,3] (None with use_viewdirs=False, RN:32) -> raw [n,S,4 (or output_ch)]."""
     flat = pts.reshape(-1, 3)
     emb = embed(flat, N_FREQ_XYZ)
-    dirs = viewdirs[:, None, :].expand(pts.shape).reshape(-1, 3)          # RN:33-34
-    emb = torch.cat([emb, embed(dirs, N_FREQ_DIR)], dim=-1)               # RN:35-36
+    if viewdirs is not None:                                                  # RN:32
+        dirs = viewdirs[:, None, :].expand(pts.shape).reshape(-1, 3)          # RN:33-34
+        emb = torch.cat([emb, embed(dirs, N_FREQ_DIR)], dim=-1)               # RN:35-36
     outs = [mlp_forward(emb[i:i + netchunk], sd) for i in range(0, emb.shape[0], netchunk)]  # RN:14-23
-    return torch.cat(outs, 0).reshape(*pts.shape[:-1], 4)
+    outs = torch.cat(outs, 0)
+    return outs.reshape(*pts.shape[:-1], outs.shape[-1])
 
 
 # --------------------------------------------------------------------------
@@ -146,7 +152,7 @@ def render_rays(ray_batch, sd_coarse, sd_fine, N_samples=64, N_importance=128,
     branch, RH:239, is discontinuous in the last bits of the coarse weights)."""
     n = ray_batch.shape[0]
     rays_o, rays_d = ray_batch[:, 0:3], ray_batch[:, 3:6]
-    viewdirs = ray_batch[:, -3:]
+    viewdirs = ray_batch[:, -3:] if ray_batch.shape[-1] > 8 else None      # RN:437
     near, far = ray_batch[:, 6:7], ray_batch[:, 7:8]
     t_vals = torch.linspace(0., 1., steps=N_samples)                          # RN:439
     if not lindisp:
@@ -201,26 +207,26 @@ def get_rays(H, W, K, c2w):
     return rays_o, rays_d
 
 
-def pack_rays(rays_o, rays_d, near, far):
-    """RN:91-112 with use_viewdirs=True, ndc=False -> [N,11] fp32."""
+def pack_rays(rays_o, rays_d, near, far, use_viewdirs=True):
+    """RN:91-112 with ndc=False -> [N,11] fp32 ([N,8] with use_viewdirs=False, RN:111)."""
     viewdirs = rays_d / torch.norm(rays_d, dim=-1, keepdim=True)
     viewdirs = viewdirs.reshape(-1, 3).float()
     rays_o = rays_o.reshape(-1, 3).float()
     rays_d = rays_d.reshape(-1, 3).float()
     nr = near * torch.ones_like(rays_d[..., :1])
     fr = far * torch.ones_like(rays_d[..., :1])
-    return torch.cat([rays_o, rays_d, nr, fr, viewdirs], -1)
+    return torch.cat([rays_o, rays_d, nr, fr] + ([viewdirs] if use_viewdirs else []), -1)
 
 
-def render(H, W, K, sd_coarse, sd_fine, chunk=512, rays=None, c2w=None, near=0., far=1.,
+def render(H, W, K, sd_coarse, sd_fine, chunk=512, rays=None, c2w=None, near=0., far=1., use_viewdirs=True,
            **kw):
-    """RN:58-123 (use_viewdirs=True, ndc=False): returns [rgb_map, disp_map, acc_map, extras]."""
+    """RN:58-123 (ndc=False): returns [rgb_map, disp_map, acc_map, extras]."""
     if c2w is not None:
         rays_o, rays_d = get_rays(H, W, K, c2w)
     else:
         rays_o, rays_d = rays
     sh = rays_d.shape
-    packed = pack_rays(rays_o, rays_d, near, far)
+    packed = pack_rays(rays_o, rays_d, near, far, use_viewdirs)
     chunks = {}
     for i in range(0, packed.shape[0], chunk):                                # RN:43-55
         r = render_rays(packed[i:i + chunk], sd_coarse, sd_fine, **kw)
@@ -293,6 +299,27 @@ def random_state_dict(seed, scale=1.0):
         sd[name + '.weight'] = torch.from_numpy(rs.uniform(-b, b, size=(o, i)).astype(np.float32) * scale)
         sd[name + '.bias'] = torch.from_numpy(rs.uniform(-b, b, size=(o,)).astype(np.float32))
     return sd
+
+
+def viewless_state_dict(sd, output_ch=5):
+    """A use_viewdirs=False network (RH:95-96: `output_linear` [output_ch, 256] instead of the feature / alpha / rgb heads; RN:263
+    leaves input_ch_views = 0, so views_linears.0 is [128, 256] and unused) made from a view-dependent state-dict: same trunk, sigma row
+    = alpha_linear, colour rows = the view-dependent head with its ReLU and its view columns dropped (some fixed linear map of h).
+    Test fixture only: the density field stays the one the trunk was fitted to."""
+    out = {k: v.clone() for k, v in sd.items() if k.startswith('pts_linears.')}
+    wv = sd['views_linears.0.weight'][:, :NET_WIDTH]
+    out['views_linears.0.weight'] = wv.clone()
+    out['views_linears.0.bias'] = sd['views_linears.0.bias'].clone()
+    w = torch.zeros(output_ch, NET_WIDTH)
+    b = torch.zeros(output_ch)
+    w[0:3] = sd['rgb_linear.weight'] @ wv @ sd['feature_linear.weight']
+    b[0:3] = sd['rgb_linear.bias'] + sd['rgb_linear.weight'] @ (wv @ sd['feature_linear.bias'] + sd['views_linears.0.bias'])
+    w[3] = sd['alpha_linear.weight'][0]
+    b[3] = sd['alpha_linear.bias'][0]
+    if output_ch > 4:
+        w[4:] = 0.01
+    out['output_linear.weight'], out['output_linear.bias'] = w, b
+    return out
 
 
 # camera used by BASELINE configs (logs/nerfdata/nerf_traindata_info.json; LL:185-198)

@@ -80,9 +80,12 @@ def build_models(sd_coarse, sd_fine):
     embed_fn, input_ch = RH.get_embedder(10, 0)
     embeddirs_fn, input_ch_views = RH.get_embedder(4, 0)
     nets = []
+    viewless = 'output_linear.weight' in sd_coarse        # use_viewdirs=False: RN:263 leaves input_ch_views = 0, embeddirs_fn = None
+    if viewless:
+        input_ch_views, embeddirs_fn = 0, None
     for sd in (sd_coarse, sd_fine):
         m = RH.NeRF(D=8, W=256, input_ch=input_ch, output_ch=5, skips=[4],
-                    input_ch_views=input_ch_views, use_viewdirs=True)
+                    input_ch_views=input_ch_views, use_viewdirs=not viewless)
         m.load_state_dict(sd)
         nets.append(m)
     query = lambda inputs, viewdirs, network_fn: RN.run_network(
@@ -94,5 +97,5 @@ def render_kwargs(sd_coarse, sd_fine, near, far, N_samples=64, N_importance=128)
     """The render_kwargs_test dict create_nerf would hand to render() (RN:318-338) plus near/far (MAIN:109-114)."""
     coarse, fine, query = build_models(sd_coarse, sd_fine)
     return dict(network_query_fn=query, perturb=False, N_importance=N_importance, network_fine=fine,
-                N_samples=N_samples, network_fn=coarse, use_viewdirs=True, white_bkgd=False,
+                N_samples=N_samples, network_fn=coarse, use_viewdirs='output_linear.weight' not in sd_coarse, white_bkgd=False,
                 raw_noise_std=0., ndc=False, lindisp=False, near=near, far=far)

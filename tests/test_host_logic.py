@@ -25,8 +25,33 @@ def test_unsupported_networks_fail_loudly():
         _net_tensors(nsr.NeRF(W=128))
     with pytest.raises(NotImplementedError):
         _net_tensors(torch.nn.Linear(3, 3))
+    with pytest.raises(ValueError):          # use_viewdirs=False needs `output_linear` networks (RH:95-96), as in the reference
+        nsr.render(4, 4, np.eye(3), rays=(torch.zeros(4, 3), torch.ones(4, 3)), use_viewdirs=False, ndc=False, network_fn=nsr.NeRF())
+
+
+def test_viewless_network_operands(wfit):
+    """use_viewdirs=False networks (RH:95-96, RH:119-120) are packed into the view-dependent operand layout: the twelve synthetic
+    tensors, pushed through the oracle's view-dependent forward, reproduce output_linear(h) (host arithmetic only, no kernel)."""
+    from neural_sim_nerf_b200.run_nerf import _is_viewless, _viewless_operands
+    sd = O.viewless_state_dict(wfit[1], output_ch=5)
+    net = nsr.NeRF(input_ch_views=0, output_ch=5, use_viewdirs=False)
+    net.load_state_dict(sd)
+    assert _is_viewless(net) and not _is_viewless(nsr.NeRF())
+    params, ws, bs = _viewless_operands(net)
+    assert len(params) == 18 and len(ws) == 12 and len(bs) == 12
+    names = [f'pts_linears.{i}' for i in range(8)] + ['views_linears.0', 'feature_linear', 'alpha_linear', 'rgb_linear']
+    full = {}
+    for nme, w, b in zip(names, ws, bs):
+        full[nme + '.weight'], full[nme + '.bias'] = w, b
+    nsr.NeRF().load_state_dict(full)                                       # shapes are those of the view-dependent module
+    x = torch.randn(200, 63, generator=torch.Generator().manual_seed(0)) * 0.5
+    x90 = torch.cat([x, torch.randn(200, 27, generator=torch.Generator().manual_seed(1))], -1)   # view columns meet zero weights
+    with torch.no_grad():
+        ref = O.mlp_forward(x, sd)[:, :4]
+        got = O.mlp_forward(x90, full)
+    assert (got - ref).abs().max() <= 2e-6 * ref.abs().max().clamp(min=1.0)
     with pytest.raises(NotImplementedError):
-        nsr.render(4, 4, np.eye(3), rays=(torch.zeros(4, 3), torch.ones(4, 3)), use_viewdirs=False, ndc=False)
+        _viewless_operands(nsr.NeRF(D=4, input_ch_views=0, use_viewdirs=False))
 
 
 def test_cpu_tensors_are_rejected_not_emulated(wfit):

@@ -112,6 +112,31 @@ def test_oracle_vs_live_reference(wfit):
 
 
 @pytest.mark.skipif(not ref_import.available(), reason='reference tree only exists in the build container')
+def test_oracle_viewless_vs_live_reference(wfit):
+    """use_viewdirs=False (RH:95-96, RH:119-120, RN:32, RN:111): the oracle's 8-column ray batches and `output_linear` head
+    against RN.render with the reference's own NeRF(use_viewdirs=False, input_ch_views=0, output_ch=5)."""
+    RN, RH = ref_import.load()
+    torch.autograd.set_detect_anomaly(False)
+    a, b = (O.viewless_state_dict(sd) for sd in wfit)
+    H = W = 400
+    c2w = O.pose_spherical(90., 22.5 - 180., 1.01)[:3, :4]
+    ro, rd = O.get_rays(H, W, O.YCBV_K_400, c2w)
+    sel = torch.arange(80000 - 2000, 80000 + 2000, 31)
+    rays = torch.stack([ro.reshape(-1, 3)[sel], rd.reshape(-1, 3)[sel]], 0)
+    kw = ref_import.render_kwargs(a, b, O.YCBV_NEAR, O.YCBV_FAR)
+    assert kw['use_viewdirs'] is False
+    with torch.no_grad():
+        ref = RN.render(H, W, torch.tensor(O.YCBV_K_400), chunk=512, rays=rays, retraw=True, **kw)
+        mine = O.render(H, W, O.YCBV_K_400, a, b, chunk=512, rays=rays, near=O.YCBV_NEAR, far=O.YCBV_FAR, retraw=True, use_viewdirs=False)
+    assert float(ref[2].max()) > 0.9 and float(ref[2].min()) < 0.1, 'the sample should hold hits and misses'
+    assert ref[3]['raw'].shape[-1] == 5
+    for x, y, nme in zip(ref[:3], mine[:3], ('rgb', 'disp', 'acc')):
+        close(y.numpy(), x.numpy(), 1e-6, nme)
+    for k in ref[3]:
+        close(mine[3][k].numpy(), ref[3][k].numpy(), 1e-6, k)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason='reference tree only exists in the build container')
 def test_oracle_autograd_vs_live_reference_tape(wfit):
     """The backward tests compare against autograd through the oracle; pin that tape to the reference's own
     (RN:168-181: autograd.grad(rgb_p, batch_rays, grad_outputs=patch_grad_E)) and to loss.backward() (RN:691-707)."""
