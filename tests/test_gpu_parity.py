@@ -343,8 +343,8 @@ def test_full_size_properties(nsr, wfit, nets):
 def test_no_silent_fallbacks(nsr, nets):
     with pytest.raises(Exception):
         nsr.render_rays(camera_rays(4, 0.0), nets[0], None, 64)          # CPU rays: no CPU path
-    with pytest.raises(NotImplementedError):
-        nsr.render_rays(camera_rays(4, 0.0)[:, :8].cuda(), nets[0], None, 64)  # use_viewdirs=False layout
+    with pytest.raises(ValueError):
+        nsr.render_rays(camera_rays(4, 0.0)[:, :8].cuda(), nets[0], None, 64)  # use_viewdirs=False layout with a view-dependent network
     small = torch.nn.Module()
     with pytest.raises(NotImplementedError):
         nsr.render_rays(camera_rays(4, 0.0).cuda(), small, None, 64)
