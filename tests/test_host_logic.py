@@ -186,16 +186,20 @@ def test_create_nerf_matches_live_reference(tmp_path):
     import neural_sim_nerf_b200 as nsr
     RN, _ = ref_import.load()
     os.makedirs(tmp_path / 'obj2')
-    ref = RN.create_nerf(_nerf_args(tmp_path, no_reload=True))
-    mine = nsr.create_nerf(_nerf_args(tmp_path, no_reload=True))
-    assert set(ref[0]) == set(mine[0]) and set(ref[1]) == set(mine[1])
-    for k in ('perturb', 'N_importance', 'N_samples', 'use_viewdirs', 'white_bkgd', 'raw_noise_std', 'ndc', 'lindisp'):
-        assert ref[0][k] == mine[0][k] and ref[1][k] == mine[1][k], k
-    for net in ('network_fn', 'network_fine'):
-        a, b = ref[0][net].state_dict(), mine[0][net].state_dict()
-        assert list(a) == list(b) and all(a[k].shape == b[k].shape for k in a)
-    assert ref[2] == mine[2] == 0 and len(ref[3]) == len(mine[3])
-    assert ref[4].defaults['lr'] == mine[4].defaults['lr'] and ref[4].defaults['betas'] == mine[4].defaults['betas']
+    for over in ({}, {'use_viewdirs': False}, {'use_viewdirs': False, 'N_importance': 0}):       # RN:263-267: input_ch_views 0, output_ch 5 / 4
+        ref = RN.create_nerf(_nerf_args(tmp_path, no_reload=True, **over))
+        mine = nsr.create_nerf(_nerf_args(tmp_path, no_reload=True, **over))
+        assert set(ref[0]) == set(mine[0]) and set(ref[1]) == set(mine[1])
+        for k in ('perturb', 'N_importance', 'N_samples', 'use_viewdirs', 'white_bkgd', 'raw_noise_std', 'ndc', 'lindisp'):
+            assert ref[0][k] == mine[0][k] and ref[1][k] == mine[1][k], k
+        for net in ('network_fn', 'network_fine'):
+            if ref[0][net] is None:
+                assert mine[0][net] is None
+                continue
+            a, b = ref[0][net].state_dict(), mine[0][net].state_dict()
+            assert list(a) == list(b) and all(a[k].shape == b[k].shape for k in a), over
+        assert ref[2] == mine[2] == 0 and len(ref[3]) == len(mine[3])
+        assert ref[4].defaults['lr'] == mine[4].defaults['lr'] and ref[4].defaults['betas'] == mine[4].defaults['betas']
 
 
 def test_philox_known_answers():
