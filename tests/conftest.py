@@ -20,6 +20,24 @@ def golden():
 
 
 @pytest.fixture(scope='session')
+def viewless_golden():
+    """Outputs of the unmodified reference with use_viewdirs=False (oracle/make_golden_viewless.py) and the state-dicts it ran."""
+    import numpy as np
+    import torch
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'viewless_golden.npz'))
+    z = np.load(os.path.join(ROOT, 'tests', 'golden', 'wfit.npz'))
+    sds = []
+    for pre, tag in (('coarse/', 'c'), ('fine/', 'f')):
+        sd = {k[len(pre):]: torch.from_numpy(z[k]) for k in z.files if k.startswith(pre + 'pts_linears.')}
+        sd['views_linears.0.weight'] = torch.from_numpy(z[pre + 'views_linears.0.weight'][:, :256].copy())
+        sd['views_linears.0.bias'] = torch.from_numpy(z[pre + 'views_linears.0.bias'])
+        sd['output_linear.weight'] = torch.from_numpy(g[tag + '_output_w'])
+        sd['output_linear.bias'] = torch.from_numpy(g[tag + '_output_b'])
+        sds.append(sd)
+    return g, tuple(sds)
+
+
+@pytest.fixture(scope='session')
 def wfit():
     """(sd_coarse, sd_fine): the analytic-scene weights made by oracle/make_weights.py."""
     import numpy as np

@@ -111,6 +111,23 @@ def test_oracle_vs_live_reference(wfit):
             close(mine[3][k].numpy(), ref[3][k].numpy(), 1e-6, k)
 
 
+def test_oracle_viewless_against_golden(viewless_golden):
+    """use_viewdirs=False: the oracle against outputs of the reference's own NeRF(use_viewdirs=False) through RN.render / RN.run_network
+    (oracle/make_golden_viewless.py); runs everywhere, the live comparison below only in the build container."""
+    g, (sdc, sdf) = viewless_golden
+    ro, rd = T(g['ro']), T(g['rd'])
+    with torch.no_grad():
+        raw_pts = O.run_network(T(g['pts']), None, sdf)
+        r = O.render(400, 400, O.YCBV_K_400, sdc, sdf, chunk=512, rays=(ro, rd), near=float(g['near']), far=float(g['far']),
+                     retraw=True, use_viewdirs=False)
+    close(raw_pts.numpy(), g['raw_pts'], 1e-5, 'run_network(viewdirs=None)')
+    for x, nme in zip(r[:3], ('rgb_map', 'disp_map', 'acc_map')):
+        close(x.numpy(), g[nme], 2e-5, nme)
+    for k in ('rgb0', 'disp0', 'acc0', 'z_std'):
+        close(r[3][k].numpy(), g[k], 2e-5, k)
+    close(r[3]['raw'].numpy()[::8], g['raw'], 2e-5, 'raw')
+
+
 @pytest.mark.skipif(not ref_import.available(), reason='reference tree only exists in the build container')
 def test_oracle_viewless_vs_live_reference(wfit):
     """use_viewdirs=False (RH:95-96, RH:119-120, RN:32, RN:111): the oracle's 8-column ray batches and `output_linear` head
